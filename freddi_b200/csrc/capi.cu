@@ -1,0 +1,489 @@
+// extern "C" layer of include/freddi_b200.h: owns device memory, resolves arguments on the host, launches
+// the kernels.  No CPU implementation of the path lives here: without a CUDA device every compute call fails.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "evolve.cuh"
+#include "resolve.hpp"
+
+using namespace fb200;
+
+namespace {
+thread_local std::string g_err;
+int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? FB200_ERR_NO_DEVICE : FB200_ERR_CUDA;
+}
+#define FB_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+}  // namespace
+
+struct fb200_ensemble {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t n = 0;
+    int Nx = 0, n_rows = 0, n_cols = 0, sm_count = 0;
+    bool is_ns = false;
+    fb200_config_t cfg{};
+    std::vector<fb200_model_info_t> info;
+    EnsembleDev dev{};
+    std::vector<void*> allocs;
+    int last_launches = 0;
+    bool timed = false;
+    double* scratch = nullptr;  // [n * Nx] read-out staging
+    size_t scratch_len = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(fb200_ensemble* e, T** p, size_t count) {
+    void* q = nullptr;
+    FB_CUDA(cudaMalloc(&q, count * sizeof(T) + 16));
+    e->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return FB200_OK;
+}
+
+int select_device(const fb200_ensemble* e) {
+    FB_CUDA(cudaSetDevice(e->device));
+    return FB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb200_abi_version(void) { return FB200_ABI_VERSION; }
+const char* fb200_last_error(void) { return g_err.c_str(); }
+
+int fb200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDeviceCount");
+        return (e == cudaErrorNoDevice) ? 0 : -1;
+    }
+    return n;
+}
+
+// defaults of cpp/pywrap/pywrap_freddi_evolution.cpp:33-83,203-224
+void fb200_args_default(fb200_args_t* a, int is_ns) {
+    std::memset(a, 0, sizeof(*a));
+    a->is_ns = is_ns ? 1 : 0;
+    const double nan = NAN;
+    a->alpha = nan; a->alphacold = nan; a->Mx = nan; a->kerr = 0.0; a->period = nan; a->Mopt = nan;
+    a->rochelobefill = 1.0; a->Topt = 0.0; a->rin = nan; a->rout = nan; a->risco = nan;
+    a->opacity = FB200_OPACITY_KRAMERS; a->boundcond = FB200_BOUNDCOND_TEFF; a->initialcond = FB200_IC_POWERF;
+    a->windtype = FB200_WIND_NO;
+    a->Mdotout = 0.0; a->Thot = 0.0; a->Qirr2Qvishot = 0.0;
+    a->F0 = nan; a->Mdisk0 = nan; a->Mdot0 = nan; a->powerorder = nan; a->gaussmu = nan; a->gausssigma = nan;
+    a->Cirr = 0.0; a->irrindex = 0.0; a->Cirrcold = 0.0; a->irrindexcold = 0.0; a->h2rcold = 0.0;
+    a->angulardistdisk = FB200_ANGDIST_PLANE; a->angulardistns = FB200_ANGDIST_ISOTROPIC;
+    a->colourfactor = 1.7;
+    a->emin = 1.0 * 1000. * FB_ELECTRON_VOLT / FB_H_PLANCK;   // kevToHertz(1.)
+    a->emax = 12.0 * 1000. * FB_ELECTRON_VOLT / FB_H_PLANCK;  // kevToHertz(12.)
+    a->staralbedo = 0.0; a->inclination = 0.0; a->ephemerist0 = 0.0; a->distance = nan;
+    a->inittime = 0.0; a->time = nan; a->tau = nan; a->eps = 1e-6;
+    a->Nx = 1000; a->gridscale = FB200_GRID_LOG; a->starlod = 3; a->nsprop = FB200_NSPROP_DUMMY;
+    a->freqx = nan; a->Rx = nan; a->Bx = nan; a->hotspotarea = 1.0; a->epsilonAlfven = 1.0; a->inversebeta = 0.0; a->Rdead = 0.0;
+    a->fptype = FB200_FP_NO_OUTFLOW; a->kappattype = FB200_KAPPAT_CONST; a->nsgravredshift = FB200_REDSHIFT_OFF;
+    a->kappatparams[0] = 1.0 / 3.0; a->kappatparams[1] = 1.0 / 3.0;
+}
+
+void fb200_config_default(fb200_config_t* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->compute_lx = 1;
+}
+
+int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg_in, fb200_ensemble_t** out,
+                          size_t* bad_model) {
+    if (bad_model) *bad_model = 0;
+    if (!args || !out || n_models == 0) return set_err(FB200_ERR_INVALID_ARGUMENT, "null argument or empty ensemble");
+    fb200_config_t cfg;
+    if (cfg_in) cfg = *cfg_in; else fb200_config_default(&cfg);
+    if (cfg.n_lambdas < 0 || cfg.n_lambdas > FB200_MAX_LAMBDAS) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_lambdas out of range");
+
+    // ---- resolve every model on the host ----
+    std::vector<Resolved> res(n_models);
+    std::vector<int> codes(n_models, FB200_OK);
+    std::vector<std::string> errs(n_models);
+    {
+        unsigned nt = cfg.host_threads > 0 ? unsigned(cfg.host_threads) : std::thread::hardware_concurrency();
+        if (nt == 0) nt = 1;
+        if (nt > n_models) nt = unsigned(n_models);
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t i; (i = next.fetch_add(1)) < n_models;) codes[i] = resolve(args[i], res[i], errs[i]);
+        };
+        if (nt <= 1) {
+            work();
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work);
+            for (auto& th : pool) th.join();
+        }
+    }
+    for (size_t i = 0; i < n_models; ++i) {
+        if (codes[i] != FB200_OK) {
+            if (bad_model) *bad_model = i;
+            return set_err(codes[i], errs[i]);
+        }
+    }
+    const int Nx = res[0].dev.Nx;
+    const bool is_ns = res[0].dev.is_ns != 0;
+    int max_Nt = 0;
+    bool anyA = false, anyB = false, anyC = false;
+    for (size_t i = 0; i < n_models; ++i) {
+        if (res[i].dev.Nx != Nx || (res[i].dev.is_ns != 0) != is_ns) {
+            if (bad_model) *bad_model = i;
+            return set_err(FB200_ERR_INVALID_ARGUMENT, "all models of one ensemble must share Nx and the model class (BH / NS)");
+        }
+        max_Nt = std::max(max_Nt, res[i].dev.Nt);
+        anyA |= !res[i].wA.empty();
+        anyB |= !res[i].wB.empty();
+        anyC |= !res[i].wC.empty();
+        if (is_ns && res[i].dev.inverse_beta != 0.) anyC = true;
+    }
+
+    // ---- device ----
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            if (e != cudaSuccess) cuda_fail(e, "cudaGetDeviceCount"); else g_err = "no CUDA device";
+            return set_err(FB200_ERR_NO_DEVICE, "no CUDA device: " + g_err + " (there is no CPU fallback)");
+        }
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) return set_err(FB200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+
+    auto* e = new fb200_ensemble();
+    auto guard_fail = [&](int code) { fb200_ensemble_destroy(e); return code; };
+    e->device = cfg.device;
+    e->cfg = cfg;
+    e->n = n_models;
+    e->Nx = Nx;
+    e->is_ns = is_ns;
+    e->n_rows = max_Nt + 1;
+    e->n_cols = FB200_N_BH_COLS + cfg.n_lambdas * (cfg.cold_disk ? 2 : 1) + (is_ns ? FB200_N_NS_COLS : 0);
+    e->info.resize(n_models);
+    for (size_t i = 0; i < n_models; ++i) e->info[i] = res[i].info;
+    {
+        int rc = select_device(e);
+        if (rc != FB200_OK) return guard_fail(rc);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, e->device) != cudaSuccess) return guard_fail(set_err(FB200_ERR_CUDA, "cudaGetDeviceProperties"));
+    e->sm_count = prop.multiProcessorCount;
+    if (size_t(prop.sharedMemPerBlockOptin) < evolve_smem_bytes())
+        return guard_fail(set_err(FB200_ERR_UNSUPPORTED, "device offers too little shared memory per block for the sm_100a kernels"));
+#define FB_TRY(x) do { int _rc = (x); if (_rc != FB200_OK) return guard_fail(_rc); } while (0)
+#define FB_TRYC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return guard_fail(cuda_fail(_e, #call)); } while (0)
+    FB_TRYC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    FB_TRYC(cudaEventCreate(&e->ev0));
+    FB_TRYC(cudaEventCreate(&e->ev1));
+
+    EnsembleDev& D = e->dev;
+    D.n_models = int(n_models);
+    D.Nx = Nx;
+    D.cfg.n_lambdas = cfg.n_lambdas;
+    D.cfg.cold_disk = cfg.cold_disk;
+    D.cfg.compute_lx = cfg.compute_lx;
+    D.cfg.record_F = cfg.record_F;
+    D.cfg.n_cols = e->n_cols;
+    D.cfg.n_rows = e->n_rows;
+    for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) D.cfg.lambdas[k] = (k < cfg.n_lambdas) ? cfg.lambdas[k] : 0.;
+
+    const size_t NN = n_models * size_t(Nx);
+    fb200_model_dev_t* d_models = nullptr;
+    ModelState* d_state = nullptr;
+    double *d_h = nullptr, *d_F = nullptr, *d_rows = nullptr;
+    FB_TRY(dev_alloc(e, &d_models, n_models));
+    FB_TRY(dev_alloc(e, &d_state, n_models));
+    FB_TRY(dev_alloc(e, &d_h, NN));
+    FB_TRY(dev_alloc(e, &d_F, NN));
+    const size_t rows_len = n_models * size_t(e->n_rows) * e->n_cols;
+    FB_TRY(dev_alloc(e, &d_rows, rows_len));
+    FB_TRY(dev_alloc(e, &D.queue, 4));
+    {
+        std::vector<fb200_model_dev_t> hm(n_models);
+        std::vector<ModelState> hs(n_models);
+        std::vector<double> hh(NN), hF(NN);
+        for (size_t i = 0; i < n_models; ++i) {
+            hm[i] = res[i].dev;
+            ModelState& s = hs[i];
+            std::memset(&s, 0, sizeof(s));
+            s.t = res[i].dev.t0;
+            s.F_in = res[i].dev.F_in0;
+            s.Mdot_in_prev = -INFINITY;  // cpp/include/freddi_state.hpp:245
+            s.first = res[i].dev.first0;
+            s.last = Nx - 1;
+            std::memcpy(&hh[i * Nx], res[i].h.data(), sizeof(double) * Nx);
+            std::memcpy(&hF[i * Nx], res[i].F.data(), sizeof(double) * Nx);
+        }
+        FB_TRYC(cudaMemcpy(d_models, hm.data(), sizeof(fb200_model_dev_t) * n_models, cudaMemcpyHostToDevice));
+        FB_TRYC(cudaMemcpy(d_state, hs.data(), sizeof(ModelState) * n_models, cudaMemcpyHostToDevice));
+        FB_TRYC(cudaMemcpy(d_h, hh.data(), sizeof(double) * NN, cudaMemcpyHostToDevice));
+        FB_TRYC(cudaMemcpy(d_F, hF.data(), sizeof(double) * NN, cudaMemcpyHostToDevice));
+    }
+    FB_TRYC(cudaMemset(d_rows, 0xFF, rows_len * sizeof(double)));  // all-ones = NaN: rows never written stay NaN
+    D.models = d_models; D.state = d_state; D.h = d_h; D.F = d_F; D.rows = d_rows;
+
+    auto upload_opt = [&](bool any, const double** dst, auto getter) -> int {
+        *dst = nullptr;
+        if (!any) return FB200_OK;
+        std::vector<double> host(NN, 0.);
+        for (size_t i = 0; i < n_models; ++i) {
+            const std::vector<double>& v = getter(res[i]);
+            if (!v.empty()) std::memcpy(&host[i * Nx], v.data(), sizeof(double) * Nx);
+        }
+        double* p = nullptr;
+        int rc = dev_alloc(e, &p, NN);
+        if (rc != FB200_OK) return rc;
+        cudaError_t ce = cudaMemcpy(p, host.data(), sizeof(double) * NN, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpy");
+        *dst = p;
+        return FB200_OK;
+    };
+    FB_TRY(upload_opt(anyA, &D.wA, [](const Resolved& r) -> const std::vector<double>& { return r.wA; }));
+    FB_TRY(upload_opt(anyB, &D.wB, [](const Resolved& r) -> const std::vector<double>& { return r.wB; }));
+    if (anyC) {  // static wind C + d2Fmagn_dh2 (FreddiNeutronStarEvolution::windC, cpp/src/ns/ns_evolution.cpp:487-493)
+        for (size_t i = 0; i < n_models; ++i) {
+            Resolved& r = res[i];
+            if (r.wC.empty()) r.wC.assign(Nx, 0.);
+            if (!r.d2Fmagn_dh2.empty())
+                for (int k = 0; k < Nx; ++k) r.wC[k] += r.d2Fmagn_dh2[k];
+        }
+    }
+    FB_TRY(upload_opt(anyC, &D.wCs, [](const Resolved& r) -> const std::vector<double>& { return r.wC; }));
+    FB_TRY(upload_opt(is_ns, &D.Fmagn, [](const Resolved& r) -> const std::vector<double>& { return r.Fmagn; }));
+    FB_TRY(upload_opt(is_ns, &D.dFmagn_dh, [](const Resolved& r) -> const std::vector<double>& { return r.dFmagn_dh; }));
+    FB_TRY(upload_opt(is_ns, &D.d2Fmagn_dh2, [](const Resolved& r) -> const std::vector<double>& { return r.d2Fmagn_dh2; }));
+    D.Fsnap = nullptr;
+    D.bounds = nullptr;
+    if (cfg.record_F) {
+        FB_TRY(dev_alloc(e, &D.Fsnap, n_models * size_t(e->n_rows) * Nx));
+        FB_TRY(dev_alloc(e, &D.bounds, n_models * size_t(e->n_rows) * 2));
+        FB_TRYC(cudaMemset(D.Fsnap, 0xFF, n_models * size_t(e->n_rows) * Nx * sizeof(double)));
+        FB_TRYC(cudaMemset(D.bounds, 0xFF, n_models * size_t(e->n_rows) * 2 * sizeof(int)));
+    }
+    FB_TRY(dev_alloc(e, &e->scratch, NN > n_models * 64 ? NN : n_models * 64));
+    e->scratch_len = NN > n_models * 64 ? NN : n_models * 64;
+#undef FB_TRY
+#undef FB_TRYC
+    *out = e;
+    return FB200_OK;
+}
+
+void fb200_ensemble_destroy(fb200_ensemble_t* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+size_t fb200_ensemble_n_models(const fb200_ensemble_t* e) { return e ? e->n : 0; }
+size_t fb200_ensemble_n_cols(const fb200_ensemble_t* e) { return e ? size_t(e->n_cols) : 0; }
+size_t fb200_ensemble_n_rows(const fb200_ensemble_t* e) { return e ? size_t(e->n_rows) : 0; }
+size_t fb200_ensemble_nx(const fb200_ensemble_t* e) { return e ? size_t(e->Nx) : 0; }
+
+int fb200_ensemble_info(const fb200_ensemble_t* e, fb200_model_info_t* out) {
+    if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    std::memcpy(out, e->info.data(), sizeof(fb200_model_info_t) * e->n);
+    return FB200_OK;
+}
+
+int fb200_ensemble_evolve_async(fb200_ensemble_t* e, int64_t n_steps) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    FB_CUDA(cudaMemsetAsync(e->dev.queue, 0, sizeof(int), e->stream));
+    e->dev.n_steps = (n_steps < 0 || n_steps > 0x7fffffff) ? -1 : int(n_steps);
+    FB_CUDA(cudaEventRecord(e->ev0, e->stream));
+    const int n_ctas = int(std::min<size_t>(e->n, size_t(e->sm_count)));
+    cudaError_t ce = launch_evolve(e->dev, n_ctas, e->stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_evolve_kernel launch");
+    FB_CUDA(cudaEventRecord(e->ev1, e->stream));
+    e->last_launches = 1;
+    e->timed = true;
+    return FB200_OK;
+}
+
+int fb200_ensemble_sync(fb200_ensemble_t* e) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
+int fb200_ensemble_evolve(fb200_ensemble_t* e, int64_t n_steps) {
+    int rc = fb200_ensemble_evolve_async(e, n_steps);
+    if (rc != FB200_OK) return rc;
+    return fb200_ensemble_sync(e);
+}
+
+int fb200_ensemble_last_evolve_ms(fb200_ensemble_t* e, float* ms) {
+    if (!e || !ms) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (!e->timed) return set_err(FB200_ERR_LOGIC, "no evolve call has been made");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    FB_CUDA(cudaEventSynchronize(e->ev1));
+    FB_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return FB200_OK;
+}
+
+int fb200_ensemble_last_launches(const fb200_ensemble_t* e) { return e ? e->last_launches : 0; }
+
+int fb200_ensemble_rows(fb200_ensemble_t* e, double* out, size_t out_len) {
+    if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    const size_t need = e->n * size_t(e->n_rows) * e->n_cols;
+    if (out_len < need) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    FB_CUDA(cudaMemcpyAsync(out, e->dev.rows, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
+int fb200_ensemble_rows_device(fb200_ensemble_t* e, const double** dptr) {
+    if (!e || !dptr) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    *dptr = e->dev.rows;
+    return FB200_OK;
+}
+
+static int fetch_state(fb200_ensemble_t* e, std::vector<ModelState>& hs) {
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    hs.resize(e->n);
+    FB_CUDA(cudaMemcpyAsync(hs.data(), e->dev.state, sizeof(ModelState) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
+int fb200_ensemble_status(fb200_ensemble_t* e, int32_t* status, int32_t* rows_valid, int64_t* picard_iters) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    std::vector<ModelState> hs;
+    int rc = fetch_state(e, hs);
+    if (rc != FB200_OK) return rc;
+    for (size_t i = 0; i < e->n; ++i) {
+        if (status) status[i] = hs[i].status;
+        if (rows_valid) rows_valid[i] = hs[i].rows_valid;
+        if (picard_iters) picard_iters[i] = hs[i].picard_iters;
+    }
+    return FB200_OK;
+}
+
+int fb200_ensemble_state(fb200_ensemble_t* e, double* t, int64_t* i_t, int64_t* first, int64_t* last) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    std::vector<ModelState> hs;
+    int rc = fetch_state(e, hs);
+    if (rc != FB200_OK) return rc;
+    for (size_t i = 0; i < e->n; ++i) {
+        if (t) t[i] = hs[i].t;
+        if (i_t) i_t[i] = hs[i].i_t;
+        if (first) first[i] = hs[i].first;
+        if (last) last[i] = hs[i].last;
+    }
+    return FB200_OK;
+}
+
+int fb200_ensemble_row_bounds(fb200_ensemble_t* e, int64_t row, int64_t* first, int64_t* last) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (!e->dev.bounds) return set_err(FB200_ERR_LOGIC, "row bounds need an ensemble created with record_F");
+    if (row < 0 || row >= e->n_rows) return set_err(FB200_ERR_INVALID_ARGUMENT, "row out of range");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    std::vector<int> hb(e->n * size_t(e->n_rows) * 2);
+    FB_CUDA(cudaMemcpyAsync(hb.data(), e->dev.bounds, hb.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->n; ++i) {
+        const int* b = &hb[(i * e->n_rows + size_t(row)) * 2];
+        if (first) first[i] = b[0];
+        if (last) last[i] = b[1];
+    }
+    return FB200_OK;
+}
+
+static int check_row(fb200_ensemble_t* e, int64_t row) {
+    if (row >= 0) {
+        if (!e->dev.Fsnap) return set_err(FB200_ERR_LOGIC, "reading a recorded row needs an ensemble created with record_F");
+        if (row >= e->n_rows) return set_err(FB200_ERR_INVALID_ARGUMENT, "row out of range");
+    }
+    return FB200_OK;
+}
+
+int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* out, size_t out_len) {
+    if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (field < 0 || field >= FB200_N_FIELDS) return set_err(FB200_ERR_INVALID_ARGUMENT, "unknown field");
+    const size_t need = e->n * size_t(e->Nx);
+    if (out_len < need) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    int rc = check_row(e, row);
+    if (rc != FB200_OK) return rc;
+    rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    cudaError_t ce = launch_field(e->dev, field, row, e->scratch, e->stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_field_kernel launch");
+    FB_CUDA(cudaMemcpyAsync(out, e->scratch, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
+int fb200_ensemble_flux(fb200_ensemble_t* e, int region, int64_t row, const double* lambdas, size_t n_lambdas, double* out,
+                        size_t out_len) {
+    if (!e || !out || !lambdas) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (region != 0 && region != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "region must be 0 (hot) or 1 (cold)");
+    if (n_lambdas == 0) return FB200_OK;
+    if (out_len < e->n * n_lambdas) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    int rc = check_row(e, row);
+    if (rc != FB200_OK) return rc;
+    rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    double *d_l = nullptr, *d_o = nullptr;
+    FB_CUDA(cudaMalloc(&d_l, n_lambdas * sizeof(double)));
+    cudaError_t ce = cudaMalloc(&d_o, e->n * n_lambdas * sizeof(double));
+    if (ce != cudaSuccess) { cudaFree(d_l); return cuda_fail(ce, "cudaMalloc"); }
+    ce = cudaMemcpyAsync(d_l, lambdas, n_lambdas * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = launch_flux(e->dev, region, row, d_l, int(n_lambdas), d_o, e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, e->n * n_lambdas * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d_l);
+    cudaFree(d_o);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_flux_kernel");
+    return FB200_OK;
+}
+
+int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size_t out_len) {
+    if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (out_len < e->n) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    int rc = check_row(e, row);
+    if (rc != FB200_OK) return rc;
+    rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    cudaError_t ce = launch_mdot_wind(e->dev, row, e->scratch, e->stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_mdot_wind_kernel launch");
+    FB_CUDA(cudaMemcpyAsync(out, e->scratch, e->n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
+}  // extern "C"

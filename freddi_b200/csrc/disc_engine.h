@@ -1,0 +1,805 @@
+// The disc-evolution engine: one implicit time step + one light-curve row for ONE model whose radial
+// points are spread over the threads of a CTA (one point per thread).
+//
+// The code is a template over an execution policy `Ex`:
+//   * evolve.cu instantiates it with the CUDA policy (threads of a CTA, __syncthreads, warp-shuffle
+//     reductions, shared memory) — that is the product;
+//   * tests/host_emu instantiates it with a sequential policy so the `-m "not gpu"` tests can run the
+//     very same step logic on a CPU against the oracle (test infrastructure only, never shipped).
+// Orchestration code below is "uniform": on the GPU every thread of the CTA executes it with identical
+// values; per-point work is in `ex.points([&](int i) {...})` lambdas, and data written by
+// one points() phase is only read by another thread after `ex.sync()`.
+//
+// Reference restated (paths relative to the reference repository):
+//   step                  FreddiEvolution::step           cpp/src/freddi_evolution.cpp:17-29
+//                         FreddiState::step               cpp/src/freddi_state.cpp:147-153
+//   solve_step            nonlinear_diffusion_nonuniform_wind_1_2   cpp/src/nonlinear_diffusion.cpp:31-89
+//   wunc                  FreddiEvolution::wunction       cpp/src/freddi_evolution.cpp:77-83
+//   truncate_outer        FreddiEvolution::truncateOuterRadius      cpp/src/freddi_evolution.cpp:32-74
+//   truncate_inner        FreddiNeutronStarEvolution::truncateInnerRadius  cpp/src/ns/ns_evolution.cpp:431-468
+//   structure/row         FreddiState lazy getters        cpp/src/freddi_state.cpp:156-312, cpp/include/freddi_state.hpp:377-424
+//                         row columns                     cpp/src/output.cpp:197-233, cpp/src/ns/ns_output.cpp:6-19
+//   planck_*              Spectrum::*                     cpp/src/spectrum.cpp:10-68
+//   dynamic winds         *Wind::update                   cpp/src/freddi_state.cpp:457-654
+#ifndef FB200_DISC_ENGINE_H
+#define FB200_DISC_ENGINE_H
+
+#include "fb200_math.h"
+
+#ifndef __CUDACC__
+// host-only builds (tests/host_emu): the two CUDA vector helpers the engine uses
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+#endif
+
+namespace fb200 {
+
+#define FB200_MAXQ 40 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], spare */
+
+// Ensemble-wide output configuration (device copy of fb200_config_t's output part)
+struct OutCfg {
+    int n_lambdas;
+    int cold_disk;
+    int compute_lx;
+    int record_F;
+    int n_cols;
+    int n_rows;  // rows allocated per model
+    double lambdas[FB200_MAX_LAMBDAS];
+};
+
+// Mutable per-model state carried between evolve calls (FreddiState::CurrentState, cpp/include/freddi_state.hpp:242-258)
+struct ModelState {
+    double t, F_in, Mdot_in_prev;
+    int first, last, i_t, status, rows_valid, row0_done;
+    long long picard_iters;
+};
+
+// Per-point values a thread keeps in registers during the Picard loop of one step
+struct StepRegs {
+    double lo, up, cc, frac;  // this step's row of the tridiagonal system (a_i, b_i, c0_i, frac_i)
+    double f, K, rhs0, y;
+    int valid, is_last;
+};
+
+// "Shared memory" arrays, one entry per radial point (length FB200_NX_MAX)
+struct SharedArrays {
+    double *h, *R, *F;                 // grid and state
+    double *hn;                        // h^n of the opacity closure
+    double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients (nonlinear_diffusion.cpp:46-51)
+    double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row (see init_points)
+    double2 *lu[2];                    // PCR ping-pong: (lower, upper) of the diagonal-normalised system
+    double *rr[2];                     // PCR ping-pong: right-hand side
+    // row temporaries alias the PCR buffers (never live at the same time)
+    double *Tph, *Tirr, *Sigma, *Tvis, *TphX, *aux;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Spectrum (cpp/src/spectrum.cpp:10-37, constants cpp/include/spectrum.hpp:15-18)
+// ------------------------------------------------------------------------------------------------
+#define FB_DOUBLE_H_OVER_C2 (2. * FB_H_PLANCK / (FB_C_LIGHT * FB_C_LIGHT))
+#define FB_H_OVER_KB (FB_H_PLANCK / FB_K_BOLTZ)
+#define FB_DOUBLE_H_C2 (2. * FB_H_PLANCK * FB_C_LIGHT * FB_C_LIGHT)
+#define FB_CH_OVER_KB (FB_C_LIGHT * (FB_H_PLANCK / FB_K_BOLTZ))
+
+FB_HD double planck_nu(double T, double nu) {
+    if (!(T > 0.)) return 0.;
+    return FB_DOUBLE_H_OVER_C2 * p3(nu) / (exp(FB_H_OVER_KB * nu / T) - 1.);
+}
+
+// B_lambda with the lambda-only factor pre-divided: pref = double_h_c2 / lambda^5 (same operation order
+// as `double_h_c2 / pow<5>(lambda) / (exp(...) - 1)`)
+FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
+    if (!(T > 0.)) return 0.;
+    return pref / (exp(FB_CH_OVER_KB / (lambda * T)) - 1.);
+}
+
+// integral of B_nu over [nu1, nu2]: boost::numeric::odeint::integrate_adaptive with
+// make_controlled(eps_abs = 0, eps_rel = tol, runge_kutta_cash_karp54<double>), initial step
+// 0.01 (nu2 - nu1) (cpp/src/spectrum.cpp:26-37).  Controller = odeint's default error checker
+// (a_x = a_dxdt = 1) and default step adjuster: reject when err > 1 with dt *= max(0.9 err^(-1/3), 0.2);
+// on acceptance grow when err < 0.5 with dt *= 0.9 max(5^-5, err)^(-1/5).  `trials` counts try_step calls.
+FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) {
+    if (trials) *trials = 0;
+    // Identically-zero integrand: T <= 0 or NaN (planck_nu returns 0), or exp() overflows to +inf already at
+    // nu1 so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros
+    // (error 0/0 = NaN compares false both ways) and returns exactly 0; skip the walk.
+    if (!(T > 0.) || FB_H_OVER_KB * nu1 / T > 710.) return 0.;
+    const double a21 = 1. / 5.;
+    const double a31 = 3. / 40., a32 = 9. / 40.;
+    const double a41 = 3. / 10., a42 = -9. / 10., a43 = 6. / 5.;
+    const double a51 = -11. / 54., a52 = 5. / 2., a53 = -70. / 27., a54 = 35. / 27.;
+    const double a61 = 1631. / 55296., a62 = 175. / 512., a63 = 575. / 13824., a64 = 44275. / 110592., a65 = 253. / 4096.;
+    const double b1 = 37. / 378., b3 = 250. / 621., b4 = 125. / 594., b6 = 512. / 1771.;
+    const double db1 = 37. / 378. - 2825. / 27648., db3 = 250. / 621. - 18575. / 48384., db4 = 125. / 594. - 13525. / 55296.,
+                 db5 = -277. / 14336., db6 = 512. / 1771. - 1. / 4.;
+    const double c2 = 1. / 5., c3 = 3. / 10., c4 = 3. / 5., c5 = 1., c6 = 7. / 8.;
+    (void)a21; (void)a31; (void)a32; (void)a41; (void)a42; (void)a43; (void)a51; (void)a52; (void)a53; (void)a54;
+    (void)a61; (void)a62; (void)a63; (void)a64; (void)a65;  // the integrand does not depend on the state
+    const double eps_mach = 2.220446049250313e-16;
+    double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
+    int fails = 0, n = 0;
+    double k1 = planck_nu(T, t);
+    while (nu2 - t > eps_mach) {
+        if ((t + dt) - nu2 > eps_mach) dt = nu2 - t;  // less_with_sign(end, t + dt, dt)
+        const double k3 = planck_nu(T, t + c3 * dt);
+        const double k4 = planck_nu(T, t + c4 * dt);
+        const double k5 = planck_nu(T, t + c5 * dt);
+        const double k6 = planck_nu(T, t + c6 * dt);
+        (void)c2;  // stage 2 has zero weight in both the solution and the error estimate (b2 = db2 = 0)
+        ++n;
+        const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
+        const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
+        const double err = fabs(xerr) / (0. + tol * (1. * fabs(x) + (1. * fabs(dt)) * fabs(k1)));
+        if (err > 1.0) {
+            const double f = 9. / 10. * pow(err, -1. / 3.);
+            dt *= (f < 1. / 5.) ? 1. / 5. : f;
+            if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand
+            continue;
+        }
+        fails = 0;
+        t += dt;
+        if (err < 0.5) {
+            const double floor_ = 0.00032;  // pow(5.0, -5)
+            const double e = (floor_ < err) ? err : floor_;
+            dt *= 9. / 10. * pow(e, -1. / 5.);
+        }
+        x = xnew;
+        k1 = planck_nu(T, t);
+    }
+    if (trials) *trials = n;
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-point set-up
+// ------------------------------------------------------------------------------------------------
+// Geometric factor of T_GR (cpp/src/spectrum.cpp:44-68) that depends on the radius only:
+//   T_GR^4 sigma = (3 Mdot c^6 / (8 pi GM^2)) * Gb(r).   Returns -1 for x < x0 (T_GR = 0 there).
+FB_HD double tgr_geom(const fb200_model_dev_t& M, double r1, int* inside) {
+    const double ak = M.kerr;
+    const double x = sqrt(r1 / M.tgr_rg);
+    const double x0 = M.tgr_x0;
+    if (x < x0) {
+        *inside = 1;
+        return 0.;
+    }
+    *inside = 0;
+    const double x1 = M.tgr_x1, x2 = M.tgr_x2, x3 = M.tgr_x3;
+    const double a = 3. * (x1 - ak) * (x1 - ak) * log((x - x1) / (x0 - x1)) / x1 / (x1 - x2) / (x1 - x3);
+    const double b = 3. * (x2 - ak) * (x2 - ak) * log((x - x2) / (x0 - x2)) / x2 / (x2 - x1) / (x2 - x3);
+    const double c = 3. * (x3 - ak) * (x3 - ak) * log((x - x3) / (x0 - x3)) / x3 / (x3 - x1) / (x3 - x2);
+    return (x - x0 - 1.5 * ak * log(x / x0) - a - b - c) / (p4(x) * (p3(x) - 3. * x + 2. * ak));
+}
+
+// ------------------------------------------------------------------------------------------------
+// dynamic winds: value of the wind term at point i for the current Mdot_in (cpp/src/freddi_state.cpp:457-654)
+// Returns C (and B through *Bout for Janiuk2015).  `inside` = first <= i <= last.
+// ------------------------------------------------------------------------------------------------
+struct WindScalars {
+    double v0, v1, v2, v3, v4;
+};
+
+FB_HD WindScalars wind_scalars(const fb200_model_dev_t& M, double Mdot, double h_first, double h_last, double h_back) {
+    WindScalars w{0, 0, 0, 0, 0};
+    const double mu = M.mu;
+    const double c2 = p2(FB_C_LIGHT);
+    const double L = Mdot * c2 * M.eta;
+    const double L_edd = (4.0 * FB_PI * M.GM * 2.0 * mu * FB_M_PROTON * FB_C_LIGHT / FB_THOMSON);
+    switch (M.windtype) {
+        case FB200_WIND_SHIELDSOSCIL1986:
+            w.v0 = sqrt(M.windparams[1]) * h_back;               // h_wind_min
+            w.v1 = -0.5 / FB_PI * M.windparams[0] * Mdot;         // prefactor
+            w.v2 = log(1 / M.windparams[1]);
+            break;
+        case FB200_WIND_JANIUK2015: {
+            w.v0 = 2 * M.GM / c2;  // R_g
+            const double lol = L / L_edd;
+            w.v1 = 1 - 1 / (1 + M.windparams[0] * p2(lol));  // fout
+            break;
+        }
+        case FB200_WIND_SHIELDS1986:
+        case FB200_WIND_WOODS1996: {
+            const double T_ic = M.windparams[1];
+            w.v0 = (M.GM * mu * FB_M_PROTON) / (FB_K_BOLTZ * T_ic);  // R_iC
+            const double L_crit = (1.0 / 8.0) * sqrt(FB_M_ELECTRON / (mu * FB_M_PROTON)) *
+                                  sqrt((FB_M_ELECTRON * FB_C_LIGHT * FB_C_LIGHT) / (FB_K_BOLTZ * T_ic)) * L_edd;
+            w.v1 = L / L_crit;  // el
+            w.v2 = L;
+            w.v3 = pow(w.v1, 2.0 / 3.0);
+            break;
+        }
+        case FB200_WIND_WOODS1996AGN: {
+            const double T_ic = M.windparams[1];
+            const double R_iC = (M.GM * mu * FB_M_PROTON) / (FB_K_BOLTZ * T_ic);
+            const double le = L / L_edd;
+            double R_tr;
+            if (le <= 0.01) R_tr = 6.0 * R_iC;
+            else R_tr = R_iC * (6.0 + 5.4 * log(le / 0.01) + 4.1 * ((log(le / 0.01)) * (log(le / 0.01))));
+            double f_L;
+            if (le <= 0.1) f_L = 1.0;
+            else f_L = pow((0.1 / le), 0.15);
+            w.v0 = R_iC; w.v1 = le; w.v2 = R_tr; w.v3 = f_L;
+            break;
+        }
+        case FB200_WIND_TOY:
+            w.v0 = Mdot; w.v1 = h_first; w.v2 = p2(h_last - h_first);
+            break;
+        default: break;
+    }
+    return w;
+}
+
+FB_HD void wind_dynamic_point(const fb200_model_dev_t& M, const WindScalars& w, double h, double R, double* Bout, double* Cout) {
+    const double GM = M.GM;
+    switch (M.windtype) {
+        case FB200_WIND_SHIELDSOSCIL1986:
+            if (h > w.v0) *Cout = w.v1 / (w.v2 * p2(R)) * (4 * FB_PI * p3(h)) / p2(GM);
+            break;
+        case FB200_WIND_JANIUK2015:
+            if (R > 70.0 * w.v0) {
+                const double C_0 = (4.0 * FB_PI * p3(h)) / (p2(GM));
+                const double Q = 2 * (3 / (8 * FB_PI)) * ((p4(GM)) / (p7(h)));
+                *Bout = -0.75 * C_0 * (1 / M.windparams[1]) * ((4 * Q * R) / (3 * GM)) * w.v1;
+            }
+            break;
+        case FB200_WIND_SHIELDS1986: {
+            const double R_iC = w.v0, el = w.v1, L = w.v2;
+            if (R > 0.1 * R_iC) {
+                const double Xi_max = M.windparams[0], T_ic = M.windparams[1], Pow = M.windparams[2];
+                const double xi = R / R_iC;
+                const double T_ch = T_ic * w.v3 * pow(xi, -2.0 / 3.0);
+                const double P_0 = L / (4.0 * FB_PI * p2(R) * Xi_max * FB_C_LIGHT);
+                const double C_ch = sqrt((FB_K_BOLTZ * T_ch) / (M.mu * FB_M_PROTON));
+                const double m_ch0 = P_0 / C_ch;
+                const double C0 = (4.0 * FB_PI * p3(h)) / (p2(GM));
+                const double q = 1.2 * xi / (xi + el) + 2.2 / (1. + p2(el) * xi);
+                const double y = sqrt(1. + 1. / (4. * p2(xi)) + ((p2(xi)) / (1. + p2(xi))) * (q * q));
+                const double Mach_cc = cbrt(((1. + (el + 1.) / xi) / (1. + 1. / ((1. + p2(xi)) * p4(el)))));
+                const double p_po = 0.5 * exp(-(((1. - 1. / y) * (1. - 1. / y)) / (2. * xi)));
+                *Cout = -2.0 * Pow * C0 * m_ch0 * Mach_cc * p_po * p2(y);
+            }
+            break;
+        }
+        case FB200_WIND_WOODS1996AGN: {
+            const double R_iC = w.v0, le = w.v1, R_tr = w.v2, f_L = w.v3;
+            const double g_R = (R <= R_tr) ? 1.0 : R / R_tr;
+            const double xi1 = R_iC / R;
+            const double C0 = (4.0 * FB_PI * p3(h)) / (p2(GM));
+            const double s = 1.0 - (1 / sqrt(1.0 + 0.25 * p2(xi1)));
+            const double ExP = exp(-((s * s) / (2.0 / xi1)));
+            *Cout = -2.0 * (2e42 / (M.Mx)) * (M.windparams[0] / 1e13) * C0 * le * p2(xi1) * f_L * g_R * ExP;
+            break;
+        }
+        case FB200_WIND_WOODS1996: {
+            const double R_iC = w.v0, el = w.v1, L = w.v2;
+            if (R > 0.1 * R_iC) {
+                const double Xi_max = M.windparams[0], T_ic = M.windparams[1], Pow = M.windparams[2];
+                const double xi = R / R_iC;
+                const double xi1 = R_iC / R;
+                const double T_ch = T_ic * w.v3 * pow(xi, -2.0 / 3.0);
+                const double C_ch = sqrt((FB_K_BOLTZ * T_ch) / (M.mu * FB_M_PROTON));
+                const double C0 = (4.0 * FB_PI * p3(h)) / (p2(GM));
+                const double Fr = L / (4.0 * FB_PI * p2(R) * Xi_max * C_ch * FB_C_LIGHT);
+                const double Fc = ((pow((1 + p2(((0.125 * el + 0.00382) * xi1))), (1.0 / 6.0))) /
+                                   pow((1 + 1. / p2((p4(el) * (1.0 + 262.0 * p2(xi))))), (1.0 / 6.0)));
+                const double s = 1.0 - (1 / sqrt(1.0 + 0.25 * p2(xi1)));
+                const double Expo = exp(-((s * s) / (2.0 * xi)));
+                *Cout = -2.0 * Pow * C0 * Fr * Fc * Expo;
+            }
+            break;
+        }
+        case FB200_WIND_TOY: {
+            const double Mdot = w.v0 * (h - w.v1) / w.v2;
+            *Cout = -2.0 * M.windparams[0] * Mdot;
+            break;
+        }
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalars of the current state that several getters share
+// ------------------------------------------------------------------------------------------------
+struct StateScalars {
+    double Mdot_plain;  // (F[first+1]-F[first])/(h[first+1]-h[first])      FreddiState::Mdot_in, freddi_state.cpp:156-158
+    double Mdot;        // virtual Mdot_in(): + dFmagn_dh[first] for NS       ns_evolution.cpp:471-474
+    double Lbol_disk;   // freddi_state.cpp:161-163 / ns_evolution.cpp:526-528
+    double Lbol_ns_rest, Lbol_ns, eta_ns, fp, R_alfven;  // ns_evolution.cpp:386-395,476-478
+};
+
+FB_HD double ns_R_alfven(const fb200_model_dev_t& M, double Mdot) {  // ns_arguments.cpp:50-52
+    return M.epsilon_Alfven * pow(p4(M.mu_magn) / (M.GM * p2(Mdot)), 1. / 7.);
+}
+
+template <class Ex>
+FB_HD StateScalars state_scalars(Ex& ex, const fb200_model_dev_t& M, const SharedArrays& S, int first, bool want_ns_lum) {
+    StateScalars s{};
+    const double F0 = S.F[first], F1 = S.F[first + 1], h0 = S.h[first], h1 = S.h[first + 1];
+    s.Mdot_plain = (F1 - F0) / (h1 - h0);
+    s.Mdot = s.Mdot_plain;
+    if (M.is_ns) {
+        s.Mdot = s.Mdot_plain + ex.dFmagn_dh(first);
+        const double R0 = S.R[first];
+        s.Lbol_disk = (F0 + 0.5 * s.Mdot * h0) * sqrt(M.GM / (R0 * R0 * R0));
+        if (want_ns_lum) {
+            s.R_alfven = ns_R_alfven(M, s.Mdot);
+            s.eta_ns = ns_eta(M, s.R_alfven, R0);
+            s.fp = ns_fp(M, R0);
+            double Mdot = s.Mdot;
+            if (Mdot < 0.0) Mdot = 0.0;
+            s.Lbol_ns_rest = s.eta_ns * s.fp * Mdot * p2(FB_C_LIGHT);
+            s.Lbol_ns = M.redshift * s.Lbol_ns_rest;
+        }
+    } else {
+        s.Lbol_disk = M.eta * s.Mdot * p2(FB_C_LIGHT);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hot-zone structure at one point (cpp/src/freddi_state.cpp:184-290, opacity_related.cpp:85-87)
+// ------------------------------------------------------------------------------------------------
+struct PointStructure {
+    double W, Sigma, Height, Kirr, Qx, Tvis, Tph, Tirr;
+};
+
+FB_HD double pow025(double x) { return sqrt(sqrt(x)); }
+
+FB_HD double wunc_point(const fb200_model_dev_t& M, double F, double hn) {
+    return pow(fabs(F), M.one_minus_m) * hn / M.one_minus_m / M.D;
+}
+
+FB_HD PointStructure hot_structure(const fb200_model_dev_t& M, const StateScalars& sc, double h, double R, double hn, double hm175,
+                                   double hotR, double F) {
+    PointStructure q;
+    q.W = wunc_point(M, F, hn);
+    q.Sigma = q.W * p2(M.GM) / (4. * FB_PI * p3(h));
+    q.Height = hotR * pow(F, M.Height_exp_F);
+    const double mu = q.Height / R;
+    q.Kirr = M.Cirr * ((M.irrindex == 0.) ? 1.0 : pow(q.Height / (R * 0.05), M.irrindex));
+    if (M.is_ns) {
+        q.Qx = q.Kirr * (sc.Lbol_disk * angular_dist(M.angdist_disk, mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, mu)) /
+               (4. * FB_PI * p2(R));
+    } else {
+        q.Qx = q.Kirr * sc.Lbol_disk * angular_dist(M.angdist_disk, mu) / (4. * FB_PI * p2(R));
+    }
+    q.Tvis = hm175 * pow025(3. / (8. * FB_PI) * F / FB_SIGMA_SB);
+    q.Tph = pow025(p4(q.Tvis) + q.Qx / FB_SIGMA_SB);
+    q.Tirr = pow025(q.Qx / FB_SIGMA_SB);
+    return q;
+}
+
+// Sigma_minus / Sigma_plus / v_cooling_front (cpp/src/freddi_state.cpp:692-722)
+FB_HD double sigma_minus(const fb200_model_dev_t& M, double r) {
+    return 74.6 * M.sigma_minus_k * pow(r / 1e10, 1.18) * M.sigma_minus_mx;
+}
+FB_HD double sigma_plus(const fb200_model_dev_t& M, double r) {
+    return 39.9 * M.sigma_plus_k * pow(r / 1e10, 1.11) * M.sigma_plus_mx;
+}
+FB_HD double v_cooling_front(const fb200_model_dev_t& M, double r, double Sigma_last) {
+    const double Sigma_plus_ = sigma_plus(M, r);
+    const double sigma = log(Sigma_last / Sigma_plus_) / log(sigma_minus(M, r) / Sigma_plus_);
+    return 1e5 * (1.439 - 5.305 * sigma + 10.440 * p2(sigma) - 10.55 * p3(sigma) + 4.142 * p4(sigma)) *
+           pow(M.alpha / 0.2, 0.85 - 0.69 * sigma) * pow(M.alphacold / 0.05, 0.05 + 0.69 * sigma) * pow(r / 1e10, 0.035) *
+           M.vcf_mx;
+}
+
+
+FB_HD bool fb_isfinite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+FB_HD bool fb_isnan(double x) { return x != x; }
+
+// ------------------------------------------------------------------------------------------------
+// The engine.  Execution policy `Ex` provides:
+//   points(f)            run f(i) for the point(s) this thread owns (no barrier)
+//   sync()               CTA barrier
+//   step(i)              StepRegs& of point i (thread-private registers on the GPU)
+//   reduce_max(f)        max over points of f(i), NaN-skipping (fmax), value returned to every thread
+//   reduce_max_int(f) / reduce_min_int(f)
+//   reduce_sums(nq, f)   sum over points of f(i, q) for q < nq; results via sum(q)
+//   scalar(k)            small shared scratch (written by one thread, read after sync)
+//   windA(i), windB(i), windC_static(i), Fmagn(i), dFmagn_dh(i)   per-model arrays in global memory (0 if absent)
+//   lambda_pref(k)       double_h_c2 / lambda_k^5
+// ------------------------------------------------------------------------------------------------
+template <class Ex>
+struct DiscEngine {
+    Ex& ex;
+    const fb200_model_dev_t& M;
+    const OutCfg& cfg;
+    SharedArrays S;
+    ModelState st;  // uniform copy (every thread holds the same values)
+
+    FB_HD DiscEngine(Ex& ex_, const fb200_model_dev_t& M_, const OutCfg& cfg_, const SharedArrays& S_, const ModelState& st_)
+        : ex(ex_), M(M_), cfg(cfg_), S(S_), st(st_) {}
+
+    // nonlinear_diffusion.cpp:46-51 for an interior point i (1 <= i <= Nx-2), wind terms A, B
+    FB_HD void interior_coeffs(int i, double A, double B) const {
+        const double xm = S.h[i - 1], x = S.h[i], xp = S.h[i + 1];
+        S.ca[i] = (xp - x) / (xp - xm) * (2.0 - A * (xp - x));
+        S.cb[i] = (x - xm) / (xp - xm) * (2.0 + A * (x - xm));
+        S.cc[i] = 2.0 - A * (xp - 2 * x + xm) - B * (xp - x) * (x - xm);
+        S.frac[i] = (xp - x) * (x - xm) / M.tau;
+    }
+
+    // ---- one-time per model: grid-derived constants.  S.h and S.F must be loaded and synced. ----
+    FB_HD void init_points() {
+        const int Nx = M.Nx;
+        ex.points([&](int i) {
+            if (i >= Nx) return;
+            const double h = S.h[i];
+            const double R = p2(h) / M.GM;  // FreddiState::DiskStructure::initialize_R, freddi_state.cpp:47-53
+            S.R[i] = R;
+            S.hn[i] = pow(h, M.n_op);
+            S.c1[i] = 3. / (8. * FB_PI) * p4(M.GM) / p7(h);                                      // freddi_state.cpp:300
+            S.hm175[i] = M.GM * pow(h, -1.75);                                                    // freddi_state.cpp:284
+            S.hotR[i] = R * M.Height_coef * pow(R / 1e10, M.Height_exp_R - M.Height_exp_F / 2.);  // opacity_related.cpp:86
+            int inside;
+            const double g = tgr_geom(M, R, &inside);
+            S.Gb[i] = inside ? 0. : g;
+            if (i > 0 && i < Nx - 1) interior_coeffs(i, ex.windA(i), ex.windB(i));
+            else { S.ca[i] = 0.; S.cb[i] = 0.; S.cc[i] = 0.; S.frac[i] = 0.; }
+        });
+        ex.sync();
+    }
+
+    // ---- truncateInnerRadius, NS only (ns_evolution.cpp:431-468).  Returns false on RadiusCollapse. ----
+    FB_HD bool truncate_inner() {
+        if (M.R_dead <= 0.) return true;
+        const StateScalars sc = state_scalars(ex, M, S, st.first, false);
+        const double Mdot = sc.Mdot;
+        if ((!fb_isfinite(st.Mdot_in_prev)) || (Mdot < 0.0) || (st.Mdot_in_prev < 0.0)) return true;
+        if (Mdot > st.Mdot_in_prev) return true;
+        const double Ra = ns_R_alfven(M, Mdot);
+        double R_m = (M.R_m_min < Ra) ? Ra : M.R_m_min;  // std::max(R_m_min, R_Alfven)
+        R_m = (M.R_dead < R_m) ? M.R_dead : R_m;         // std::min(R_m, R_dead)
+        const int first = st.first, last = st.last;
+        // smallest ii in [first, last-2] with R[ii+1] > R_m, else the loop runs out at last-1
+        int ii = ex.reduce_min_int([&](int i) -> int {
+            if (i >= first && i <= last - 2 && S.R[i + 1] > R_m) return i;
+            return 0x7fffffff;
+        });
+        if (ii == 0x7fffffff) ii = last - 1;
+        if (ii >= last - 2) return false;
+        R_m = S.R[ii];
+        st.first = ii;
+        double new_F_in = 0;
+        if (M.inverse_beta <= 0.) {
+            if (R_m <= M.R_cor) new_F_in = kappa_t(M, R_m) * p2(M.mu_magn) / p3(M.R_cor);
+            else new_F_in = kappa_t(M, R_m) * p2(M.mu_magn) / p3(R_m);
+        }
+        st.F_in = new_F_in;
+        return true;
+    }
+
+    // ---- the implicit step (nonlinear_diffusion.cpp:31-89) ----
+    // On entry S.F holds y(t); on exit y(t+tau).  Returns Picard iterations, or -1 if the guard tripped.
+    FB_HD int solve_step(double Mdot_in_for_wind) {
+        const int first = st.first, last = st.last;
+        const int m = last - first;  // unknowns first+1..last
+        const int Nx = M.Nx;
+        const double tau = M.tau, F_in = st.F_in, rbc = M.Mdot_out;
+        WindScalars ws{0, 0, 0, 0, 0};
+        if (M.wind_dynamic) ws = wind_scalars(M, Mdot_in_for_wind, S.h[first], S.h[last], S.h[Nx - 1]);
+        const bool janiuk = (M.windtype == FB200_WIND_JANIUK2015);
+
+        if (janiuk) {  // B changes with Mdot_in: refresh the interior coefficients
+            ex.points([&](int i) {
+                if (i > 0 && i < Nx - 1) {
+                    double Bd = 0., Cd = 0.;
+                    if (i >= first && i <= last) wind_dynamic_point(M, ws, S.h[i], S.R[i], &Bd, &Cd);
+                    interior_coeffs(i, 0., Bd);
+                }
+            });
+            // each thread rewrites only its own entries and reads them back itself: no barrier needed
+        }
+
+        ex.points([&](int i) {
+            StepRegs& r = ex.step(i);
+            r.valid = (i > first && i <= last);
+            r.is_last = (i == last);
+            r.K = 0.; r.f = 0.; r.y = 0.; r.lo = 0.; r.up = 0.; r.cc = 1.; r.frac = 0.; r.rhs0 = 0.;
+            if (!r.valid) return;
+            const double h = S.h[i], R = S.R[i];
+            double A = ex.windA(i), B = ex.windB(i), C = ex.windC_static(i);
+            if (M.wind_dynamic) {
+                double Bd = 0., Cd = 0.;
+                wind_dynamic_point(M, ws, h, R, &Bd, &Cd);  // update() rewrites the points of [first, last]
+                if (janiuk) B = Bd; else C = Cd + C;
+            }
+            const double y = S.F[i];
+            const double W = wunc_point(M, y, S.hn[i]);
+            if (!r.is_last) {
+                r.lo = S.ca[i]; r.up = S.cb[i]; r.cc = S.cc[i]; r.frac = S.frac[i];
+                r.f = r.frac * (W + tau * C);
+                r.K = r.f / y;            // nonlinear_diffusion.cpp:61 — includes tau*C
+                r.rhs0 = r.f;
+            } else {
+                const double d = h - S.h[i - 1];
+                const double aL = 1 - 0.5 * A * d;
+                r.lo = aL; r.up = 0.;
+                r.cc = aL - 0.5 * B * d * d;
+                r.frac = d * d * 0.5 / tau;
+                r.f = r.frac * (W + tau * C);
+                r.K = r.frac * W / y;     // nonlinear_diffusion.cpp:65 — no C, never updated in the loop
+                r.rhs0 = d * rbc + r.f;
+            }
+            if (i == first + 1) { r.rhs0 += r.lo * F_in; r.lo = 0.; }  // y[first] = F_in is known
+        });
+
+        int iters = 0;
+        double maxrel;
+        do {
+            // -- tridiagonal solve: parallel cyclic reduction on the diagonal-normalised system --
+            ex.points([&](int i) {
+                StepRegs& r = ex.step(i);
+                double l = 0., u = 0., rhs = 0.;
+                if (r.valid) {
+                    const double inv = 1.0 / (r.cc + r.K);
+                    l = -r.lo * inv; u = -r.up * inv; rhs = r.rhs0 * inv;
+                }
+                S.lu[0][i] = make_double2(l, u);
+                S.rr[0][i] = rhs;
+                r.y = rhs;
+            });
+            ex.sync();
+            int cur = 0;
+            for (int s = 1; s < m; s <<= 1) {
+                ex.points([&](int i) {
+                    StepRegs& r = ex.step(i);
+                    if (!r.valid) return;  // rows outside (first, last] are never read
+                    const double2 me = S.lu[cur][i];
+                    const double rme = S.rr[cur][i];
+                    const int im = i - s, ip = i + s;
+                    double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
+                    double ra = 0., rb = 0.;
+                    if (im > first) { a = S.lu[cur][im]; ra = S.rr[cur][im]; }
+                    if (ip <= last) { b = S.lu[cur][ip]; rb = S.rr[cur][ip]; }
+                    const double inv = 1.0 / (1.0 - me.x * a.y - me.y * b.x);
+                    const double l = -me.x * a.x * inv;
+                    const double u = -me.y * b.y * inv;
+                    const double rhs = (rme - me.x * ra - me.y * rb) * inv;
+                    S.lu[cur ^ 1][i] = make_double2(l, u);
+                    S.rr[cur ^ 1][i] = rhs;
+                    r.y = rhs;
+                });
+                ex.sync();
+                cur ^= 1;
+            }
+            // -- y, W, K update and convergence norm (nonlinear_diffusion.cpp:83-88) --
+            maxrel = ex.reduce_max([&](int i) -> double {
+                StepRegs& r = ex.step(i);
+                if (i == first) S.F[i] = F_in;
+                if (!r.valid) return 0.;
+                S.F[i] = r.y;
+                if (r.is_last) return 0.;  // K[last] stays at its pre-step value
+                const double W = wunc_point(M, r.y, S.hn[i]);
+                const double K1 = r.frac * W / r.y;
+                const double rel = fabs((K1 - r.K) / K1);
+                r.K = K1;
+                return rel;  // a NaN is skipped by the reduction, as `x > max` does in max_dif_rel
+            });
+            ++iters;
+            if (iters >= 100000) return -1;
+        } while (maxrel > M.eps);
+        ex.sync();
+        return iters;
+    }
+
+    // ---- structure pass + truncateOuterRadius + one row ----
+    // do_truncate: after a step (truncateOuterRadius, freddi_evolution.cpp:32-74); false for row 0.
+    // Returns false on RadiusCollapse (no row is written then).  row may be null (no output wanted).
+    FB_HD bool structure_and_row(bool do_truncate, double* row, double* Fsnap_row, int* bounds_row) {
+        const int Nx = M.Nx;
+        const int first = st.first;
+        int last = st.last;
+        const StateScalars sc = state_scalars(ex, M, S, first, true);
+
+        // hot-zone structure of every point of [first, last]
+        ex.points([&](int i) {
+            if (i >= Nx) return;
+            double Tph = 0., Tirr = 0., Sigma = 0., Tvis = 0.;
+            if (i >= first && i <= last) {
+                const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i]);
+                Tph = q.Tph; Tirr = q.Tirr; Sigma = q.Sigma; Tvis = q.Tvis;
+                if (i == last) { ex.scalar(0) = q.Kirr; ex.scalar(1) = q.Height / S.R[i]; }
+            }
+            S.Tph[i] = Tph; S.Tirr[i] = Tirr; S.Sigma[i] = Sigma; S.Tvis[i] = Tvis;
+        });
+        ex.sync();
+
+        if (do_truncate && M.Thot > 0. && fb_isfinite(st.Mdot_in_prev) && !(sc.Mdot < 0.0) && !(st.Mdot_in_prev < 0.0) &&
+            !(sc.Mdot > st.Mdot_in_prev)) {
+            int branch;  // 0: cooling front, 1: Teff, 2: Tirr
+            if (S.Tirr[last] / S.Tvis[last] < M.Tirr2Tvishot) branch = 0;
+            else branch = (M.boundcond == FB200_BOUNDCOND_TEFF) ? 1 : 2;
+            const double Sigma_last = S.Sigma[last], R_last = S.R[last];
+            // the do-while walks ii = last, last-1, ... and stops at the first ii whose condition is false
+            const int jmax = ex.reduce_max_int([&](int i) -> int {
+                if (!(i > first && i <= last)) return -1;
+                bool cond;
+                if (branch == 0) {
+                    const double r = S.R[i];
+                    const double R_cf = R_last - v_cooling_front(M, r, Sigma_last) * M.tau;
+                    cond = (r > R_cf) && (S.Sigma[i] < sigma_minus(M, r)) && (S.Tirr[i] < M.Thot);
+                } else if (branch == 1) {
+                    cond = S.Tph[i] < M.Thot;
+                } else {
+                    cond = S.Tirr[i] < M.Thot;
+                }
+                return cond ? -1 : i;
+            });
+            if (jmax < 0) return false;  // ii <= first: RadiusCollapseException
+            if (jmax <= last - 1) {
+                last = jmax;
+                st.last = last;
+                ex.points([&](int i) {  // Kirr and H/R at the new outer edge
+                    if (i == last) {
+                        const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i]);
+                        ex.scalar(0) = q.Kirr; ex.scalar(1) = q.Height / S.R[i];
+                    }
+                });
+                ex.sync();
+            }
+        }
+        if (!row) return true;
+
+        // ---- Tph_X over the hot zone, freddi_state.cpp:292-312 ----
+        const double absMdot = fabs(sc.Mdot_plain);
+        const double KM = 3. * absMdot * p6(FB_C_LIGHT) / (8. * FB_PI * p2(M.GM));
+        const double F_first = S.F[first];
+        ex.points([&](int i) {
+            if (i >= Nx) return;
+            double T = 0.;
+            if (i >= first && i <= last) {
+                double x = S.c1[i] * F_first;
+                const double g = KM * S.Gb[i];  // = T_GR^4 sigma; T_GR = pow(., 0.25) is NaN for a negative argument
+                x += (g < 0.) ? NAN : g;
+                T = M.colourfactor * pow025(x / FB_SIGMA_SB);
+            }
+            S.TphX[i] = T;
+        });
+        ex.sync();
+
+        // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
+        const int nl = cfg.n_lambdas;
+        const int nq = 2 + nl * (cfg.cold_disk ? 2 : 1);
+        double cold_K = 0.;
+        const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
+        if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
+        ex.reduce_sums(nq, [&](int i, int q) -> double {
+            if (i >= Nx) return 0.;
+            const bool cold = (q >= 2 + nl);
+            int rf = first, rl = last;
+            if (cold) { rf = last + 1; rl = Nx - 1; }
+            if (rf >= rl || i < rf || i > rl) return 0.;
+            double w;  // trapezoid weight in R
+            if (i == rf) w = S.R[i + 1] - S.R[i];
+            else if (i == rl) w = S.R[i] - S.R[i - 1];
+            else w = S.R[i + 1] - S.R[i - 1];
+            double y;
+            if (q == 0) {
+                y = S.Sigma[i];
+            } else if (q == 1) {
+                if (!cfg.compute_lx) return 0.;
+                y = planck_nu1_nu2(S.TphX[i], M.emin, M.emax, 1e-4, nullptr);
+            } else if (!cold) {
+                const int k = q - 2;
+                y = planck_lambda_pref(S.Tph[i], cfg.lambdas[k], ex.lambda_pref(k));
+            } else {
+                const int k = q - 2 - nl;
+                const double R = S.R[i];
+                double Qx;
+                if (M.is_ns)
+                    Qx = cold_K * (sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, cold_mu)) /
+                         (4. * FB_PI * p2(R));
+                else
+                    Qx = cold_K * sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) / (4. * FB_PI * p2(R));
+                y = planck_lambda_pref(pow025(Qx / FB_SIGMA_SB), cfg.lambdas[k], ex.lambda_pref(k));
+            }
+            return 2 * FB_PI * S.R[i] * y * w;
+        });
+        // max Tph_X over [first, last] with std::max_element's NaN behaviour (output.cpp:208)
+        double TphXmax = ex.reduce_max([&](int i) -> double {
+            if (i >= first && i <= last) return S.TphX[i];
+            return -INFINITY;
+        });
+        if (fb_isnan(S.TphX[first])) TphXmax = NAN;
+
+        // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----
+        const double Mdisk = 0.5 * ex.sum(0);
+        const double Lx = cfg.compute_lx ? (2. * FB_PI * (0.5 * ex.sum(1))) / p4(M.colourfactor) : NAN;
+        const double d2 = 4.0 * FB_PI * p2(M.distance);
+        const double psi = angular_dist(M.angdist_disk, M.cosi);
+        const int ncol = cfg.n_cols;
+        const double t_now = st.t;
+        ex.points([&](int i) {
+            if (i >= ncol) return;
+            double v;
+            switch (i) {
+                case FB200_COL_T: v = t_now / 86400.; break;
+                case FB200_COL_MDOT: v = sc.Mdot; break;
+                case FB200_COL_MDISK: v = Mdisk; break;
+                case FB200_COL_RHOT: v = S.R[last] / FB_SOLAR_RADIUS; break;
+                case FB200_COL_SIGMAOUT: v = S.Sigma[last]; break;
+                case FB200_COL_KIRROUT: v = ex.scalar(0); break;
+                case FB200_COL_H2R: v = ex.scalar(1); break;
+                case FB200_COL_TEFFOUT: v = S.Tph[last]; break;
+                case FB200_COL_TIRROUT: v = S.Tirr[last]; break;
+                case FB200_COL_QIRR2QVISOUT: v = p4(S.Tirr[last] / S.Tvis[last]); break;
+                case FB200_COL_TPHXMAX: v = TphXmax * FB_K_BOLTZ / (1000. * FB_ELECTRON_VOLT); break;
+                case FB200_COL_LX: v = Lx; break;
+                case FB200_COL_LBOL: v = sc.Lbol_disk; break;
+                case FB200_COL_FX: v = Lx * psi / d2; break;
+                case FB200_COL_FBOL: v = sc.Lbol_disk * psi / d2; break;
+                default: {
+                    const int k = i - FB200_N_BH_COLS;
+                    const int per = cfg.cold_disk ? 2 : 1;
+                    if (k < nl * per) {
+                        const int kl = k / per;
+                        const bool cold = (k % per) == 1;
+                        const double lam = cfg.lambdas[kl];
+                        const double I = 0.5 * ex.sum(cold ? 2 + nl + kl : 2 + kl);
+                        v = I * p2(lam) / FB_C_LIGHT * M.cosiOverD2;  // freddi_state.hpp:405-407
+                    } else {
+                        v = ns_column(k - nl * per, sc);
+                    }
+                }
+            }
+            row[i] = v;
+        });
+        if (Fsnap_row) {
+            ex.points([&](int i) { if (i < Nx) Fsnap_row[i] = S.F[i]; });
+        }
+        if (bounds_row) {
+            ex.points([&](int i) { if (i == 0) { bounds_row[0] = first; bounds_row[1] = last; } });
+        }
+        ex.sync();
+        return true;
+    }
+
+    // NS columns (ns_output.cpp:6-19); each evaluated by one thread
+    FB_HD double ns_column(int k, const StateScalars& sc) const {
+        const int first = st.first;
+        const double area = 4 * FB_PI * M.hot_spot_area * p2(M.R_x);
+        switch (k) {
+            case FB200_NSCOL_RIN: return S.R[first];
+            case FB200_NSCOL_ETANS: return sc.eta_ns;
+            case FB200_NSCOL_LXNS:
+            case FB200_NSCOL_FXNS: {  // ns_evolution.cpp:398-422
+                const double T = pow025(sc.Lbol_ns_rest / (area * FB_SIGMA_SB));
+                const double intensity =
+                    cfg.compute_lx ? planck_nu1_nu2(T, M.emin / M.redshift, M.emax / M.redshift, 1e-4, nullptr) : NAN;
+                const double Lx_ns = M.redshift * (area * FB_PI * intensity);
+                if (k == FB200_NSCOL_LXNS) return Lx_ns;
+                return Lx_ns * angular_dist(M.angdist_ns, M.cosi) / (4.0 * FB_PI * p2(M.distance));
+            }
+            case FB200_NSCOL_LBOLNS: return sc.Lbol_ns;
+            case FB200_NSCOL_FBOLNS: return sc.Lbol_ns * angular_dist(M.angdist_ns, M.cosi) / (4.0 * FB_PI * p2(M.distance));
+            case FB200_NSCOL_THOTSPOT: return pow025(sc.Lbol_ns_rest / (area * FB_SIGMA_SB)) * FB_K_BOLTZ / (1000. * FB_ELECTRON_VOLT);
+            case FB200_NSCOL_FPIN: return sc.fp;
+            case FB200_NSCOL_FMAGNIN: return ex.Fmagn(first);
+            case FB200_NSCOL_FIN: return S.F[first];
+            default: return NAN;
+        }
+    }
+
+    // ---- one FreddiEvolution::step (freddi_evolution.cpp:17-29) followed by the row of the new state ----
+    // Returns false when the model stops (collapse / failure); st.status says why.
+    FB_HD bool step_and_row(double* row, double* Fsnap_row, int* bounds_row) {
+        if (M.is_ns) {
+            if (!truncate_inner()) { st.status = FB200_MODEL_COLLAPSED; return false; }
+        }
+        // FreddiState::step, freddi_state.cpp:147-153
+        const StateScalars sc = state_scalars(ex, M, S, st.first, false);
+        st.Mdot_in_prev = sc.Mdot;
+        st.i_t += 1;
+        st.t += M.tau;
+        const int it = solve_step(sc.Mdot);
+        if (it < 0) { st.status = FB200_MODEL_FAILED; return false; }
+        st.picard_iters += it;
+        if (!structure_and_row(true, row, Fsnap_row, bounds_row)) { st.status = FB200_MODEL_COLLAPSED; return false; }
+        return true;
+    }
+};
+
+}  // namespace fb200
+#endif

@@ -1,0 +1,74 @@
+// The persistent ensemble kernel: each CTA pulls model indices from a device-side queue, stages the
+// model's FP64 state (h, F and the grid-derived constants) into shared memory once, and runs the whole
+// multi-step loop there: FreddiEvolution::step (cpp/src/freddi_evolution.cpp:17-29) + one light-curve row
+// (cpp/src/output.cpp:197-233) per step.  Only rows (and optional F snapshots) go back to HBM.
+#include "gpu_exec.cuh"
+
+namespace fb200 {
+
+__global__ void __launch_bounds__(kNT, 1) fb200_evolve_kernel(const EnsembleDev E) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* base = reinterpret_cast<double*>(smem_raw);
+    const SharedArrays S = carve_shared(base);
+    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    __shared__ int s_model;
+
+    GpuEx ex;
+    ex.init(scratch);
+    const int tid = threadIdx.x;
+    const int Nx = E.Nx;
+    const int ncol = E.cfg.n_cols, nrows = E.cfg.n_rows;
+
+    for (;;) {
+        __syncthreads();  // previous model fully done with shared memory and s_model
+        if (tid == 0) s_model = atomicAdd(E.queue, 1);
+        __syncthreads();
+        const int model = s_model;
+        if (model >= E.n_models) break;
+
+        ModelState st = E.state[model];
+        if (st.status != FB200_MODEL_OK) continue;
+        load_model(E, model, Msh, S, ex, E.F + size_t(model) * Nx);
+        const fb200_model_dev_t& M = *Msh;
+
+        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        eng.init_points();
+
+        double* rows = E.rows + size_t(model) * nrows * ncol;
+        double* Fsnap = E.Fsnap ? E.Fsnap + size_t(model) * nrows * Nx : nullptr;
+        int* bounds = E.bounds ? E.bounds + size_t(model) * nrows * 2 : nullptr;
+
+        if (!eng.st.row0_done) {
+            // the state at t0 is dumped before the first step (cpp/include/application.hpp:25-29)
+            eng.structure_and_row(false, rows, Fsnap, bounds);
+            eng.st.row0_done = 1;
+            eng.st.rows_valid = 1;
+        }
+        int todo = M.Nt - eng.st.i_t;
+        if (E.n_steps >= 0 && E.n_steps < todo) todo = E.n_steps;
+        for (int s = 0; s < todo; ++s) {
+            const int r = eng.st.i_t + 1;
+            const bool ok = eng.step_and_row(rows + size_t(r) * ncol, Fsnap ? Fsnap + size_t(r) * Nx : nullptr,
+                                             bounds ? bounds + size_t(r) * 2 : nullptr);
+            if (!ok) break;
+            eng.st.rows_valid = r + 1;
+        }
+        // write the state back for the next evolve call / the read-out kernels
+        __syncthreads();
+        if (tid < Nx) E.F[size_t(model) * Nx + tid] = S.F[tid];
+        if (tid == 0) E.state[model] = eng.st;
+    }
+}
+
+size_t evolve_smem_bytes() { return SmemLayout::bytes(); }
+
+cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream) {
+    // per device and cheap: set on every launch so that several devices in one process all get it
+    cudaError_t e = cudaFuncSetAttribute(fb200_evolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
+    if (e != cudaSuccess) return e;
+    fb200_evolve_kernel<<<n_ctas, kNT, SmemLayout::bytes(), stream>>>(E);
+    return cudaGetLastError();
+}
+
+}  // namespace fb200

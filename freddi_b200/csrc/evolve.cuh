@@ -1,0 +1,40 @@
+// Device-side view of an ensemble and the launch interface of the evolve kernel (evolve.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "disc_engine.h"
+
+namespace fb200 {
+
+struct EnsembleDev {
+    int n_models;
+    int Nx;            // every model of an ensemble has the same Nx
+    int n_steps;       // steps requested by this launch (clipped per model at Nt - i_t)
+    OutCfg cfg;
+    const fb200_model_dev_t* models;  // [n_models]
+    ModelState* state;                // [n_models]
+    const double* h;                  // [n_models][Nx]
+    double* F;                        // [n_models][Nx] current state
+    const double* wA;                 // [n_models][Nx] or null: static wind A
+    const double* wB;                 // [n_models][Nx] or null
+    const double* wCs;                // [n_models][Nx] or null: static wind C + d2Fmagn_dh2
+    const double* Fmagn;              // [n_models][Nx] or null
+    const double* dFmagn_dh;          // [n_models][Nx] or null
+    const double* d2Fmagn_dh2;        // [n_models][Nx] or null (read-out only; the solver uses wCs)
+    double* rows;                     // [n_models][n_rows][n_cols]
+    double* Fsnap;                    // [n_models][n_rows][Nx] or null (record_F)
+    int* bounds;                      // [n_models][n_rows][2] or null (first,last per row; record_F)
+    int* queue;                       // work-queue counter
+};
+
+size_t evolve_smem_bytes();
+// Launches the persistent evolve kernel on `stream`; returns cudaGetLastError().
+cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream);
+
+// field / flux read-out kernels (fields.cu)
+cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream);
+cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
+                        cudaStream_t stream);
+cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, cudaStream_t stream);
+
+}  // namespace fb200

@@ -1,0 +1,266 @@
+// Read-out kernels: radial fields, spectral flux densities and Mdot_wind of a recorded or the current state.
+// They restate the array getters of FreddiState (cpp/src/freddi_state.cpp:184-312), flux_region<Region>(lambda)
+// (cpp/include/freddi_state.hpp:377-407) and Mdot_wind (cpp/src/freddi_state.cpp:364-383) on top of the same
+// per-point device functions the evolve kernel uses.  One CTA per model.
+#include "gpu_exec.cuh"
+
+namespace fb200 {
+namespace {
+
+struct Loaded {
+    int first, last;
+};
+
+// Stages model `model` at `row` (row < 0: current state).  Returns first/last of that state.
+__device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long long row, fb200_model_dev_t* Msh, const SharedArrays& S,
+                                        GpuEx& ex) {
+    const int Nx = E.Nx;
+    const double* F_src = E.F + size_t(model) * Nx;
+    Loaded L;
+    const ModelState st = E.state[model];
+    L.first = st.first;
+    L.last = st.last;
+    if (row >= 0 && E.Fsnap) {
+        F_src = E.Fsnap + (size_t(model) * E.cfg.n_rows + size_t(row)) * Nx;
+        const int* b = E.bounds + (size_t(model) * E.cfg.n_rows + size_t(row)) * 2;
+        L.first = b[0];
+        L.last = b[1];
+    }
+    load_model(E, model, Msh, S, ex, F_src);
+    return L;
+}
+
+__global__ void __launch_bounds__(kNT, 1) fb200_field_kernel(const EnsembleDev E, int field, long long row, double* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* base = reinterpret_cast<double*>(smem_raw);
+    const SharedArrays S = carve_shared(base);
+    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuEx ex;
+    ex.init(scratch);
+    const int i = threadIdx.x;
+    const int Nx = E.Nx;
+    for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
+        __syncthreads();
+        const Loaded L = stage(E, model, row, Msh, S, ex);
+        const fb200_model_dev_t& M = *Msh;
+        ModelState st{};
+        st.first = L.first; st.last = L.last;
+        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        eng.init_points();
+        const int first = L.first, last = L.last;
+        const StateScalars sc = state_scalars(ex, M, S, first, true);
+        double v = 0.;
+        if (i < Nx) {
+            const double h = S.h[i], R = S.R[i], F = S.F[i];
+            const bool hot = (i >= first && i <= last);
+            PointStructure q{};
+            if (hot) q = hot_structure(M, sc, h, R, S.hn[i], S.hm175[i], S.hotR[i], F);
+            // cold zone (freddi_state.cpp:256-258,271-273): Height = h2rcold R, Kirr from the cold parameters
+            const double Hc = M.h2rcold * R;
+            const double Kc = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow(Hc / (R * 0.05), M.irrindex_cold));
+            const double H = hot ? q.Height : Hc;
+            const double K = hot ? q.Kirr : Kc;
+            double Qx = 0.;
+            if (i >= first) {
+                const double mu = H / R;
+                if (M.is_ns) Qx = K * (sc.Lbol_disk * angular_dist(M.angdist_disk, mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, mu)) / (4. * FB_PI * p2(R));
+                else Qx = K * sc.Lbol_disk * angular_dist(M.angdist_disk, mu) / (4. * FB_PI * p2(R));
+            }
+            switch (field) {
+                case FB200_FIELD_H: v = h; break;
+                case FB200_FIELD_R: v = R; break;
+                case FB200_FIELD_F: v = F; break;
+                case FB200_FIELD_W: v = hot ? q.W : 0.; break;
+                case FB200_FIELD_SIGMA: v = hot ? q.Sigma : 0.; break;
+                case FB200_FIELD_TPH_VIS: v = hot ? q.Tvis : 0.; break;
+                case FB200_FIELD_TPH: v = (i >= first) ? pow025(p4(hot ? q.Tvis : 0.) + Qx / FB_SIGMA_SB) : 0.; break;
+                case FB200_FIELD_TIRR: v = (i >= first) ? pow025(Qx / FB_SIGMA_SB) : 0.; break;
+                case FB200_FIELD_KIRR: v = (i >= first) ? K : 0.; break;
+                case FB200_FIELD_HEIGHT: v = (i >= first) ? H : 0.; break;
+                case FB200_FIELD_QX: v = Qx; break;
+                case FB200_FIELD_TPH_X: {
+                    v = 0.;
+                    if (hot) {
+                        const double KM = 3. * fabs(sc.Mdot_plain) * p6(FB_C_LIGHT) / (8. * FB_PI * p2(M.GM));
+                        double x = S.c1[i] * S.F[first];
+                        const double g = KM * S.Gb[i];
+                        x += (g < 0.) ? NAN : g;
+                        v = M.colourfactor * pow025(x / FB_SIGMA_SB);
+                    }
+                    break;
+                }
+                case FB200_FIELD_WINDA: v = ex.windA(i); break;
+                case FB200_FIELD_WINDB:
+                case FB200_FIELD_WINDC: {
+                    double B = ex.windB(i), C = ex.windC_static(i);
+                    if (M.wind_dynamic && hot) {
+                        // dynamic winds: value for the Mdot_in of THIS state (the reference holds the value of its
+                        // last update(), i.e. of the state before the last solve)
+                        const WindScalars ws = wind_scalars(M, sc.Mdot, S.h[first], S.h[last], S.h[Nx - 1]);
+                        double Bd = 0., Cd = 0.;
+                        wind_dynamic_point(M, ws, h, R, &Bd, &Cd);
+                        if (M.windtype == FB200_WIND_JANIUK2015) B = Bd; else C = Cd + C;
+                    }
+                    v = (field == FB200_FIELD_WINDB) ? B : C;
+                    break;
+                }
+                case FB200_FIELD_FMAGN: v = ex.Fmagn(i); break;
+                case FB200_FIELD_DFMAGN_DH: v = ex.dFmagn_dh(i); break;
+                case FB200_FIELD_D2FMAGN_DH2: v = E.d2Fmagn_dh2 ? E.d2Fmagn_dh2[size_t(model) * Nx + i] : 0.; break;
+                default: v = NAN;
+            }
+            out[size_t(model) * Nx + i] = v;
+        }
+    }
+}
+
+// out[model][k] = flux_region<region>(lambdas[k]); region 0 hot (Tph over [first,last]), 1 cold (Tirr over [last+1,Nx-1])
+__global__ void __launch_bounds__(kNT, 1) fb200_flux_kernel(const EnsembleDev E, int region, long long row, const double* lambdas,
+                                                            int n_lambdas, double* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* base = reinterpret_cast<double*>(smem_raw);
+    const SharedArrays S = carve_shared(base);
+    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuEx ex;
+    ex.init(scratch);
+    const int Nx = E.Nx;
+    for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
+        __syncthreads();
+        const Loaded L = stage(E, model, row, Msh, S, ex);
+        const fb200_model_dev_t& M = *Msh;
+        ModelState st{};
+        st.first = L.first; st.last = L.last;
+        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        eng.init_points();
+        const int first = L.first, last = L.last;
+        const StateScalars sc = state_scalars(ex, M, S, first, true);
+        // temperature of the region at every point
+        ex.points([&](int i) {
+            double T = 0.;
+            if (i < Nx) {
+                const double R = S.R[i];
+                if (region == 0) {
+                    if (i >= first && i <= last) T = hot_structure(M, sc, S.h[i], R, S.hn[i], S.hm175[i], S.hotR[i], S.F[i]).Tph;
+                } else if (i > last) {
+                    const double Hc = M.h2rcold * R;
+                    const double Kc = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow(Hc / (R * 0.05), M.irrindex_cold));
+                    const double mu = Hc / R;
+                    double Qx;
+                    if (M.is_ns) Qx = Kc * (sc.Lbol_disk * angular_dist(M.angdist_disk, mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, mu)) / (4. * FB_PI * p2(R));
+                    else Qx = Kc * sc.Lbol_disk * angular_dist(M.angdist_disk, mu) / (4. * FB_PI * p2(R));
+                    T = pow025(Qx / FB_SIGMA_SB);
+                }
+            }
+            S.Tph[i] = T;
+        });
+        ex.sync();
+        const int rf = (region == 0) ? first : last + 1;
+        const int rl = (region == 0) ? last : Nx - 1;
+        for (int k0 = 0; k0 < n_lambdas; k0 += FB200_MAXQ) {
+            const int nq = min(FB200_MAXQ, n_lambdas - k0);
+            ex.reduce_sums(nq, [&](int i, int q) -> double {
+                if (rf >= rl || i < rf || i > rl) return 0.;
+                double w;
+                if (i == rf) w = S.R[i + 1] - S.R[i];
+                else if (i == rl) w = S.R[i] - S.R[i - 1];
+                else w = S.R[i + 1] - S.R[i - 1];
+                const double lam = lambdas[k0 + q];
+                const double y = planck_lambda_pref(S.Tph[i], lam, FB_DOUBLE_H_C2 / p5(lam));
+                return 2 * FB_PI * S.R[i] * y * w;
+            });
+            if (threadIdx.x < nq) {
+                const double lam = lambdas[k0 + threadIdx.x];
+                out[size_t(model) * n_lambdas + k0 + threadIdx.x] = 0.5 * ex.sum(threadIdx.x) * p2(lam) / FB_C_LIGHT * M.cosiOverD2;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Mdot_wind (cpp/src/freddi_state.cpp:364-383): - trapz over h of (A dF/dh + B F + C) on [first, last]
+__global__ void __launch_bounds__(kNT, 1) fb200_mdot_wind_kernel(const EnsembleDev E, long long row, double* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* base = reinterpret_cast<double*>(smem_raw);
+    const SharedArrays S = carve_shared(base);
+    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuEx ex;
+    ex.init(scratch);
+    const int Nx = E.Nx;
+    for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
+        __syncthreads();
+        const Loaded L = stage(E, model, row, Msh, S, ex);
+        const fb200_model_dev_t& M = *Msh;
+        ModelState st{};
+        st.first = L.first; st.last = L.last;
+        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        eng.init_points();
+        const int first = L.first, last = L.last;
+        const StateScalars sc = state_scalars(ex, M, S, first, false);
+        WindScalars ws{0, 0, 0, 0, 0};
+        if (M.wind_dynamic) ws = wind_scalars(M, sc.Mdot, S.h[first], S.h[last], S.h[Nx - 1]);
+        ex.reduce_sums(1, [&](int i, int) -> double {
+            if (first >= last || i < first || i > last) return 0.;
+            const double* h = S.h;
+            const double* F = S.F;
+            double dFdh;
+            if (i == first) {
+                dFdh = (F[i + 1] - F[i]) / (h[i + 1] - h[i]);
+            } else if (i == last) {
+                dFdh = (F[i] - F[i - 1]) / (h[i] - h[i - 1]);
+            } else {
+                const double delta_0 = h[i] - h[i - 1];
+                const double delta_1 = h[i + 1] - h[i];
+                dFdh = (F[i + 1] * delta_0 * delta_0 / (delta_0 + delta_1) + F[i] * (delta_1 - delta_0) -
+                        F[i - 1] * delta_1 * delta_1 / (delta_0 + delta_1)) /
+                       (delta_0 * delta_1);
+            }
+            double A = ex.windA(i), B = ex.windB(i), C = ex.windC_static(i);
+            if (M.wind_dynamic) {
+                double Bd = 0., Cd = 0.;
+                wind_dynamic_point(M, ws, h[i], S.R[i], &Bd, &Cd);
+                if (M.windtype == FB200_WIND_JANIUK2015) B = Bd; else C = Cd + C;
+            }
+            const double y = -(A * dFdh + B * F[i] + C);
+            double w;
+            if (i == first) w = h[i + 1] - h[i];
+            else if (i == last) w = h[i] - h[i - 1];
+            else w = h[i + 1] - h[i - 1];
+            return y * w;
+        });
+        if (threadIdx.x == 0) out[model] = 0.5 * ex.sum(0);
+    }
+}
+
+cudaError_t prep(const void* fn) { return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes())); }
+
+}  // namespace
+
+cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream) {
+    cudaError_t e = prep(reinterpret_cast<const void*>(fb200_field_kernel));
+    if (e != cudaSuccess) return e;
+    const int grid = E.n_models < 1184 ? E.n_models : 1184;
+    fb200_field_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, field, row, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
+                        cudaStream_t stream) {
+    cudaError_t e = prep(reinterpret_cast<const void*>(fb200_flux_kernel));
+    if (e != cudaSuccess) return e;
+    const int grid = E.n_models < 1184 ? E.n_models : 1184;
+    fb200_flux_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, region, row, lambdas_dev, n_lambdas, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, cudaStream_t stream) {
+    cudaError_t e = prep(reinterpret_cast<const void*>(fb200_mdot_wind_kernel));
+    if (e != cudaSuccess) return e;
+    const int grid = E.n_models < 1184 ? E.n_models : 1184;
+    fb200_mdot_wind_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, row, out);
+    return cudaGetLastError();
+}
+
+}  // namespace fb200

@@ -1,0 +1,27 @@
+// Host-side argument resolution for the ensemble engine: fb200_args_t -> what the kernels read.
+// Stands in for the constructors the reference runs once per model
+// (cpp/src/arguments.cpp:30-351, cpp/src/ns/ns_arguments.cpp:17-189, cpp/src/freddi_state.cpp:13-122,387-450,
+//  cpp/src/ns/ns_evolution.cpp:45-139,322-383).  Runs on the host in IEEE double with the same libm the
+// reference links, in the reference's operation order, because it defines F(t=0), the grid and every
+// per-model constant.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/freddi_b200.h"
+#include "fb200_model.h"
+
+namespace fb200 {
+
+struct Resolved {
+    fb200_model_dev_t dev;
+    fb200_model_info_t info;
+    std::vector<double> h, F;              // [Nx]
+    std::vector<double> wA, wB, wC;        // static wind arrays [Nx]; empty when identically zero
+    std::vector<double> Fmagn, dFmagn_dh, d2Fmagn_dh2;  // NS [Nx]; empty for BH
+};
+
+// Returns FB200_OK or the error class the reference's constructor would have thrown, message in err.
+int resolve(const fb200_args_t& a, Resolved& out, std::string& err);
+
+}  // namespace fb200

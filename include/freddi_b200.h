@@ -1,0 +1,245 @@
+/*
+ * freddi_b200 — C ABI of the B200 ensemble engine for Freddi's disc-evolution hot path.
+ *
+ * The reference (hombit/freddi) has no FFI for this path; its seams are C++ classes.  Each entry
+ * point below names the reference interface it stands in for (paths relative to the reference
+ * repository root).  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ *   fb200_args_t                <- FreddiArguments / FreddiNeutronStarArguments
+ *                                  (cpp/include/arguments.hpp:336-354, cpp/include/ns/ns_arguments.hpp:143-165)
+ *                                  with the keyword names and defaults of the Python constructor
+ *                                  (cpp/pywrap/pywrap_freddi_evolution.cpp:15-83,194-224), all values CGS.
+ *   fb200_ensemble_create       <- FreddiEvolution(const FreddiArguments&)                (cpp/include/freddi_evolution.hpp:50)
+ *                                  FreddiNeutronStarEvolution(const FreddiNeutronStarArguments&) (cpp/include/ns/ns_evolution.hpp:228)
+ *   fb200_ensemble_evolve       <- FreddiEvolution::step() repeated, i.e. the driver loops
+ *                                  cpp/include/application.hpp:25-43 and EvolutionIterator (cpp/include/freddi_evolution.hpp:34-39)
+ *   fb200_ensemble_rows         <- the light-curve row of FreddiFileOutput::initializeShortFields
+ *                                  (cpp/src/output.cpp:197-292, cpp/src/ns/ns_output.cpp:6-19)
+ *   fb200_ensemble_field        <- the array getters of FreddiState (cpp/include/freddi_state.hpp:393-400,
+ *                                  cpp/pywrap/pywrap_freddi_state.cpp:35-47), NaN outside [first,last]
+ *                                  like EvolutionResult (python/freddi/evolution_result.py:55-71)
+ *   fb200_ensemble_state        <- FreddiState::t/i_t/first/last (cpp/include/freddi_state.hpp:309-312)
+ *   fb200_ensemble_flux         <- FreddiState::flux_region<Region>(lambda) (cpp/include/freddi_state.hpp:405-407)
+ *
+ * Errors: the reference throws std::invalid_argument / std::runtime_error / std::logic_error at
+ * construction and RadiusCollapseException during step(); nothing is thrown across this ABI.
+ * Every call returns FB200_OK or a negative code, fb200_last_error() holds the message, and a
+ * collapsed model is reported per model (status, rows_valid), never as a call failure.
+ *
+ * There is no CPU implementation behind these entry points: without a CUDA device every compute
+ * call fails with FB200_ERR_NO_DEVICE.
+ */
+#ifndef FREDDI_B200_H
+#define FREDDI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_ABI_VERSION 1
+
+/* ---- return codes ---- */
+enum {
+    FB200_OK = 0,
+    FB200_ERR_INVALID_ARGUMENT = -1, /* reference: std::invalid_argument (bad enum value)           */
+    FB200_ERR_RUNTIME = -2,          /* reference: std::runtime_error (bad parameter combination)   */
+    FB200_ERR_LOGIC = -3,            /* reference: std::logic_error                                 */
+    FB200_ERR_NO_DEVICE = -4,        /* no CUDA device / driver: there is no fallback               */
+    FB200_ERR_CUDA = -5,             /* a CUDA runtime call failed                                  */
+    FB200_ERR_UNSUPPORTED = -6,      /* outside the supported sizes (e.g. Nx too large for smem)    */
+    FB200_ERR_BAD_HANDLE = -7
+};
+
+/* ---- per-model status ---- */
+enum {
+    FB200_MODEL_OK = 0,
+    FB200_MODEL_COLLAPSED = 1, /* RadiusCollapseException "Rout <= Rin" (cpp/include/exceptions.hpp:6-11) */
+    FB200_MODEL_FAILED = 2     /* Picard loop exceeded the iteration guard / non-finite state          */
+};
+
+/* ---- enumerations for the string options of the reference ---- */
+enum { FB200_OPACITY_KRAMERS = 0, FB200_OPACITY_OPAL = 1 };              /* cpp/src/opacity_related.cpp:17-23 */
+enum { FB200_BOUNDCOND_TEFF = 0, FB200_BOUNDCOND_TIRR = 1 };             /* cpp/src/freddi_evolution.cpp:54-68 */
+enum { FB200_GRID_LOG = 0, FB200_GRID_LINEAR = 1 };                      /* cpp/src/freddi_state.cpp:36-42 */
+enum { FB200_ANGDIST_PLANE = 0, FB200_ANGDIST_ISOTROPIC = 1 };           /* cpp/src/freddi_state.cpp:125-133 */
+enum {                                                                     /* cpp/src/arguments.cpp:70-268, ns_arguments.cpp:148 */
+    FB200_IC_POWERF = 0, FB200_IC_LINEARF = 1, FB200_IC_POWERSIGMA = 2, FB200_IC_SINEF = 3,
+    FB200_IC_GAUSSF = 4, FB200_IC_QUASISTAT = 5, FB200_IC_QUASISTAT_NS = 6
+};
+enum {                                                                     /* cpp/src/freddi_state.cpp:94-122 */
+    FB200_WIND_NO = 0,
+    FB200_WIND_SS73C = 1,            /* windparams: -                       */
+    FB200_WIND_CAMBIER2013 = 2,      /* windparams: kC, RIC                 */
+    FB200_WIND_TESTA = 3,            /* windparams: kA                      */
+    FB200_WIND_TESTB = 4,            /* windparams: kB                      */
+    FB200_WIND_TESTC = 5,            /* windparams: kC                      */
+    FB200_WIND_SHIELDSOSCIL1986 = 6, /* windparams: C_w, R_w                */
+    FB200_WIND_JANIUK2015 = 7,       /* windparams: A_0, B_1                */
+    FB200_WIND_SHIELDS1986 = 8,      /* windparams: Xi_max, T_ic, Pow       */
+    FB200_WIND_WOODS1996AGN = 9,     /* windparams: C_0, T_ic               */
+    FB200_WIND_WOODS1996 = 10,       /* windparams: Xi_max, T_ic, Pow       */
+    FB200_WIND_TOY = 11              /* windparams: C_w                     */
+};
+enum { FB200_NSPROP_DUMMY = 0, FB200_NSPROP_SIBSUN2000 = 1, FB200_NSPROP_NEWT = 2 }; /* cpp/src/ns/ns_evolution.cpp:371-383 */
+enum {                                                                     /* cpp/src/ns/ns_evolution.cpp:342-369 */
+    FB200_FP_NO_OUTFLOW = 0, FB200_FP_PROPELLER = 1, FB200_FP_COROTATION_BLOCK = 2,
+    FB200_FP_EKSI_KUTLU2010 = 3,
+    FB200_FP_ROMANOVA2018 = 4, /* fpparams: par1, par2 */
+    FB200_FP_GEOMETRICAL = 5   /* fpparams: chi [deg]  */
+};
+enum {                                                                     /* cpp/src/ns/ns_evolution.cpp:79-91 */
+    FB200_KAPPAT_CONST = 0,       /* kappatparams: value               */
+    FB200_KAPPAT_CORSTEP = 1,     /* kappatparams: in, out             */
+    FB200_KAPPAT_ROMANOVA2018 = 2 /* kappatparams: in, out, par1, par2 */
+};
+enum { FB200_REDSHIFT_OFF = 0, FB200_REDSHIFT_ON = 1 };                 /* cpp/src/ns/ns_evolution.cpp:68-76 */
+
+/*
+ * One model's arguments, CGS units, keyword names of the reference's Python constructor.
+ * Optional values of the reference (std::optional / Python None) are "unset" when NaN.
+ * Fill with fb200_args_default() first, then override.
+ */
+typedef struct fb200_args {
+    int32_t is_ns; /* 0: Freddi (black hole), 1: FreddiNeutronStar */
+    int32_t _pad0;
+    /* BasicDiskBinaryArguments, cpp/include/arguments.hpp:46-97 */
+    double alpha, alphacold /*opt*/, Mx, kerr, period, Mopt, rochelobefill, Topt;
+    double rin /*opt*/, rout /*opt*/, risco /*opt*/;
+    /* DiskStructureArguments, cpp/include/arguments.hpp:177-239 */
+    int32_t opacity, boundcond, initialcond, windtype;
+    double Mdotout, Thot, Qirr2Qvishot;
+    double F0 /*opt*/, Mdisk0 /*opt*/, Mdot0 /*opt*/, powerorder /*opt*/, gaussmu /*opt*/, gausssigma /*opt*/;
+    double windparams[4]; /* meaning per windtype, see enum */
+    /* SelfIrradiationArguments, cpp/include/arguments.hpp:242-265 */
+    double Cirr, irrindex, Cirrcold, irrindexcold, h2rcold;
+    int32_t angulardistdisk, angulardistns;
+    /* FluxArguments, cpp/include/arguments.hpp:268-304 (lambdas/passbands are ensemble-wide, see fb200_config_t) */
+    double colourfactor, emin, emax, staralbedo, inclination, ephemerist0, distance;
+    /* CalculationArguments, cpp/include/arguments.hpp:307-333 */
+    double inittime, time, tau /*opt*/, eps;
+    uint32_t Nx;
+    int32_t gridscale;
+    int32_t starlod; /* accepted and ignored: the companion star is outside the hot path */
+    int32_t nsprop;
+    /* NeutronStarArguments, cpp/include/ns/ns_arguments.hpp:16-67 (ignored when !is_ns) */
+    double freqx /*opt*/, Rx /*opt*/, Bx, hotspotarea, epsilonAlfven, inversebeta, Rdead;
+    int32_t fptype, kappattype, nsgravredshift, _pad1;
+    double fpparams[2];
+    double kappatparams[4];
+} fb200_args_t;
+
+/* Ensemble-wide configuration: the outputs every model of the ensemble produces. */
+#define FB200_MAX_LAMBDAS 16
+typedef struct fb200_config {
+    int32_t device;         /* CUDA device ordinal                                                        */
+    int32_t n_lambdas;      /* Fnu columns, FluxArguments::lambdas (cpp/include/arguments.hpp:286)        */
+    double lambdas[FB200_MAX_LAMBDAS]; /* cm                                                               */
+    int32_t cold_disk;      /* add Fnu{k}_cold columns (--colddiskflux, cpp/src/output.cpp:226-233)       */
+    int32_t record_F;       /* keep F(h) of every row in HBM so fb200_ensemble_field can serve any row    */
+    int32_t compute_lx;     /* 1 (reference behaviour): Lx/Fx by the adaptive quadrature; 0: columns NaN  */
+    int32_t host_threads;   /* threads for host-side argument resolution, 0 = all cores                   */
+    int32_t threads_per_model; /* CTA size, 0 = default                                                  */
+    int32_t _pad;
+} fb200_config_t;
+
+/* Row layout: cpp/src/output.cpp:197-214, then Fnu columns, then cpp/src/ns/ns_output.cpp:6-19 for NS. */
+enum {
+    FB200_COL_T = 0,        /* days */
+    FB200_COL_MDOT = 1, FB200_COL_MDISK = 2,
+    FB200_COL_RHOT = 3,     /* Rsun */
+    FB200_COL_SIGMAOUT = 4, FB200_COL_KIRROUT = 5, FB200_COL_H2R = 6, FB200_COL_TEFFOUT = 7,
+    FB200_COL_TIRROUT = 8, FB200_COL_QIRR2QVISOUT = 9,
+    FB200_COL_TPHXMAX = 10, /* keV */
+    FB200_COL_LX = 11, FB200_COL_LBOL = 12, FB200_COL_FX = 13, FB200_COL_FBOL = 14,
+    FB200_N_BH_COLS = 15,
+    /* NS extras follow the Fnu columns, in this order */
+    FB200_NSCOL_RIN = 0, FB200_NSCOL_ETANS = 1, FB200_NSCOL_LXNS = 2, FB200_NSCOL_LBOLNS = 3,
+    FB200_NSCOL_FXNS = 4, FB200_NSCOL_FBOLNS = 5, FB200_NSCOL_THOTSPOT = 6 /* keV */,
+    FB200_NSCOL_FPIN = 7, FB200_NSCOL_FMAGNIN = 8, FB200_NSCOL_FIN = 9,
+    FB200_N_NS_COLS = 10
+};
+
+/* Radial fields served by fb200_ensemble_field (cpp/pywrap/pywrap_freddi_state.cpp:35-47, ns: pywrap_freddi_evolution.cpp:317-319) */
+enum {
+    FB200_FIELD_H = 0, FB200_FIELD_R = 1, FB200_FIELD_F = 2, FB200_FIELD_W = 3, FB200_FIELD_SIGMA = 4,
+    FB200_FIELD_TPH = 5, FB200_FIELD_TPH_VIS = 6, FB200_FIELD_TIRR = 7, FB200_FIELD_KIRR = 8,
+    FB200_FIELD_HEIGHT = 9, FB200_FIELD_QX = 10, FB200_FIELD_TPH_X = 11,
+    FB200_FIELD_WINDA = 12, FB200_FIELD_WINDB = 13, FB200_FIELD_WINDC = 14,
+    FB200_FIELD_FMAGN = 15, FB200_FIELD_DFMAGN_DH = 16, FB200_FIELD_D2FMAGN_DH2 = 17,
+    FB200_N_FIELDS = 18
+};
+
+/* Per-model scalar constants resolved at construction (FreddiState getters, cpp/include/freddi_state.hpp:286-295) */
+typedef struct fb200_model_info {
+    double GM, eta, R_g, cosi, distance, cosiOverD2, tau, h_in, h_out, rin, rout, risco;
+    double F0, Mdisk0, Mdot0;                 /* as normalised by the initial condition (cpp/src/arguments.cpp:57-269) */
+    double mu_magn, R_cor, R_dead, inverse_beta, R_x, redshift; /* NS, cpp/include/ns/ns_evolution.hpp:185-198 */
+    int64_t Nx, Nt, first0;
+} fb200_model_info_t;
+
+typedef struct fb200_ensemble fb200_ensemble_t;
+
+/* --- library --- */
+int fb200_abi_version(void);
+const char* fb200_last_error(void); /* thread-local message of the last failing call */
+int fb200_device_count(void);       /* number of CUDA devices visible, <0 on driver error */
+
+/* --- arguments --- */
+void fb200_args_default(fb200_args_t* args, int is_ns); /* defaults of pywrap_freddi_evolution.cpp:33-83,203-224 */
+void fb200_config_default(fb200_config_t* cfg);
+
+/* --- ensemble life cycle --- */
+/* Resolves every model's arguments on the host (ISCO, tidal radius, opacity constants, grid h, initial
+ * F(h), static wind and magnetic-torque arrays: cpp/src/freddi_state.cpp:13-71, cpp/src/arguments.cpp:57-351,
+ * cpp/src/ns/ns_evolution.cpp:45-139,322-340), uploads them and allocates row storage for Nt+1 rows.
+ * All models of one ensemble share is_ns and Nx; time/tau may differ (rows are padded to the largest Nt+1).
+ * On a bad argument returns the reference's error class and *bad_model = index of the offending model. */
+int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg,
+                          fb200_ensemble_t** out, size_t* bad_model);
+void fb200_ensemble_destroy(fb200_ensemble_t* e);
+
+size_t fb200_ensemble_n_models(const fb200_ensemble_t* e);
+size_t fb200_ensemble_n_cols(const fb200_ensemble_t* e);  /* columns per row                     */
+size_t fb200_ensemble_n_rows(const fb200_ensemble_t* e);  /* rows per model = max(Nt)+1          */
+size_t fb200_ensemble_nx(const fb200_ensemble_t* e);
+int fb200_ensemble_info(const fb200_ensemble_t* e, fb200_model_info_t* out /*[n_models]*/);
+
+/* Advance every model by n_steps (clipped per model at its Nt; n_steps<0: to the end).  Row i_t is
+ * written when state i_t is reached; row 0 is written by the first call.  Blocks until done. */
+int fb200_ensemble_evolve(fb200_ensemble_t* e, int64_t n_steps);
+/* Same, but only enqueues on the ensemble's stream; pair with fb200_ensemble_sync. */
+int fb200_ensemble_evolve_async(fb200_ensemble_t* e, int64_t n_steps);
+int fb200_ensemble_sync(fb200_ensemble_t* e);
+/* Device time of the last evolve call in milliseconds (CUDA events on the ensemble's stream). */
+int fb200_ensemble_last_evolve_ms(fb200_ensemble_t* e, float* ms);
+/* Number of kernel launches issued by the last evolve call. */
+int fb200_ensemble_last_launches(const fb200_ensemble_t* e);
+
+/* Copy rows to host memory: out[model][row][col], n_rows x n_cols per model; rows >= rows_valid are NaN. */
+int fb200_ensemble_rows(fb200_ensemble_t* e, double* out, size_t out_len);
+/* Device pointer of the same buffer (for callers that keep results in HBM). */
+int fb200_ensemble_rows_device(fb200_ensemble_t* e, const double** dptr);
+/* Per-model status, number of valid rows, Picard iterations summed over steps. */
+int fb200_ensemble_status(fb200_ensemble_t* e, int32_t* status, int32_t* rows_valid, int64_t* picard_iters);
+/* Current t [s], i_t, first, last per model (any pointer may be NULL). */
+int fb200_ensemble_state(fb200_ensemble_t* e, double* t, int64_t* i_t, int64_t* first, int64_t* last);
+/* State of a recorded row (requires record_F): first/last per model at that row. */
+int fb200_ensemble_row_bounds(fb200_ensemble_t* e, int64_t row, int64_t* first, int64_t* last);
+
+/* Radial field of every model: out[model][Nx].  row<0: the current state; row>=0: that recorded row
+ * (requires cfg.record_F).  Values outside [first,last] are NaN for state-dependent fields. */
+int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* out, size_t out_len);
+/* Spectral flux density of the hot (region 0) or cold (region 1) disc at wavelengths lambdas[cm]:
+ * out[model][n_lambdas], evaluated on the state of `row` (row<0: current). */
+int fb200_ensemble_flux(fb200_ensemble_t* e, int region, int64_t row, const double* lambdas, size_t n_lambdas,
+                        double* out, size_t out_len);
+/* Mdot_wind of FreddiState::Mdot_wind (cpp/src/freddi_state.cpp:364-383), per model, on the state of `row`. */
+int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size_t out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREDDI_B200_H */

@@ -1,0 +1,145 @@
+// TEST INFRASTRUCTURE — not part of the product, never linked into libfreddi_b200.so.
+//
+// Runs DiscEngine (freddi_b200/csrc/disc_engine.h — the very code the CUDA kernel executes) under a
+// sequential execution policy: points() becomes a loop over the radial points, barriers are no-ops and
+// reductions are plain loops.  This lets the CPU test suite check the step/row logic against the oracle
+// without a GPU.  It cannot see races or barrier mistakes; the `-m gpu` tests and compute-sanitizer do.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../freddi_b200/csrc/disc_engine.h"
+#include "../../freddi_b200/csrc/resolve.hpp"
+
+using namespace fb200;
+
+namespace {
+
+struct HostEx {
+    static constexpr int NT = FB200_NX_MAX;
+    std::vector<StepRegs> sr = std::vector<StepRegs>(NT);
+    double scal[8] = {0};
+    double sums[FB200_MAXQ] = {0};
+    double lampref[FB200_MAX_LAMBDAS] = {0};
+    const double *gA = nullptr, *gB = nullptr, *gCs = nullptr, *gFm = nullptr, *gdFm = nullptr;
+
+    template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) f(i); }
+    void sync() {}
+    StepRegs& step(int i) { return sr[i]; }
+    double& scalar(int k) { return scal[k]; }
+    double sum(int q) const { return sums[q]; }
+    double lambda_pref(int k) const { return lampref[k]; }
+    double windA(int i) const { return gA ? gA[i] : 0.; }
+    double windB(int i) const { return gB ? gB[i] : 0.; }
+    double windC_static(int i) const { return gCs ? gCs[i] : 0.; }
+    double Fmagn(int i) const { return gFm ? gFm[i] : 0.; }
+    double dFmagn_dh(int i) const { return gdFm ? gdFm[i] : 0.; }
+    template <class F> double reduce_max(F&& f) {
+        double m = -INFINITY;
+        for (int i = 0; i < NT; ++i) { const double v = f(i); if (v == v) m = std::fmax(m, v); }
+        return m;
+    }
+    template <class F> int reduce_max_int(F&& f) { int m = f(0); for (int i = 1; i < NT; ++i) m = std::max(m, f(i)); return m; }
+    template <class F> int reduce_min_int(F&& f) { int m = f(0); for (int i = 1; i < NT; ++i) m = std::min(m, f(i)); return m; }
+    template <class F> void reduce_sums(int nq, F&& f) {
+        for (int q = 0; q < nq; ++q) { double s = 0.; for (int i = 0; i < NT; ++i) s += f(i, q); sums[q] = s; }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Same contract as ref_run (oracle/ref_driver.cpp): returns the number of valid rows, <0 on a resolve error.
+int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int cold_disk, double* rows, int64_t rows_cap,
+                double* Fsnap, int64_t* first, int64_t* last, int64_t* picard, char* err, size_t err_len) {
+    Resolved res;
+    std::string msg;
+    const int rc = resolve(*a, res, msg);
+    if (rc != FB200_OK) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", msg.c_str());
+        return rc;
+    }
+    const fb200_model_dev_t& M = res.dev;
+    const int Nx = M.Nx;
+    OutCfg cfg{};
+    cfg.n_lambdas = n_lambdas;
+    cfg.cold_disk = cold_disk;
+    cfg.compute_lx = 1;
+    cfg.n_cols = FB200_N_BH_COLS + n_lambdas * (cold_disk ? 2 : 1) + (M.is_ns ? FB200_N_NS_COLS : 0);
+    cfg.n_rows = M.Nt + 1;
+    for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
+
+    const int N = FB200_NX_MAX;
+    std::vector<double> pool(18 * size_t(N), 0.);
+    double* base = pool.data();
+    SharedArrays S;
+    S.h = base + 0 * N; S.R = base + 1 * N; S.F = base + 2 * N; S.hn = base + 3 * N;
+    S.ca = base + 4 * N; S.cb = base + 5 * N; S.cc = base + 6 * N; S.frac = base + 7 * N;
+    S.c1 = base + 8 * N; S.hm175 = base + 9 * N; S.hotR = base + 10 * N; S.Gb = base + 11 * N;
+    S.lu[0] = reinterpret_cast<double2*>(base + 12 * N);
+    S.lu[1] = reinterpret_cast<double2*>(base + 14 * N);
+    S.rr[0] = base + 16 * N; S.rr[1] = base + 17 * N;
+    S.Tph = base + 12 * N; S.Tirr = base + 13 * N; S.Sigma = base + 14 * N; S.Tvis = base + 15 * N;
+    S.TphX = base + 16 * N; S.aux = base + 17 * N;
+    for (int i = 0; i < Nx; ++i) { S.h[i] = res.h[i]; S.F[i] = res.F[i]; }
+
+    HostEx ex;
+    for (int k = 0; k < n_lambdas; ++k) ex.lampref[k] = FB_DOUBLE_H_C2 / p5(lambdas[k]);
+    std::vector<double> wCs;
+    if (!res.wC.empty() || (M.is_ns && M.inverse_beta != 0.)) {
+        wCs = res.wC.empty() ? std::vector<double>(Nx, 0.) : res.wC;
+        if (!res.d2Fmagn_dh2.empty()) for (int i = 0; i < Nx; ++i) wCs[i] += res.d2Fmagn_dh2[i];
+        ex.gCs = wCs.data();
+    }
+    if (!res.wA.empty()) ex.gA = res.wA.data();
+    if (!res.wB.empty()) ex.gB = res.wB.data();
+    if (!res.Fmagn.empty()) ex.gFm = res.Fmagn.data();
+    if (!res.dFmagn_dh.empty()) ex.gdFm = res.dFmagn_dh.data();
+
+    ModelState st{};
+    st.t = M.t0; st.F_in = M.F_in0; st.Mdot_in_prev = -INFINITY; st.first = M.first0; st.last = Nx - 1;
+    DiscEngine<HostEx> eng(ex, M, cfg, S, st);
+    eng.init_points();
+
+    const int nc = cfg.n_cols;
+    std::vector<double> rowbuf(nc);
+    std::vector<double> Fbuf(N);
+    int bounds[2];
+    int64_t r = 0;
+    for (; r <= M.Nt && r < rows_cap; ++r) {
+        bool ok;
+        const long long before = eng.st.picard_iters;
+        if (r == 0) ok = eng.structure_and_row(false, rowbuf.data(), Fbuf.data(), bounds);
+        else ok = eng.step_and_row(rowbuf.data(), Fbuf.data(), bounds);
+        if (!ok) break;
+        std::memcpy(rows + r * nc, rowbuf.data(), sizeof(double) * nc);
+        if (Fsnap) std::memcpy(Fsnap + r * Nx, Fbuf.data(), sizeof(double) * Nx);
+        if (first) first[r] = bounds[0];
+        if (last) last[r] = bounds[1];
+        if (picard) picard[r] = eng.st.picard_iters - before;
+    }
+    return r;
+}
+
+// host resolver only: h[Nx], F[Nx] of the initial state + info (no device involved)
+int emu_resolve(const fb200_args_t* a, fb200_model_info_t* info, double* h, double* F, char* err, size_t err_len) {
+    Resolved res;
+    std::string msg;
+    const int rc = resolve(*a, res, msg);
+    if (rc != FB200_OK) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", msg.c_str());
+        return rc;
+    }
+    if (info) *info = res.info;
+    if (h) std::memcpy(h, res.h.data(), sizeof(double) * res.h.size());
+    if (F) std::memcpy(F, res.F.data(), sizeof(double) * res.F.size());
+    return FB200_OK;
+}
+
+double emu_planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) { return planck_nu1_nu2(T, nu1, nu2, tol, trials); }
+
+}  // extern "C"

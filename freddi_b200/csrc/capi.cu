@@ -82,6 +82,16 @@ int fb200_device_count(void) {
     return n;
 }
 
+int fb200_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return set_err(FB200_ERR_INVALID_ARGUMENT, "null argument");
+    FB_CUDA(cudaSetDevice(device));
+    double tf = 0.;
+    cudaError_t ce = fb200::measure_fp64_peak(&tf);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fp64 peak kernel");
+    *tflops = tf;
+    return FB200_OK;
+}
+
 // defaults of cpp/pywrap/pywrap_freddi_evolution.cpp:33-83,203-224
 void fb200_args_default(fb200_args_t* a, int is_ns) {
     std::memset(a, 0, sizeof(*a));
@@ -109,6 +119,18 @@ void fb200_args_default(fb200_args_t* a, int is_ns) {
 void fb200_config_default(fb200_config_t* c) {
     std::memset(c, 0, sizeof(*c));
     c->compute_lx = 1;
+}
+
+int fb200_args_resolve(const fb200_args_t* args, fb200_model_info_t* info, double* h, double* F) {
+    if (!args) return set_err(FB200_ERR_INVALID_ARGUMENT, "null argument");
+    Resolved r;
+    std::string msg;
+    const int rc = resolve(*args, r, msg);
+    if (rc != FB200_OK) return set_err(rc, msg);
+    if (info) *info = r.info;
+    if (h) std::memcpy(h, r.h.data(), sizeof(double) * r.h.size());
+    if (F) std::memcpy(F, r.F.data(), sizeof(double) * r.F.size());
+    return FB200_OK;
 }
 
 int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg_in, fb200_ensemble_t** out,
@@ -389,6 +411,18 @@ int fb200_ensemble_status(fb200_ensemble_t* e, int32_t* status, int32_t* rows_va
         if (status) status[i] = hs[i].status;
         if (rows_valid) rows_valid[i] = hs[i].rows_valid;
         if (picard_iters) picard_iters[i] = hs[i].picard_iters;
+    }
+    return FB200_OK;
+}
+
+int fb200_ensemble_counters(fb200_ensemble_t* e, int64_t* picard_iters, int64_t* lx_trial_steps) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    std::vector<ModelState> hs;
+    int rc = fetch_state(e, hs);
+    if (rc != FB200_OK) return rc;
+    for (size_t i = 0; i < e->n; ++i) {
+        if (picard_iters) picard_iters[i] = hs[i].picard_iters;
+        if (lx_trial_steps) lx_trial_steps[i] = hs[i].lx_trials;
     }
     return FB200_OK;
 }

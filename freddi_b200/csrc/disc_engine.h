@@ -34,7 +34,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace fb200 {
 
-#define FB200_MAXQ 40 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], spare */
+#define FB200_MAXQ 40 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], Lx trial count, spare */
 
 // Ensemble-wide output configuration (device copy of fb200_config_t's output part)
 struct OutCfg {
@@ -52,6 +52,7 @@ struct ModelState {
     double t, F_in, Mdot_in_prev;
     int first, last, i_t, status, rows_valid, row0_done;
     long long picard_iters;
+    long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
 };
 
 // Per-point values a thread keeps in registers during the Picard loop of one step
@@ -665,8 +666,10 @@ struct DiscEngine {
         double cold_K = 0.;
         const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
-        ex.reduce_sums(nq, [&](int i, int q) -> double {
+        ex.points([&](int i) { ex.step(i).valid = 0; });  // reused as this point's Lx trial-step counter
+        ex.reduce_sums(nq + 1, [&](int i, int q) -> double {
             if (i >= Nx) return 0.;
+            if (q == nq) return double(ex.step(i).valid);
             const bool cold = (q >= 2 + nl);
             int rf = first, rl = last;
             if (cold) { rf = last + 1; rl = Nx - 1; }
@@ -680,7 +683,9 @@ struct DiscEngine {
                 y = S.Sigma[i];
             } else if (q == 1) {
                 if (!cfg.compute_lx) return 0.;
-                y = planck_nu1_nu2(S.TphX[i], M.emin, M.emax, 1e-4, nullptr);
+                int trials;
+                y = planck_nu1_nu2(S.TphX[i], M.emin, M.emax, 1e-4, &trials);
+                ex.step(i).valid = trials;
             } else if (!cold) {
                 const int k = q - 2;
                 y = planck_lambda_pref(S.Tph[i], cfg.lambdas[k], ex.lambda_pref(k));
@@ -705,6 +710,7 @@ struct DiscEngine {
         if (fb_isnan(S.TphX[first])) TphXmax = NAN;
 
         // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----
+        st.lx_trials += (long long)(ex.sum(nq) + 0.5);
         const double Mdisk = 0.5 * ex.sum(0);
         const double Lx = cfg.compute_lx ? (2. * FB_PI * (0.5 * ex.sum(1))) / p4(M.colourfactor) : NAN;
         const double d2 = 4.0 * FB_PI * p2(M.distance);

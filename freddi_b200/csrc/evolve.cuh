@@ -31,6 +31,9 @@ size_t evolve_smem_bytes();
 // Launches the persistent evolve kernel on `stream`; returns cudaGetLastError().
 cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream);
 
+// FP64 DFMA peak of the current device in TFLOP/s (fields.cu)
+cudaError_t measure_fp64_peak(double* tflops);
+
 // field / flux read-out kernels (fields.cu)
 cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream);
 cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,

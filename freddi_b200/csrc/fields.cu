@@ -234,9 +234,56 @@ __global__ void __launch_bounds__(kNT, 1) fb200_mdot_wind_kernel(const EnsembleD
     }
 }
 
+// 16 independent DFMA chains per thread, 4096 iterations: 2 * 16 * 4096 flop per thread
+__global__ void __launch_bounds__(256) fb200_dfma_peak_kernel(double* out, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = a + k + threadIdx.x;
+    for (int it = 0; it < 4096; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
+    }
+    double s = 0.;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 123.456) out[0] = s;  // keeps the chains alive
+}
+
 cudaError_t prep(const void* fn) { return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes())); }
 
 }  // namespace
+
+cudaError_t measure_fp64_peak(double* tflops) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* d = nullptr;
+    e = cudaMalloc(&d, 64);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = sms * 32, block = 256;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fb200_dfma_peak_kernel<<<grid, block>>>(d, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    const double flop = 2.0 * 16 * 4096 * double(grid) * block;
+    *tflops = flop / (best_ms * 1e-3) / 1e12;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_field_kernel));

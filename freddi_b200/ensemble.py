@@ -1,0 +1,204 @@
+"""Ensemble of independent Freddi / FreddiNeutronStar models evolved on one B200 (thin layer over the C ABI)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .args import FB200Args, FB200Config, FB200ModelInfo, FB200_MAX_LAMBDAS, args_array
+
+N_BH_COLS = 15
+N_NS_COLS = 10
+# cpp/src/output.cpp:197-214 and cpp/src/ns/ns_output.cpp:6-19
+BH_COLS = ['t', 'Mdot', 'Mdisk', 'Rhot', 'Sigmaout', 'Kirrout', 'H2R', 'Teffout', 'Tirrout', 'Qirr2Qvisout',
+           'TphXmax', 'Lx', 'Lbol', 'Fx', 'Fbol']
+NS_COLS = ['Rin', 'etans', 'Lxns', 'Lbolns', 'Fxns', 'Fbolns', 'Thotspot', 'fpin', 'Fmagnin', 'Fin']
+FIELDS = {'h': 0, 'R': 1, 'F': 2, 'W': 3, 'Sigma': 4, 'Tph': 5, 'Tph_vis': 6, 'Tirr': 7, 'Kirr': 8, 'Height': 9,
+          'Qx': 10, 'Tph_X': 11, 'windA': 12, 'windB': 13, 'windC': 14, 'Fmagn': 15, 'dFmagn_dh': 16,
+          'd2Fmagn_dh2': 17}
+
+
+def column_names(n_lambdas=0, cold_disk=False, is_ns=False):
+    cols = list(BH_COLS)
+    for k in range(n_lambdas):
+        cols.append('Fnu{}'.format(k))
+        if cold_disk:
+            cols.append('Fnu{}_cold'.format(k))
+    if is_ns:
+        cols += NS_COLS
+    return cols
+
+
+def resolve(args):
+    """Host-only: (info, h, F0) of one model — what the reference's constructors compute."""
+    info = FB200ModelInfo()
+    h = np.empty(int(args.Nx))
+    F = np.empty(int(args.Nx))
+    dp = C.POINTER(C.c_double)
+    _lib.check(_lib.lib.fb200_args_resolve(C.byref(args), C.byref(info), h.ctypes.data_as(dp), F.ctypes.data_as(dp)))
+    return info, h, F
+
+
+class Ensemble:
+    """``n`` models, one CTA each, evolved by a persistent sm_100a kernel.
+
+    args      : sequence of FB200Args (freddi_b200.args.make_args) or a ctypes array of them
+    lambdas   : wavelengths [cm] of the Fnu columns every row carries (FluxArguments::lambdas)
+    cold_disk : add the Fnu_cold columns (--colddiskflux)
+    record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
+    """
+
+    def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0):
+        self._h = None
+        arr = args if isinstance(args, C.Array) else args_array(list(args))
+        cfg = FB200Config()
+        _lib.lib.fb200_config_default(C.byref(cfg))
+        lambdas = [float(x) for x in lambdas]
+        if len(lambdas) > FB200_MAX_LAMBDAS:
+            raise ValueError('at most {} lambdas per ensemble'.format(FB200_MAX_LAMBDAS))
+        cfg.device = int(device)
+        cfg.n_lambdas = len(lambdas)
+        for k, x in enumerate(lambdas):
+            cfg.lambdas[k] = x
+        cfg.cold_disk = int(bool(cold_disk))
+        cfg.record_F = int(bool(record_F))
+        cfg.compute_lx = int(bool(compute_lx))
+        cfg.host_threads = int(host_threads)
+        handle = C.c_void_p()
+        bad = C.c_size_t()
+        rc = _lib.lib.fb200_ensemble_create(arr, len(arr), C.byref(cfg), C.byref(handle), C.byref(bad))
+        self.bad_model = int(bad.value)
+        _lib.check(rc)
+        self._h = handle
+        self.lambdas = lambdas
+        self.cold_disk = bool(cold_disk)
+        self.record_F = bool(record_F)
+        self.is_ns = bool(arr[0].is_ns)
+        self.n_models = int(_lib.lib.fb200_ensemble_n_models(handle))
+        self.n_rows = int(_lib.lib.fb200_ensemble_n_rows(handle))
+        self.n_cols = int(_lib.lib.fb200_ensemble_n_cols(handle))
+        self.Nx = int(_lib.lib.fb200_ensemble_nx(handle))
+        self.columns = column_names(len(lambdas), cold_disk, self.is_ns)
+        self._info = None
+
+    # -- life cycle --
+    def close(self):
+        if self._h is not None:
+            _lib.lib.fb200_ensemble_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- evolution --
+    def evolve(self, n_steps=-1):
+        _lib.check(_lib.lib.fb200_ensemble_evolve(self._h, int(n_steps)))
+        return self
+
+    def evolve_async(self, n_steps=-1):
+        _lib.check(_lib.lib.fb200_ensemble_evolve_async(self._h, int(n_steps)))
+        return self
+
+    def sync(self):
+        _lib.check(_lib.lib.fb200_ensemble_sync(self._h))
+
+    def last_evolve_ms(self):
+        ms = C.c_float()
+        _lib.check(_lib.lib.fb200_ensemble_last_evolve_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def last_launches(self):
+        return int(_lib.lib.fb200_ensemble_last_launches(self._h))
+
+    # -- read-out --
+    def rows(self, out=None):
+        """(n_models, n_rows, n_cols) float64; rows a model never reached are NaN."""
+        if out is None:
+            out = np.empty((self.n_models, self.n_rows, self.n_cols))
+        _lib.check(_lib.lib.fb200_ensemble_rows(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out
+
+    def rows_device_ptr(self):
+        p = C.c_void_p()
+        _lib.check(_lib.lib.fb200_ensemble_rows_device(self._h, C.byref(p)))
+        return p.value
+
+    def status(self):
+        st = np.empty(self.n_models, dtype=np.int32)
+        rv = np.empty(self.n_models, dtype=np.int32)
+        pi = np.empty(self.n_models, dtype=np.int64)
+        _lib.check(_lib.lib.fb200_ensemble_status(self._h, st.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  rv.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  pi.ctypes.data_as(C.POINTER(C.c_int64))))
+        return st, rv, pi
+
+    def counters(self):
+        """(picard_iters, lx_trial_steps) per model, summed over the steps done so far."""
+        pi, lx = (np.empty(self.n_models, dtype=np.int64) for _ in range(2))
+        ip = C.POINTER(C.c_int64)
+        _lib.check(_lib.lib.fb200_ensemble_counters(self._h, pi.ctypes.data_as(ip), lx.ctypes.data_as(ip)))
+        return pi, lx
+
+    def state(self):
+        t = np.empty(self.n_models)
+        i_t, first, last = (np.empty(self.n_models, dtype=np.int64) for _ in range(3))
+        ip = C.POINTER(C.c_int64)
+        _lib.check(_lib.lib.fb200_ensemble_state(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), i_t.ctypes.data_as(ip),
+                                                 first.ctypes.data_as(ip), last.ctypes.data_as(ip)))
+        return dict(t=t, i_t=i_t, first=first, last=last)
+
+    def row_bounds(self, row):
+        first, last = (np.empty(self.n_models, dtype=np.int64) for _ in range(2))
+        ip = C.POINTER(C.c_int64)
+        _lib.check(_lib.lib.fb200_ensemble_row_bounds(self._h, int(row), first.ctypes.data_as(ip), last.ctypes.data_as(ip)))
+        return first, last
+
+    def info(self):
+        if self._info is None:
+            arr = (FB200ModelInfo * self.n_models)()
+            _lib.check(_lib.lib.fb200_ensemble_info(self._h, arr))
+            self._info = arr
+        return self._info
+
+    def field(self, name, row=-1):
+        """(n_models, Nx): the reference getter's array (zeros below first, cold-zone values beyond last)."""
+        out = np.empty((self.n_models, self.Nx))
+        _lib.check(_lib.lib.fb200_ensemble_field(self._h, FIELDS[name], int(row), out.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 out.size))
+        return out
+
+    def flux(self, lambdas, region='hot', row=-1):
+        """(n_models, len(lambdas)) spectral flux density of the hot or cold disc region."""
+        lam = np.ascontiguousarray(np.atleast_1d(lambdas), dtype=np.float64).ravel()
+        out = np.empty((self.n_models, lam.size))
+        reg = {'hot': 0, 'cold': 1}[region]
+        dp = C.POINTER(C.c_double)
+        _lib.check(_lib.lib.fb200_ensemble_flux(self._h, reg, int(row), lam.ctypes.data_as(dp), lam.size,
+                                                out.ctypes.data_as(dp), out.size))
+        return out
+
+    def mdot_wind(self, row=-1):
+        out = np.empty(self.n_models)
+        _lib.check(_lib.lib.fb200_ensemble_mdot_wind(self._h, int(row), out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out
+
+
+def measure_fp64_peak(device=0):
+    """Measured FP64 (DFMA) peak of the device in TFLOP/s."""
+    v = C.c_double()
+    _lib.check(_lib.lib.fb200_measure_fp64_peak(int(device), C.byref(v)))
+    return float(v.value)
+
+
+def shard_indices(n_models, rank, world_size):
+    """Model indices of one rank: interleaved (k -> GPU k mod G) so that cost correlated with the sweep
+    parameters is spread evenly; no rank ever needs another rank's models."""
+    return np.arange(rank, n_models, world_size)

@@ -1,0 +1,70 @@
+"""The BASELINE.json workloads as concrete argument lists, shared by bench.py and the tests."""
+import numpy as np
+
+from .args import make_args
+
+LAM3 = [3e-5, 5e-5, 8e-5]  # 3000, 5000, 8000 Angstrom [cm]
+
+# freddi.ini (config #1 of BASELINE.json), CLI units
+INI = dict(alpha=0.25, Mx=5, Mopt=0.5, period=0.25, F0=2e38, initialcond='powerF', powerorder=6, gaussmu=1, gausssigma=0.25,
+           distance=10, time=50, tau=0.25, __cgs=False)
+
+
+def ini_args(is_ns=False, **kw):
+    d = dict(INI)
+    d.update(kw)
+    return make_args(is_ns, **d)
+
+
+def config2_args(alphas, cirrs, **kw):
+    """BASELINE config #2: quasistat, Thot=1e4, boundcond=Tirr, isotropic; sweep alpha x Cirr."""
+    out = []
+    for a in alphas:
+        for c in cirrs:
+            out.append(ini_args(initialcond='quasistat', Thot=1e4, boundcond='Tirr', angulardistdisk='isotropic',
+                                alpha=float(a), Cirr=float(c), **kw))
+    return out
+
+
+NS_CI = dict(Mx=1.4, alpha=0.25, Mopt=0.5, Mdot0=1e17, F0=None, initialcond='quasistat', Bx=1e8, period=0.25, distance=10,
+             time=50, tau=0.25, powerorder=None)
+
+
+def config3_args(bxs, alphas, **kw):
+    """BASELINE config #3: freddi-ns CI command, sweep Bx x alpha."""
+    out = []
+    for b in bxs:
+        for a in alphas:
+            d = dict(NS_CI)
+            d.update(Bx=float(b), alpha=float(a))
+            d.update(kw)
+            out.append(ini_args(True, **d))
+    return out
+
+
+WOODS = dict(alpha=0.5, Mx=9, rout=1, period=0.5, Mopt=0.5, F0=2e37, kerr=0.4, Cirr=1e-3, opacity='OPAL',
+             initialcond='quasistat', windtype='Woods1996', windparams={'Xi_max': 10, 'T_ic': 1e8, 'Pow': 1}, distance=5)
+
+
+def config4_args(alphas, cirrs, **kw):
+    """BASELINE config #4: README wind example (Readme.md:997-1003), sweep alpha x Cirr, 3 lambdas every row."""
+    out = []
+    for a in alphas:
+        for c in cirrs:
+            d = dict(WOODS)
+            d.update(alpha=float(a), Cirr=float(c))
+            d.update(kw)
+            out.append(ini_args(False, **d))
+    return out
+
+
+def config5_args(mxs, alphas, mdisks, cirrs, **kw):
+    """BASELINE config #5: Mx x alpha x Mdisk0 x Cirr, quasistat, Thot=1e4, boundcond=Tirr, isotropic."""
+    out = []
+    for m in mxs:
+        for a in alphas:
+            for md in mdisks:
+                for c in cirrs:
+                    out.append(ini_args(initialcond='quasistat', Thot=1e4, boundcond='Tirr', angulardistdisk='isotropic',
+                                        Mx=float(m), alpha=float(a), Mdisk0=float(md), F0=None, Cirr=float(c), **kw))
+    return out

@@ -186,10 +186,20 @@ typedef struct fb200_ensemble fb200_ensemble_t;
 int fb200_abi_version(void);
 const char* fb200_last_error(void); /* thread-local message of the last failing call */
 int fb200_device_count(void);       /* number of CUDA devices visible, <0 on driver error */
+/* Measured FP64 peak of `device` [TFLOP/s, 2 flop per DFMA]: a register-resident DFMA micro-kernel timed with
+ * CUDA events.  It is the denominator of the roofline this path is reported against (the path is bound by
+ * the FP64 pipe, not by HBM). */
+int fb200_measure_fp64_peak(int device, double* tflops);
 
 /* --- arguments --- */
 void fb200_args_default(fb200_args_t* args, int is_ns); /* defaults of pywrap_freddi_evolution.cpp:33-83,203-224 */
 void fb200_config_default(fb200_config_t* cfg);
+
+/* Host-only resolution of one model's arguments (no device needed): the constants, the grid h[Nx] and the
+ * initial F[Nx] that fb200_ensemble_create uploads.  Stands in for constructing the reference's Arguments
+ * blocks + FreddiState (cpp/src/arguments.cpp:30-351, cpp/src/freddi_state.cpp:13-71).  h / F may be NULL;
+ * when given they must hold args->Nx doubles.  Returns the error class the reference would throw. */
+int fb200_args_resolve(const fb200_args_t* args, fb200_model_info_t* info, double* h, double* F);
 
 /* --- ensemble life cycle --- */
 /* Resolves every model's arguments on the host (ISCO, tidal radius, opacity constants, grid h, initial
@@ -224,13 +234,17 @@ int fb200_ensemble_rows(fb200_ensemble_t* e, double* out, size_t out_len);
 int fb200_ensemble_rows_device(fb200_ensemble_t* e, const double** dptr);
 /* Per-model status, number of valid rows, Picard iterations summed over steps. */
 int fb200_ensemble_status(fb200_ensemble_t* e, int32_t* status, int32_t* rows_valid, int64_t* picard_iters);
+/* Work counters per model, summed over the steps done so far: Picard iterations of the solver and try_step
+ * calls of the Lx quadrature (6 Planck evaluations each in the reference).  For the roofline arithmetic. */
+int fb200_ensemble_counters(fb200_ensemble_t* e, int64_t* picard_iters, int64_t* lx_trial_steps);
 /* Current t [s], i_t, first, last per model (any pointer may be NULL). */
 int fb200_ensemble_state(fb200_ensemble_t* e, double* t, int64_t* i_t, int64_t* first, int64_t* last);
 /* State of a recorded row (requires record_F): first/last per model at that row. */
 int fb200_ensemble_row_bounds(fb200_ensemble_t* e, int64_t row, int64_t* first, int64_t* last);
 
-/* Radial field of every model: out[model][Nx].  row<0: the current state; row>=0: that recorded row
- * (requires cfg.record_F).  Values outside [first,last] are NaN for state-dependent fields. */
+/* Radial field of every model: out[model][Nx], exactly as the reference getter returns it (zeros below
+ * `first`, cold-zone values beyond `last`; the NaN padding of EvolutionResult is done by the Python layer).
+ * row<0: the current state; row>=0: that recorded row (requires cfg.record_F). */
 int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* out, size_t out_len);
 /* Spectral flux density of the hot (region 0) or cold (region 1) disc at wavelengths lambdas[cm]:
  * out[model][n_lambdas], evaluated on the state of `row` (row<0: current). */

@@ -801,8 +801,8 @@ struct DiscEngine {
         st.t += M.tau;
         const int it = solve_step(sc.Mdot);
         if (it < 0) { st.status = FB200_MODEL_FAILED; return false; }
-        st.picard_iters += it;
         if (!structure_and_row(true, row, Fsnap_row, bounds_row)) { st.status = FB200_MODEL_COLLAPSED; return false; }
+        st.picard_iters += it;  // counted like rows_valid: completed steps only
         return true;
     }
 };

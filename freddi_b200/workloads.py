@@ -5,9 +5,11 @@ from .args import make_args
 
 LAM3 = [3e-5, 5e-5, 8e-5]  # 3000, 5000, 8000 Angstrom [cm]
 
-# freddi.ini (config #1 of BASELINE.json), CLI units
+# freddi.ini (config #1 of BASELINE.json), CLI units.  emin/emax are spelled out [keV] as the golden files' headers do:
+# with __cgs=False the reference converts them keV -> Hz even when they come from its (already Hz) defaults
+# (cpp/pywrap/pywrap_freddi_evolution.cpp:117-118), which would put the X-ray band at ~1e35 Hz and make Lx == 0.
 INI = dict(alpha=0.25, Mx=5, Mopt=0.5, period=0.25, F0=2e38, initialcond='powerF', powerorder=6, gaussmu=1, gausssigma=0.25,
-           distance=10, time=50, tau=0.25, __cgs=False)
+           distance=10, time=50, tau=0.25, emin=1, emax=12, __cgs=False)
 
 
 def ini_args(is_ns=False, **kw):

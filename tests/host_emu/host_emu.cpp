@@ -51,6 +51,8 @@ struct HostEx {
 
 }  // namespace
 
+static long long g_last_lx_trials = 0;
+
 extern "C" {
 
 // Same contract as ref_run (oracle/ref_driver.cpp): returns the number of valid rows, <0 on a resolve error.
@@ -122,8 +124,11 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
         if (last) last[r] = bounds[1];
         if (picard) picard[r] = eng.st.picard_iters - before;
     }
+    g_last_lx_trials = eng.st.lx_trials;
     return r;
 }
+
+long long emu_last_lx_trials() { return g_last_lx_trials; }
 
 // host resolver only: h[Nx], F[Nx] of the initial state + info (no device involved)
 int emu_resolve(const fb200_args_t* a, fb200_model_info_t* info, double* h, double* F, char* err, size_t err_len) {

@@ -1,0 +1,192 @@
+"""CPU tests of everything around the kernels: the C ABI loads and exports what include/freddi_b200.h declares,
+the host-side argument resolver reproduces the reference's constructors, and DiscEngine — the single source the
+CUDA kernel is compiled from — run under the sequential host policy (tests/host_emu, test infrastructure)
+matches the oracle to 1e-10 with identical Picard counts, row counts and first/last."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from tests import common as cm
+from freddi_b200.args import make_args, FB200Args, merge_kwargs
+
+
+def test_c_abi_exports_every_declared_symbol(built):
+    from freddi_b200 import _lib
+    header = open(os.path.join(cm.ROOT, 'include', 'freddi_b200.h')).read()
+    declared = set(re.findall(r'\b(fb200_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.fb200_abi_version() == 1
+
+
+def test_args_struct_layout_matches_the_header(built):
+    """sizeof(fb200_args_t) seen by C equals the ctypes image: defaults written by C read back correctly."""
+    from freddi_b200 import _lib
+    a = FB200Args()
+    _lib.lib.fb200_args_default(C.byref(a), 1)
+    assert a.is_ns == 1 and a.Nx == 1000 and a.eps == 1e-6 and a.colourfactor == 1.7 and a.hotspotarea == 1.0
+    assert abs(a.kappatparams[0] - 1 / 3) < 1e-16 and a.starlod == 3 and np.isnan(a.Bx)
+    assert abs(a.emax / a.emin - 12) < 1e-12
+
+
+def test_no_device_fails_loudly(built):
+    """There is no CPU fallback: without a CUDA device creation raises."""
+    from freddi_b200 import _lib, Ensemble
+    if _lib.lib.fb200_device_count() > 0:
+        pytest.skip('a CUDA device is present')
+    with pytest.raises(_lib.NoDeviceError):
+        Ensemble([cm.ini_args()])
+
+
+def test_kwargs_surface_matches_reference_constructor():
+    """cpp/pywrap/pywrap_freddi_evolution.cpp:86-104: unknown keyword -> TypeError, missing required -> KeyError."""
+    with pytest.raises(TypeError):
+        merge_kwargs(dict(cm.INI, nosuch=1), False)
+    bad = dict(cm.INI)
+    del bad['alpha']
+    with pytest.raises(KeyError):
+        merge_kwargs(bad, False)
+    with pytest.raises(TypeError):
+        merge_kwargs(dict(cm.INI, Bx=1e8), False)  # NS-only keyword on a BH model
+    a = make_args(True, **dict(cm.INI, Bx=1e8))
+    assert a.is_ns == 1 and a.Bx == 1e8
+
+
+RESOLVE_CASES = {
+    'default': (False, {}),
+    'quasistat_Mdisk0': (False, dict(initialcond='quasistat', Mdisk0=1e26, F0=None)),
+    'quasistat_Mdot0_opal': (False, dict(initialcond='quasistat', Mdot0=1e18, F0=None, opacity='OPAL')),
+    'sine_Mdot0': (False, dict(initialcond='sineF', Mdot0=1e18, F0=None)),
+    'gauss': (False, dict(initialcond='gaussF', gaussmu=0.8, gausssigma=0.1)),
+    'gauss_underflow_ramp': (False, dict(initialcond='gaussF', gaussmu=1.0, gausssigma=0.01)),
+    'powerSigma': (False, dict(initialcond='powerSigma', powerorder=1, Mdisk0=1e25, F0=None)),
+    'linear_grid_kerr': (False, dict(gridscale='linear', kerr=0.7, Nx=257, initialcond='linearF')),
+    'rin_rout_given': (False, dict(rin=10, rout=2.0, alphacold=0.02)),
+    'ns_dummy': (True, dict(cm.NS_CI)),
+    'ns_sibsun_invbeta': (True, dict(cm.NS_CI, inversebeta=0.5, freqx=300, nsprop='sibgatullinsunyaev2000', nsgravredshift='on')),
+    'ns_quasistat_ns': (True, dict(cm.NS_CI, initialcond='quasistat-ns', freqx=400, Rx=1e6, Bx=3e8, nsprop='newt')),
+}
+
+
+@pytest.mark.parametrize('name', sorted(RESOLVE_CASES))
+def test_resolver_reproduces_reference_constructors(ref, built, name):
+    """h, F(t=0), first and the derived constants are bit-identical to what the reference's constructors produce
+    (same libm, same operation order): cpp/src/arguments.cpp:57-351, cpp/src/freddi_state.cpp:13-71."""
+    from freddi_b200.ensemble import resolve
+    is_ns, kw = RESOLVE_CASES[name]
+    a = cm.ini_args(is_ns, **kw)
+    info, h, F = resolve(a)
+    m = ref.model(a)
+    ri = m.info()
+    np.testing.assert_array_equal(h, m.field('h'))
+    np.testing.assert_array_equal(F, m.field('F'))
+    for f in ('GM', 'eta', 'R_g', 'cosi', 'distance', 'cosiOverD2', 'tau', 'h_in', 'h_out', 'rin', 'rout', 'risco'):
+        assert getattr(info, f) == getattr(ri, f), f
+    assert (info.Nx, info.Nt, info.first0) == (ri.Nx, ri.Nt, ri.first0)
+    if is_ns:
+        for f in ('mu_magn', 'R_cor', 'R_dead', 'inverse_beta', 'R_x', 'redshift'):
+            assert getattr(info, f) == getattr(ri, f), f
+
+
+@pytest.mark.parametrize('kw,exc', [
+    (dict(F0=None), RuntimeError),                       # One of F0, Mdisk0 or Mdot0 must be specified
+    (dict(Mdot0=1e18), RuntimeError),                    # Set Mdisk0 or F0 instead of Mdot0 if initialcond=powerF
+    (dict(powerorder=None), RuntimeError),               # powerorder must be specified
+    (dict(initialcond='gaussF', gaussmu=1.5), RuntimeError),
+    (dict(opacity='nope'), ValueError),                  # std::invalid_argument
+    (dict(gridscale='nope'), ValueError),
+    (dict(windtype='nope'), ValueError),
+    (dict(angulardistdisk='nope'), ValueError),
+    (dict(initialcond='nope'), RuntimeError),            # Invalid value of initialcond
+])
+def test_resolver_error_classes(ref, built, kw, exc):
+    """Bad arguments come back as the exception class the reference throws; the oracle agrees on the class."""
+    from freddi_b200.ensemble import resolve
+    a = cm.ini_args(**kw)
+    with pytest.raises(exc):
+        resolve(a)
+    with pytest.raises(pyoracle.CheckerError) as ei:
+        ref.model(a)
+    assert (ei.value.code == -1) == (exc is ValueError)
+
+
+def emu_vs_ref(ref, emu, a, lam=(), cold=False):
+    r = ref.run(a, lam, cold_disk=cold)
+    e = emu.run(a, r['Nt'], r['Nx'], lam, cold)
+    names = pyoracle.column_names(len(lam), cold, bool(a.is_ns))
+    n = r['rows_valid']
+    assert e['rows_valid'] == n
+    np.testing.assert_array_equal(e['picard'][:n], r['picard'][:n])
+    np.testing.assert_array_equal(e['first'][:n], r['first'][:n])
+    np.testing.assert_array_equal(e['last'][:n], r['last'][:n])
+    cm.assert_rows_close(e['rows'][:n], r['rows'][:n], names)
+    assert cm.rel_err(e['F'][:n], r['F'][:n]).max() <= cm.RTOL
+    assert (e['rows'][:n, 0] == r['rows'][:n, 0]).all()  # t is accumulated, bit-exact
+    return r, e
+
+
+@pytest.mark.parametrize('path', cm.golden_files(), ids=os.path.basename)
+def test_engine_host_policy_matches_oracle_on_golden_configurations(ref, emu, path):
+    kw, lam, _pb, _data = pyoracle.load_golden(path)
+    emu_vs_ref(ref, emu, make_args(False, **kw), lam)
+
+
+ENGINE_CASES = {
+    'woods1996_irr_opal': (False, dict(cm.WOODS), cm.LAM3, False),
+    'shields1986': (False, dict(cm.WOODS, windtype='Shields1986', time=10), cm.LAM3, False),
+    'janiuk2015': (False, dict(windtype='Janiuk2015', windparams={'A_0': 10, 'B_1': 0.5}, initialcond='quasistat', time=10), (), False),
+    'testA': (False, dict(windtype='__testA__', windparams={'kA': 2.0}, time=10), (), False),
+    'testC_mdotout': (False, dict(windtype='__testC__', windparams={'kC': 3.0}, Mdotout=-1e18, time=10), (), False),
+    'cold_disk_plane_teff': (False, dict(initialcond='quasistat', Thot=1e4, Cirr=3e-4, Cirrcold=1e-4, h2rcold=0.03, irrindex=0.5,
+                                         irrindexcold=0.2, boundcond='Teff', angulardistdisk='plane', inclination=30, time=25), cm.LAM3, True),
+    'ns_ci': (True, dict(cm.NS_CI, time=25), cm.LAM3, False),
+    'ns_collapse_invbeta': (True, dict(cm.NS_CI, inversebeta=0.5, freqx=300, Rx=1.2e6, fptype='romanova2018',
+                                       fpparams={'par1': 0.15, 'par2': 0.92}, kappattype='romanova2018',
+                                       kappatparams={'in': 1 / 3, 'out': 1 / 3, 'par1': 0.15, 'par2': 0.92},
+                                       nsprop='sibgatullinsunyaev2000', nsgravredshift='on', Cirr=1e-4, Thot=1e4,
+                                       boundcond='Tirr', angulardistns='plane', time=30), cm.LAM3, False),
+    'ns_quasistat_ns_geometrical': (True, dict(cm.NS_CI, initialcond='quasistat-ns', freqx=400, Rx=1e6, Bx=3e8, nsprop='newt',
+                                               fptype='geometrical', fpparams={'chi': 30.0}, kappattype='corstep',
+                                               kappatparams={'in': 0.3, 'out': 0.4}, time=20), cm.LAM3, False),
+    'small_grid_nx64': (False, dict(Nx=64, initialcond='quasistat', time=10), cm.LAM3, False),
+}
+
+
+@pytest.mark.parametrize('name', sorted(ENGINE_CASES))
+def test_engine_host_policy_matches_oracle(ref, emu, name):
+    is_ns, kw, lam, cold = ENGINE_CASES[name]
+    emu_vs_ref(ref, emu, cm.ini_args(is_ns, **kw), lam, cold)
+
+
+def test_ns_moving_inner_radius(ref, emu):
+    """python/test/test_ns.py:37-55 set-up: the magnetosphere pushes `first` outwards during the decay."""
+    kw = dict(Mx=1.4, alpha=0.25, Mopt=0.5, period=0.25, F0=None, Mdot0=1e16, initialcond='quasistat', Bx=1e8, freqx=500, Rx=1e6,
+              rin=1.3e6 * 2.99792458e10 ** 2 / (6.673e-8 * 1.4 * 1.98892e33), rout=1e11 / 6.955e10, Rdead=5e6, time=40, tau=0.1,
+              powerorder=None, fptype='eksi-kutlu2010')
+    r, e = emu_vs_ref(ref, emu, cm.ini_args(True, **kw), cm.LAM3)
+    assert r['first'][-1] > r['first'][0]
+
+
+def test_planck_band_integral_controller(emu):
+    """The adaptive Cash-Karp quadrature: exact zeros for cold rings, agreement with a fine trapezoid within the
+    controller's tolerance, monotone in T; trial-step counts are those of odeint's controller (>= 4: the step can
+    grow by at most x4.5 from 1% of the interval)."""
+    nu1, nu2 = 2.417989e17, 2.9015868e18
+    assert emu.planck(1e4, nu1, nu2) == (0.0, 0)     # exp overflows at nu1: identically zero integrand
+    assert emu.planck(0.0, nu1, nu2) == (0.0, 0)
+    assert emu.planck(float('nan'), nu1, nu2) == (0.0, 0)
+    prev = 0.0
+    for T in (3e5, 1e6, 3e6, 1e7, 3e7, 1e8):
+        v, n = emu.planck(T, nu1, nu2)
+        nu = np.linspace(nu1, nu2, 400001)
+        with np.errstate(over='ignore'):
+            B = 2 * 6.62606896e-27 / 2.99792458e10 ** 2 * nu ** 3 / np.expm1(6.62606896e-27 / 1.3806504e-16 * nu / T)
+        exact = np.trapezoid(B, nu)
+        assert abs(v / exact - 1) < 2e-3, (T, v, exact)
+        assert v > prev and n >= 4
+        prev = v

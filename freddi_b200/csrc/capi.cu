@@ -242,6 +242,8 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     const size_t rows_len = n_models * size_t(e->n_rows) * e->n_cols;
     FB_TRY(dev_alloc(e, &d_rows, rows_len));
     FB_TRY(dev_alloc(e, &D.queue, 4));
+    D.max_ctas = e->sm_count * evolve_ctas_per_sm();
+    FB_TRY(dev_alloc(e, &D.cta_scratch, size_t(D.max_ctas) * evolve_scratch_doubles_per_cta()));
     {
         std::vector<fb200_model_dev_t> hm(n_models);
         std::vector<ModelState> hs(n_models);
@@ -341,7 +343,7 @@ int fb200_ensemble_evolve_async(fb200_ensemble_t* e, int64_t n_steps) {
     FB_CUDA(cudaMemsetAsync(e->dev.queue, 0, sizeof(int), e->stream));
     e->dev.n_steps = (n_steps < 0 || n_steps > 0x7fffffff) ? -1 : int(n_steps);
     FB_CUDA(cudaEventRecord(e->ev0, e->stream));
-    const int n_ctas = int(std::min<size_t>(e->n, size_t(e->sm_count)));
+    const int n_ctas = int(std::min<size_t>(e->n, size_t(e->dev.max_ctas)));
     cudaError_t ce = launch_evolve(e->dev, n_ctas, e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_evolve_kernel launch");
     FB_CUDA(cudaEventRecord(e->ev1, e->stream));

@@ -7,7 +7,7 @@
 //   * tests/host_emu instantiates it with a sequential policy so the `-m "not gpu"` tests can run the
 //     very same step logic on a CPU against the oracle (test infrastructure only, never shipped).
 // Orchestration code below is "uniform": on the GPU every thread of the CTA executes it with identical
-// values; per-point work is in `ex.points([&](int i) {...})` lambdas, and data written by
+// values; per-point work is in `ex.points([&](int i, int k) {...})` lambdas, and data written by
 // one points() phase is only read by another thread after `ex.sync()`.
 //
 // Reference restated (paths relative to the reference repository):
@@ -55,19 +55,23 @@ struct ModelState {
     long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
 };
 
-// Per-point values a thread keeps in registers during the Picard loop of one step
+// Per-point values a thread keeps in registers during the Picard loop of one step (one per point slot)
 struct StepRegs {
-    double lo, up, cc, frac;  // this step's row of the tridiagonal system (a_i, b_i, c0_i, frac_i)
-    double f, K, rhs0, y;
+    double K, y;
     int valid, is_last;
 };
 
-// "Shared memory" arrays, one entry per radial point (length FB200_NX_MAX)
+// Per-point arrays of one model (length FB200_NX_MAX).  On the GPU the ones touched in every Picard
+// iteration live in shared memory; the ones read once per step (grid, row constants, interior
+// coefficients) live in an L2-resident global scratch slot of the CTA — the engine does not care.
 struct SharedArrays {
-    double *h, *R, *F;                 // grid and state
-    double *hn;                        // h^n of the opacity closure
-    double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients (nonlinear_diffusion.cpp:46-51)
-    double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row (see init_points)
+    const double* h;                   // grid (global: the ensemble's h array)
+    double *R;                         // radius (scratch)
+    double *F;                         // state (shared)
+    double *hn;                        // h^n of the opacity closure (shared)
+    double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients, nonlinear_diffusion.cpp:46-51 (scratch)
+    double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row, see init_points (scratch)
+    double *s_lo, *s_up, *s_cc, *s_frac, *s_rhs;  // this step's tridiagonal rows a_i, b_i, c0_i, frac_i, rhs (shared)
     double2 *lu[2];                    // PCR ping-pong: (lower, upper) of the diagonal-normalised system
     double *rr[2];                     // PCR ping-pong: right-hand side
     // row temporaries alias the PCR buffers (never live at the same time)
@@ -424,7 +428,7 @@ struct DiscEngine {
     // ---- one-time per model: grid-derived constants.  S.h and S.F must be loaded and synced. ----
     FB_HD void init_points() {
         const int Nx = M.Nx;
-        ex.points([&](int i) {
+        ex.points([&](int i, int k) {
             if (i >= Nx) return;
             const double h = S.h[i];
             const double R = p2(h) / M.GM;  // FreddiState::DiskStructure::initialize_R, freddi_state.cpp:47-53
@@ -454,7 +458,7 @@ struct DiscEngine {
         R_m = (M.R_dead < R_m) ? M.R_dead : R_m;         // std::min(R_m, R_dead)
         const int first = st.first, last = st.last;
         // smallest ii in [first, last-2] with R[ii+1] > R_m, else the loop runs out at last-1
-        int ii = ex.reduce_min_int([&](int i) -> int {
+        int ii = ex.reduce_min_int([&](int i, int k) -> int {
             if (i >= first && i <= last - 2 && S.R[i + 1] > R_m) return i;
             return 0x7fffffff;
         });
@@ -483,7 +487,7 @@ struct DiscEngine {
         const bool janiuk = (M.windtype == FB200_WIND_JANIUK2015);
 
         if (janiuk) {  // B changes with Mdot_in: refresh the interior coefficients
-            ex.points([&](int i) {
+            ex.points([&](int i, int k) {
                 if (i > 0 && i < Nx - 1) {
                     double Bd = 0., Cd = 0.;
                     if (i >= first && i <= last) wind_dynamic_point(M, ws, S.h[i], S.R[i], &Bd, &Cd);
@@ -493,11 +497,11 @@ struct DiscEngine {
             // each thread rewrites only its own entries and reads them back itself: no barrier needed
         }
 
-        ex.points([&](int i) {
-            StepRegs& r = ex.step(i);
+        ex.points([&](int i, int k) {
+            StepRegs& r = ex.step(k);
             r.valid = (i > first && i <= last);
             r.is_last = (i == last);
-            r.K = 0.; r.f = 0.; r.y = 0.; r.lo = 0.; r.up = 0.; r.cc = 1.; r.frac = 0.; r.rhs0 = 0.;
+            r.K = 0.; r.y = 0.;
             if (!r.valid) return;
             const double h = S.h[i], R = S.R[i];
             double A = ex.windA(i), B = ex.windB(i), C = ex.windC_static(i);
@@ -508,34 +512,37 @@ struct DiscEngine {
             }
             const double y = S.F[i];
             const double W = wunc_point(M, y, S.hn[i]);
+            double lo, up, cc, frac, rhs;
             if (!r.is_last) {
-                r.lo = S.ca[i]; r.up = S.cb[i]; r.cc = S.cc[i]; r.frac = S.frac[i];
-                r.f = r.frac * (W + tau * C);
-                r.K = r.f / y;            // nonlinear_diffusion.cpp:61 — includes tau*C
-                r.rhs0 = r.f;
+                lo = S.ca[i]; up = S.cb[i]; cc = S.cc[i]; frac = S.frac[i];
+                const double f = frac * (W + tau * C);
+                r.K = f / y;              // nonlinear_diffusion.cpp:61 — includes tau*C
+                rhs = f;
             } else {
                 const double d = h - S.h[i - 1];
                 const double aL = 1 - 0.5 * A * d;
-                r.lo = aL; r.up = 0.;
-                r.cc = aL - 0.5 * B * d * d;
-                r.frac = d * d * 0.5 / tau;
-                r.f = r.frac * (W + tau * C);
-                r.K = r.frac * W / y;     // nonlinear_diffusion.cpp:65 — no C, never updated in the loop
-                r.rhs0 = d * rbc + r.f;
+                lo = aL; up = 0.;
+                cc = aL - 0.5 * B * d * d;
+                frac = d * d * 0.5 / tau;
+                const double f = frac * (W + tau * C);
+                r.K = frac * W / y;       // nonlinear_diffusion.cpp:65 — no C, never updated in the loop
+                rhs = d * rbc + f;
             }
-            if (i == first + 1) { r.rhs0 += r.lo * F_in; r.lo = 0.; }  // y[first] = F_in is known
+            if (i == first + 1) { rhs += lo * F_in; lo = 0.; }  // y[first] = F_in is known
+            S.s_lo[i] = lo; S.s_up[i] = up; S.s_cc[i] = cc; S.s_frac[i] = frac; S.s_rhs[i] = rhs;
         });
+        // each thread reads back only the rows it wrote itself: no barrier needed here
 
         int iters = 0;
         double maxrel;
         do {
             // -- tridiagonal solve: parallel cyclic reduction on the diagonal-normalised system --
-            ex.points([&](int i) {
-                StepRegs& r = ex.step(i);
+            ex.points([&](int i, int k) {
+                StepRegs& r = ex.step(k);
                 double l = 0., u = 0., rhs = 0.;
                 if (r.valid) {
-                    const double inv = 1.0 / (r.cc + r.K);
-                    l = -r.lo * inv; u = -r.up * inv; rhs = r.rhs0 * inv;
+                    const double inv = 1.0 / (S.s_cc[i] + r.K);
+                    l = -S.s_lo[i] * inv; u = -S.s_up[i] * inv; rhs = S.s_rhs[i] * inv;
                 }
                 S.lu[0][i] = make_double2(l, u);
                 S.rr[0][i] = rhs;
@@ -544,8 +551,8 @@ struct DiscEngine {
             ex.sync();
             int cur = 0;
             for (int s = 1; s < m; s <<= 1) {
-                ex.points([&](int i) {
-                    StepRegs& r = ex.step(i);
+                ex.points([&](int i, int k) {
+                    StepRegs& r = ex.step(k);
                     if (!r.valid) return;  // rows outside (first, last] are never read
                     const double2 me = S.lu[cur][i];
                     const double rme = S.rr[cur][i];
@@ -566,14 +573,14 @@ struct DiscEngine {
                 cur ^= 1;
             }
             // -- y, W, K update and convergence norm (nonlinear_diffusion.cpp:83-88) --
-            maxrel = ex.reduce_max([&](int i) -> double {
-                StepRegs& r = ex.step(i);
+            maxrel = ex.reduce_max([&](int i, int k) -> double {
+                StepRegs& r = ex.step(k);
                 if (i == first) S.F[i] = F_in;
                 if (!r.valid) return 0.;
                 S.F[i] = r.y;
                 if (r.is_last) return 0.;  // K[last] stays at its pre-step value
                 const double W = wunc_point(M, r.y, S.hn[i]);
-                const double K1 = r.frac * W / r.y;
+                const double K1 = S.s_frac[i] * W / r.y;
                 const double rel = fabs((K1 - r.K) / K1);
                 r.K = K1;
                 return rel;  // a NaN is skipped by the reduction, as `x > max` does in max_dif_rel
@@ -595,7 +602,7 @@ struct DiscEngine {
         const StateScalars sc = state_scalars(ex, M, S, first, true);
 
         // hot-zone structure of every point of [first, last]
-        ex.points([&](int i) {
+        ex.points([&](int i, int k) {
             if (i >= Nx) return;
             double Tph = 0., Tirr = 0., Sigma = 0., Tvis = 0.;
             if (i >= first && i <= last) {
@@ -614,7 +621,7 @@ struct DiscEngine {
             else branch = (M.boundcond == FB200_BOUNDCOND_TEFF) ? 1 : 2;
             const double Sigma_last = S.Sigma[last], R_last = S.R[last];
             // the do-while walks ii = last, last-1, ... and stops at the first ii whose condition is false
-            const int jmax = ex.reduce_max_int([&](int i) -> int {
+            const int jmax = ex.reduce_max_int([&](int i, int k) -> int {
                 if (!(i > first && i <= last)) return -1;
                 bool cond;
                 if (branch == 0) {
@@ -632,7 +639,7 @@ struct DiscEngine {
             if (jmax <= last - 1) {
                 last = jmax;
                 st.last = last;
-                ex.points([&](int i) {  // Kirr and H/R at the new outer edge
+                ex.points([&](int i, int k) {  // Kirr and H/R at the new outer edge
                     if (i == last) {
                         const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i]);
                         ex.scalar(0) = q.Kirr; ex.scalar(1) = q.Height / S.R[i];
@@ -647,7 +654,7 @@ struct DiscEngine {
         const double absMdot = fabs(sc.Mdot_plain);
         const double KM = 3. * absMdot * p6(FB_C_LIGHT) / (8. * FB_PI * p2(M.GM));
         const double F_first = S.F[first];
-        ex.points([&](int i) {
+        ex.points([&](int i, int k) {
             if (i >= Nx) return;
             double T = 0.;
             if (i >= first && i <= last) {
@@ -666,10 +673,10 @@ struct DiscEngine {
         double cold_K = 0.;
         const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
-        ex.points([&](int i) { ex.step(i).valid = 0; });  // reused as this point's Lx trial-step counter
-        ex.reduce_sums(nq + 1, [&](int i, int q) -> double {
+        ex.points([&](int, int k) { ex.step(k).valid = 0; });  // reused as this point's Lx trial-step counter
+        ex.reduce_sums(nq + 1, [&](int i, int k, int q) -> double {
             if (i >= Nx) return 0.;
-            if (q == nq) return double(ex.step(i).valid);
+            if (q == nq) return double(ex.step(k).valid);
             const bool cold = (q >= 2 + nl);
             int rf = first, rl = last;
             if (cold) { rf = last + 1; rl = Nx - 1; }
@@ -685,7 +692,7 @@ struct DiscEngine {
                 if (!cfg.compute_lx) return 0.;
                 int trials;
                 y = planck_nu1_nu2(S.TphX[i], M.emin, M.emax, 1e-4, &trials);
-                ex.step(i).valid = trials;
+                ex.step(k).valid = trials;
             } else if (!cold) {
                 const int k = q - 2;
                 y = planck_lambda_pref(S.Tph[i], cfg.lambdas[k], ex.lambda_pref(k));
@@ -703,7 +710,7 @@ struct DiscEngine {
             return 2 * FB_PI * S.R[i] * y * w;
         });
         // max Tph_X over [first, last] with std::max_element's NaN behaviour (output.cpp:208)
-        double TphXmax = ex.reduce_max([&](int i) -> double {
+        double TphXmax = ex.reduce_max([&](int i, int k) -> double {
             if (i >= first && i <= last) return S.TphX[i];
             return -INFINITY;
         });
@@ -717,7 +724,7 @@ struct DiscEngine {
         const double psi = angular_dist(M.angdist_disk, M.cosi);
         const int ncol = cfg.n_cols;
         const double t_now = st.t;
-        ex.points([&](int i) {
+        ex.points([&](int i, int k) {
             if (i >= ncol) return;
             double v;
             switch (i) {
@@ -753,10 +760,10 @@ struct DiscEngine {
             row[i] = v;
         });
         if (Fsnap_row) {
-            ex.points([&](int i) { if (i < Nx) Fsnap_row[i] = S.F[i]; });
+            ex.points([&](int i, int k) { if (i < Nx) Fsnap_row[i] = S.F[i]; });
         }
         if (bounds_row) {
-            ex.points([&](int i) { if (i == 0) { bounds_row[0] = first; bounds_row[1] = last; } });
+            ex.points([&](int i, int k) { if (i == 0) { bounds_row[0] = first; bounds_row[1] = last; } });
         }
         ex.sync();
         return true;

@@ -6,10 +6,10 @@
 
 namespace fb200 {
 
-__global__ void __launch_bounds__(kNT, 1) fb200_evolve_kernel(const EnsembleDev E) {
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const EnsembleDev E) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
-    const SharedArrays S = carve_shared(base);
+    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     __shared__ int s_model;
@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kNT, 1) fb200_evolve_kernel(const EnsembleDev 
 
         ModelState st = E.state[model];
         if (st.status != FB200_MODEL_OK) continue;
+        S.h = E.h + size_t(model) * Nx;
         load_model(E, model, Msh, S, ex, E.F + size_t(model) * Nx);
         const fb200_model_dev_t& M = *Msh;
 
@@ -56,17 +57,20 @@ __global__ void __launch_bounds__(kNT, 1) fb200_evolve_kernel(const EnsembleDev 
         }
         // write the state back for the next evolve call / the read-out kernels
         __syncthreads();
-        if (tid < Nx) E.F[size_t(model) * Nx + tid] = S.F[tid];
+        for (int i = tid; i < Nx; i += kNT) E.F[size_t(model) * Nx + i] = S.F[i];
         if (tid == 0) E.state[model] = eng.st;
     }
 }
 
 size_t evolve_smem_bytes() { return SmemLayout::bytes(); }
+size_t evolve_scratch_doubles_per_cta() { return SmemLayout::scratch_doubles_per_cta(); }
+int evolve_ctas_per_sm() { return kCtasPerSm; }
 
 cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream) {
     // per device and cheap: set on every launch so that several devices in one process all get it
     cudaError_t e = cudaFuncSetAttribute(fb200_evolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
     if (e != cudaSuccess) return e;
+    if (n_ctas > E.max_ctas) n_ctas = E.max_ctas;
     fb200_evolve_kernel<<<n_ctas, kNT, SmemLayout::bytes(), stream>>>(E);
     return cudaGetLastError();
 }

@@ -25,9 +25,13 @@ struct EnsembleDev {
     double* Fsnap;                    // [n_models][n_rows][Nx] or null (record_F)
     int* bounds;                      // [n_models][n_rows][2] or null (first,last per row; record_F)
     int* queue;                       // work-queue counter
+    double* cta_scratch;              // [max_ctas][scratch_doubles_per_cta()] once-per-step arrays of the model a CTA holds
+    int max_ctas;                     // CTAs the scratch was sized for (2 per SM)
 };
 
 size_t evolve_smem_bytes();
+size_t evolve_scratch_doubles_per_cta();
+int evolve_ctas_per_sm();
 // Launches the persistent evolve kernel on `stream`; returns cudaGetLastError().
 cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream);
 

@@ -12,7 +12,7 @@ struct Loaded {
 };
 
 // Stages model `model` at `row` (row < 0: current state).  Returns first/last of that state.
-__device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long long row, fb200_model_dev_t* Msh, const SharedArrays& S,
+__device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long long row, fb200_model_dev_t* Msh, SharedArrays& S,
                                         GpuEx& ex) {
     const int Nx = E.Nx;
     const double* F_src = E.F + size_t(model) * Nx;
@@ -26,19 +26,19 @@ __device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long lo
         L.first = b[0];
         L.last = b[1];
     }
+    S.h = E.h + size_t(model) * Nx;
     load_model(E, model, Msh, S, ex, F_src);
     return L;
 }
 
-__global__ void __launch_bounds__(kNT, 1) fb200_field_kernel(const EnsembleDev E, int field, long long row, double* out) {
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const EnsembleDev E, int field, long long row, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
-    const SharedArrays S = carve_shared(base);
+    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
-    const int i = threadIdx.x;
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(kNT, 1) fb200_field_kernel(const EnsembleDev E
         eng.init_points();
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, true);
-        double v = 0.;
-        if (i < Nx) {
+        for (int i = threadIdx.x; i < Nx; i += kNT) {
+            double v = 0.;
             const double h = S.h[i], R = S.R[i], F = S.F[i];
             const bool hot = (i >= first && i <= last);
             PointStructure q{};
@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(kNT, 1) fb200_field_kernel(const EnsembleDev E
 }
 
 // out[model][k] = flux_region<region>(lambdas[k]); region 0 hot (Tph over [first,last]), 1 cold (Tirr over [last+1,Nx-1])
-__global__ void __launch_bounds__(kNT, 1) fb200_flux_kernel(const EnsembleDev E, int region, long long row, const double* lambdas,
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const EnsembleDev E, int region, long long row, const double* lambdas,
                                                             int n_lambdas, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
-    const SharedArrays S = carve_shared(base);
+    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kNT, 1) fb200_flux_kernel(const EnsembleDev E,
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, true);
         // temperature of the region at every point
-        ex.points([&](int i) {
+        ex.points([&](int i, int) {
             double T = 0.;
             if (i < Nx) {
                 const double R = S.R[i];
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kNT, 1) fb200_flux_kernel(const EnsembleDev E,
         const int rl = (region == 0) ? last : Nx - 1;
         for (int k0 = 0; k0 < n_lambdas; k0 += FB200_MAXQ) {
             const int nq = min(FB200_MAXQ, n_lambdas - k0);
-            ex.reduce_sums(nq, [&](int i, int q) -> double {
+            ex.reduce_sums(nq, [&](int i, int, int q) -> double {
                 if (rf >= rl || i < rf || i > rl) return 0.;
                 double w;
                 if (i == rf) w = S.R[i + 1] - S.R[i];
@@ -180,10 +180,10 @@ __global__ void __launch_bounds__(kNT, 1) fb200_flux_kernel(const EnsembleDev E,
 }
 
 // Mdot_wind (cpp/src/freddi_state.cpp:364-383): - trapz over h of (A dF/dh + B F + C) on [first, last]
-__global__ void __launch_bounds__(kNT, 1) fb200_mdot_wind_kernel(const EnsembleDev E, long long row, double* out) {
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const EnsembleDev E, long long row, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
-    const SharedArrays S = carve_shared(base);
+    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kNT, 1) fb200_mdot_wind_kernel(const EnsembleD
         const StateScalars sc = state_scalars(ex, M, S, first, false);
         WindScalars ws{0, 0, 0, 0, 0};
         if (M.wind_dynamic) ws = wind_scalars(M, sc.Mdot, S.h[first], S.h[last], S.h[Nx - 1]);
-        ex.reduce_sums(1, [&](int i, int) -> double {
+        ex.reduce_sums(1, [&](int i, int, int) -> double {
             if (first >= last || i < first || i > last) return 0.;
             const double* h = S.h;
             const double* F = S.F;
@@ -288,7 +288,7 @@ cudaError_t measure_fp64_peak(double* tflops) {
 cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_field_kernel));
     if (e != cudaSuccess) return e;
-    const int grid = E.n_models < 1184 ? E.n_models : 1184;
+    const int grid = E.n_models < E.max_ctas ? E.n_models : E.max_ctas;
     fb200_field_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, field, row, out);
     return cudaGetLastError();
 }
@@ -297,7 +297,7 @@ cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const d
                         cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_flux_kernel));
     if (e != cudaSuccess) return e;
-    const int grid = E.n_models < 1184 ? E.n_models : 1184;
+    const int grid = E.n_models < E.max_ctas ? E.n_models : E.max_ctas;
     fb200_flux_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, region, row, lambdas_dev, n_lambdas, out);
     return cudaGetLastError();
 }
@@ -305,7 +305,7 @@ cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const d
 cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_mdot_wind_kernel));
     if (e != cudaSuccess) return e;
-    const int grid = E.n_models < 1184 ? E.n_models : 1184;
+    const int grid = E.n_models < E.max_ctas ? E.n_models : E.max_ctas;
     fb200_mdot_wind_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, row, out);
     return cudaGetLastError();
 }

@@ -1,6 +1,8 @@
-// CUDA execution policy of DiscEngine: one CTA per model, one radial point per thread (NT = 1024 threads).
-// Reductions are warp-shuffle trees finished through shared memory; every reduction returns its result
-// to all threads so the orchestration code stays uniform across the CTA.
+// CUDA execution policy of DiscEngine: one CTA of kNT = 256 threads per model, kPPT = 4 radial points per
+// thread (point i = tid + k*kNT lives in slot k), two CTAs resident per SM (128 registers per thread, no
+// spills; ~107 KB of shared memory per CTA) so that one model's barriers and latency-bound phases overlap
+// with the other's FP64 work.  Reductions are warp-shuffle trees finished through shared memory; every
+// reduction returns its result to all threads so the orchestration code stays uniform across the CTA.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -8,38 +10,47 @@
 
 namespace fb200 {
 
-constexpr int kNT = 1024;      // threads per CTA = FB200_NX_MAX
-constexpr int kNW = kNT / 32;  // warps per CTA
+constexpr int kNT = 256;                   // threads per CTA
+constexpr int kPPT = FB200_NX_MAX / kNT;   // radial points per thread
+constexpr int kNW = kNT / 32;              // warps per CTA
+constexpr int kCtasPerSm = 2;
 
+// Shared memory: F, hn, the 5 per-step row arrays and the PCR ping-pong (6 arrays) = 13 point arrays.
+// Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb = 9 point arrays (read once per step).
 struct SmemLayout {
-    // 18 point arrays of FB200_NX_MAX doubles, then the small scratch areas
-    static constexpr int kPointArrays = 18;
-    static constexpr size_t kRedDoubles = 2 * kNW + kNW * FB200_MAXQ + FB200_MAXQ + 8 + FB200_MAX_LAMBDAS;
+    static constexpr int kPointArrays = 13;
+    static constexpr int kScratchArrays = 9;
+    static constexpr size_t kRedDoubles = 2 * 32 + kNW * FB200_MAXQ + FB200_MAXQ + 8 + FB200_MAX_LAMBDAS;
     static constexpr size_t bytes() {
         return sizeof(double) * (size_t(kPointArrays) * FB200_NX_MAX + kRedDoubles) + sizeof(fb200_model_dev_t) + 64;
     }
+    static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX;
+    static constexpr size_t scratch_doubles_per_cta() { return kScratchDoublesPerCta; }
 };
 
-__device__ __forceinline__ SharedArrays carve_shared(double* base) {
+__device__ __forceinline__ SharedArrays carve_shared(double* base, double* gscratch, const double* h_global) {
     SharedArrays S;
     const int N = FB200_NX_MAX;
-    S.h = base + 0 * N; S.R = base + 1 * N; S.F = base + 2 * N; S.hn = base + 3 * N;
-    S.ca = base + 4 * N; S.cb = base + 5 * N; S.cc = base + 6 * N; S.frac = base + 7 * N;
-    S.c1 = base + 8 * N; S.hm175 = base + 9 * N; S.hotR = base + 10 * N; S.Gb = base + 11 * N;
-    S.lu[0] = reinterpret_cast<double2*>(base + 12 * N);  // 2N doubles
-    S.lu[1] = reinterpret_cast<double2*>(base + 14 * N);  // 2N doubles
-    S.rr[0] = base + 16 * N;
-    S.rr[1] = base + 17 * N;
+    S.h = h_global;
+    S.F = base + 0 * N; S.hn = base + 1 * N;
+    S.s_lo = base + 2 * N; S.s_up = base + 3 * N; S.s_cc = base + 4 * N; S.s_frac = base + 5 * N; S.s_rhs = base + 6 * N;
+    S.lu[0] = reinterpret_cast<double2*>(base + 7 * N);  // 2N doubles
+    S.lu[1] = reinterpret_cast<double2*>(base + 9 * N);  // 2N doubles
+    S.rr[0] = base + 11 * N;
+    S.rr[1] = base + 12 * N;
     // row temporaries alias the PCR buffers
-    S.Tph = base + 12 * N; S.Tirr = base + 13 * N; S.Sigma = base + 14 * N; S.Tvis = base + 15 * N;
-    S.TphX = base + 16 * N; S.aux = base + 17 * N;
+    S.Tph = base + 7 * N; S.Tirr = base + 8 * N; S.Sigma = base + 9 * N; S.Tvis = base + 10 * N;
+    S.TphX = base + 11 * N; S.aux = base + 12 * N;
+    // once-per-step arrays in the CTA's global scratch slot
+    S.R = gscratch + 0 * N; S.ca = gscratch + 1 * N; S.cb = gscratch + 2 * N; S.cc = gscratch + 3 * N; S.frac = gscratch + 4 * N;
+    S.c1 = gscratch + 5 * N; S.hm175 = gscratch + 6 * N; S.hotR = gscratch + 7 * N; S.Gb = gscratch + 8 * N;
     return S;
 }
 
 struct GpuEx {
     int tid, lane, warp;
-    StepRegs sr;
-    double* redA;     // [2][kNW] double-buffered scalar reductions
+    StepRegs sr[kPPT];
+    double* redA;     // [2][32] double-buffered scalar reductions
     double* redQ;     // [kNW][FB200_MAXQ]
     double* sums;     // [FB200_MAXQ]
     double* scal;     // [8]
@@ -50,12 +61,16 @@ struct GpuEx {
 
     __device__ __forceinline__ void init(double* scratch) {
         tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; flip = 0;
-        redA = scratch; redQ = redA + 2 * kNW; sums = redQ + kNW * FB200_MAXQ; scal = sums + FB200_MAXQ; lampref = scal + 8;
+        redA = scratch; redQ = redA + 2 * 32; sums = redQ + kNW * FB200_MAXQ; scal = sums + FB200_MAXQ; lampref = scal + 8;
         gA = gB = gCs = gFm = gdFm = nullptr;
     }
-    template <class F> __device__ __forceinline__ void points(F&& f) { f(tid); }
+    // f(i, k): point index i, register slot k (a compile-time constant after unrolling)
+    template <class F> __device__ __forceinline__ void points(F&& f) {
+#pragma unroll
+        for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
+    }
     __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ StepRegs& step(int) { return sr; }
+    __device__ __forceinline__ StepRegs& step(int k) { return sr[k]; }
     __device__ __forceinline__ double& scalar(int k) { return scal[k]; }
     __device__ __forceinline__ double sum(int q) const { return sums[q]; }
     __device__ __forceinline__ double lambda_pref(int k) const { return lampref[k]; }
@@ -68,40 +83,51 @@ struct GpuEx {
     // One barrier per reduction: consecutive reductions alternate between two scratch rows, so a row is
     // rewritten only after every thread has passed the barrier of the reduction in between.
     template <class F> __device__ __forceinline__ double reduce_max(F&& f) {
-        double v = f(tid);
-        if (v != v) v = -INFINITY;  // skip NaN like `if (x > max)`
+        double v = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kPPT; ++k) {
+            const double x = f(tid + k * kNT, k);
+            v = fmax(v, x);  // fmax skips a NaN like `if (x > max)` does
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        double* row = redA + flip * kNW;
+        double* row = redA + flip * 32;
         flip ^= 1;
         if (lane == 0) row[warp] = v;
         __syncthreads();
-        double r = row[lane];
+        double r = (lane < kNW) ? row[lane] : -INFINITY;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
-        return r;
+        for (int o = kNW / 2; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        return __shfl_sync(0xffffffffu, r, 0);
     }
     template <class F> __device__ __forceinline__ int reduce_max_int(F&& f) {
-        int v = f(tid);
+        int v = 0x80000000;
+#pragma unroll
+        for (int k = 0; k < kPPT; ++k) v = max(v, f(tid + k * kNT, k));
         v = __reduce_max_sync(0xffffffffu, v);
-        int* row = reinterpret_cast<int*>(redA + flip * kNW);
+        int* row = reinterpret_cast<int*>(redA + flip * 32);
         flip ^= 1;
         if (lane == 0) row[warp] = v;
         __syncthreads();
-        return __reduce_max_sync(0xffffffffu, row[lane]);
+        return __reduce_max_sync(0xffffffffu, (lane < kNW) ? row[lane] : int(0x80000000));
     }
     template <class F> __device__ __forceinline__ int reduce_min_int(F&& f) {
-        int v = f(tid);
+        int v = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < kPPT; ++k) v = min(v, f(tid + k * kNT, k));
         v = __reduce_min_sync(0xffffffffu, v);
-        int* row = reinterpret_cast<int*>(redA + flip * kNW);
+        int* row = reinterpret_cast<int*>(redA + flip * 32);
         flip ^= 1;
         if (lane == 0) row[warp] = v;
         __syncthreads();
-        return __reduce_min_sync(0xffffffffu, row[lane]);
+        return __reduce_min_sync(0xffffffffu, (lane < kNW) ? row[lane] : 0x7fffffff);
     }
+    // sums[q] = sum over all points of f(i, k, q), q < nq
     template <class F> __device__ __forceinline__ void reduce_sums(int nq, F&& f) {
         for (int q = 0; q < nq; ++q) {
-            double v = f(tid, q);
+            double v = 0.;
+#pragma unroll
+            for (int k = 0; k < kPPT; ++k) v += f(tid + k * kNT, k, q);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) redQ[warp * FB200_MAXQ + q] = v;
@@ -109,7 +135,7 @@ struct GpuEx {
         __syncthreads();
         if (tid < nq) {
             double s = 0.;
-#pragma unroll 8
+#pragma unroll
             for (int w = 0; w < kNW; ++w) s += redQ[w * FB200_MAXQ + tid];
             sums[tid] = s;
         }
@@ -117,8 +143,7 @@ struct GpuEx {
     }
 };
 
-// Loads one model's constants, grid and state into shared memory and builds the engine inputs.
-// Returns the CTA-uniform ModelState.  All threads must call it.
+// Loads one model's constants and state into shared memory and binds its global arrays.  All threads call it.
 __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, fb200_model_dev_t* Msh, const SharedArrays& S, GpuEx& ex,
                                            const double* F_src) {
     const int tid = threadIdx.x;
@@ -129,11 +154,11 @@ __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, fb20
     }
     const int Nx = E.Nx;
     const size_t off = size_t(model) * Nx;
-    if (tid < Nx) {
-        S.h[tid] = E.h[off + tid];
-        S.F[tid] = F_src[tid];
-    } else {
-        S.h[tid] = 0.; S.F[tid] = 0.; S.R[tid] = 0.;
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+        const int i = tid + k * kNT;
+        S.F[i] = (i < Nx) ? F_src[i] : 0.;
+        if (i >= Nx) S.R[i] = 0.;
     }
     if (tid < E.cfg.n_lambdas) ex.lampref[tid] = FB_DOUBLE_H_C2 / p5(E.cfg.lambdas[tid]);
     ex.gA = E.wA ? E.wA + off : nullptr;

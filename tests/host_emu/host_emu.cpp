@@ -26,9 +26,10 @@ struct HostEx {
     double lampref[FB200_MAX_LAMBDAS] = {0};
     const double *gA = nullptr, *gB = nullptr, *gCs = nullptr, *gFm = nullptr, *gdFm = nullptr;
 
-    template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) f(i); }
+    int cur = 0;  // point the lambda is running for: the host policy has one register slot per point
+    template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) { cur = i; f(i, 0); } }
     void sync() {}
-    StepRegs& step(int i) { return sr[i]; }
+    StepRegs& step(int) { return sr[cur]; }
     double& scalar(int k) { return scal[k]; }
     double sum(int q) const { return sums[q]; }
     double lambda_pref(int k) const { return lampref[k]; }
@@ -39,13 +40,13 @@ struct HostEx {
     double dFmagn_dh(int i) const { return gdFm ? gdFm[i] : 0.; }
     template <class F> double reduce_max(F&& f) {
         double m = -INFINITY;
-        for (int i = 0; i < NT; ++i) { const double v = f(i); if (v == v) m = std::fmax(m, v); }
+        for (int i = 0; i < NT; ++i) { cur = i; const double v = f(i, 0); if (v == v) m = std::fmax(m, v); }
         return m;
     }
-    template <class F> int reduce_max_int(F&& f) { int m = f(0); for (int i = 1; i < NT; ++i) m = std::max(m, f(i)); return m; }
-    template <class F> int reduce_min_int(F&& f) { int m = f(0); for (int i = 1; i < NT; ++i) m = std::min(m, f(i)); return m; }
+    template <class F> int reduce_max_int(F&& f) { int m = 0x80000000; for (int i = 0; i < NT; ++i) { cur = i; m = std::max(m, f(i, 0)); } return m; }
+    template <class F> int reduce_min_int(F&& f) { int m = 0x7fffffff; for (int i = 0; i < NT; ++i) { cur = i; m = std::min(m, f(i, 0)); } return m; }
     template <class F> void reduce_sums(int nq, F&& f) {
-        for (int q = 0; q < nq; ++q) { double s = 0.; for (int i = 0; i < NT; ++i) s += f(i, q); sums[q] = s; }
+        for (int q = 0; q < nq; ++q) { double s = 0.; for (int i = 0; i < NT; ++i) { cur = i; s += f(i, 0, q); } sums[q] = s; }
     }
 };
 
@@ -76,10 +77,12 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
 
     const int N = FB200_NX_MAX;
-    std::vector<double> pool(18 * size_t(N), 0.);
+    std::vector<double> pool(24 * size_t(N), 0.);
     double* base = pool.data();
+    double* hbuf = base + 0 * N;
     SharedArrays S;
-    S.h = base + 0 * N; S.R = base + 1 * N; S.F = base + 2 * N; S.hn = base + 3 * N;
+    S.h = hbuf; S.R = base + 1 * N; S.F = base + 2 * N; S.hn = base + 3 * N;
+    S.s_lo = base + 18 * N; S.s_up = base + 19 * N; S.s_cc = base + 20 * N; S.s_frac = base + 21 * N; S.s_rhs = base + 22 * N;
     S.ca = base + 4 * N; S.cb = base + 5 * N; S.cc = base + 6 * N; S.frac = base + 7 * N;
     S.c1 = base + 8 * N; S.hm175 = base + 9 * N; S.hotR = base + 10 * N; S.Gb = base + 11 * N;
     S.lu[0] = reinterpret_cast<double2*>(base + 12 * N);
@@ -87,7 +90,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     S.rr[0] = base + 16 * N; S.rr[1] = base + 17 * N;
     S.Tph = base + 12 * N; S.Tirr = base + 13 * N; S.Sigma = base + 14 * N; S.Tvis = base + 15 * N;
     S.TphX = base + 16 * N; S.aux = base + 17 * N;
-    for (int i = 0; i < Nx; ++i) { S.h[i] = res.h[i]; S.F[i] = res.F[i]; }
+    for (int i = 0; i < Nx; ++i) { hbuf[i] = res.h[i]; S.F[i] = res.F[i]; }
 
     HostEx ex;
     for (int k = 0; k < n_lambdas; ++k) ex.lampref[k] = FB_DOUBLE_H_C2 / p5(lambdas[k]);

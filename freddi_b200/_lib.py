@@ -10,7 +10,7 @@ import os
 from .args import FB200Args, FB200Config, FB200ModelInfo
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libfreddi_b200.so')
+LIB_PATH = os.environ.get('FB200_LIB') or os.path.join(HERE, 'libfreddi_b200.so')  # FB200_LIB: kernel-variant experiments
 
 FB200_OK = 0
 ERR_INVALID_ARGUMENT, ERR_RUNTIME, ERR_LOGIC, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_BAD_HANDLE = -1, -2, -3, -4, -5, -6, -7

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -243,7 +244,12 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     FB_TRY(dev_alloc(e, &d_rows, rows_len));
     FB_TRY(dev_alloc(e, &D.queue, 4));
     D.max_ctas = e->sm_count * evolve_ctas_per_sm();
+    if (getenv("FB200_DEBUG"))
+        fprintf(stderr, "[fb200] smem/CTA %zu B, CTAs/SM designed %d, resident %d, SMs %d\n", evolve_smem_bytes(), evolve_ctas_per_sm(),
+                evolve_resident_ctas_per_sm(), e->sm_count);
     FB_TRY(dev_alloc(e, &D.cta_scratch, size_t(D.max_ctas) * evolve_scratch_doubles_per_cta()));
+    FB_TRY(dev_alloc(e, &D.prof, 8));
+    FB_TRYC(cudaMemset(D.prof, 0, 8 * sizeof(long long)));
     {
         std::vector<fb200_model_dev_t> hm(n_models);
         std::vector<ModelState> hs(n_models);
@@ -377,6 +383,14 @@ int fb200_ensemble_last_evolve_ms(fb200_ensemble_t* e, float* ms) {
 }
 
 int fb200_ensemble_last_launches(const fb200_ensemble_t* e) { return e ? e->last_launches : 0; }
+
+// Diagnostic (not part of include/freddi_b200.h): per-phase cycle sums of FB_PROFILE builds, zeros otherwise.
+int fb200_debug_phase_cycles(fb200_ensemble_t* e, long long* out8) {
+    if (!e || !out8) return FB200_ERR_BAD_HANDLE;
+    if (select_device(e) != FB200_OK) return FB200_ERR_CUDA;
+    cudaStreamSynchronize(e->stream);
+    return cudaMemcpy(out8, e->dev.prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? FB200_OK : FB200_ERR_CUDA;
+}
 
 int fb200_ensemble_rows(fb200_ensemble_t* e, double* out, size_t out_len) {
     if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");

@@ -71,9 +71,12 @@ struct SharedArrays {
     double *hn;                        // h^n of the opacity closure (shared)
     double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients, nonlinear_diffusion.cpp:46-51 (scratch)
     double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row, see init_points (scratch)
-    double *s_lo, *s_up, *s_cc, *s_frac, *s_rhs;  // this step's tridiagonal rows a_i, b_i, c0_i, frac_i, rhs (shared)
-    double2 *lu[2];                    // PCR ping-pong: (lower, upper) of the diagonal-normalised system
-    double *rr[2];                     // PCR ping-pong: right-hand side
+    // this step's tridiagonal system  l_i y_{i-1} + d_i y_i + u_i y_{i+1} = rhs_i  (l = -a_i, u = -b_i, d = c0_i + K_i);
+    // s_l, s_u, s_d, s_rhs and the block-elimination results p_a, p_c, p_g use the padded index pidx() (shared)
+    double *s_l, *s_u, *s_d, *s_rhs, *s_cc, *s_frac;
+    double *p_a, *p_c, *p_g;
+    double2 *lu[2];                    // PCR ping-pong of the reduced system: (lower, upper), diagonal normalised to 1
+    double *rr[2];                     // PCR ping-pong of the reduced system: right-hand side
     // row temporaries alias the PCR buffers (never live at the same time)
     double *Tph, *Tirr, *Sigma, *Tvis, *TphX, *aux;
 };
@@ -85,6 +88,16 @@ struct SharedArrays {
 #define FB_H_OVER_KB (FB_H_PLANCK / FB_K_BOLTZ)
 #define FB_DOUBLE_H_C2 (2. * FB_H_PLANCK * FB_C_LIGHT * FB_C_LIGHT)
 #define FB_CH_OVER_KB (FB_C_LIGHT * (FB_H_PLANCK / FB_K_BOLTZ))
+
+// x^(-1/3) and x^(-1/5) for the step-size controller (x in (0, inf) resp. [5^-5, 0.5])
+FB_HD double fb_rcbrt(double x) {
+#ifdef __CUDA_ARCH__
+    return rcbrt(x);
+#else
+    return 1.0 / cbrt(x);
+#endif
+}
+FB_HD double fb_pow_m02(double x) { return exp2(-0.2 * log2(x)); }
 
 FB_HD double planck_nu(double T, double nu) {
     if (!(T > 0.)) return 0.;
@@ -136,20 +149,21 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
         const double err = fabs(xerr) / (0. + tol * (1. * fabs(x) + (1. * fabs(dt)) * fabs(k1)));
         if (err > 1.0) {
-            const double f = 9. / 10. * pow(err, -1. / 3.);
+            // dt *= max(0.9 err^(-1/3), 0.2); rcbrt is within 1 ulp of pow(err, -1/3) and only steers the step size
+            const double f = 9. / 10. * fb_rcbrt(err);
             dt *= (f < 1. / 5.) ? 1. / 5. : f;
             if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand
             continue;
         }
         fails = 0;
-        t += dt;
+        t += dt;  // == the abscissa of stage 5 (c5 = 1): the derivative at the new t is k5, bit for bit
         if (err < 0.5) {
             const double floor_ = 0.00032;  // pow(5.0, -5)
             const double e = (floor_ < err) ? err : floor_;
-            dt *= 9. / 10. * pow(e, -1. / 5.);
+            dt *= 9. / 10. * fb_pow_m02(e);
         }
         x = xnew;
-        k1 = planck_nu(T, t);
+        k1 = k5;
     }
     if (trials) *trials = n;
     return x;
@@ -390,6 +404,16 @@ FB_HD double v_cooling_front(const fb200_model_dev_t& M, double r, double Sigma_
 }
 
 
+// The tridiagonal solve is block-partitioned: FB200_BLK consecutive unknowns are eliminated sequentially by
+// one thread (Thomas-style, in registers), which leaves a tridiagonal "reduced" system in the first and last
+// unknown of every block (2 per block, <= FB200_NRED_MAX) that is solved by parallel cyclic reduction.
+#define FB200_BLK 8
+#define FB200_NRED_MAX (2 * (FB200_NX_MAX / FB200_BLK))
+// One pad word per 8: a thread walking its own block (stride-8 words across the lanes of a warp) then hits
+// 16 distinct 8-byte bank pairs instead of 2.
+FB_HD int pidx(int i) { return i + (i >> 3); }
+#define FB200_NPAD (FB200_NX_MAX + FB200_NX_MAX / 8)
+
 FB_HD bool fb_isfinite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 FB_HD bool fb_isnan(double x) { return x != x; }
 
@@ -404,6 +428,9 @@ FB_HD bool fb_isnan(double x) { return x != x; }
 //   scalar(k)            small shared scratch (written by one thread, read after sync)
 //   windA(i), windB(i), windC_static(i), Fmagn(i), dFmagn_dh(i)   per-model arrays in global memory (0 if absent)
 //   lambda_pref(k)       double_h_c2 / lambda_k^5
+//   blocks(n, f)         run f(b) for b < n, one thread per b (the in-thread block elimination of the solve)
+//   reduced(n, f)        run f(q) for q < n, one thread per q (reduced-system PCR)
+//   tick(p)              phase boundary marker (cycle accounting in FB_PROFILE builds, otherwise a no-op)
 // ------------------------------------------------------------------------------------------------
 template <class Ex>
 struct DiscEngine {
@@ -529,62 +556,113 @@ struct DiscEngine {
                 rhs = d * rbc + f;
             }
             if (i == first + 1) { rhs += lo * F_in; lo = 0.; }  // y[first] = F_in is known
-            S.s_lo[i] = lo; S.s_up[i] = up; S.s_cc[i] = cc; S.s_frac[i] = frac; S.s_rhs[i] = rhs;
+            const int pi = pidx(i);
+            S.s_l[pi] = -lo; S.s_u[pi] = -up; S.s_rhs[pi] = rhs; S.s_d[pi] = cc + r.K;
+            S.s_cc[i] = cc; S.s_frac[i] = frac;
         });
-        // each thread reads back only the rows it wrote itself: no barrier needed here
+        ex.sync();
+        const int nblk = (m + FB200_BLK - 1) / FB200_BLK;  // blocks of unknowns first+1+8b .. first+8b+8
+        const int nred = 2 * nblk;
 
+        ex.tick(0);
         int iters = 0;
         double maxrel;
         do {
-            // -- tridiagonal solve: parallel cyclic reduction on the diagonal-normalised system --
-            ex.points([&](int i, int k) {
-                StepRegs& r = ex.step(k);
-                double l = 0., u = 0., rhs = 0.;
-                if (r.valid) {
-                    const double inv = 1.0 / (S.s_cc[i] + r.K);
-                    l = -S.s_lo[i] * inv; u = -S.s_up[i] * inv; rhs = S.s_rhs[i] * inv;
+            // -- block elimination: every block thread reduces its <= 8 rows to two rows in (x_0, x_last) --
+            ex.blocks(nblk, [&](int b) {
+                const int i0 = first + 1 + b * FB200_BLK;          // first row of the block
+                const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
+                const int p0 = pidx(i0);
+                // the pad word sits after every 8th point: walk the padded index alongside
+                double a[FB200_BLK], c[FB200_BLK], g[FB200_BLK];
+                double L0, D0, U0, R0, L1, D1, U1, R1;
+                const double l0 = S.s_l[p0], d0 = S.s_d[p0], u0 = S.s_u[p0], r0 = S.s_rhs[p0];
+                if (nb == 1) {
+                    L0 = l0; D0 = d0; U0 = 0.; R0 = r0;   // a lone row can only be the last block: no upper coupling
+                    L1 = 0.; D1 = 1.; U1 = 0.; R1 = 0.;   // dummy row, decoupled
+                } else {
+                    // forward: row j becomes  a_j x_0 + x_j + c_j x_{j+1} = g_j
+#pragma unroll
+                    for (int j = 1; j < FB200_BLK; ++j) {
+                        if (j < nb) {
+                            const int pj = pidx(i0 + j);
+                            const double l = S.s_l[pj], d = S.s_d[pj], u = S.s_u[pj], r = S.s_rhs[pj];
+                            if (j == 1) {
+                                const double inv = 1.0 / d;
+                                a[1] = l * inv; c[1] = u * inv; g[1] = r * inv;
+                            } else {
+                                const double inv = 1.0 / (d - l * c[j - 1]);
+                                a[j] = -l * a[j - 1] * inv; c[j] = u * inv; g[j] = (r - l * g[j - 1]) * inv;
+                            }
+                        }
+                    }
+                    // backward: row j becomes  a_j x_0 + x_j + c_j x_last = g_j   (1 <= j <= nb-2)
+#pragma unroll
+                    for (int j = FB200_BLK - 3; j >= 1; --j) {
+                        if (j <= nb - 3) {
+                            a[j] -= c[j] * a[j + 1]; g[j] -= c[j] * g[j + 1]; c[j] = -c[j] * c[j + 1];
+                        }
+                    }
+                    // reduced rows: x_0 couples (previous block's last, x_0, x_last); x_last couples (x_0, x_last, next first)
+                    if (nb == 2) { L0 = l0; D0 = d0; U0 = u0; R0 = r0; }
+                    else { L0 = l0; D0 = d0 - u0 * a[1]; U0 = -u0 * c[1]; R0 = r0 - u0 * g[1]; }
+                    double al = 0., cl = 0., gl = 0.;
+#pragma unroll
+                    for (int j = 1; j < FB200_BLK; ++j) {
+                        if (j == nb - 1) { al = a[j]; cl = c[j]; gl = g[j]; }
+                        else if (j < nb - 1) { const int pj = pidx(i0 + j); S.p_a[pj] = a[j]; S.p_c[pj] = c[j]; S.p_g[pj] = g[j]; }
+                    }
+                    L1 = al; D1 = 1.; U1 = cl; R1 = gl;
                 }
-                S.lu[0][i] = make_double2(l, u);
-                S.rr[0][i] = rhs;
-                r.y = rhs;
+                const double inv0 = 1.0 / D0, inv1 = 1.0 / D1;
+                S.lu[0][2 * b] = make_double2(L0 * inv0, U0 * inv0);
+                S.rr[0][2 * b] = R0 * inv0;
+                S.lu[0][2 * b + 1] = make_double2(L1 * inv1, U1 * inv1);
+                S.rr[0][2 * b + 1] = R1 * inv1;
             });
             ex.sync();
+            // -- reduced system (nred unknowns): parallel cyclic reduction, diagonal normalised to 1 --
             int cur = 0;
-            for (int s = 1; s < m; s <<= 1) {
-                ex.points([&](int i, int k) {
-                    StepRegs& r = ex.step(k);
-                    if (!r.valid) return;  // rows outside (first, last] are never read
-                    const double2 me = S.lu[cur][i];
-                    const double rme = S.rr[cur][i];
-                    const int im = i - s, ip = i + s;
+            for (int s = 1; s < nred; s <<= 1) {
+                ex.reduced(nred, [&](int q) {
+                    const double2 me = S.lu[cur][q];
+                    const double rme = S.rr[cur][q];
+                    const int qm = q - s, qp = q + s;
                     double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
                     double ra = 0., rb = 0.;
-                    if (im > first) { a = S.lu[cur][im]; ra = S.rr[cur][im]; }
-                    if (ip <= last) { b = S.lu[cur][ip]; rb = S.rr[cur][ip]; }
+                    if (qm >= 0) { a = S.lu[cur][qm]; ra = S.rr[cur][qm]; }
+                    if (qp < nred) { b = S.lu[cur][qp]; rb = S.rr[cur][qp]; }
                     const double inv = 1.0 / (1.0 - me.x * a.y - me.y * b.x);
-                    const double l = -me.x * a.x * inv;
-                    const double u = -me.y * b.y * inv;
-                    const double rhs = (rme - me.x * ra - me.y * rb) * inv;
-                    S.lu[cur ^ 1][i] = make_double2(l, u);
-                    S.rr[cur ^ 1][i] = rhs;
-                    r.y = rhs;
+                    S.lu[cur ^ 1][q] = make_double2(-me.x * a.x * inv, -me.y * b.y * inv);
+                    S.rr[cur ^ 1][q] = (rme - me.x * ra - me.y * rb) * inv;
                 });
                 ex.sync();
                 cur ^= 1;
             }
-            // -- y, W, K update and convergence norm (nonlinear_diffusion.cpp:83-88) --
+            const double* z = S.rr[cur];
+            ex.tick(1);
+            // -- back-substitution fused with the y, W, K update and the convergence norm (nonlinear_diffusion.cpp:83-88) --
             maxrel = ex.reduce_max([&](int i, int k) -> double {
                 StepRegs& r = ex.step(k);
                 if (i == first) S.F[i] = F_in;
                 if (!r.valid) return 0.;
-                S.F[i] = r.y;
+                const int un = i - first - 1, b = un / FB200_BLK, j = un - b * FB200_BLK;
+                const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
+                const int pi = pidx(i);
+                double y;
+                if (j == 0) y = z[2 * b];
+                else if (j == nb - 1) y = z[2 * b + 1];
+                else y = S.p_g[pi] - S.p_a[pi] * z[2 * b] - S.p_c[pi] * z[2 * b + 1];
+                S.F[i] = y;
                 if (r.is_last) return 0.;  // K[last] stays at its pre-step value
-                const double W = wunc_point(M, r.y, S.hn[i]);
-                const double K1 = S.s_frac[i] * W / r.y;
+                const double W = wunc_point(M, y, S.hn[i]);
+                const double K1 = S.s_frac[i] * W / y;
                 const double rel = fabs((K1 - r.K) / K1);
                 r.K = K1;
+                S.s_d[pi] = S.s_cc[i] + K1;
                 return rel;  // a NaN is skipped by the reduction, as `x > max` does in max_dif_rel
             });
+            ex.tick(2);
             ++iters;
             if (iters >= 100000) return -1;
         } while (maxrel > M.eps);
@@ -648,6 +726,7 @@ struct DiscEngine {
                 ex.sync();
             }
         }
+        ex.tick(3);
         if (!row) return true;
 
         // ---- Tph_X over the hot zone, freddi_state.cpp:292-312 ----
@@ -709,6 +788,7 @@ struct DiscEngine {
             }
             return 2 * FB_PI * S.R[i] * y * w;
         });
+        ex.tick(4);
         // max Tph_X over [first, last] with std::max_element's NaN behaviour (output.cpp:208)
         double TphXmax = ex.reduce_max([&](int i, int k) -> double {
             if (i >= first && i <= last) return S.TphX[i];
@@ -766,6 +846,7 @@ struct DiscEngine {
             ex.points([&](int i, int k) { if (i == 0) { bounds_row[0] = first; bounds_row[1] = last; } });
         }
         ex.sync();
+        ex.tick(5);
         return true;
     }
 
@@ -806,6 +887,7 @@ struct DiscEngine {
         st.Mdot_in_prev = sc.Mdot;
         st.i_t += 1;
         st.t += M.tau;
+        ex.tick(6);
         const int it = solve_step(sc.Mdot);
         if (it < 0) { st.status = FB200_MODEL_FAILED; return false; }
         if (!structure_and_row(true, row, Fsnap_row, bounds_row)) { st.status = FB200_MODEL_COLLAPSED; return false; }

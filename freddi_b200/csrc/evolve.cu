@@ -10,12 +10,16 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
     SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    double* scratch = base + SmemLayout::kPointDoubles;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     __shared__ int s_model;
 
     GpuEx ex;
     ex.init(scratch);
+#ifdef FB_PROFILE
+    for (int p = 0; p < 8; ++p) ex.prof[p] = 0;
+    ex.prof_last = clock64();
+#endif
     const int tid = threadIdx.x;
     const int Nx = E.Nx;
     const int ncol = E.cfg.n_cols, nrows = E.cfg.n_rows;
@@ -59,10 +63,21 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         __syncthreads();
         for (int i = tid; i < Nx; i += kNT) E.F[size_t(model) * Nx + i] = S.F[i];
         if (tid == 0) E.state[model] = eng.st;
+        ex.tick(7);
     }
+#ifdef FB_PROFILE
+    if (tid == 0 && E.prof)
+        for (int p = 0; p < 8; ++p) atomicAdd(reinterpret_cast<unsigned long long*>(E.prof + p), (unsigned long long)ex.prof[p]);
+#endif
 }
 
 size_t evolve_smem_bytes() { return SmemLayout::bytes(); }
+int evolve_resident_ctas_per_sm() {
+    int n = 0;
+    cudaFuncSetAttribute(fb200_evolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fb200_evolve_kernel, kNT, SmemLayout::bytes()) != cudaSuccess) return -1;
+    return n;
+}
 size_t evolve_scratch_doubles_per_cta() { return SmemLayout::scratch_doubles_per_cta(); }
 int evolve_ctas_per_sm() { return kCtasPerSm; }
 

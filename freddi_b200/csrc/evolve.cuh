@@ -27,11 +27,13 @@ struct EnsembleDev {
     int* queue;                       // work-queue counter
     double* cta_scratch;              // [max_ctas][scratch_doubles_per_cta()] once-per-step arrays of the model a CTA holds
     int max_ctas;                     // CTAs the scratch was sized for (2 per SM)
+    long long* prof;                  // [8] per-phase cycle sums (FB_PROFILE builds only), else null
 };
 
 size_t evolve_smem_bytes();
 size_t evolve_scratch_doubles_per_cta();
 int evolve_ctas_per_sm();
+int evolve_resident_ctas_per_sm();  // what the occupancy calculator grants on the current device
 // Launches the persistent evolve kernel on `stream`; returns cudaGetLastError().
 cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream);
 

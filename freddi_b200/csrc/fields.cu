@@ -9,6 +9,7 @@ namespace {
 
 struct Loaded {
     int first, last;
+    bool valid;  // false: the requested row was never reached by this model (collapsed earlier)
 };
 
 // Stages model `model` at `row` (row < 0: current state).  Returns first/last of that state.
@@ -26,6 +27,8 @@ __device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long lo
         L.first = b[0];
         L.last = b[1];
     }
+    L.valid = (L.first >= 0 && L.last > L.first && L.last < Nx);
+    if (!L.valid) { L.first = 0; L.last = Nx - 1; F_src = E.F + size_t(model) * Nx; }
     S.h = E.h + size_t(model) * Nx;
     load_model(E, model, Msh, S, ex, F_src);
     return L;
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
     SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    double* scratch = base + SmemLayout::kPointDoubles;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
                 case FB200_FIELD_D2FMAGN_DH2: v = E.d2Fmagn_dh2 ? E.d2Fmagn_dh2[size_t(model) * Nx + i] : 0.; break;
                 default: v = NAN;
             }
-            out[size_t(model) * Nx + i] = v;
+            out[size_t(model) * Nx + i] = L.valid ? v : NAN;
         }
     }
 }
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
     SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    double* scratch = base + SmemLayout::kPointDoubles;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
@@ -172,7 +175,8 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
             });
             if (threadIdx.x < nq) {
                 const double lam = lambdas[k0 + threadIdx.x];
-                out[size_t(model) * n_lambdas + k0 + threadIdx.x] = 0.5 * ex.sum(threadIdx.x) * p2(lam) / FB_C_LIGHT * M.cosiOverD2;
+                out[size_t(model) * n_lambdas + k0 + threadIdx.x] =
+                    L.valid ? 0.5 * ex.sum(threadIdx.x) * p2(lam) / FB_C_LIGHT * M.cosiOverD2 : NAN;
             }
             __syncthreads();
         }
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* base = reinterpret_cast<double*>(smem_raw);
     SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + size_t(SmemLayout::kPointArrays) * FB200_NX_MAX;
+    double* scratch = base + SmemLayout::kPointDoubles;
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
             else w = h[i + 1] - h[i - 1];
             return y * w;
         });
-        if (threadIdx.x == 0) out[model] = 0.5 * ex.sum(0);
+        if (threadIdx.x == 0) out[model] = L.valid ? 0.5 * ex.sum(0) : NAN;
     }
 }
 

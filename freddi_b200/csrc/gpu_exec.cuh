@@ -1,7 +1,7 @@
-// CUDA execution policy of DiscEngine: one CTA of kNT = 256 threads per model, kPPT = 4 radial points per
-// thread (point i = tid + k*kNT lives in slot k), two CTAs resident per SM (128 registers per thread, no
-// spills; ~107 KB of shared memory per CTA) so that one model's barriers and latency-bound phases overlap
-// with the other's FP64 work.  Reductions are warp-shuffle trees finished through shared memory; every
+// CUDA execution policy of DiscEngine: one CTA of kNT threads per model, kPPT = 1024 / kNT radial points per
+// thread (point i = tid + k*kNT lives in register slot k).  Default 512 threads x 2 points, one CTA per SM:
+// 128 registers per thread (no spills) — measured best of {1024x1, 512x2 CTAs, 512x1, 256x2, 256x1}
+// (profiles/r01_layout_variants.txt).  Reductions are warp-shuffle trees finished through shared memory; every
 // reduction returns its result to all threads so the orchestration code stays uniform across the CTA.
 #pragma once
 #include <cuda_runtime.h>
@@ -10,37 +10,49 @@
 
 namespace fb200 {
 
-constexpr int kNT = 256;                   // threads per CTA
+#ifndef FB_NT
+#define FB_NT 512
+#endif
+#ifndef FB_CTAS_PER_SM
+#define FB_CTAS_PER_SM 1
+#endif
+constexpr int kNT = FB_NT;                 // threads per CTA
 constexpr int kPPT = FB200_NX_MAX / kNT;   // radial points per thread
 constexpr int kNW = kNT / 32;              // warps per CTA
-constexpr int kCtasPerSm = 2;
+constexpr int kCtasPerSm = FB_CTAS_PER_SM;
+static_assert(kNT * kPPT == FB200_NX_MAX && kNW >= 1 && kNW <= 32, "FB_NT must divide FB200_NX_MAX");
 
-// Shared memory: F, hn, the 5 per-step row arrays and the PCR ping-pong (6 arrays) = 13 point arrays.
-// Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb = 9 point arrays (read once per step).
+// Shared memory per CTA: F, hn, s_cc, s_frac (plain index) + s_l, s_u, s_d, s_rhs, p_a, p_c, p_g (padded index)
+// + the reduced-system PCR ping-pong.  Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb
+// (9 point arrays, read once per step, L2-resident).
 struct SmemLayout {
-    static constexpr int kPointArrays = 13;
+    static constexpr int kPlainArrays = 4;
+    static constexpr int kPaddedArrays = 7;
     static constexpr int kScratchArrays = 9;
+    static constexpr size_t kPointDoubles = size_t(kPlainArrays) * FB200_NX_MAX + size_t(kPaddedArrays) * FB200_NPAD + 6 * size_t(FB200_NRED_MAX);
     static constexpr size_t kRedDoubles = 2 * 32 + kNW * FB200_MAXQ + FB200_MAXQ + 8 + FB200_MAX_LAMBDAS;
-    static constexpr size_t bytes() {
-        return sizeof(double) * (size_t(kPointArrays) * FB200_NX_MAX + kRedDoubles) + sizeof(fb200_model_dev_t) + 64;
-    }
+    static constexpr size_t bytes() { return sizeof(double) * (kPointDoubles + kRedDoubles) + sizeof(fb200_model_dev_t) + 64; }
     static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX;
     static constexpr size_t scratch_doubles_per_cta() { return kScratchDoublesPerCta; }
 };
 
 __device__ __forceinline__ SharedArrays carve_shared(double* base, double* gscratch, const double* h_global) {
     SharedArrays S;
-    const int N = FB200_NX_MAX;
+    const int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
     S.h = h_global;
-    S.F = base + 0 * N; S.hn = base + 1 * N;
-    S.s_lo = base + 2 * N; S.s_up = base + 3 * N; S.s_cc = base + 4 * N; S.s_frac = base + 5 * N; S.s_rhs = base + 6 * N;
-    S.lu[0] = reinterpret_cast<double2*>(base + 7 * N);  // 2N doubles
-    S.lu[1] = reinterpret_cast<double2*>(base + 9 * N);  // 2N doubles
-    S.rr[0] = base + 11 * N;
-    S.rr[1] = base + 12 * N;
-    // row temporaries alias the PCR buffers
-    S.Tph = base + 7 * N; S.Tirr = base + 8 * N; S.Sigma = base + 9 * N; S.Tvis = base + 10 * N;
-    S.TphX = base + 11 * N; S.aux = base + 12 * N;
+    double* p = base;
+    S.lu[0] = reinterpret_cast<double2*>(p); p += 2 * NR;   // 16-byte aligned: first in the carve-up
+    S.lu[1] = reinterpret_cast<double2*>(p); p += 2 * NR;
+    S.rr[0] = p; p += NR;
+    S.rr[1] = p; p += NR;
+    S.F = p; p += N;
+    S.hn = p; p += N;
+    S.s_cc = p; p += N;
+    S.s_frac = p; p += N;
+    S.s_l = p; p += NP; S.s_u = p; p += NP; S.s_d = p; p += NP; S.s_rhs = p; p += NP;
+    S.p_a = p; p += NP; S.p_c = p; p += NP; S.p_g = p; p += NP;
+    // row temporaries alias the solver arrays (rebuilt at the start of every step)
+    S.Tph = S.s_l; S.Tirr = S.s_u; S.Sigma = S.s_d; S.Tvis = S.s_rhs; S.TphX = S.p_a; S.aux = S.p_c;
     // once-per-step arrays in the CTA's global scratch slot
     S.R = gscratch + 0 * N; S.ca = gscratch + 1 * N; S.cb = gscratch + 2 * N; S.cc = gscratch + 3 * N; S.frac = gscratch + 4 * N;
     S.c1 = gscratch + 5 * N; S.hm175 = gscratch + 6 * N; S.hotR = gscratch + 7 * N; S.Gb = gscratch + 8 * N;
@@ -69,7 +81,24 @@ struct GpuEx {
 #pragma unroll
         for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
     }
+    // one thread per block / per reduced unknown of the tridiagonal solve
+    template <class F> __device__ __forceinline__ void blocks(int n, F&& f) {
+        if (tid < n) f(tid);
+    }
+    template <class F> __device__ __forceinline__ void reduced(int n, F&& f) {
+        for (int q = tid; q < n; q += kNT) f(q);
+    }
     __device__ __forceinline__ void sync() { __syncthreads(); }
+#ifdef FB_PROFILE
+    // cycle accounting per phase (thread 0 only): phase p collects the cycles since the previous tick
+    long long prof_last;
+    long long prof[8];
+    __device__ __forceinline__ void tick(int p) {
+        if (tid == 0) { const long long c = clock64(); prof[p] += c - prof_last; prof_last = c; }
+    }
+#else
+    __device__ __forceinline__ void tick(int) {}
+#endif
     __device__ __forceinline__ StepRegs& step(int k) { return sr[k]; }
     __device__ __forceinline__ double& scalar(int k) { return scal[k]; }
     __device__ __forceinline__ double sum(int q) const { return sums[q]; }

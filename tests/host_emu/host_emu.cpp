@@ -29,6 +29,9 @@ struct HostEx {
     int cur = 0;  // point the lambda is running for: the host policy has one register slot per point
     template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) { cur = i; f(i, 0); } }
     void sync() {}
+    void tick(int) {}
+    template <class F> void blocks(int n, F&& f) { for (int b = 0; b < n; ++b) f(b); }
+    template <class F> void reduced(int n, F&& f) { for (int q = 0; q < n; ++q) f(q); }
     StepRegs& step(int) { return sr[cur]; }
     double& scalar(int k) { return scal[k]; }
     double sum(int q) const { return sums[q]; }
@@ -76,20 +79,20 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     cfg.n_rows = M.Nt + 1;
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
 
-    const int N = FB200_NX_MAX;
-    std::vector<double> pool(24 * size_t(N), 0.);
-    double* base = pool.data();
-    double* hbuf = base + 0 * N;
+    const int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
+    std::vector<double> pool(14 * size_t(N) + 7 * size_t(NP) + 6 * size_t(NR), 0.);
+    double* p = pool.data();
+    auto take = [&](size_t n) { double* q = p; p += n; return q; };
+    double* hbuf = take(N);
     SharedArrays S;
-    S.h = hbuf; S.R = base + 1 * N; S.F = base + 2 * N; S.hn = base + 3 * N;
-    S.s_lo = base + 18 * N; S.s_up = base + 19 * N; S.s_cc = base + 20 * N; S.s_frac = base + 21 * N; S.s_rhs = base + 22 * N;
-    S.ca = base + 4 * N; S.cb = base + 5 * N; S.cc = base + 6 * N; S.frac = base + 7 * N;
-    S.c1 = base + 8 * N; S.hm175 = base + 9 * N; S.hotR = base + 10 * N; S.Gb = base + 11 * N;
-    S.lu[0] = reinterpret_cast<double2*>(base + 12 * N);
-    S.lu[1] = reinterpret_cast<double2*>(base + 14 * N);
-    S.rr[0] = base + 16 * N; S.rr[1] = base + 17 * N;
-    S.Tph = base + 12 * N; S.Tirr = base + 13 * N; S.Sigma = base + 14 * N; S.Tvis = base + 15 * N;
-    S.TphX = base + 16 * N; S.aux = base + 17 * N;
+    S.h = hbuf; S.R = take(N); S.F = take(N); S.hn = take(N);
+    S.ca = take(N); S.cb = take(N); S.cc = take(N); S.frac = take(N);
+    S.c1 = take(N); S.hm175 = take(N); S.hotR = take(N); S.Gb = take(N);
+    S.s_cc = take(N); S.s_frac = take(N);
+    S.s_l = take(NP); S.s_u = take(NP); S.s_d = take(NP); S.s_rhs = take(NP); S.p_a = take(NP); S.p_c = take(NP); S.p_g = take(NP);
+    S.lu[0] = reinterpret_cast<double2*>(take(2 * NR)); S.lu[1] = reinterpret_cast<double2*>(take(2 * NR));
+    S.rr[0] = take(NR); S.rr[1] = take(NR);
+    S.Tph = S.s_l; S.Tirr = S.s_u; S.Sigma = S.s_d; S.Tvis = S.s_rhs; S.TphX = S.p_a; S.aux = S.p_c;
     for (int i = 0; i < Nx; ++i) { hbuf[i] = res.h[i]; S.F[i] = res.F[i]; }
 
     HostEx ex;

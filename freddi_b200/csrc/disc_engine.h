@@ -148,20 +148,22 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
         const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
         const double err = fabs(xerr) / (0. + tol * (1. * fabs(x) + (1. * fabs(dt)) * fabs(k1)));
-        if (err > 1.0) {
-            // dt *= max(0.9 err^(-1/3), 0.2); rcbrt is within 1 ulp of pow(err, -1/3) and only steers the step size
-            const double f = 9. / 10. * fb_rcbrt(err);
-            dt *= (f < 1. / 5.) ? 1. / 5. : f;
+        // Step-size controller.  Both adjustments are powers of the error, so one log2/exp2 pair serves the
+        // rejecting and the accepting lanes of a warp alike (no divergent code paths):
+        //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
+        //   accept, err < 0.5:     dt *= 0.9 max(5^-5, err)^(-1/5)
+        const bool reject = err > 1.0;
+        const double floor_ = 0.00032;  // pow(5.0, -5)
+        const double base = reject ? err : ((floor_ < err) ? err : floor_);
+        double fac = 9. / 10. * exp2((reject ? -1. / 3. : -1. / 5.) * log2(base));
+        if (reject) {
+            dt *= (fac < 1. / 5.) ? 1. / 5. : fac;
             if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand
             continue;
         }
         fails = 0;
         t += dt;  // == the abscissa of stage 5 (c5 = 1): the derivative at the new t is k5, bit for bit
-        if (err < 0.5) {
-            const double floor_ = 0.00032;  // pow(5.0, -5)
-            const double e = (floor_ < err) ? err : floor_;
-            dt *= 9. / 10. * fb_pow_m02(e);
-        }
+        if (err < 0.5) dt *= fac;
         x = xnew;
         k1 = k5;
     }

@@ -16,13 +16,14 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 
     GpuEx ex;
     ex.init(scratch);
+    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
 #ifdef FB_PROFILE
     for (int p = 0; p < 8; ++p) ex.prof[p] = 0;
     ex.prof_last = clock64();
 #endif
     const int tid = threadIdx.x;
     const int Nx = E.Nx;
-    const int ncol = E.cfg.n_cols, nrows = E.cfg.n_rows;
+    const int ncol = cfg.n_cols, nrows = cfg.n_rows;
 
     for (;;) {
         __syncthreads();  // previous model fully done with shared memory and s_model
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         load_model(E, model, Msh, S, ex, E.F + size_t(model) * Nx);
         const fb200_model_dev_t& M = *Msh;
 
-        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
         eng.init_points();
 
         double* rows = E.rows + size_t(model) * nrows * ncol;

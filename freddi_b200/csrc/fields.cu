@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
+    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
         const fb200_model_dev_t& M = *Msh;
         ModelState st{};
         st.first = L.first; st.last = L.last;
-        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
         eng.init_points();
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, true);
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
+    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
         const fb200_model_dev_t& M = *Msh;
         ModelState st{};
         st.first = L.first; st.last = L.last;
-        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
         eng.init_points();
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, true);
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
     fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
     GpuEx ex;
     ex.init(scratch);
+    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
         const fb200_model_dev_t& M = *Msh;
         ModelState st{};
         st.first = L.first; st.last = L.last;
-        DiscEngine<GpuEx> eng(ex, M, E.cfg, S, st);
+        DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
         eng.init_points();
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, false);

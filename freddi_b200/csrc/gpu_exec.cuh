@@ -31,7 +31,7 @@ struct SmemLayout {
     static constexpr int kScratchArrays = 9;
     static constexpr size_t kPointDoubles = size_t(kPlainArrays) * FB200_NX_MAX + size_t(kPaddedArrays) * FB200_NPAD + 6 * size_t(FB200_NRED_MAX);
     static constexpr size_t kRedDoubles = 2 * 32 + kNW * FB200_MAXQ + FB200_MAXQ + 8 + FB200_MAX_LAMBDAS;
-    static constexpr size_t bytes() { return sizeof(double) * (kPointDoubles + kRedDoubles) + sizeof(fb200_model_dev_t) + 64; }
+    static constexpr size_t bytes() { return sizeof(double) * (kPointDoubles + kRedDoubles) + sizeof(fb200_model_dev_t) + sizeof(OutCfg) + 64; }
     static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX;
     static constexpr size_t scratch_doubles_per_cta() { return kScratchDoublesPerCta; }
 };
@@ -172,6 +172,24 @@ struct GpuEx {
     }
 };
 
+// Copies the output configuration into shared memory with compile-time indices only: indexing a kernel
+// parameter dynamically would make the compiler spill the whole parameter block to local memory.
+__device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E, double* after_model, GpuEx& ex) {
+    OutCfg* c = reinterpret_cast<OutCfg*>(after_model);
+    if (threadIdx.x == 0) {
+        c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
+        c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows;
+#pragma unroll
+        for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) {
+            const double lam = E.cfg.lambdas[k];
+            c->lambdas[k] = lam;
+            ex.lampref[k] = FB_DOUBLE_H_C2 / p5(lam);
+        }
+    }
+    __syncthreads();
+    return *c;
+}
+
 // Loads one model's constants and state into shared memory and binds its global arrays.  All threads call it.
 __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, fb200_model_dev_t* Msh, const SharedArrays& S, GpuEx& ex,
                                            const double* F_src) {
@@ -189,7 +207,7 @@ __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, fb20
         S.F[i] = (i < Nx) ? F_src[i] : 0.;
         if (i >= Nx) S.R[i] = 0.;
     }
-    if (tid < E.cfg.n_lambdas) ex.lampref[tid] = FB_DOUBLE_H_C2 / p5(E.cfg.lambdas[tid]);
+    // (ex.lampref is filled once per kernel by stage_cfg)
     ex.gA = E.wA ? E.wA + off : nullptr;
     ex.gB = E.wB ? E.wB + off : nullptr;
     ex.gCs = E.wCs ? E.wCs + off : nullptr;

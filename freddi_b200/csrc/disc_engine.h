@@ -61,10 +61,12 @@ struct StepRegs {
     int valid, is_last;
 };
 
-// Per-point arrays of one model (length FB200_NX_MAX).  On the GPU the ones touched in every Picard
-// iteration live in shared memory; the ones read once per step (grid, row constants, interior
-// coefficients) live in an L2-resident global scratch slot of the CTA — the engine does not care.
-struct SharedArrays {
+// Per-point arrays of one model (length FB200_NX_MAX).  The engine only needs `S.name[i]`; each execution
+// policy supplies its own `Ex::Arrays` type with these members.  PtrArrays is the plain-pointer version (host
+// policy).  On the GPU the arrays touched in every Picard iteration are shared-memory windows at compile-time
+// offsets (so that accesses compile to LDS/STS with immediate offsets and cost no registers), the ones read
+// once per step (grid, row constants, interior coefficients) live in an L2-resident global scratch slot.
+struct PtrArrays {
     const double* h;                   // grid (global: the ensemble's h array)
     double *R;                         // radius (scratch)
     double *F;                         // state (shared)
@@ -333,7 +335,7 @@ FB_HD double ns_R_alfven(const fb200_model_dev_t& M, double Mdot) {  // ns_argum
 }
 
 template <class Ex>
-FB_HD StateScalars state_scalars(Ex& ex, const fb200_model_dev_t& M, const SharedArrays& S, int first, bool want_ns_lum) {
+FB_HD StateScalars state_scalars(Ex& ex, const fb200_model_dev_t& M, const typename Ex::Arrays& S, int first, bool want_ns_lum) {
     StateScalars s{};
     const double F0 = S.F[first], F1 = S.F[first + 1], h0 = S.h[first], h1 = S.h[first + 1];
     s.Mdot_plain = (F1 - F0) / (h1 - h0);
@@ -439,10 +441,10 @@ struct DiscEngine {
     Ex& ex;
     const fb200_model_dev_t& M;
     const OutCfg& cfg;
-    SharedArrays S;
+    typename Ex::Arrays S;
     ModelState st;  // uniform copy (every thread holds the same values)
 
-    FB_HD DiscEngine(Ex& ex_, const fb200_model_dev_t& M_, const OutCfg& cfg_, const SharedArrays& S_, const ModelState& st_)
+    FB_HD DiscEngine(Ex& ex_, const fb200_model_dev_t& M_, const OutCfg& cfg_, const typename Ex::Arrays& S_, const ModelState& st_)
         : ex(ex_), M(M_), cfg(cfg_), S(S_), st(st_) {}
 
     // nonlinear_diffusion.cpp:46-51 for an interior point i (1 <= i <= Nx-2), wind terms A, B
@@ -575,46 +577,43 @@ struct DiscEngine {
                 const int i0 = first + 1 + b * FB200_BLK;          // first row of the block
                 const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
                 const int p0 = pidx(i0);
-                // the pad word sits after every 8th point: walk the padded index alongside
-                double a[FB200_BLK], c[FB200_BLK], g[FB200_BLK];
                 double L0, D0, U0, R0, L1, D1, U1, R1;
                 const double l0 = S.s_l[p0], d0 = S.s_d[p0], u0 = S.s_u[p0], r0 = S.s_rhs[p0];
                 if (nb == 1) {
                     L0 = l0; D0 = d0; U0 = 0.; R0 = r0;   // a lone row can only be the last block: no upper coupling
                     L1 = 0.; D1 = 1.; U1 = 0.; R1 = 0.;   // dummy row, decoupled
                 } else {
-                    // forward: row j becomes  a_j x_0 + x_j + c_j x_{j+1} = g_j
-#pragma unroll
-                    for (int j = 1; j < FB200_BLK; ++j) {
-                        if (j < nb) {
-                            const int pj = pidx(i0 + j);
-                            const double l = S.s_l[pj], d = S.s_d[pj], u = S.s_u[pj], r = S.s_rhs[pj];
-                            if (j == 1) {
-                                const double inv = 1.0 / d;
-                                a[1] = l * inv; c[1] = u * inv; g[1] = r * inv;
-                            } else {
-                                const double inv = 1.0 / (d - l * c[j - 1]);
-                                a[j] = -l * a[j - 1] * inv; c[j] = u * inv; g[j] = (r - l * g[j - 1]) * inv;
-                            }
-                        }
+                    // forward: row j becomes  a_j x_0 + x_j + c_j x_{j+1} = g_j ; rolling, results parked in p_a/p_c/p_g
+                    double a, c, g;
+                    {
+                        const int pj = pidx(i0 + 1);
+                        const double inv = 1.0 / S.s_d[pj];
+                        a = S.s_l[pj] * inv; c = S.s_u[pj] * inv; g = S.s_rhs[pj] * inv;
+                        S.p_a[pj] = a; S.p_c[pj] = c; S.p_g[pj] = g;
                     }
+                    for (int j = 2; j < nb; ++j) {
+                        const int pj = pidx(i0 + j);
+                        const double l = S.s_l[pj];
+                        const double inv = 1.0 / (S.s_d[pj] - l * c);
+                        a = -l * a * inv; c = S.s_u[pj] * inv; g = (S.s_rhs[pj] - l * g) * inv;
+                        S.p_a[pj] = a; S.p_c[pj] = c; S.p_g[pj] = g;
+                    }
+                    L1 = a; D1 = 1.; U1 = c; R1 = g;      // row nb-1:  a x_0 + x_last + c x_next = g
                     // backward: row j becomes  a_j x_0 + x_j + c_j x_last = g_j   (1 <= j <= nb-2)
-#pragma unroll
-                    for (int j = FB200_BLK - 3; j >= 1; --j) {
-                        if (j <= nb - 3) {
-                            a[j] -= c[j] * a[j + 1]; g[j] -= c[j] * g[j + 1]; c[j] = -c[j] * c[j + 1];
+                    if (nb == 2) {
+                        L0 = l0; D0 = d0; U0 = u0; R0 = r0;
+                    } else {
+                        int pj = pidx(i0 + nb - 2);
+                        double an = S.p_a[pj], cn = S.p_c[pj], gn = S.p_g[pj];  // row nb-2 already couples to x_last
+                        for (int j = nb - 3; j >= 1; --j) {
+                            pj = pidx(i0 + j);
+                            const double cj = S.p_c[pj];
+                            an = S.p_a[pj] - cj * an; gn = S.p_g[pj] - cj * gn; cn = -cj * cn;
+                            S.p_a[pj] = an; S.p_c[pj] = cn; S.p_g[pj] = gn;
                         }
+                        // row 0 with x_1 = g_1 - a_1 x_0 - c_1 x_last substituted
+                        L0 = l0; D0 = d0 - u0 * an; U0 = -u0 * cn; R0 = r0 - u0 * gn;
                     }
-                    // reduced rows: x_0 couples (previous block's last, x_0, x_last); x_last couples (x_0, x_last, next first)
-                    if (nb == 2) { L0 = l0; D0 = d0; U0 = u0; R0 = r0; }
-                    else { L0 = l0; D0 = d0 - u0 * a[1]; U0 = -u0 * c[1]; R0 = r0 - u0 * g[1]; }
-                    double al = 0., cl = 0., gl = 0.;
-#pragma unroll
-                    for (int j = 1; j < FB200_BLK; ++j) {
-                        if (j == nb - 1) { al = a[j]; cl = c[j]; gl = g[j]; }
-                        else if (j < nb - 1) { const int pj = pidx(i0 + j); S.p_a[pj] = a[j]; S.p_c[pj] = c[j]; S.p_g[pj] = g[j]; }
-                    }
-                    L1 = al; D1 = 1.; U1 = cl; R1 = gl;
                 }
                 const double inv0 = 1.0 / D0, inv1 = 1.0 / D1;
                 S.lu[0][2 * b] = make_double2(L0 * inv0, U0 * inv0);
@@ -641,7 +640,7 @@ struct DiscEngine {
                 ex.sync();
                 cur ^= 1;
             }
-            const double* z = S.rr[cur];
+            const auto z = S.rr[cur];
             ex.tick(1);
             // -- back-substitution fused with the y, W, K update and the convergence norm (nonlinear_diffusion.cpp:83-88) --
             maxrel = ex.reduce_max([&](int i, int k) -> double {

@@ -7,16 +7,12 @@
 namespace fb200 {
 
 __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const EnsembleDev E) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* base = reinterpret_cast<double*>(smem_raw);
-    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + SmemLayout::kPointDoubles;
-    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     __shared__ int s_model;
 
     GpuEx ex;
-    ex.init(scratch);
-    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
+    ex.init();
+    const OutCfg& cfg = stage_cfg(E);
 #ifdef FB_PROFILE
     for (int p = 0; p < 8; ++p) ex.prof[p] = 0;
     ex.prof_last = clock64();
@@ -35,8 +31,8 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         ModelState st = E.state[model];
         if (st.status != FB200_MODEL_OK) continue;
         S.h = E.h + size_t(model) * Nx;
-        load_model(E, model, Msh, S, ex, E.F + size_t(model) * Nx);
-        const fb200_model_dev_t& M = *Msh;
+        load_model(E, model, S, ex, E.F + size_t(model) * Nx);
+        const fb200_model_dev_t& M = *smem_model();
 
         DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
         eng.init_points();

@@ -13,8 +13,7 @@ struct Loaded {
 };
 
 // Stages model `model` at `row` (row < 0: current state).  Returns first/last of that state.
-__device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long long row, fb200_model_dev_t* Msh, SharedArrays& S,
-                                        GpuEx& ex) {
+__device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long long row, GpuArrays& S, GpuEx& ex) {
     const int Nx = E.Nx;
     const double* F_src = E.F + size_t(model) * Nx;
     Loaded L;
@@ -30,24 +29,20 @@ __device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long lo
     L.valid = (L.first >= 0 && L.last > L.first && L.last < Nx);
     if (!L.valid) { L.first = 0; L.last = Nx - 1; F_src = E.F + size_t(model) * Nx; }
     S.h = E.h + size_t(model) * Nx;
-    load_model(E, model, Msh, S, ex, F_src);
+    load_model(E, model, S, ex, F_src);
     return L;
 }
 
 __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const EnsembleDev E, int field, long long row, double* out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* base = reinterpret_cast<double*>(smem_raw);
-    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + SmemLayout::kPointDoubles;
-    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
-    ex.init(scratch);
-    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
+    ex.init();
+    const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
-        const Loaded L = stage(E, model, row, Msh, S, ex);
-        const fb200_model_dev_t& M = *Msh;
+        const Loaded L = stage(E, model, row, S, ex);
+        const fb200_model_dev_t& M = *smem_model();
         ModelState st{};
         st.first = L.first; st.last = L.last;
         DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
@@ -122,19 +117,15 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
 // out[model][k] = flux_region<region>(lambdas[k]); region 0 hot (Tph over [first,last]), 1 cold (Tirr over [last+1,Nx-1])
 __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const EnsembleDev E, int region, long long row, const double* lambdas,
                                                             int n_lambdas, double* out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* base = reinterpret_cast<double*>(smem_raw);
-    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + SmemLayout::kPointDoubles;
-    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
-    ex.init(scratch);
-    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
+    ex.init();
+    const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
-        const Loaded L = stage(E, model, row, Msh, S, ex);
-        const fb200_model_dev_t& M = *Msh;
+        const Loaded L = stage(E, model, row, S, ex);
+        const fb200_model_dev_t& M = *smem_model();
         ModelState st{};
         st.first = L.first; st.last = L.last;
         DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
@@ -187,19 +178,15 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
 
 // Mdot_wind (cpp/src/freddi_state.cpp:364-383): - trapz over h of (A dF/dh + B F + C) on [first, last]
 __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const EnsembleDev E, long long row, double* out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* base = reinterpret_cast<double*>(smem_raw);
-    SharedArrays S = carve_shared(base, E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
-    double* scratch = base + SmemLayout::kPointDoubles;
-    fb200_model_dev_t* Msh = reinterpret_cast<fb200_model_dev_t*>(scratch + SmemLayout::kRedDoubles);
+    GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
-    ex.init(scratch);
-    const OutCfg& cfg = stage_cfg(E, reinterpret_cast<double*>(Msh + 1), ex);
+    ex.init();
+    const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
         __syncthreads();
-        const Loaded L = stage(E, model, row, Msh, S, ex);
-        const fb200_model_dev_t& M = *Msh;
+        const Loaded L = stage(E, model, row, S, ex);
+        const fb200_model_dev_t& M = *smem_model();
         ModelState st{};
         st.first = L.first; st.last = L.last;
         DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
@@ -211,7 +198,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
         ex.reduce_sums(1, [&](int i, int, int) -> double {
             if (first >= last || i < first || i > last) return 0.;
             const double* h = S.h;
-            const double* F = S.F;
+            const auto& F = S.F;
             double dFdh;
             if (i == first) {
                 dFdh = (F[i + 1] - F[i]) / (h[i + 1] - h[i]);

@@ -22,58 +22,83 @@ constexpr int kNW = kNT / 32;              // warps per CTA
 constexpr int kCtasPerSm = FB_CTAS_PER_SM;
 static_assert(kNT * kPPT == FB200_NX_MAX && kNW >= 1 && kNW <= 32, "FB_NT must divide FB200_NX_MAX");
 
-// Shared memory per CTA: F, hn, s_cc, s_frac (plain index) + s_l, s_u, s_d, s_rhs, p_a, p_c, p_g (padded index)
-// + the reduced-system PCR ping-pong.  Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb
-// (9 point arrays, read once per step, L2-resident).
+// The CTA's dynamic shared memory.  Every kernel of this library declares the same window; all array
+// accessors below index it with compile-time offsets, so the compiler emits LDS/STS with immediate offsets.
+extern __shared__ __align__(16) double fb_smem[];
+
+// Shared memory per CTA: reduced-system PCR ping-pong, F, hn, s_cc, s_frac (plain index), s_l, s_u, s_d, s_rhs,
+// p_a, p_c, p_g (padded index), then the reduction scratch, the model constants and the output configuration.
+// Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb (9 point arrays, read once per step).
 struct SmemLayout {
-    static constexpr int kPlainArrays = 4;
-    static constexpr int kPaddedArrays = 7;
+    static constexpr int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
+    static constexpr int o_lu0 = 0, o_lu1 = o_lu0 + 2 * NR, o_rr0 = o_lu1 + 2 * NR, o_rr1 = o_rr0 + NR;
+    static constexpr int o_F = o_rr1 + NR, o_hn = o_F + N, o_cc = o_hn + N, o_frac = o_cc + N;
+    static constexpr int o_l = o_frac + N, o_u = o_l + NP, o_d = o_u + NP, o_rhs = o_d + NP;
+    static constexpr int o_pa = o_rhs + NP, o_pc = o_pa + NP, o_pg = o_pc + NP;
+    static constexpr int kPointDoubles = o_pg + NP;
+    // reduction scratch
+    static constexpr int o_redA = kPointDoubles, o_redQ = o_redA + 2 * 32, o_sums = o_redQ + kNW * FB200_MAXQ;
+    static constexpr int o_scal = o_sums + FB200_MAXQ, o_lampref = o_scal + 8, o_model = o_lampref + FB200_MAX_LAMBDAS;
+    static constexpr int kModelDoubles = int((sizeof(fb200_model_dev_t) + 7) / 8);
+    static constexpr int o_cfg = o_model + kModelDoubles;
+    static constexpr int kCfgDoubles = int((sizeof(OutCfg) + 7) / 8);
+    static constexpr int kTotalDoubles = o_cfg + kCfgDoubles + 2;
+    static constexpr size_t bytes() { return sizeof(double) * size_t(kTotalDoubles); }
     static constexpr int kScratchArrays = 9;
-    static constexpr size_t kPointDoubles = size_t(kPlainArrays) * FB200_NX_MAX + size_t(kPaddedArrays) * FB200_NPAD + 6 * size_t(FB200_NRED_MAX);
-    static constexpr size_t kRedDoubles = 2 * 32 + kNW * FB200_MAXQ + FB200_MAXQ + 8 + FB200_MAX_LAMBDAS;
-    static constexpr size_t bytes() { return sizeof(double) * (kPointDoubles + kRedDoubles) + sizeof(fb200_model_dev_t) + sizeof(OutCfg) + 64; }
     static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX;
     static constexpr size_t scratch_doubles_per_cta() { return kScratchDoublesPerCta; }
 };
 
-__device__ __forceinline__ SharedArrays carve_shared(double* base, double* gscratch, const double* h_global) {
-    SharedArrays S;
-    const int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
-    S.h = h_global;
-    double* p = base;
-    S.lu[0] = reinterpret_cast<double2*>(p); p += 2 * NR;   // 16-byte aligned: first in the carve-up
-    S.lu[1] = reinterpret_cast<double2*>(p); p += 2 * NR;
-    S.rr[0] = p; p += NR;
-    S.rr[1] = p; p += NR;
-    S.F = p; p += N;
-    S.hn = p; p += N;
-    S.s_cc = p; p += N;
-    S.s_frac = p; p += N;
-    S.s_l = p; p += NP; S.s_u = p; p += NP; S.s_d = p; p += NP; S.s_rhs = p; p += NP;
-    S.p_a = p; p += NP; S.p_c = p; p += NP; S.p_g = p; p += NP;
+template <int OFF> struct ShD {   // window of doubles at a compile-time offset of the CTA's shared memory
+    __device__ __forceinline__ double& operator[](int i) const { return fb_smem[OFF + i]; }
+};
+struct ShDyn {                    // same with a run-time offset (the ping-pong buffers)
+    int off;
+    __device__ __forceinline__ double& operator[](int i) const { return fb_smem[off + i]; }
+};
+struct ShDyn2 {
+    int off;
+    __device__ __forceinline__ double2& operator[](int i) const { return reinterpret_cast<double2*>(fb_smem + off)[i]; }
+};
+
+struct GpuArrays {
+    typedef SmemLayout L;
+    const double* h;                                   // the ensemble's grid array of this model (global)
+    double *R, *ca, *cb, *cc, *frac, *c1, *hm175, *hotR, *Gb;  // the CTA's global scratch slot
+    ShD<L::o_F> F; ShD<L::o_hn> hn; ShD<L::o_cc> s_cc; ShD<L::o_frac> s_frac;
+    ShD<L::o_l> s_l; ShD<L::o_u> s_u; ShD<L::o_d> s_d; ShD<L::o_rhs> s_rhs;
+    ShD<L::o_pa> p_a; ShD<L::o_pc> p_c; ShD<L::o_pg> p_g;
+    // ping-pong pairs: operator[](cur) selects the window arithmetically (a real array indexed at run time
+    // would force the whole struct, and the engine object holding it, into local memory)
+    struct PP2 { __device__ __forceinline__ ShDyn2 operator[](int cur) const { return ShDyn2{cur ? L::o_lu1 : L::o_lu0}; } } lu;
+    struct PP1 { __device__ __forceinline__ ShDyn operator[](int cur) const { return ShDyn{cur ? L::o_rr1 : L::o_rr0}; } } rr;
     // row temporaries alias the solver arrays (rebuilt at the start of every step)
-    S.Tph = S.s_l; S.Tirr = S.s_u; S.Sigma = S.s_d; S.Tvis = S.s_rhs; S.TphX = S.p_a; S.aux = S.p_c;
-    // once-per-step arrays in the CTA's global scratch slot
+    ShD<L::o_l> Tph; ShD<L::o_u> Tirr; ShD<L::o_d> Sigma; ShD<L::o_rhs> Tvis; ShD<L::o_pa> TphX; ShD<L::o_pc> aux;
+};
+
+__device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double* h_global) {
+    GpuArrays S;
+    const int N = FB200_NX_MAX;
+    S.h = h_global;
     S.R = gscratch + 0 * N; S.ca = gscratch + 1 * N; S.cb = gscratch + 2 * N; S.cc = gscratch + 3 * N; S.frac = gscratch + 4 * N;
     S.c1 = gscratch + 5 * N; S.hm175 = gscratch + 6 * N; S.hotR = gscratch + 7 * N; S.Gb = gscratch + 8 * N;
     return S;
 }
 
+__device__ __forceinline__ fb200_model_dev_t* smem_model() { return reinterpret_cast<fb200_model_dev_t*>(fb_smem + SmemLayout::o_model); }
+__device__ __forceinline__ OutCfg* smem_cfg() { return reinterpret_cast<OutCfg*>(fb_smem + SmemLayout::o_cfg); }
+
 struct GpuEx {
+    typedef GpuArrays Arrays;
+    typedef SmemLayout L;
     int tid, lane, warp;
     StepRegs sr[kPPT];
-    double* redA;     // [2][32] double-buffered scalar reductions
-    double* redQ;     // [kNW][FB200_MAXQ]
-    double* sums;     // [FB200_MAXQ]
-    double* scal;     // [8]
-    double* lampref;  // [FB200_MAX_LAMBDAS]
     int flip;
     // per-model global arrays (already offset to this model), null when absent
     const double *gA, *gB, *gCs, *gFm, *gdFm;
 
-    __device__ __forceinline__ void init(double* scratch) {
+    __device__ __forceinline__ void init() {
         tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; flip = 0;
-        redA = scratch; redQ = redA + 2 * 32; sums = redQ + kNW * FB200_MAXQ; scal = sums + FB200_MAXQ; lampref = scal + 8;
         gA = gB = gCs = gFm = gdFm = nullptr;
     }
     // f(i, k): point index i, register slot k (a compile-time constant after unrolling)
@@ -100,9 +125,9 @@ struct GpuEx {
     __device__ __forceinline__ void tick(int) {}
 #endif
     __device__ __forceinline__ StepRegs& step(int k) { return sr[k]; }
-    __device__ __forceinline__ double& scalar(int k) { return scal[k]; }
-    __device__ __forceinline__ double sum(int q) const { return sums[q]; }
-    __device__ __forceinline__ double lambda_pref(int k) const { return lampref[k]; }
+    __device__ __forceinline__ double& scalar(int k) { return fb_smem[L::o_scal + k]; }
+    __device__ __forceinline__ double sum(int q) const { return fb_smem[L::o_sums + q]; }
+    __device__ __forceinline__ double lambda_pref(int k) const { return fb_smem[L::o_lampref + k]; }
     __device__ __forceinline__ double windA(int i) const { return gA ? __ldg(gA + i) : 0.; }
     __device__ __forceinline__ double windB(int i) const { return gB ? __ldg(gB + i) : 0.; }
     __device__ __forceinline__ double windC_static(int i) const { return gCs ? __ldg(gCs + i) : 0.; }
@@ -120,7 +145,7 @@ struct GpuEx {
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        double* row = redA + flip * 32;
+        double* row = fb_smem + L::o_redA + flip * 32;
         flip ^= 1;
         if (lane == 0) row[warp] = v;
         __syncthreads();
@@ -134,7 +159,7 @@ struct GpuEx {
 #pragma unroll
         for (int k = 0; k < kPPT; ++k) v = max(v, f(tid + k * kNT, k));
         v = __reduce_max_sync(0xffffffffu, v);
-        int* row = reinterpret_cast<int*>(redA + flip * 32);
+        int* row = reinterpret_cast<int*>(fb_smem + L::o_redA + flip * 32);
         flip ^= 1;
         if (lane == 0) row[warp] = v;
         __syncthreads();
@@ -145,7 +170,7 @@ struct GpuEx {
 #pragma unroll
         for (int k = 0; k < kPPT; ++k) v = min(v, f(tid + k * kNT, k));
         v = __reduce_min_sync(0xffffffffu, v);
-        int* row = reinterpret_cast<int*>(redA + flip * 32);
+        int* row = reinterpret_cast<int*>(fb_smem + L::o_redA + flip * 32);
         flip ^= 1;
         if (lane == 0) row[warp] = v;
         __syncthreads();
@@ -159,14 +184,14 @@ struct GpuEx {
             for (int k = 0; k < kPPT; ++k) v += f(tid + k * kNT, k, q);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) redQ[warp * FB200_MAXQ + q] = v;
+            if (lane == 0) fb_smem[L::o_redQ + warp * FB200_MAXQ + q] = v;
         }
         __syncthreads();
         if (tid < nq) {
             double s = 0.;
 #pragma unroll
-            for (int w = 0; w < kNW; ++w) s += redQ[w * FB200_MAXQ + tid];
-            sums[tid] = s;
+            for (int w = 0; w < kNW; ++w) s += fb_smem[L::o_redQ + w * FB200_MAXQ + tid];
+            fb_smem[L::o_sums + tid] = s;
         }
         __syncthreads();
     }
@@ -174,8 +199,8 @@ struct GpuEx {
 
 // Copies the output configuration into shared memory with compile-time indices only: indexing a kernel
 // parameter dynamically would make the compiler spill the whole parameter block to local memory.
-__device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E, double* after_model, GpuEx& ex) {
-    OutCfg* c = reinterpret_cast<OutCfg*>(after_model);
+__device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E) {
+    OutCfg* c = smem_cfg();
     if (threadIdx.x == 0) {
         c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
         c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows;
@@ -183,7 +208,7 @@ __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E, double*
         for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) {
             const double lam = E.cfg.lambdas[k];
             c->lambdas[k] = lam;
-            ex.lampref[k] = FB_DOUBLE_H_C2 / p5(lam);
+            fb_smem[SmemLayout::o_lampref + k] = FB_DOUBLE_H_C2 / p5(lam);
         }
     }
     __syncthreads();
@@ -191,8 +216,8 @@ __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E, double*
 }
 
 // Loads one model's constants and state into shared memory and binds its global arrays.  All threads call it.
-__device__ __forceinline__ void load_model(const EnsembleDev& E, int model, fb200_model_dev_t* Msh, const SharedArrays& S, GpuEx& ex,
-                                           const double* F_src) {
+__device__ __forceinline__ void load_model(const EnsembleDev& E, int model, const GpuArrays& S, GpuEx& ex, const double* F_src) {
+    fb200_model_dev_t* Msh = smem_model();
     const int tid = threadIdx.x;
     {
         const double* src = reinterpret_cast<const double*>(E.models + model);

@@ -19,6 +19,7 @@ using namespace fb200;
 namespace {
 
 struct HostEx {
+    typedef PtrArrays Arrays;
     static constexpr int NT = FB200_NX_MAX;
     std::vector<StepRegs> sr = std::vector<StepRegs>(NT);
     double scal[8] = {0};
@@ -84,7 +85,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     double* p = pool.data();
     auto take = [&](size_t n) { double* q = p; p += n; return q; };
     double* hbuf = take(N);
-    SharedArrays S;
+    PtrArrays S;
     S.h = hbuf; S.R = take(N); S.F = take(N); S.hn = take(N);
     S.ca = take(N); S.cb = take(N); S.cc = take(N); S.frac = take(N);
     S.c1 = take(N); S.hm175 = take(N); S.hotR = take(N); S.Gb = take(N);

@@ -91,19 +91,20 @@ struct PtrArrays {
 #define FB_DOUBLE_H_C2 (2. * FB_H_PLANCK * FB_C_LIGHT * FB_C_LIGHT)
 #define FB_CH_OVER_KB (FB_C_LIGHT * (FB_H_PLANCK / FB_K_BOLTZ))
 
-// x^(-1/3) and x^(-1/5) for the step-size controller (x in (0, inf) resp. [5^-5, 0.5])
-FB_HD double fb_rcbrt(double x) {
-#ifdef __CUDA_ARCH__
-    return rcbrt(x);
-#else
-    return 1.0 / cbrt(x);
-#endif
-}
-FB_HD double fb_pow_m02(double x) { return exp2(-0.2 * log2(x)); }
-
+// B_nu (cpp/src/spectrum.cpp:10-15).  The exact form is used wherever a single value matters (none on the hot
+// path); the quadrature below uses planck_nu_fast.
 FB_HD double planck_nu(double T, double nu) {
     if (!(T > 0.)) return 0.;
     return FB_DOUBLE_H_OVER_C2 * p3(nu) / (exp(FB_H_OVER_KB * nu / T) - 1.);
+}
+
+// B_nu for T > 0 with the lean exp/reciprocal: hk_over_T = (h/k_B)/T.  For h nu / k T > 700 the value
+// (< 1e-295 of the peak) is returned as exactly 0.
+FB_HD double planck_nu_fast(double hk_over_T, double nu) {
+    const double a = hk_over_T * nu;
+    const double em1 = fb_exp((a < 700.) ? a : 700.) - 1.;
+    const double b = FB_DOUBLE_H_OVER_C2 * p3(nu) * fb_rcp(em1);
+    return (a < 700.) ? b : 0.;
 }
 
 // B_lambda with the lambda-only factor pre-divided: pref = double_h_c2 / lambda^5 (same operation order
@@ -138,18 +139,19 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
     const double eps_mach = 2.220446049250313e-16;
     double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
     int fails = 0, n = 0;
-    double k1 = planck_nu(T, t);
+    const double hkT = FB_H_OVER_KB / T;
+    double k1 = planck_nu_fast(hkT, t);
     while (nu2 - t > eps_mach) {
         if ((t + dt) - nu2 > eps_mach) dt = nu2 - t;  // less_with_sign(end, t + dt, dt)
-        const double k3 = planck_nu(T, t + c3 * dt);
-        const double k4 = planck_nu(T, t + c4 * dt);
-        const double k5 = planck_nu(T, t + c5 * dt);
-        const double k6 = planck_nu(T, t + c6 * dt);
+        const double k3 = planck_nu_fast(hkT, t + c3 * dt);
+        const double k4 = planck_nu_fast(hkT, t + c4 * dt);
+        const double k5 = planck_nu_fast(hkT, t + c5 * dt);
+        const double k6 = planck_nu_fast(hkT, t + c6 * dt);
         (void)c2;  // stage 2 has zero weight in both the solution and the error estimate (b2 = db2 = 0)
         ++n;
         const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
         const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
-        const double err = fabs(xerr) / (0. + tol * (1. * fabs(x) + (1. * fabs(dt)) * fabs(k1)));
+        const double err = fabs(xerr) / (tol * (fabs(x) + fabs(dt) * fabs(k1)));
         // Step-size controller.  Both adjustments are powers of the error, so one log2/exp2 pair serves the
         // rejecting and the accepting lanes of a warp alike (no divergent code paths):
         //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
@@ -157,7 +159,7 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         const bool reject = err > 1.0;
         const double floor_ = 0.00032;  // pow(5.0, -5)
         const double base = reject ? err : ((floor_ < err) ? err : floor_);
-        double fac = 9. / 10. * exp2((reject ? -1. / 3. : -1. / 5.) * log2(base));
+        const double fac = 9. / 10. * fb_pow_coarse((base < 1e300) ? base : 1e300, reject ? -1. / 3. : -1. / 5.);
         if (reject) {
             dt *= (fac < 1. / 5.) ? 1. / 5. : fac;
             if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand

@@ -114,6 +114,129 @@ FB_HD double ns_eta(const fb200_model_dev_t& m, double Rm, double R_in) {
            p2(omega_ns) / 2.0 / p2(FB_C_LIGHT) * (Rx - Reff) * (Rx + Reff) + k * p2(1.0 - omega_ns / omega_Kepl_Rin);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lean elementary functions for the Planck quadrature (the hottest loop of the row).  They are branch-free
+// (so the compiler can interleave the independent stage evaluations of one Cash-Karp step) and are written
+// with explicit fma() so that the host build (tests/host_emu) and the device build produce the same bits.
+// ------------------------------------------------------------------------------------------------
+FB_HD double fb_scale2(double p, int k) {  // p * 2^k for p in [0.5, 2) and a result that stays normal
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    union { double d; long long i; } u;
+    u.d = p;
+    u.i += (long long)k << 52;
+    return u.d;
+#endif
+}
+
+// exp(x) for -700 <= x <= 709, within ~1 ulp: k = rint(x log2 e), r = x - k ln2 (two-piece ln2), 13th-degree
+// Taylor polynomial on |r| <= 0.347 (truncation 4e-18), scaling through the exponent field.
+FB_HD double fb_exp(double x) {
+    const double shift = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double t = fma(x, 1.4426950408889634074, shift);
+    const double k = t - shift;
+#ifdef __CUDA_ARCH__
+    const int ki = __double2loint(t);
+#else
+    union { double d; long long i; } u;
+    u.d = t;
+    const int ki = (int)(u.i & 0xffffffffLL);
+#endif
+    double r = fma(k, -6.93147180369123816490e-01, x);
+    r = fma(k, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;           // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);         // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);        // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return fb_scale2(p, ki);
+}
+
+// 1/y for normal positive y, ~1 ulp (device: hardware seed + two Newton steps; host: IEEE division)
+FB_HD double fb_rcp(double y) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / y;
+#endif
+}
+
+// base^p for base in [1e-5, 1e300], |p| <= 1/3, relative accuracy ~1e-12: only steers the step size of the
+// adaptive quadrature, where it needs no more.
+FB_HD double fb_pow_coarse(double base, double p) {
+#ifdef __CUDA_ARCH__
+    int hi = __double2hiint(base);
+    const int lo = __double2loint(base);
+#else
+    union { double d; long long i; } u;
+    u.d = base;
+    int hi = (int)(u.i >> 32);
+    const int lo = (int)(u.i & 0xffffffffLL);
+#endif
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;       // mantissa in [1, 2)
+    if (hi >= 0x3ff6a09e) { hi -= 0x00100000; e += 1; }  // fold [sqrt2, 2) to [sqrt(1/2), 1)
+#ifdef __CUDA_ARCH__
+    const double m = __hiloint2double(hi, lo);
+#else
+    u.i = ((long long)hi << 32) | (unsigned int)lo;
+    const double m = u.d;
+#endif
+    // log2(m) = (2/ln2) atanh(s), s = (m-1)/(m+1), |s| <= 0.1716
+    const double s = (m - 1.0) * fb_rcp(m + 1.0);
+    const double s2 = s * s;
+    double q = 1. / 15.;
+    q = fma(q, s2, 1. / 13.);
+    q = fma(q, s2, 1. / 11.);
+    q = fma(q, s2, 1. / 9.);
+    q = fma(q, s2, 1. / 7.);
+    q = fma(q, s2, 1. / 5.);
+    q = fma(q, s2, 1. / 3.);
+    q = fma(q * s2, s, s);
+    const double lg = fma(q, 2.8853900817779268, (double)e);  // 2/ln2
+    // 2^(p lg)
+    const double y = p * lg;
+    const double shift = 6755399441055744.0;
+    const double t = y + shift;
+    const double k = t - shift;
+#ifdef __CUDA_ARCH__
+    const int ki = __double2loint(t);
+#else
+    u.d = t;
+    const int ki = (int)(u.i & 0xffffffffLL);
+#endif
+    const double f = (y - k) * 0.6931471805599453;  // ln2
+    double w = 2.505210838544172e-08;            // 1/11!
+    w = fma(w, f, 2.755731922398589e-07);
+    w = fma(w, f, 2.7557319223985893e-06);
+    w = fma(w, f, 2.48015873015873e-05);
+    w = fma(w, f, 1.984126984126984e-04);
+    w = fma(w, f, 1.388888888888889e-03);
+    w = fma(w, f, 8.333333333333333e-03);
+    w = fma(w, f, 4.1666666666666664e-02);
+    w = fma(w, f, 1.6666666666666666e-01);
+    w = fma(w, f, 0.5);
+    w = fma(w, f, 1.0);
+    w = fma(w, f, 1.0);
+    return fb_scale2(w, ki);
+}
+
 FB_HD double angular_dist(int type, double mu) { return type == FB200_ANGDIST_ISOTROPIC ? 1.0 : 2.0 * mu; }
 
 }  // namespace fb200

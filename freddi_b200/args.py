@@ -65,7 +65,7 @@ class FB200Config(C.Structure):
         ('device', C.c_int32), ('n_lambdas', C.c_int32),
         ('lambdas', C.c_double * FB200_MAX_LAMBDAS),
         ('cold_disk', C.c_int32), ('record_F', C.c_int32), ('compute_lx', C.c_int32), ('host_threads', C.c_int32),
-        ('threads_per_model', C.c_int32), ('_pad', C.c_int32),
+        ('threads_per_model', C.c_int32), ('exact_lx_walk', C.c_int32),
     ]
 
 

@@ -228,6 +228,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     D.cfg.cold_disk = cfg.cold_disk;
     D.cfg.compute_lx = cfg.compute_lx;
     D.cfg.record_F = cfg.record_F;
+    D.cfg.lx_prune = cfg.exact_lx_walk ? 0 : 1;
     D.cfg.n_cols = e->n_cols;
     D.cfg.n_rows = e->n_rows;
     for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) D.cfg.lambdas[k] = (k < cfg.n_lambdas) ? cfg.lambdas[k] : 0.;

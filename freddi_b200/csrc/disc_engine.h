@@ -34,6 +34,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace fb200 {
 
+#define FB200_LX_PRUNE 100.0 /* see structure_and_row: rings fainter than exp(-100) of the hottest one in the X-ray band */
 #define FB200_MAXQ 40 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], Lx trial count, spare */
 
 // Ensemble-wide output configuration (device copy of fb200_config_t's output part)
@@ -44,6 +45,8 @@ struct OutCfg {
     int record_F;
     int n_cols;
     int n_rows;  // rows allocated per model
+    int lx_prune;  // 1: skip the Lx quadrature of rings that cannot contribute (bound in structure_and_row)
+    int _pad;
     double lambdas[FB200_MAX_LAMBDAS];
 };
 
@@ -749,6 +752,20 @@ struct DiscEngine {
         });
         ex.sync();
 
+        // max Tph_X over [first, last] with std::max_element's NaN behaviour (output.cpp:208)
+        const double TphX_hottest = ex.reduce_max([&](int i, int k) -> double {
+            if (i >= first && i <= last) return S.TphX[i];
+            return -INFINITY;
+        });
+        double TphXmax = TphX_hottest;
+        if (fb_isnan(S.TphX[first])) TphXmax = NAN;
+        // Rings whose X-ray band emission is below exp(-FB200_LX_PRUNE) = 4e-44 of the hottest ring's are not
+        // integrated: B_nu(T_i)/B_nu(T_hot) <= exp(-(a_i - a_hot)) for every nu of the band (a = h nu1 / k T), and
+        // Lx >= the hottest ring's share, so even with an area ratio of 1e12 the omitted rings change Lx by
+        // < 1e-31 relative — twenty orders below the 1e-10 parity tolerance.  (The reference walks them all.)
+        const double a_hot = (TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / TphX_hottest : 0.;
+        const double T_prune = (cfg.lx_prune && TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / (a_hot + FB200_LX_PRUNE) : 0.;
+
         // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
         const int nl = cfg.n_lambdas;
         const int nq = 2 + nl * (cfg.cold_disk ? 2 : 1);
@@ -772,8 +789,9 @@ struct DiscEngine {
                 y = S.Sigma[i];
             } else if (q == 1) {
                 if (!cfg.compute_lx) return 0.;
-                int trials;
-                y = planck_nu1_nu2(S.TphX[i], M.emin, M.emax, 1e-4, &trials);
+                int trials = 0;
+                const double T = S.TphX[i];
+                y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, 1e-4, &trials);
                 ex.step(k).valid = trials;
             } else if (!cold) {
                 const int k = q - 2;
@@ -792,13 +810,6 @@ struct DiscEngine {
             return 2 * FB_PI * S.R[i] * y * w;
         });
         ex.tick(4);
-        // max Tph_X over [first, last] with std::max_element's NaN behaviour (output.cpp:208)
-        double TphXmax = ex.reduce_max([&](int i, int k) -> double {
-            if (i >= first && i <= last) return S.TphX[i];
-            return -INFINITY;
-        });
-        if (fb_isnan(S.TphX[first])) TphXmax = NAN;
-
         // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----
         st.lx_trials += (long long)(ex.sum(nq) + 0.5);
         const double Mdisk = 0.5 * ex.sum(0);

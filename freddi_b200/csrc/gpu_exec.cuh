@@ -1,7 +1,7 @@
 // CUDA execution policy of DiscEngine: one CTA of kNT threads per model, kPPT = 1024 / kNT radial points per
-// thread (point i = tid + k*kNT lives in register slot k).  Default 512 threads x 2 points, one CTA per SM:
-// 128 registers per thread (no spills) — measured best of {1024x1, 512x2 CTAs, 512x1, 256x2, 256x1}
-// (profiles/r01_layout_variants.txt).  Reductions are warp-shuffle trees finished through shared memory; every
+// thread (point i = tid + k*kNT lives in register slot k).  Default 256 threads x 4 points, two CTAs per SM
+// (128 registers per thread, no spills; ~110 KB of shared memory per CTA) — measured best of {1024x1, 512x2,
+// 512x1, 256x2} (profiles/r01_layout_variants.txt).  Reductions are warp-shuffle trees finished through shared memory; every
 // reduction returns its result to all threads so the orchestration code stays uniform across the CTA.
 #pragma once
 #include <cuda_runtime.h>
@@ -11,10 +11,10 @@
 namespace fb200 {
 
 #ifndef FB_NT
-#define FB_NT 512
+#define FB_NT 256
 #endif
 #ifndef FB_CTAS_PER_SM
-#define FB_CTAS_PER_SM 1
+#define FB_CTAS_PER_SM 2
 #endif
 constexpr int kNT = FB_NT;                 // threads per CTA
 constexpr int kPPT = FB200_NX_MAX / kNT;   // radial points per thread
@@ -203,7 +203,7 @@ __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E) {
     OutCfg* c = smem_cfg();
     if (threadIdx.x == 0) {
         c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
-        c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows;
+        c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows; c->lx_prune = E.cfg.lx_prune;
 #pragma unroll
         for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) {
             const double lam = E.cfg.lambdas[k];

@@ -45,9 +45,12 @@ class Ensemble:
     lambdas   : wavelengths [cm] of the Fnu columns every row carries (FluxArguments::lambdas)
     cold_disk : add the Fnu_cold columns (--colddiskflux)
     record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
+    exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip rings that are
+                    > 43 decades fainter than the hottest one in the X-ray band; changes Lx by < 1e-31 relative)
     """
 
-    def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0):
+    def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0,
+                 exact_lx_walk=False):
         self._h = None
         arr = args if isinstance(args, C.Array) else args_array(list(args))
         cfg = FB200Config()
@@ -63,6 +66,7 @@ class Ensemble:
         cfg.record_F = int(bool(record_F))
         cfg.compute_lx = int(bool(compute_lx))
         cfg.host_threads = int(host_threads)
+        cfg.exact_lx_walk = int(bool(exact_lx_walk))
         handle = C.c_void_p()
         bad = C.c_size_t()
         rc = _lib.lib.fb200_ensemble_create(arr, len(arr), C.byref(cfg), C.byref(handle), C.byref(bad))

@@ -141,8 +141,10 @@ typedef struct fb200_config {
     int32_t record_F;       /* keep F(h) of every row in HBM so fb200_ensemble_field can serve any row    */
     int32_t compute_lx;     /* 1 (reference behaviour): Lx/Fx by the adaptive quadrature; 0: columns NaN  */
     int32_t host_threads;   /* threads for host-side argument resolution, 0 = all cores                   */
-    int32_t threads_per_model; /* CTA size, 0 = default                                                  */
-    int32_t _pad;
+    int32_t threads_per_model; /* reserved (the CTA size is a build-time constant)                       */
+    int32_t exact_lx_walk;  /* 0 (default): rings whose X-ray band emission is < exp(-100) of the hottest
+                             * ring's are not integrated (changes Lx by < 1e-31 relative); 1: integrate every
+                             * ring like the reference does                                                 */
 } fb200_config_t;
 
 /* Row layout: cpp/src/output.cpp:197-214, then Fnu columns, then cpp/src/ns/ns_output.cpp:6-19 for NS. */

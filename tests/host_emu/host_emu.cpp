@@ -76,6 +76,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     cfg.n_lambdas = n_lambdas;
     cfg.cold_disk = cold_disk;
     cfg.compute_lx = 1;
+    cfg.lx_prune = 1;
     cfg.n_cols = FB200_N_BH_COLS + n_lambdas * (cold_disk ? 2 : 1) + (M.is_ns ? FB200_N_NS_COLS : 0);
     cfg.n_rows = M.Nt + 1;
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];

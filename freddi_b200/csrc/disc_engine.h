@@ -58,11 +58,6 @@ struct ModelState {
     long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
 };
 
-// Per-point values a thread keeps in registers during the Picard loop of one step (one per point slot)
-struct StepRegs {
-    double K, y;
-    int valid, is_last;
-};
 
 // Per-point arrays of one model (length FB200_NX_MAX).  The engine only needs `S.name[i]`; each execution
 // policy supplies its own `Ex::Arrays` type with these members.  PtrArrays is the plain-pointer version (host
@@ -77,8 +72,9 @@ struct PtrArrays {
     double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients, nonlinear_diffusion.cpp:46-51 (scratch)
     double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row, see init_points (scratch)
     // this step's tridiagonal system  l_i y_{i-1} + d_i y_i + u_i y_{i+1} = rhs_i  (l = -a_i, u = -b_i, d = c0_i + K_i);
-    // s_l, s_u, s_d, s_rhs and the block-elimination results p_a, p_c, p_g use the padded index pidx() (shared)
+    // s_l, s_u, s_d, s_rhs and the block-elimination results p_a, p_c, p_g use the swizzled index pidx() (shared)
     double *s_l, *s_u, *s_d, *s_rhs, *s_cc, *s_frac;
+    double *s_K;                       // K_i = frac_i W_i / y_i of the Picard iteration (shared, plain index)
     double *p_a, *p_c, *p_g;
     double2 *lu[2];                    // PCR ping-pong of the reduced system: (lower, upper), diagonal normalised to 1
     double *rr[2];                     // PCR ping-pong of the reduced system: right-hand side
@@ -418,10 +414,11 @@ FB_HD double v_cooling_front(const fb200_model_dev_t& M, double r, double Sigma_
 // unknown of every block (2 per block, <= FB200_NRED_MAX) that is solved by parallel cyclic reduction.
 #define FB200_BLK 8
 #define FB200_NRED_MAX (2 * (FB200_NX_MAX / FB200_BLK))
-// One pad word per 8: a thread walking its own block (stride-8 words across the lanes of a warp) then hits
-// 16 distinct 8-byte bank pairs instead of 2.
-FB_HD int pidx(int i) { return i + (i >> 3); }
-#define FB200_NPAD (FB200_NX_MAX + FB200_NX_MAX / 8)
+// XOR swizzle inside aligned groups of 8: a thread walking its own block (stride-8 words across the lanes of a
+// warp) then hits 16 distinct 8-byte bank pairs per half-warp instead of 2, while a warp reading 32 consecutive
+// points still covers 32 consecutive words.  No padding needed.
+FB_HD int pidx(int i) { return i ^ ((i >> 4) & 7); }
+#define FB200_NPAD FB200_NX_MAX
 
 FB_HD bool fb_isfinite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 FB_HD bool fb_isnan(double x) { return x != x; }
@@ -430,7 +427,6 @@ FB_HD bool fb_isnan(double x) { return x != x; }
 // The engine.  Execution policy `Ex` provides:
 //   points(f)            run f(i) for the point(s) this thread owns (no barrier)
 //   sync()               CTA barrier
-//   step(i)              StepRegs& of point i (thread-private registers on the GPU)
 //   reduce_max(f)        max over points of f(i), NaN-skipping (fmax), value returned to every thread
 //   reduce_max_int(f) / reduce_min_int(f)
 //   reduce_sums(nq, f)   sum over points of f(i, q) for q < nq; results via sum(q)
@@ -534,11 +530,9 @@ struct DiscEngine {
         }
 
         ex.points([&](int i, int k) {
-            StepRegs& r = ex.step(k);
-            r.valid = (i > first && i <= last);
-            r.is_last = (i == last);
-            r.K = 0.; r.y = 0.;
-            if (!r.valid) return;
+            if (!(i > first && i <= last)) return;
+            const bool is_last = (i == last);
+            double K;
             const double h = S.h[i], R = S.R[i];
             double A = ex.windA(i), B = ex.windB(i), C = ex.windC_static(i);
             if (M.wind_dynamic) {
@@ -549,10 +543,10 @@ struct DiscEngine {
             const double y = S.F[i];
             const double W = wunc_point(M, y, S.hn[i]);
             double lo, up, cc, frac, rhs;
-            if (!r.is_last) {
+            if (!is_last) {
                 lo = S.ca[i]; up = S.cb[i]; cc = S.cc[i]; frac = S.frac[i];
                 const double f = frac * (W + tau * C);
-                r.K = f / y;              // nonlinear_diffusion.cpp:61 — includes tau*C
+                K = f / y;                // nonlinear_diffusion.cpp:61 — includes tau*C
                 rhs = f;
             } else {
                 const double d = h - S.h[i - 1];
@@ -561,13 +555,13 @@ struct DiscEngine {
                 cc = aL - 0.5 * B * d * d;
                 frac = d * d * 0.5 / tau;
                 const double f = frac * (W + tau * C);
-                r.K = frac * W / y;       // nonlinear_diffusion.cpp:65 — no C, never updated in the loop
+                K = frac * W / y;         // nonlinear_diffusion.cpp:65 — no C, never updated in the loop
                 rhs = d * rbc + f;
             }
             if (i == first + 1) { rhs += lo * F_in; lo = 0.; }  // y[first] = F_in is known
             const int pi = pidx(i);
-            S.s_l[pi] = -lo; S.s_u[pi] = -up; S.s_rhs[pi] = rhs; S.s_d[pi] = cc + r.K;
-            S.s_cc[i] = cc; S.s_frac[i] = frac;
+            S.s_l[pi] = -lo; S.s_u[pi] = -up; S.s_rhs[pi] = rhs; S.s_d[pi] = cc + K;
+            S.s_cc[i] = cc; S.s_frac[i] = frac; S.s_K[i] = K;
         });
         ex.sync();
         const int nblk = (m + FB200_BLK - 1) / FB200_BLK;  // blocks of unknowns first+1+8b .. first+8b+8
@@ -649,9 +643,8 @@ struct DiscEngine {
             ex.tick(1);
             // -- back-substitution fused with the y, W, K update and the convergence norm (nonlinear_diffusion.cpp:83-88) --
             maxrel = ex.reduce_max([&](int i, int k) -> double {
-                StepRegs& r = ex.step(k);
                 if (i == first) S.F[i] = F_in;
-                if (!r.valid) return 0.;
+                if (!(i > first && i <= last)) return 0.;
                 const int un = i - first - 1, b = un / FB200_BLK, j = un - b * FB200_BLK;
                 const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
                 const int pi = pidx(i);
@@ -660,11 +653,11 @@ struct DiscEngine {
                 else if (j == nb - 1) y = z[2 * b + 1];
                 else y = S.p_g[pi] - S.p_a[pi] * z[2 * b] - S.p_c[pi] * z[2 * b + 1];
                 S.F[i] = y;
-                if (r.is_last) return 0.;  // K[last] stays at its pre-step value
+                if (i == last) return 0.;  // K[last] stays at its pre-step value
                 const double W = wunc_point(M, y, S.hn[i]);
                 const double K1 = S.s_frac[i] * W / y;
-                const double rel = fabs((K1 - r.K) / K1);
-                r.K = K1;
+                const double rel = fabs((K1 - S.s_K[i]) / K1);
+                S.s_K[i] = K1;
                 S.s_d[pi] = S.s_cc[i] + K1;
                 return rel;  // a NaN is skipped by the reduction, as `x > max` does in max_dif_rel
             });
@@ -772,10 +765,10 @@ struct DiscEngine {
         double cold_K = 0.;
         const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
-        ex.points([&](int, int k) { ex.step(k).valid = 0; });  // reused as this point's Lx trial-step counter
         ex.reduce_sums(nq + 1, [&](int i, int k, int q) -> double {
             if (i >= Nx) return 0.;
-            if (q == nq) return double(ex.step(k).valid);
+            if (q == 1) S.aux[i] = 0.;
+            if (q == nq) return S.aux[i];  // this point's Lx trial-step count, parked by q == 1
             const bool cold = (q >= 2 + nl);
             int rf = first, rl = last;
             if (cold) { rf = last + 1; rl = Nx - 1; }
@@ -792,7 +785,7 @@ struct DiscEngine {
                 int trials = 0;
                 const double T = S.TphX[i];
                 y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, 1e-4, &trials);
-                ex.step(k).valid = trials;
+                S.aux[i] = double(trials);
             } else if (!cold) {
                 const int k = q - 2;
                 y = planck_lambda_pref(S.Tph[i], cfg.lambdas[k], ex.lambda_pref(k));

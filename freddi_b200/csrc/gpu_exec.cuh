@@ -32,8 +32,8 @@ extern __shared__ __align__(16) double fb_smem[];
 struct SmemLayout {
     static constexpr int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
     static constexpr int o_lu0 = 0, o_lu1 = o_lu0 + 2 * NR, o_rr0 = o_lu1 + 2 * NR, o_rr1 = o_rr0 + NR;
-    static constexpr int o_F = o_rr1 + NR, o_hn = o_F + N, o_cc = o_hn + N, o_frac = o_cc + N;
-    static constexpr int o_l = o_frac + N, o_u = o_l + NP, o_d = o_u + NP, o_rhs = o_d + NP;
+    static constexpr int o_F = o_rr1 + NR, o_hn = o_F + N, o_cc = o_hn + N, o_frac = o_cc + N, o_K = o_frac + N;
+    static constexpr int o_l = o_K + N, o_u = o_l + NP, o_d = o_u + NP, o_rhs = o_d + NP;
     static constexpr int o_pa = o_rhs + NP, o_pc = o_pa + NP, o_pg = o_pc + NP;
     static constexpr int kPointDoubles = o_pg + NP;
     // reduction scratch
@@ -65,7 +65,7 @@ struct GpuArrays {
     typedef SmemLayout L;
     const double* h;                                   // the ensemble's grid array of this model (global)
     double *R, *ca, *cb, *cc, *frac, *c1, *hm175, *hotR, *Gb;  // the CTA's global scratch slot
-    ShD<L::o_F> F; ShD<L::o_hn> hn; ShD<L::o_cc> s_cc; ShD<L::o_frac> s_frac;
+    ShD<L::o_F> F; ShD<L::o_hn> hn; ShD<L::o_cc> s_cc; ShD<L::o_frac> s_frac; ShD<L::o_K> s_K;
     ShD<L::o_l> s_l; ShD<L::o_u> s_u; ShD<L::o_d> s_d; ShD<L::o_rhs> s_rhs;
     ShD<L::o_pa> p_a; ShD<L::o_pc> p_c; ShD<L::o_pg> p_g;
     // ping-pong pairs: operator[](cur) selects the window arithmetically (a real array indexed at run time
@@ -92,7 +92,6 @@ struct GpuEx {
     typedef GpuArrays Arrays;
     typedef SmemLayout L;
     int tid, lane, warp;
-    StepRegs sr[kPPT];
     int flip;
     // per-model global arrays (already offset to this model), null when absent
     const double *gA, *gB, *gCs, *gFm, *gdFm;
@@ -102,8 +101,10 @@ struct GpuEx {
         gA = gB = gCs = gFm = gdFm = nullptr;
     }
     // f(i, k): point index i, register slot k (a compile-time constant after unrolling)
+    // The slot loops are deliberately NOT unrolled: the kernel is large and unrolling every per-point lambda
+    // kPPT times costs more in instruction-cache misses than it gains in ILP (profiles/r01_v3_ncu_full_metrics.txt).
     template <class F> __device__ __forceinline__ void points(F&& f) {
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
     }
     // one thread per block / per reduced unknown of the tridiagonal solve
@@ -124,7 +125,6 @@ struct GpuEx {
 #else
     __device__ __forceinline__ void tick(int) {}
 #endif
-    __device__ __forceinline__ StepRegs& step(int k) { return sr[k]; }
     __device__ __forceinline__ double& scalar(int k) { return fb_smem[L::o_scal + k]; }
     __device__ __forceinline__ double sum(int q) const { return fb_smem[L::o_sums + q]; }
     __device__ __forceinline__ double lambda_pref(int k) const { return fb_smem[L::o_lampref + k]; }
@@ -138,7 +138,7 @@ struct GpuEx {
     // rewritten only after every thread has passed the barrier of the reduction in between.
     template <class F> __device__ __forceinline__ double reduce_max(F&& f) {
         double v = -INFINITY;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < kPPT; ++k) {
             const double x = f(tid + k * kNT, k);
             v = fmax(v, x);  // fmax skips a NaN like `if (x > max)` does
@@ -156,7 +156,7 @@ struct GpuEx {
     }
     template <class F> __device__ __forceinline__ int reduce_max_int(F&& f) {
         int v = 0x80000000;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < kPPT; ++k) v = max(v, f(tid + k * kNT, k));
         v = __reduce_max_sync(0xffffffffu, v);
         int* row = reinterpret_cast<int*>(fb_smem + L::o_redA + flip * 32);
@@ -167,7 +167,7 @@ struct GpuEx {
     }
     template <class F> __device__ __forceinline__ int reduce_min_int(F&& f) {
         int v = 0x7fffffff;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < kPPT; ++k) v = min(v, f(tid + k * kNT, k));
         v = __reduce_min_sync(0xffffffffu, v);
         int* row = reinterpret_cast<int*>(fb_smem + L::o_redA + flip * 32);
@@ -180,7 +180,7 @@ struct GpuEx {
     template <class F> __device__ __forceinline__ void reduce_sums(int nq, F&& f) {
         for (int q = 0; q < nq; ++q) {
             double v = 0.;
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < kPPT; ++k) v += f(tid + k * kNT, k, q);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -21,7 +21,6 @@ namespace {
 struct HostEx {
     typedef PtrArrays Arrays;
     static constexpr int NT = FB200_NX_MAX;
-    std::vector<StepRegs> sr = std::vector<StepRegs>(NT);
     double scal[8] = {0};
     double sums[FB200_MAXQ] = {0};
     double lampref[FB200_MAX_LAMBDAS] = {0};
@@ -33,7 +32,6 @@ struct HostEx {
     void tick(int) {}
     template <class F> void blocks(int n, F&& f) { for (int b = 0; b < n; ++b) f(b); }
     template <class F> void reduced(int n, F&& f) { for (int q = 0; q < n; ++q) f(q); }
-    StepRegs& step(int) { return sr[cur]; }
     double& scalar(int k) { return scal[k]; }
     double sum(int q) const { return sums[q]; }
     double lambda_pref(int k) const { return lampref[k]; }
@@ -82,7 +80,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
 
     const int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
-    std::vector<double> pool(14 * size_t(N) + 7 * size_t(NP) + 6 * size_t(NR), 0.);
+    std::vector<double> pool(15 * size_t(N) + 7 * size_t(NP) + 6 * size_t(NR), 0.);
     double* p = pool.data();
     auto take = [&](size_t n) { double* q = p; p += n; return q; };
     double* hbuf = take(N);
@@ -90,7 +88,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     S.h = hbuf; S.R = take(N); S.F = take(N); S.hn = take(N);
     S.ca = take(N); S.cb = take(N); S.cc = take(N); S.frac = take(N);
     S.c1 = take(N); S.hm175 = take(N); S.hotR = take(N); S.Gb = take(N);
-    S.s_cc = take(N); S.s_frac = take(N);
+    S.s_cc = take(N); S.s_frac = take(N); S.s_K = take(N);
     S.s_l = take(NP); S.s_u = take(NP); S.s_d = take(NP); S.s_rhs = take(NP); S.p_a = take(NP); S.p_c = take(NP); S.p_g = take(NP);
     S.lu[0] = reinterpret_cast<double2*>(take(2 * NR)); S.lu[1] = reinterpret_cast<double2*>(take(2 * NR));
     S.rr[0] = take(NR); S.rr[1] = take(NR);

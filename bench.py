@@ -31,7 +31,8 @@ N_ALPHA, N_CIRR = 40, 25
 LAMBDAS = [3e-5, 5e-5, 8e-5]  # 3000/5000/8000 A band fluxes in every row
 
 # Algorithmic FP64 work, SURVEY.md 8(d): fixed op counts per radial point, weights in flop (DFMA = 2).
-W_POW, W_EXP, W_LOG, W_DIV, W_SQRT, W_ADDMUL = 240., 60., 80., 24., 24., 1.
+# weights = FP64 flop of the fast path of CUDA 12.9's sm_100a math functions, counted in SASS
+W_POW, W_EXP, W_LOG, W_DIV, W_SQRT, W_ADDMUL = 100., 31., 45., 20., 20., 1.
 
 
 def flops_per_model_step(P, S, n_lambda, n):
@@ -248,13 +249,18 @@ def run_gpu(opts):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))['dram_bytes_per_launch']
+        except Exception:
+            pass
         per_gpu_rate = value / n_gpus
         achieved_tf = per_gpu_rate * fl / 1e12
         hbm_bytes_per_step = 8 * (15 + len(LAMBDAS))
         roofline = dict(bound='fp64', achieved=achieved_tf, peak=peak, unit='TFLOP/s',
-                        frac=(achieved_tf / peak) if peak else None, traffic=None,
+                        frac=(achieved_tf / peak) if peak else None, traffic=traffic,
                         peak_source='DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)',
-                        flop_model='SURVEY.md 8(d) op counts x provisional weights (pow 240, exp 60, log 80, div 24, sqrt 24); '
+                        flop_model='SURVEY.md 8(d) op counts x SASS-counted FP64 flop per call (pow 100, exp 31, log 45, div 20, sqrt 20); '
                                    'measured P={:.2f} Picard iterations/step, S={:.2f} quadrature trial steps/point/row'.format(P, S),
                         flops_per_model_step=fl,
                         hbm=dict(achieved=per_gpu_rate * hbm_bytes_per_step / 1e9, peak=peaks.get('hbm_gbs'), unit='GB/s',

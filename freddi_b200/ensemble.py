@@ -202,7 +202,4 @@ def measure_fp64_peak(device=0):
     return float(v.value)
 
 
-def shard_indices(n_models, rank, world_size):
-    """Model indices of one rank: interleaved (k -> GPU k mod G) so that cost correlated with the sweep
-    parameters is spread evenly; no rank ever needs another rank's models."""
-    return np.arange(rank, n_models, world_size)
+from .sharding import shard_indices  # noqa: E402,F401

@@ -68,7 +68,7 @@ struct PtrArrays {
     const double* h;                   // grid (global: the ensemble's h array)
     double *R;                         // radius (scratch)
     double *F;                         // state (shared)
-    double *hn;                        // h^n of the opacity closure (shared)
+    double *hn;                        // h^n / (1-m) / D of the opacity closure (shared)
     double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients, nonlinear_diffusion.cpp:46-51 (scratch)
     double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row, see init_points (scratch)
     // this step's tridiagonal system  l_i y_{i-1} + d_i y_i + u_i y_{i+1} = rhs_i  (l = -a_i, u = -b_i, d = c0_i + K_i);
@@ -110,7 +110,9 @@ FB_HD double planck_nu_fast(double hk_over_T, double nu) {
 // as `double_h_c2 / pow<5>(lambda) / (exp(...) - 1)`)
 FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
     if (!(T > 0.)) return 0.;
-    return pref / (exp(FB_CH_OVER_KB / (lambda * T)) - 1.);
+    const double a = FB_CH_OVER_KB / (lambda * T);
+    const double b = pref * fb_rcp(fb_exp((a < 700.) ? a : 700.) - 1.);
+    return (a < 700.) ? b : 0.;  // beyond exp(700) the value is < 1e-300 of the Rayleigh-Jeans level
 }
 
 // integral of B_nu over [nu1, nu2]: boost::numeric::odeint::integrate_adaptive with
@@ -369,8 +371,10 @@ struct PointStructure {
 
 FB_HD double pow025(double x) { return sqrt(sqrt(x)); }
 
-FB_HD double wunc_point(const fb200_model_dev_t& M, double F, double hn) {
-    return pow(fabs(F), M.one_minus_m) * hn / M.one_minus_m / M.D;
+// W = |F|^(1-m) h^n / (1-m) / D (freddi_evolution.cpp:80); hnD = h^n / (1-m) / D is a per-ring constant
+// (init_points), so one multiplication replaces the two divisions (re-association: <= 1 ulp).
+FB_HD double wunc_point(const fb200_model_dev_t& M, double F, double hnD) {
+    return pow(fabs(F), M.one_minus_m) * hnD;
 }
 
 FB_HD PointStructure hot_structure(const fb200_model_dev_t& M, const StateScalars& sc, double h, double R, double hn, double hm175,
@@ -465,7 +469,7 @@ struct DiscEngine {
             const double h = S.h[i];
             const double R = p2(h) / M.GM;  // FreddiState::DiskStructure::initialize_R, freddi_state.cpp:47-53
             S.R[i] = R;
-            S.hn[i] = pow(h, M.n_op);
+            S.hn[i] = pow(h, M.n_op) / M.one_minus_m / M.D;
             S.c1[i] = 3. / (8. * FB_PI) * p4(M.GM) / p7(h);                                      // freddi_state.cpp:300
             S.hm175[i] = M.GM * pow(h, -1.75);                                                    // freddi_state.cpp:284
             S.hotR[i] = R * M.Height_coef * pow(R / 1e10, M.Height_exp_R - M.Height_exp_F / 2.);  // opacity_related.cpp:86
@@ -586,14 +590,14 @@ struct DiscEngine {
                     double a, c, g;
                     {
                         const int pj = pidx(i0 + 1);
-                        const double inv = 1.0 / S.s_d[pj];
+                        const double inv = fb_rcp(S.s_d[pj]);
                         a = S.s_l[pj] * inv; c = S.s_u[pj] * inv; g = S.s_rhs[pj] * inv;
                         S.p_a[pj] = a; S.p_c[pj] = c; S.p_g[pj] = g;
                     }
                     for (int j = 2; j < nb; ++j) {
                         const int pj = pidx(i0 + j);
                         const double l = S.s_l[pj];
-                        const double inv = 1.0 / (S.s_d[pj] - l * c);
+                        const double inv = fb_rcp(S.s_d[pj] - l * c);
                         a = -l * a * inv; c = S.s_u[pj] * inv; g = (S.s_rhs[pj] - l * g) * inv;
                         S.p_a[pj] = a; S.p_c[pj] = c; S.p_g[pj] = g;
                     }
@@ -614,7 +618,7 @@ struct DiscEngine {
                         L0 = l0; D0 = d0 - u0 * an; U0 = -u0 * cn; R0 = r0 - u0 * gn;
                     }
                 }
-                const double inv0 = 1.0 / D0, inv1 = 1.0 / D1;
+                const double inv0 = fb_rcp(D0), inv1 = fb_rcp(D1);
                 S.lu[0][2 * b] = make_double2(L0 * inv0, U0 * inv0);
                 S.rr[0][2 * b] = R0 * inv0;
                 S.lu[0][2 * b + 1] = make_double2(L1 * inv1, U1 * inv1);
@@ -632,7 +636,7 @@ struct DiscEngine {
                     double ra = 0., rb = 0.;
                     if (qm >= 0) { a = S.lu[cur][qm]; ra = S.rr[cur][qm]; }
                     if (qp < nred) { b = S.lu[cur][qp]; rb = S.rr[cur][qp]; }
-                    const double inv = 1.0 / (1.0 - me.x * a.y - me.y * b.x);
+                    const double inv = fb_rcp(1.0 - me.x * a.y - me.y * b.x);
                     S.lu[cur ^ 1][q] = make_double2(-me.x * a.x * inv, -me.y * b.y * inv);
                     S.rr[cur ^ 1][q] = (rme - me.x * ra - me.y * rb) * inv;
                 });
@@ -656,7 +660,7 @@ struct DiscEngine {
                 if (i == last) return 0.;  // K[last] stays at its pre-step value
                 const double W = wunc_point(M, y, S.hn[i]);
                 const double K1 = S.s_frac[i] * W / y;
-                const double rel = fabs((K1 - S.s_K[i]) / K1);
+                const double rel = fabs((K1 - S.s_K[i]) * fb_rcp(fabs(K1)));  // only compared with eps
                 S.s_K[i] = K1;
                 S.s_d[pi] = S.s_cc[i] + K1;
                 return rel;  // a NaN is skipped by the reduction, as `x > max` does in max_dif_rel

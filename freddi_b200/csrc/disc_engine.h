@@ -374,7 +374,7 @@ FB_HD double pow025(double x) { return sqrt(sqrt(x)); }
 // W = |F|^(1-m) h^n / (1-m) / D (freddi_evolution.cpp:80); hnD = h^n / (1-m) / D is a per-ring constant
 // (init_points), so one multiplication replaces the two divisions (re-association: <= 1 ulp).
 FB_HD double wunc_point(const fb200_model_dev_t& M, double F, double hnD) {
-    return pow(fabs(F), M.one_minus_m) * hnD;
+    return fb_pow_pos(fabs(F), M.one_minus_m) * hnD;
 }
 
 FB_HD PointStructure hot_structure(const fb200_model_dev_t& M, const StateScalars& sc, double h, double R, double hn, double hm175,
@@ -382,7 +382,7 @@ FB_HD PointStructure hot_structure(const fb200_model_dev_t& M, const StateScalar
     PointStructure q;
     q.W = wunc_point(M, F, hn);
     q.Sigma = q.W * p2(M.GM) / (4. * FB_PI * p3(h));
-    q.Height = hotR * pow(F, M.Height_exp_F);
+    q.Height = hotR * fb_pow_pos(F, M.Height_exp_F);
     const double mu = q.Height / R;
     q.Kirr = M.Cirr * ((M.irrindex == 0.) ? 1.0 : pow(q.Height / (R * 0.05), M.irrindex));
     if (M.is_ns) {

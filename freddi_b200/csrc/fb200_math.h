@@ -177,6 +177,93 @@ FB_HD double fb_rcp(double y) {
 #endif
 }
 
+// x^a for normal positive x and |a log2 x| < 1000, ~1 ulp — the opacity closure W ~ |F|^(1-m) and the disc height
+// ~ F^(3/20), evaluated once per ring per Picard iteration.  Same structure as a libm pow without its special-case
+// branches: log2 x in double-double (x = 2^e m, m in [sqrt(1/2), sqrt 2), log m = 2 atanh((m-1)/(m+1)) with the leading
+// term carried as hi+lo and the s^3.. tail in double), y = a log2 x in double-double, 2^y = 2^k exp(f ln2).
+// Anything else (zero, negative, NaN, inf, subnormal) goes to the library pow.
+FB_HD double fb_pow_pos(double x, double a) {
+#ifdef __CUDA_ARCH__
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+#else
+    union { double d; long long i; } u_;
+    u_.d = x;
+    int hi = (int)(u_.i >> 32);
+    const int lo = (int)(u_.i & 0xffffffffLL);
+#endif
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return pow(x, a);  // not a positive normal number
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09e) { hi -= 0x00100000; e += 1; }
+#ifdef __CUDA_ARCH__
+    const double m = __hiloint2double(hi, lo);
+#else
+    u_.i = ((long long)hi << 32) | (unsigned int)lo;
+    const double m = u_.d;
+#endif
+    // s = (m - 1) / (m + 1) as s_hi + s_lo
+    const double um = m - 1.0;                  // exact
+    const double v_hi = m + 1.0;
+    const double v_lo = m - (v_hi - 1.0);       // exact residual of the sum
+    const double r = fb_rcp(v_hi);
+    const double s_hi = um * r;
+    double t = fma(-s_hi, v_hi, um);
+    t = fma(-s_hi, v_lo, t);
+    const double s_lo = t * r;
+    // atanh(s) = s + s (s^2/3 + s^4/5 + ... + s^20/21), |s| <= 0.1716
+    const double s2 = s_hi * s_hi;
+    double q = 0.047619047619047616;
+    q = fma(q, s2, 0.05263157894736842);
+    q = fma(q, s2, 0.058823529411764705);
+    q = fma(q, s2, 0.06666666666666667);
+    q = fma(q, s2, 0.07692307692307693);
+    q = fma(q, s2, 0.09090909090909091);
+    q = fma(q, s2, 0.1111111111111111);
+    q = fma(q, s2, 0.14285714285714285);
+    q = fma(q, s2, 0.2);
+    q = fma(q, s2, 0.3333333333333333);
+    const double a_lo = fma(s_hi * s2, q, s_lo);        // tail + s_lo
+    // log2 m = (2/ln2) (s_hi + a_lo), double-double product
+    const double c_hi = 2.8853900817779268, c_lo = 4.0710547481862066e-17;
+    const double p_hi = s_hi * c_hi;
+    const double p_lo = fma(s_hi, c_hi, -p_hi) + fma(s_hi, c_lo, a_lo * c_hi);
+    // log2 x = e + p_hi + p_lo
+    const double ed = (double)e;
+    const double l_hi = ed + p_hi;
+    const double l_lo = (p_hi - (l_hi - ed)) + p_lo;
+    // y = a log2 x
+    const double y_hi = a * l_hi;
+    const double y_lo = fma(a, l_hi, -y_hi) + a * l_lo;
+    const double shift = 6755399441055744.0;
+    const double tk = y_hi + shift;
+    const double k = tk - shift;
+#ifdef __CUDA_ARCH__
+    const int ki = __double2loint(tk);
+#else
+    u_.d = tk;
+    const int ki = (int)(u_.i & 0xffffffffLL);
+#endif
+    if (ki > 1000 || ki < -1000) return pow(x, a);
+    const double f = (y_hi - k) + y_lo;
+    const double g = f * 0.6931471805599453 + f * 2.3190468138462996e-17;
+    double w = 1.6059043836821613e-10;
+    w = fma(w, g, 2.08767569878681e-09);
+    w = fma(w, g, 2.505210838544172e-08);
+    w = fma(w, g, 2.755731922398589e-07);
+    w = fma(w, g, 2.7557319223985893e-06);
+    w = fma(w, g, 2.48015873015873e-05);
+    w = fma(w, g, 1.984126984126984e-04);
+    w = fma(w, g, 1.388888888888889e-03);
+    w = fma(w, g, 8.333333333333333e-03);
+    w = fma(w, g, 4.1666666666666664e-02);
+    w = fma(w, g, 1.6666666666666666e-01);
+    w = fma(w, g, 0.5);
+    w = fma(w, g, 1.0);
+    w = fma(w, g, 1.0);
+    return fb_scale2(w, ki);
+}
+
 // base^p for base in [1e-5, 1e300], |p| <= 1/3, relative accuracy ~1e-12: only steers the step size of the
 // adaptive quadrature, where it needs no more.
 FB_HD double fb_pow_coarse(double base, double p) {

@@ -16,6 +16,18 @@ namespace fb200 {
 #ifndef FB_CTAS_PER_SM
 #define FB_CTAS_PER_SM 2
 #endif
+// unroll factors of the per-thread slot loops (ILP against kernel size; measured in profiles/r01_layout_variants.txt)
+#ifndef FB_UNROLL_POINTS
+#define FB_UNROLL_POINTS 1
+#endif
+#ifndef FB_UNROLL_MAX
+#define FB_UNROLL_MAX 1
+#endif
+#ifndef FB_UNROLL_SUMS
+#define FB_UNROLL_SUMS 1
+#endif
+#define FB_PRAGMA(x) _Pragma(#x)
+#define FB_UNROLL(n) FB_PRAGMA(unroll n)
 constexpr int kNT = FB_NT;                 // threads per CTA
 constexpr int kPPT = FB200_NX_MAX / kNT;   // radial points per thread
 constexpr int kNW = kNT / 32;              // warps per CTA
@@ -104,7 +116,7 @@ struct GpuEx {
     // The slot loops are deliberately NOT unrolled: the kernel is large and unrolling every per-point lambda
     // kPPT times costs more in instruction-cache misses than it gains in ILP (profiles/r01_v3_ncu_full_metrics.txt).
     template <class F> __device__ __forceinline__ void points(F&& f) {
-#pragma unroll 1
+        FB_UNROLL(FB_UNROLL_POINTS)
         for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
     }
     // one thread per block / per reduced unknown of the tridiagonal solve
@@ -138,7 +150,7 @@ struct GpuEx {
     // rewritten only after every thread has passed the barrier of the reduction in between.
     template <class F> __device__ __forceinline__ double reduce_max(F&& f) {
         double v = -INFINITY;
-#pragma unroll 1
+        FB_UNROLL(FB_UNROLL_MAX)
         for (int k = 0; k < kPPT; ++k) {
             const double x = f(tid + k * kNT, k);
             v = fmax(v, x);  // fmax skips a NaN like `if (x > max)` does
@@ -180,7 +192,7 @@ struct GpuEx {
     template <class F> __device__ __forceinline__ void reduce_sums(int nq, F&& f) {
         for (int q = 0; q < nq; ++q) {
             double v = 0.;
-#pragma unroll 1
+            FB_UNROLL(FB_UNROLL_SUMS)
             for (int k = 0; k < kPPT; ++k) v += f(tid + k * kNT, k, q);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

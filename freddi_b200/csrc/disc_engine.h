@@ -79,7 +79,7 @@ struct PtrArrays {
     double2 *lu[2];                    // PCR ping-pong of the reduced system: (lower, upper), diagonal normalised to 1
     double *rr[2];                     // PCR ping-pong of the reduced system: right-hand side
     // row temporaries alias the PCR buffers (never live at the same time)
-    double *Tph, *Tirr, *Sigma, *Tvis, *TphX, *aux;
+    double *Tph, *Tirr, *Sigma, *Tvis, *TphX, *aux, *wq;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -110,7 +110,7 @@ FB_HD double planck_nu_fast(double hk_over_T, double nu) {
 // as `double_h_c2 / pow<5>(lambda) / (exp(...) - 1)`)
 FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
     if (!(T > 0.)) return 0.;
-    const double a = FB_CH_OVER_KB / (lambda * T);
+    const double a = FB_CH_OVER_KB * fb_rcp(lambda * T);
     const double b = pref * fb_rcp(fb_exp((a < 700.) ? a : 700.) - 1.);
     return (a < 700.) ? b : 0.;  // beyond exp(700) the value is < 1e-300 of the Rayleigh-Jeans level
 }
@@ -152,7 +152,7 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         ++n;
         const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
         const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
-        const double err = fabs(xerr) / (tol * (fabs(x) + fabs(dt) * fabs(k1)));
+        const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
         // Step-size controller.  Both adjustments are powers of the error, so one log2/exp2 pair serves the
         // rejecting and the accepting lanes of a warp alike (no divergent code paths):
         //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
@@ -738,14 +738,24 @@ struct DiscEngine {
         const double F_first = S.F[first];
         ex.points([&](int i, int k) {
             if (i >= Nx) return;
-            double T = 0.;
+            double T = 0., wq = 0.;
             if (i >= first && i <= last) {
                 double x = S.c1[i] * F_first;
                 const double g = KM * S.Gb[i];  // = T_GR^4 sigma; T_GR = pow(., 0.25) is NaN for a negative argument
                 x += (g < 0.) ? NAN : g;
                 T = M.colourfactor * pow025(x / FB_SIGMA_SB);
+                // weight of this ring in the radial trapezoid of the hot zone: 2 pi R_i (R_{i+1} - R_{i-1}) (ends one-sided)
+                if (first < last) {
+                    const double R = S.R[i];
+                    double w;
+                    if (i == first) w = S.R[i + 1] - R;
+                    else if (i == last) w = R - S.R[i - 1];
+                    else w = S.R[i + 1] - S.R[i - 1];
+                    wq = 2 * FB_PI * R * w;
+                }
             }
             S.TphX[i] = T;
+            S.wq[i] = wq;
         });
         ex.sync();
 
@@ -773,38 +783,40 @@ struct DiscEngine {
             if (i >= Nx) return 0.;
             if (q == 1) S.aux[i] = 0.;
             if (q == nq) return S.aux[i];  // this point's Lx trial-step count, parked by q == 1
-            const bool cold = (q >= 2 + nl);
-            int rf = first, rl = last;
-            if (cold) { rf = last + 1; rl = Nx - 1; }
-            if (rf >= rl || i < rf || i > rl) return 0.;
-            double w;  // trapezoid weight in R
-            if (i == rf) w = S.R[i + 1] - S.R[i];
-            else if (i == rl) w = S.R[i] - S.R[i - 1];
-            else w = S.R[i + 1] - S.R[i - 1];
-            double y;
-            if (q == 0) {
-                y = S.Sigma[i];
-            } else if (q == 1) {
-                if (!cfg.compute_lx) return 0.;
-                int trials = 0;
-                const double T = S.TphX[i];
-                y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, 1e-4, &trials);
-                S.aux[i] = double(trials);
-            } else if (!cold) {
-                const int k = q - 2;
-                y = planck_lambda_pref(S.Tph[i], cfg.lambdas[k], ex.lambda_pref(k));
-            } else {
-                const int k = q - 2 - nl;
-                const double R = S.R[i];
-                double Qx;
-                if (M.is_ns)
-                    Qx = cold_K * (sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, cold_mu)) /
-                         (4. * FB_PI * p2(R));
-                else
-                    Qx = cold_K * sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) / (4. * FB_PI * p2(R));
-                y = planck_lambda_pref(pow025(Qx / FB_SIGMA_SB), cfg.lambdas[k], ex.lambda_pref(k));
+            if (q < 2 + nl) {  // hot zone [first, last]: weights prepared above (0 outside)
+                const double wq = S.wq[i];
+                if (wq == 0.) return 0.;
+                double y;
+                if (q == 0) {
+                    y = S.Sigma[i];
+                } else if (q == 1) {
+                    if (!cfg.compute_lx) return 0.;
+                    int trials = 0;
+                    const double T = S.TphX[i];
+                    y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, 1e-4, &trials);
+                    S.aux[i] = double(trials);
+                } else {
+                    y = planck_lambda_pref(S.Tph[i], cfg.lambdas[q - 2], ex.lambda_pref(q - 2));
+                }
+                return y * wq;
             }
-            return 2 * FB_PI * S.R[i] * y * w;
+            // cold zone [last + 1, Nx - 1] (--colddiskflux): Height = h2rcold R, Kirr from the cold parameters
+            const int rf = last + 1, rl = Nx - 1;
+            if (rf >= rl || i < rf || i > rl) return 0.;
+            const double R = S.R[i];
+            double w;
+            if (i == rf) w = S.R[i + 1] - R;
+            else if (i == rl) w = R - S.R[i - 1];
+            else w = S.R[i + 1] - S.R[i - 1];
+            const int kl = q - 2 - nl;
+            double Qx;
+            if (M.is_ns)
+                Qx = cold_K * (sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, cold_mu)) /
+                     (4. * FB_PI * p2(R));
+            else
+                Qx = cold_K * sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) / (4. * FB_PI * p2(R));
+            const double y = planck_lambda_pref(pow025(Qx / FB_SIGMA_SB), cfg.lambdas[kl], ex.lambda_pref(kl));
+            return 2 * FB_PI * R * y * w;
         });
         ex.tick(4);
         // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----

@@ -85,7 +85,7 @@ struct GpuArrays {
     struct PP2 { __device__ __forceinline__ ShDyn2 operator[](int cur) const { return ShDyn2{cur ? L::o_lu1 : L::o_lu0}; } } lu;
     struct PP1 { __device__ __forceinline__ ShDyn operator[](int cur) const { return ShDyn{cur ? L::o_rr1 : L::o_rr0}; } } rr;
     // row temporaries alias the solver arrays (rebuilt at the start of every step)
-    ShD<L::o_l> Tph; ShD<L::o_u> Tirr; ShD<L::o_d> Sigma; ShD<L::o_rhs> Tvis; ShD<L::o_pa> TphX; ShD<L::o_pc> aux;
+    ShD<L::o_l> Tph; ShD<L::o_u> Tirr; ShD<L::o_d> Sigma; ShD<L::o_rhs> Tvis; ShD<L::o_pa> TphX; ShD<L::o_pc> aux; ShD<L::o_pg> wq;
 };
 
 __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double* h_global) {

@@ -21,7 +21,7 @@ SYMBOLS = (
     'fb200_abi_version', 'fb200_last_error', 'fb200_device_count', 'fb200_measure_fp64_peak', 'fb200_ensemble_counters', 'fb200_args_default', 'fb200_config_default',
     'fb200_args_resolve', 'fb200_ensemble_create', 'fb200_ensemble_destroy', 'fb200_ensemble_n_models',
     'fb200_ensemble_n_cols', 'fb200_ensemble_n_rows', 'fb200_ensemble_nx', 'fb200_ensemble_info', 'fb200_ensemble_evolve',
-    'fb200_ensemble_evolve_async', 'fb200_ensemble_sync', 'fb200_ensemble_last_evolve_ms', 'fb200_ensemble_last_launches',
+    'fb200_ensemble_evolve_async', 'fb200_ensemble_reset', 'fb200_ensemble_sync', 'fb200_ensemble_last_evolve_ms', 'fb200_ensemble_last_launches',
     'fb200_ensemble_rows', 'fb200_ensemble_rows_device', 'fb200_ensemble_status', 'fb200_ensemble_state',
     'fb200_ensemble_row_bounds', 'fb200_ensemble_field', 'fb200_ensemble_flux', 'fb200_ensemble_mdot_wind',
 )
@@ -67,6 +67,7 @@ def _load():
     lib.fb200_ensemble_evolve.argtypes = [vp, C.c_int64]
     lib.fb200_ensemble_evolve_async.argtypes = [vp, C.c_int64]
     lib.fb200_ensemble_sync.argtypes = [vp]
+    lib.fb200_ensemble_reset.argtypes = [vp]
     lib.fb200_ensemble_last_evolve_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.fb200_ensemble_last_launches.argtypes = [vp]
     lib.fb200_ensemble_rows.argtypes = [vp, dp, C.c_size_t]

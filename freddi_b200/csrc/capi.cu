@@ -48,6 +48,11 @@ struct fb200_ensemble {
     bool timed = false;
     double* scratch = nullptr;  // [n * Nx] read-out staging
     size_t scratch_len = 0;
+    // initial conditions kept on the host for fb200_ensemble_reset (pinned staging is allocated on first use)
+    std::vector<double> host_F0;
+    std::vector<ModelState> host_state0;
+    double* pinned_F0 = nullptr;
+    ModelState* pinned_state0 = nullptr;
 };
 
 namespace {
@@ -271,6 +276,8 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
         FB_TRYC(cudaMemcpy(d_state, hs.data(), sizeof(ModelState) * n_models, cudaMemcpyHostToDevice));
         FB_TRYC(cudaMemcpy(d_h, hh.data(), sizeof(double) * NN, cudaMemcpyHostToDevice));
         FB_TRYC(cudaMemcpy(d_F, hF.data(), sizeof(double) * NN, cudaMemcpyHostToDevice));
+        e->host_F0.swap(hF);
+        e->host_state0.swap(hs);
     }
     FB_TRYC(cudaMemset(d_rows, 0xFF, rows_len * sizeof(double)));  // all-ones = NaN: rows never written stay NaN
     D.models = d_models; D.state = d_state; D.h = d_h; D.F = d_F; D.rows = d_rows;
@@ -326,6 +333,8 @@ void fb200_ensemble_destroy(fb200_ensemble_t* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void* p : e->allocs) cudaFree(p);
+    if (e->pinned_F0) cudaFreeHost(e->pinned_F0);
+    if (e->pinned_state0) cudaFreeHost(e->pinned_state0);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -340,6 +349,27 @@ size_t fb200_ensemble_nx(const fb200_ensemble_t* e) { return e ? size_t(e->Nx) :
 int fb200_ensemble_info(const fb200_ensemble_t* e, fb200_model_info_t* out) {
     if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
     std::memcpy(out, e->info.data(), sizeof(fb200_model_info_t) * e->n);
+    return FB200_OK;
+}
+
+int fb200_ensemble_reset(fb200_ensemble_t* e) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    const size_t NN = e->n * size_t(e->Nx);
+    if (!e->pinned_F0) {
+        FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->pinned_F0), NN * sizeof(double)));
+        FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->pinned_state0), e->n * sizeof(ModelState)));
+        std::memcpy(e->pinned_F0, e->host_F0.data(), NN * sizeof(double));
+        std::memcpy(e->pinned_state0, e->host_state0.data(), e->n * sizeof(ModelState));
+    }
+    FB_CUDA(cudaMemcpyAsync(e->dev.F, e->pinned_F0, NN * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(cudaMemcpyAsync(e->dev.state, e->pinned_state0, e->n * sizeof(ModelState), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(cudaMemsetAsync(e->dev.rows, 0xFF, e->n * size_t(e->n_rows) * e->n_cols * sizeof(double), e->stream));
+    if (e->dev.Fsnap) {
+        FB_CUDA(cudaMemsetAsync(e->dev.Fsnap, 0xFF, e->n * size_t(e->n_rows) * e->Nx * sizeof(double), e->stream));
+        FB_CUDA(cudaMemsetAsync(e->dev.bounds, 0xFF, e->n * size_t(e->n_rows) * 2 * sizeof(int), e->stream));
+    }
     return FB200_OK;
 }
 

@@ -107,6 +107,11 @@ class Ensemble:
         _lib.check(_lib.lib.fb200_ensemble_evolve(self._h, int(n_steps)))
         return self
 
+    def reset(self):
+        """Back to the initial state: the resolved initial conditions are copied again host (pinned) -> device."""
+        _lib.check(_lib.lib.fb200_ensemble_reset(self._h))
+        return self
+
     def evolve_async(self, n_steps=-1):
         _lib.check(_lib.lib.fb200_ensemble_evolve_async(self._h, int(n_steps)))
         return self

@@ -219,6 +219,11 @@ size_t fb200_ensemble_n_rows(const fb200_ensemble_t* e);  /* rows per model = ma
 size_t fb200_ensemble_nx(const fb200_ensemble_t* e);
 int fb200_ensemble_info(const fb200_ensemble_t* e, fb200_model_info_t* out /*[n_models]*/);
 
+/* Put every model back to its initial state (t = inittime, F = F(t=0), first/last, no rows) by copying the
+ * resolved initial conditions again from pinned host memory to the device: the equivalent of constructing the same
+ * FreddiEvolution objects again (cpp/include/freddi_evolution.hpp:50) without repeating the argument resolution. */
+int fb200_ensemble_reset(fb200_ensemble_t* e);
+
 /* Advance every model by n_steps (clipped per model at its Nt; n_steps<0: to the end).  Row i_t is
  * written when state i_t is reached; row 0 is written by the first call.  Blocks until done. */
 int fb200_ensemble_evolve(fb200_ensemble_t* e, int64_t n_steps);

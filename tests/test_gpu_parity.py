@@ -199,3 +199,23 @@ def test_invalid_arguments_raise_reference_error_classes():
         Ensemble([cm.ini_args(opacity='nope')])
     with pytest.raises(NotImplementedError):
         Ensemble([cm.ini_args(Nx=5000)])
+
+
+def test_reset_replays_the_ensemble_bit_for_bit():
+    """fb200_ensemble_reset: initial conditions copied again from pinned host memory; the replay is bit-identical."""
+    from freddi_b200 import Ensemble
+    args = cm.config2_args([0.2, 0.9], [1e-4, 2e-3], time=10)
+    with Ensemble(args, lambdas=cm.LAM3, record_F=True) as ens:
+        ens.evolve(-1)
+        rows1, F1 = ens.rows(), ens.field('F', 20)
+        st1 = ens.status()
+        ens.reset()
+        assert ens.state()['i_t'].tolist() == [0, 0, 0, 0]
+        ens.evolve(13)
+        ens.evolve(-1)
+        rows2, F2 = ens.rows(), ens.field('F', 20)
+        st2 = ens.status()
+    np.testing.assert_array_equal(rows1, rows2)
+    np.testing.assert_array_equal(F1, F2)
+    for a, b in zip(st1, st2):
+        np.testing.assert_array_equal(a, b)

@@ -38,7 +38,7 @@ struct fb200_ensemble {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     size_t n = 0;
-    int Nx = 0, n_rows = 0, n_cols = 0, sm_count = 0;
+    int Nx = 0, n_rows = 0, n_cols = 0, sm_count = 0, max_Nt = 0, chunk_steps = 25;
     bool is_ns = false;
     fb200_config_t cfg{};
     std::vector<fb200_model_info_t> info;
@@ -208,6 +208,8 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     e->Nx = Nx;
     e->is_ns = is_ns;
     e->n_rows = max_Nt + 1;
+    e->max_Nt = max_Nt;
+    if (const char* c = getenv("FB200_CHUNK_STEPS")) e->chunk_steps = atoi(c) > 0 ? atoi(c) : 0x3fffffff;
     e->n_cols = FB200_N_BH_COLS + cfg.n_lambdas * (cfg.cold_disk ? 2 : 1) + (is_ns ? FB200_N_NS_COLS : 0);
     e->info.resize(n_models);
     for (size_t i = 0; i < n_models; ++i) e->info[i] = res[i].info;
@@ -249,7 +251,14 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     const size_t rows_len = n_models * size_t(e->n_rows) * e->n_cols;
     FB_TRY(dev_alloc(e, &d_rows, rows_len));
     FB_TRY(dev_alloc(e, &D.queue, 4));
-    D.max_ctas = e->sm_count * evolve_ctas_per_sm();
+    {
+        // the chunked scheduler lets a CTA wait for another one: never launch more CTAs than can be resident
+        int resident = evolve_resident_ctas_per_sm();
+        if (resident < 1) return guard_fail(set_err(FB200_ERR_UNSUPPORTED, "the evolve kernel does not fit on this device"));
+        if (resident > evolve_ctas_per_sm()) resident = evolve_ctas_per_sm();
+        D.max_ctas = e->sm_count * resident;
+    }
+    FB_TRY(dev_alloc(e, &D.progress, n_models));
     if (getenv("FB200_DEBUG"))
         fprintf(stderr, "[fb200] smem/CTA %zu B, CTAs/SM designed %d, resident %d, SMs %d\n", evolve_smem_bytes(), evolve_ctas_per_sm(),
                 evolve_resident_ctas_per_sm(), e->sm_count);
@@ -378,7 +387,13 @@ int fb200_ensemble_evolve_async(fb200_ensemble_t* e, int64_t n_steps) {
     int rc = select_device(e);
     if (rc != FB200_OK) return rc;
     FB_CUDA(cudaMemsetAsync(e->dev.queue, 0, sizeof(int), e->stream));
+    FB_CUDA(cudaMemsetAsync(e->dev.progress, 0, sizeof(int) * e->n, e->stream));
     e->dev.n_steps = (n_steps < 0 || n_steps > 0x7fffffff) ? -1 : int(n_steps);
+    {
+        const long long most = (e->dev.n_steps < 0 || e->dev.n_steps > e->max_Nt) ? e->max_Nt : e->dev.n_steps;
+        e->dev.chunk_steps = e->chunk_steps;
+        e->dev.n_rounds = int(std::max<long long>(1, (most + e->chunk_steps - 1) / e->chunk_steps));
+    }
     FB_CUDA(cudaEventRecord(e->ev0, e->stream));
     const int n_ctas = int(std::min<size_t>(e->n, size_t(e->dev.max_ctas)));
     cudaError_t ce = launch_evolve(e->dev, n_ctas, e->stream);

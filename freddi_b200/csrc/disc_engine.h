@@ -54,6 +54,7 @@ struct OutCfg {
 struct ModelState {
     double t, F_in, Mdot_in_prev;
     int first, last, i_t, status, rows_valid, row0_done;
+    int target_i_t, _pad;  // i_t this launch runs to (set by the first work item of the launch)
     long long picard_iters;
     long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
 };

@@ -21,45 +21,86 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
     const int Nx = E.Nx;
     const int ncol = cfg.n_cols, nrows = cfg.n_rows;
 
+    // Work items are (round, model) pairs in round-major order: a model runs chunk_steps steps per item and goes
+    // back to the queue, so that the tail of the launch is a fraction of a model's run instead of a whole one.
+    // Item (r, m) needs item (r-1, m) finished: it was handed out earlier (the queue is ordered), to a CTA that is
+    // resident (grid <= resident capacity) and never waits on a later item, so the wait below cannot deadlock.
+    const int n_items = E.n_rounds * E.n_models;
+    __shared__ int s_abort;
     for (;;) {
-        __syncthreads();  // previous model fully done with shared memory and s_model
+        __syncthreads();  // previous item fully done with shared memory and s_model
         if (tid == 0) s_model = atomicAdd(E.queue, 1);
         __syncthreads();
-        const int model = s_model;
-        if (model >= E.n_models) break;
-
-        ModelState st = E.state[model];
-        if (st.status != FB200_MODEL_OK) continue;
-        S.h = E.h + size_t(model) * Nx;
-        load_model(E, model, S, ex, E.F + size_t(model) * Nx);
-        const fb200_model_dev_t& M = *smem_model();
-
-        DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
-        eng.init_points();
-
-        double* rows = E.rows + size_t(model) * nrows * ncol;
-        double* Fsnap = E.Fsnap ? E.Fsnap + size_t(model) * nrows * Nx : nullptr;
-        int* bounds = E.bounds ? E.bounds + size_t(model) * nrows * 2 : nullptr;
-
-        if (!eng.st.row0_done) {
-            // the state at t0 is dumped before the first step (cpp/include/application.hpp:25-29)
-            eng.structure_and_row(false, rows, Fsnap, bounds);
-            eng.st.row0_done = 1;
-            eng.st.rows_valid = 1;
+        const int item = s_model;
+        if (item >= n_items) break;
+        const int round = item / E.n_models;
+        const int model = item - round * E.n_models;
+        if (tid == 0) {
+            s_abort = 0;
+            if (round > 0) {
+                const volatile int* p = E.progress + model;
+                long long spins = 0;
+                while (*p < round) {
+                    __nanosleep(100);
+                    if (++spins > (1ll << 26)) { s_abort = 1; break; }  // seconds: the producer is gone, give up on this model
+                }
+                __threadfence();
+            }
         }
-        int todo = M.Nt - eng.st.i_t;
-        if (E.n_steps >= 0 && E.n_steps < todo) todo = E.n_steps;
-        for (int s = 0; s < todo; ++s) {
-            const int r = eng.st.i_t + 1;
-            const bool ok = eng.step_and_row(rows + size_t(r) * ncol, Fsnap ? Fsnap + size_t(r) * Nx : nullptr,
-                                             bounds ? bounds + size_t(r) * 2 : nullptr);
-            if (!ok) break;
-            eng.st.rows_valid = r + 1;
-        }
-        // write the state back for the next evolve call / the read-out kernels
         __syncthreads();
-        for (int i = tid; i < Nx; i += kNT) E.F[size_t(model) * Nx + i] = S.F[i];
-        if (tid == 0) E.state[model] = eng.st;
+
+        ModelState st;
+        {
+            const long long* src = reinterpret_cast<const long long*>(E.state + model);
+            long long* dst = reinterpret_cast<long long*>(&st);
+#pragma unroll
+            for (int w = 0; w < int(sizeof(ModelState) / 8); ++w) dst[w] = __ldcg(src + w);
+        }
+        if (s_abort) st.status = FB200_MODEL_FAILED;
+        bool active = (st.status == FB200_MODEL_OK);
+        if (active && round == 0) {
+            const int Nt_m = E.models[model].Nt;
+            int target = Nt_m;
+            if (E.n_steps >= 0 && st.i_t + E.n_steps < Nt_m) target = st.i_t + E.n_steps;
+            st.target_i_t = target;
+        }
+        if (active && st.row0_done && st.i_t >= st.target_i_t) active = false;  // nothing left for this model in this launch
+        if (active) {
+            S.h = E.h + size_t(model) * Nx;
+            load_model(E, model, S, ex, E.F + size_t(model) * Nx);
+            const fb200_model_dev_t& M = *smem_model();
+
+            DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
+            eng.init_points();
+
+            double* rows = E.rows + size_t(model) * nrows * ncol;
+            double* Fsnap = E.Fsnap ? E.Fsnap + size_t(model) * nrows * Nx : nullptr;
+            int* bounds = E.bounds ? E.bounds + size_t(model) * nrows * 2 : nullptr;
+
+            if (!eng.st.row0_done) {
+                // the state at t0 is dumped before the first step (cpp/include/application.hpp:25-29)
+                eng.structure_and_row(false, rows, Fsnap, bounds);
+                eng.st.row0_done = 1;
+                eng.st.rows_valid = 1;
+            }
+            int todo = eng.st.target_i_t - eng.st.i_t;
+            if (todo > E.chunk_steps) todo = E.chunk_steps;
+            for (int s = 0; s < todo; ++s) {
+                const int r = eng.st.i_t + 1;
+                const bool ok = eng.step_and_row(rows + size_t(r) * ncol, Fsnap ? Fsnap + size_t(r) * Nx : nullptr,
+                                                 bounds ? bounds + size_t(r) * 2 : nullptr);
+                if (!ok) break;
+                eng.st.rows_valid = r + 1;
+            }
+            // write the state back for the next work item / evolve call / the read-out kernels
+            __syncthreads();
+            for (int i = tid; i < Nx; i += kNT) E.F[size_t(model) * Nx + i] = S.F[i];
+            st = eng.st;
+        }
+        if (tid == 0 && (active || round == 0 || s_abort)) E.state[model] = st;
+        __threadfence();   // F, rows and state are visible device-wide before the round is published
+        __syncthreads();
+        if (tid == 0) atomicExch(E.progress + model, round + 1);
         ex.tick(7);
     }
 #ifdef FB_PROFILE

@@ -25,6 +25,9 @@ struct EnsembleDev {
     double* Fsnap;                    // [n_models][n_rows][Nx] or null (record_F)
     int* bounds;                      // [n_models][n_rows][2] or null (first,last per row; record_F)
     int* queue;                       // work-queue counter
+    int* progress;                    // [n_models] rounds completed in this launch (chunked scheduling)
+    int chunk_steps;                  // steps per work item; a model is handed back to the queue after that many
+    int n_rounds;                     // work items per model in this launch
     double* cta_scratch;              // [max_ctas][scratch_doubles_per_cta()] once-per-step arrays of the model a CTA holds
     int max_ctas;                     // CTAs the scratch was sized for (2 per SM)
     long long* prof;                  // [8] per-phase cycle sums (FB_PROFILE builds only), else null

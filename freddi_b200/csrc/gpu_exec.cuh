@@ -241,7 +241,7 @@ __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, cons
 #pragma unroll
     for (int k = 0; k < kPPT; ++k) {
         const int i = tid + k * kNT;
-        S.F[i] = (i < Nx) ? F_src[i] : 0.;
+        S.F[i] = (i < Nx) ? __ldcg(F_src + i) : 0.;  // L2: another SM may have written it in the previous round
         if (i >= Nx) S.R[i] = 0.;
     }
     // (ex.lampref is filled once per kernel by stage_cfg)

@@ -154,14 +154,18 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
         const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
         const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
-        // Step-size controller.  Both adjustments are powers of the error, so one log2/exp2 pair serves the
-        // rejecting and the accepting lanes of a warp alike (no divergent code paths):
+        // Step-size controller.  Both adjustments are powers of the error, so one power evaluation serves the
+        // rejecting and the accepting lanes of a warp alike:
         //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
         //   accept, err < 0.5:     dt *= 0.9 max(5^-5, err)^(-1/5)
         const bool reject = err > 1.0;
         const double floor_ = 0.00032;  // pow(5.0, -5)
-        const double base = reject ? err : ((floor_ < err) ? err : floor_);
-        const double fac = 9. / 10. * fb_pow_coarse((base < 1e300) ? base : 1e300, reject ? -1. / 3. : -1. / 5.);
+        double fac;
+        if (!reject && !(floor_ < err)) {
+            fac = 4.5;  // 0.9 * (5^-5)^(-1/5): the growth limit — the common case on the exponential tail of the band
+        } else {
+            fac = 9. / 10. * fb_pow_coarse((err < 1e300) ? err : 1e300, reject ? -1. / 3. : -1. / 5.);
+        }
         if (reject) {
             dt *= (fac < 1. / 5.) ? 1. / 5. : fac;
             if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand
@@ -660,7 +664,7 @@ struct DiscEngine {
                 S.F[i] = y;
                 if (i == last) return 0.;  // K[last] stays at its pre-step value
                 const double W = wunc_point(M, y, S.hn[i]);
-                const double K1 = S.s_frac[i] * W / y;
+                const double K1 = S.s_frac[i] * W * fb_rcp(y);  // d = c0 + K absorbs far more than the last ulp of K
                 const double rel = fabs((K1 - S.s_K[i]) * fb_rcp(fabs(K1)));  // only compared with eps
                 S.s_K[i] = K1;
                 S.s_d[pi] = S.s_cc[i] + K1;

@@ -91,14 +91,7 @@ struct PtrArrays {
 #define FB_DOUBLE_H_C2 (2. * FB_H_PLANCK * FB_C_LIGHT * FB_C_LIGHT)
 #define FB_CH_OVER_KB (FB_C_LIGHT * (FB_H_PLANCK / FB_K_BOLTZ))
 
-// B_nu (cpp/src/spectrum.cpp:10-15).  The exact form is used wherever a single value matters (none on the hot
-// path); the quadrature below uses planck_nu_fast.
-FB_HD double planck_nu(double T, double nu) {
-    if (!(T > 0.)) return 0.;
-    return FB_DOUBLE_H_OVER_C2 * p3(nu) / (exp(FB_H_OVER_KB * nu / T) - 1.);
-}
-
-// B_nu for T > 0 with the lean exp/reciprocal: hk_over_T = (h/k_B)/T.  For h nu / k T > 700 the value
+// B_nu (cpp/src/spectrum.cpp:10-15) for T > 0 with the lean exp/reciprocal: hk_over_T = (h/k_B)/T.  For h nu / k T > 700 the value
 // (< 1e-295 of the peak) is returned as exactly 0.
 FB_HD double planck_nu_fast(double hk_over_T, double nu) {
     const double a = hk_over_T * nu;
@@ -123,7 +116,7 @@ FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
 // on acceptance grow when err < 0.5 with dt *= 0.9 max(5^-5, err)^(-1/5).  `trials` counts try_step calls.
 FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) {
     if (trials) *trials = 0;
-    // Identically-zero integrand: T <= 0 or NaN (planck_nu returns 0), or exp() overflows to +inf already at
+    // Identically-zero integrand: T <= 0 or NaN (Planck_nu returns 0), or exp() overflows to +inf already at
     // nu1 so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros
     // (error 0/0 = NaN compares false both ways) and returns exactly 0; skip the walk.
     if (!(T > 0.) || FB_H_OVER_KB * nu1 / T > 710.) return 0.;

@@ -80,7 +80,7 @@ struct PtrArrays {
     double2 *lu[2];                    // PCR ping-pong of the reduced system: (lower, upper), diagonal normalised to 1
     double *rr[2];                     // PCR ping-pong of the reduced system: right-hand side
     // row temporaries alias the PCR buffers (never live at the same time)
-    double *Tph, *Tirr, *Sigma, *Tvis, *TphX, *aux, *wq, *yLx;
+    double *Tph, *Tirr, *Sigma, *Tvis, *TphX, *aux, *wq;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -113,81 +113,65 @@ FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
 // make_controlled(eps_abs = 0, eps_rel = tol, runge_kutta_cash_karp54<double>), initial step
 // 0.01 (nu2 - nu1) (cpp/src/spectrum.cpp:26-37).  Controller = odeint's default error checker
 // (a_x = a_dxdt = 1) and default step adjuster: reject when err > 1 with dt *= max(0.9 err^(-1/3), 0.2);
-// on acceptance grow when err < 0.5 with dt *= 0.9 max(5^-5, err)^(-1/5).
-//
-// The walk is written as a branch-free state machine (one try_step per trial() call, every decision a select), so
-// that a thread can advance TWO rings' quadratures in lock step (planck_nu1_nu2_pair): the two independent
-// dependency chains interleave and keep the FP64 pipe busy, which a single chain cannot at 16 warps per SM.
-// The state is a scalar and the integrand does not depend on it, so of the Cash-Karp tableau only the weights
-// b (solution), db (error estimate) and the nodes c are needed; stage 2 has zero weight in both and is not
-// evaluated; stage 5 sits at t + dt (c5 = 1) and is reused, bit for bit, as the first derivative of the next step.
-struct PlanckQuad {
-    double hkT, x, t, dt, k1;
-    int fails, n;
-    bool active;
-
-    FB_HD void init(double T, double nu1, double nu2) {
-        // Identically-zero integrand: T <= 0 or NaN (Planck_nu returns 0), or exp() overflows to +inf already at nu1
-        // so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros (error
-        // 0/0 = NaN compares false both ways) and returns exactly 0: skip the walk.
-        const bool live = (T > 0.) && !(FB_H_OVER_KB * nu1 / T > 710.);
-        hkT = live ? FB_H_OVER_KB / T : 0.;
-        x = 0.; t = nu1; dt = 1e-2 * (nu2 - nu1);
-        fails = 0; n = 0;
-        k1 = live ? planck_nu_fast(hkT, t) : 0.;
-        active = live && (nu2 - t > 2.220446049250313e-16);
-    }
-
-    FB_HD void trial(double nu2, double tol) {
-        const double eps_mach = 2.220446049250313e-16;
-        const double b1 = 37. / 378., b3 = 250. / 621., b4 = 125. / 594., b6 = 512. / 1771.;
-        const double db1 = 37. / 378. - 2825. / 27648., db3 = 250. / 621. - 18575. / 48384., db4 = 125. / 594. - 13525. / 55296.,
-                     db5 = -277. / 14336., db6 = 512. / 1771. - 1. / 4.;
-        const double c3 = 3. / 10., c4 = 3. / 5., c5 = 1., c6 = 7. / 8.;
-        const double h = ((t + dt) - nu2 > eps_mach) ? nu2 - t : dt;  // less_with_sign(end, t + dt, dt): clip to the end
-        const double k3 = planck_nu_fast(hkT, t + c3 * h);
-        const double k4 = planck_nu_fast(hkT, t + c4 * h);
-        const double k5 = planck_nu_fast(hkT, t + c5 * h);
-        const double k6 = planck_nu_fast(hkT, t + c6 * h);
-        const double xnew = 1. * x + (b1 * h) * k1 + (b3 * h) * k3 + (b4 * h) * k4 + (b6 * h) * k6;
-        const double xerr = (db1 * h) * k1 + (db3 * h) * k3 + (db4 * h) * k4 + (db5 * h) * k5 + (db6 * h) * k6;
-        const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(h) * fabs(k1)));  // feeds comparisons and the step factor only
+// on acceptance grow when err < 0.5 with dt *= 0.9 max(5^-5, err)^(-1/5).  `trials` counts try_step calls.
+FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) {
+    if (trials) *trials = 0;
+    // Identically-zero integrand: T <= 0 or NaN (Planck_nu returns 0), or exp() overflows to +inf already at
+    // nu1 so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros
+    // (error 0/0 = NaN compares false both ways) and returns exactly 0; skip the walk.
+    if (!(T > 0.) || FB_H_OVER_KB * nu1 / T > 710.) return 0.;
+    const double a21 = 1. / 5.;
+    const double a31 = 3. / 40., a32 = 9. / 40.;
+    const double a41 = 3. / 10., a42 = -9. / 10., a43 = 6. / 5.;
+    const double a51 = -11. / 54., a52 = 5. / 2., a53 = -70. / 27., a54 = 35. / 27.;
+    const double a61 = 1631. / 55296., a62 = 175. / 512., a63 = 575. / 13824., a64 = 44275. / 110592., a65 = 253. / 4096.;
+    const double b1 = 37. / 378., b3 = 250. / 621., b4 = 125. / 594., b6 = 512. / 1771.;
+    const double db1 = 37. / 378. - 2825. / 27648., db3 = 250. / 621. - 18575. / 48384., db4 = 125. / 594. - 13525. / 55296.,
+                 db5 = -277. / 14336., db6 = 512. / 1771. - 1. / 4.;
+    const double c2 = 1. / 5., c3 = 3. / 10., c4 = 3. / 5., c5 = 1., c6 = 7. / 8.;
+    (void)a21; (void)a31; (void)a32; (void)a41; (void)a42; (void)a43; (void)a51; (void)a52; (void)a53; (void)a54;
+    (void)a61; (void)a62; (void)a63; (void)a64; (void)a65;  // the integrand does not depend on the state
+    const double eps_mach = 2.220446049250313e-16;
+    double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
+    int fails = 0, n = 0;
+    const double hkT = FB_H_OVER_KB / T;
+    double k1 = planck_nu_fast(hkT, t);
+    while (nu2 - t > eps_mach) {
+        if ((t + dt) - nu2 > eps_mach) dt = nu2 - t;  // less_with_sign(end, t + dt, dt)
+        const double k3 = planck_nu_fast(hkT, t + c3 * dt);
+        const double k4 = planck_nu_fast(hkT, t + c4 * dt);
+        const double k5 = planck_nu_fast(hkT, t + c5 * dt);
+        const double k6 = planck_nu_fast(hkT, t + c6 * dt);
+        (void)c2;  // stage 2 has zero weight in both the solution and the error estimate (b2 = db2 = 0)
+        ++n;
+        const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
+        const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
+        const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
+        // Step-size controller.  Both adjustments are powers of the error, so one power evaluation serves the
+        // rejecting and the accepting lanes of a warp alike:
+        //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
+        //   accept, err < 0.5:     dt *= 0.9 max(5^-5, err)^(-1/5)
         const bool reject = err > 1.0;
         const double floor_ = 0.00032;  // pow(5.0, -5)
-        double base = reject ? err : ((floor_ < err) ? err : floor_);
-        base = (base < 1e300) ? base : 1e300;
-        const double fac = 9. / 10. * fb_pow_coarse(base, reject ? -1. / 3. : -1. / 5.);
-        const double h_rej = h * ((fac < 1. / 5.) ? 1. / 5. : fac);
-        const double h_acc = (err < 0.5) ? h * fac : h;
-        if (active) {  // a select per member; nothing above has side effects
-            n += 1;
-            fails = reject ? fails + 1 : 0;
-            dt = reject ? h_rej : h_acc;
-            t = reject ? t : t + h;
-            x = reject ? x : xnew;
-            k1 = reject ? k1 : k5;
-            active = (nu2 - t > eps_mach) && (fails < 500);  // odeint throws after 500 rejections; unreachable here
+        double fac;
+        if (!reject && !(floor_ < err)) {
+            fac = 4.5;  // 0.9 * (5^-5)^(-1/5): the growth limit — the common case on the exponential tail of the band
+        } else {
+            fac = 9. / 10. * fb_pow_coarse((err < 1e300) ? err : 1e300, reject ? -1. / 3. : -1. / 5.);
         }
+        if (reject) {
+            dt *= (fac < 1. / 5.) ? 1. / 5. : fac;
+            if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand
+            continue;
+        }
+        fails = 0;
+        t += dt;  // == the abscissa of stage 5 (c5 = 1): the derivative at the new t is k5, bit for bit
+        if (err < 0.5) dt *= fac;
+        x = xnew;
+        k1 = k5;
     }
-};
-
-FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) {
-    PlanckQuad q;
-    q.init(T, nu1, nu2);
-    while (q.active) q.trial(nu2, tol);
-    if (trials) *trials = q.n;
-    return q.x;
-}
-
-FB_HD void planck_nu1_nu2_pair(double Ta, double Tb, double nu1, double nu2, double tol, double* ya, double* yb, int* na, int* nb) {
-    PlanckQuad A, B;
-    A.init(Ta, nu1, nu2);
-    B.init(Tb, nu1, nu2);
-    while (A.active || B.active) {
-        A.trial(nu2, tol);
-        B.trial(nu2, tol);
-    }
-    *ya = A.x; *yb = B.x; *na = A.n; *nb = B.n;
+    if (trials) *trials = n;
+    return x;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -451,7 +435,6 @@ FB_HD bool fb_isnan(double x) { return x != x; }
 //   scalar(k)            small shared scratch (written by one thread, read after sync)
 //   windA(i), windB(i), windC_static(i), Fmagn(i), dFmagn_dh(i)   per-model arrays in global memory (0 if absent)
 //   lambda_pref(k)       double_h_c2 / lambda_k^5
-//   pairs(f)             run f(i0, i1) for every ring exactly once, two rings per call (i1 may be out of range)
 //   blocks(n, f)         run f(b) for b < n, one thread per b (the in-thread block elimination of the solve)
 //   reduced(n, f)        run f(q) for q < n, one thread per q (reduced-system PCR)
 //   tick(p)              phase boundary marker (cycle accounting in FB_PROFILE builds, otherwise a no-op)
@@ -788,22 +771,6 @@ struct DiscEngine {
         const double a_hot = (TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / TphX_hottest : 0.;
         const double T_prune = (cfg.lx_prune && TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / (a_hot + FB200_LX_PRUNE) : 0.;
 
-        // ---- Lx: the band integral of every (unpruned) hot ring, two rings per thread in lock step ----
-        if (cfg.compute_lx) {
-            ex.pairs([&](int i0, int i1) {
-                const bool in0 = (i0 >= first && i0 <= last), in1 = (i1 >= first && i1 <= last);
-                double T0 = in0 ? S.TphX[i0] : 0., T1 = in1 ? S.TphX[i1] : 0.;
-                if (T0 < T_prune) T0 = 0.;   // (a NaN temperature compares false and is integrated as 0 like Planck_nu does)
-                if (T1 < T_prune) T1 = 0.;
-                double y0, y1;
-                int n0, n1;
-                planck_nu1_nu2_pair(T0, T1, M.emin, M.emax, 1e-4, &y0, &y1, &n0, &n1);
-                if (i0 < Nx) { S.yLx[i0] = y0; S.aux[i0] = double(n0); }
-                if (i1 < Nx) { S.yLx[i1] = y1; S.aux[i1] = double(n1); }
-            });
-        }
-        // (each thread reads back only what it wrote: the reductions below use the same ring-to-thread mapping)
-
         // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
         const int nl = cfg.n_lambdas;
         const int nq = 2 + nl * (cfg.cold_disk ? 2 : 1);
@@ -812,7 +779,8 @@ struct DiscEngine {
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
         ex.reduce_sums(nq + 1, [&](int i, int k, int q) -> double {
             if (i >= Nx) return 0.;
-            if (q == nq) return cfg.compute_lx ? S.aux[i] : 0.;  // this ring's Lx trial-step count
+            if (q == 1) S.aux[i] = 0.;
+            if (q == nq) return S.aux[i];  // this point's Lx trial-step count, parked by q == 1
             if (q < 2 + nl) {  // hot zone [first, last]: weights prepared above (0 outside)
                 const double wq = S.wq[i];
                 if (wq == 0.) return 0.;
@@ -821,7 +789,10 @@ struct DiscEngine {
                     y = S.Sigma[i];
                 } else if (q == 1) {
                     if (!cfg.compute_lx) return 0.;
-                    y = S.yLx[i];
+                    int trials = 0;
+                    const double T = S.TphX[i];
+                    y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, 1e-4, &trials);
+                    S.aux[i] = double(trials);
                 } else {
                     y = planck_lambda_pref(S.Tph[i], cfg.lambdas[q - 2], ex.lambda_pref(q - 2));
                 }

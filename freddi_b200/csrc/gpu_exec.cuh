@@ -85,7 +85,7 @@ struct GpuArrays {
     struct PP2 { __device__ __forceinline__ ShDyn2 operator[](int cur) const { return ShDyn2{cur ? L::o_lu1 : L::o_lu0}; } } lu;
     struct PP1 { __device__ __forceinline__ ShDyn operator[](int cur) const { return ShDyn{cur ? L::o_rr1 : L::o_rr0}; } } rr;
     // row temporaries alias the solver arrays (rebuilt at the start of every step)
-    ShD<L::o_l> Tph; ShD<L::o_u> Tirr; ShD<L::o_d> Sigma; ShD<L::o_rhs> Tvis; ShD<L::o_pa> TphX; ShD<L::o_pc> aux; ShD<L::o_pg> wq; ShD<L::o_K> yLx;
+    ShD<L::o_l> Tph; ShD<L::o_u> Tirr; ShD<L::o_d> Sigma; ShD<L::o_rhs> Tvis; ShD<L::o_pa> TphX; ShD<L::o_pc> aux; ShD<L::o_pg> wq;
 };
 
 __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double* h_global) {
@@ -118,16 +118,6 @@ struct GpuEx {
     template <class F> __device__ __forceinline__ void points(F&& f) {
         FB_UNROLL(FB_UNROLL_POINTS)
         for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
-    }
-    // two rings per call (slots 2j and 2j+1 of this thread)
-    template <class F> __device__ __forceinline__ void pairs(F&& f) {
-        static_assert(kPPT == 1 || kPPT % 2 == 0, "kPPT must be 1 or even");
-        if (kPPT == 1) {
-            f(tid, FB200_NX_MAX);
-        } else {
-#pragma unroll 1
-            for (int k = 0; k < kPPT; k += 2) f(tid + k * kNT, tid + (k + 1) * kNT);
-        }
     }
     // one thread per block / per reduced unknown of the tridiagonal solve
     template <class F> __device__ __forceinline__ void blocks(int n, F&& f) {

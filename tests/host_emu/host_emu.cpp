@@ -30,7 +30,6 @@ struct HostEx {
     template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) { cur = i; f(i, 0); } }
     void sync() {}
     void tick(int) {}
-    template <class F> void pairs(F&& f) { for (int i = 0; i < NT; i += 2) f(i, i + 1); }
     template <class F> void blocks(int n, F&& f) { for (int b = 0; b < n; ++b) f(b); }
     template <class F> void reduced(int n, F&& f) { for (int q = 0; q < n; ++q) f(q); }
     double& scalar(int k) { return scal[k]; }
@@ -93,7 +92,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     S.s_l = take(NP); S.s_u = take(NP); S.s_d = take(NP); S.s_rhs = take(NP); S.p_a = take(NP); S.p_c = take(NP); S.p_g = take(NP);
     S.lu[0] = reinterpret_cast<double2*>(take(2 * NR)); S.lu[1] = reinterpret_cast<double2*>(take(2 * NR));
     S.rr[0] = take(NR); S.rr[1] = take(NR);
-    S.Tph = S.s_l; S.Tirr = S.s_u; S.Sigma = S.s_d; S.Tvis = S.s_rhs; S.TphX = S.p_a; S.aux = S.p_c; S.wq = S.p_g; S.yLx = S.s_K;
+    S.Tph = S.s_l; S.Tirr = S.s_u; S.Sigma = S.s_d; S.Tvis = S.s_rhs; S.TphX = S.p_a; S.aux = S.p_c; S.wq = S.p_g;
     for (int i = 0; i < Nx; ++i) { hbuf[i] = res.h[i]; S.F[i] = res.F[i]; }
 
     HostEx ex;

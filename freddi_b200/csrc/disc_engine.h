@@ -95,7 +95,7 @@ struct PtrArrays {
 // (< 1e-295 of the peak) is returned as exactly 0.
 FB_HD double planck_nu_fast(double hk_over_T, double nu) {
     const double a = hk_over_T * nu;
-    const double em1 = fb_exp((a < 700.) ? a : 700.) - 1.;
+    const double em1 = fb_exp_tab((a < 700.) ? a : 700.) - 1.;
     const double b = FB_DOUBLE_H_OVER_C2 * p3(nu) * fb_rcp(em1);
     return (a < 700.) ? b : 0.;
 }
@@ -105,7 +105,7 @@ FB_HD double planck_nu_fast(double hk_over_T, double nu) {
 FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
     if (!(T > 0.)) return 0.;
     const double a = FB_CH_OVER_KB * fb_rcp(lambda * T);
-    const double b = pref * fb_rcp(fb_exp((a < 700.) ? a : 700.) - 1.);
+    const double b = pref * fb_rcp(fb_exp_tab((a < 700.) ? a : 700.) - 1.);
     return (a < 700.) ? b : 0.;  // beyond exp(700) the value is < 1e-300 of the Rayleigh-Jeans level
 }
 

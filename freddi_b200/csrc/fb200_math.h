@@ -162,6 +162,51 @@ FB_HD double fb_exp(double x) {
     return fb_scale2(p, ki);
 }
 
+// 2^(j/32), j = 0..31, correctly rounded.  On the device the table lives in the first 32 doubles of the CTA's
+// dynamic shared memory (every kernel of the library fills it at start, gpu_exec.cuh: stage_cfg): the index
+// differs from lane to lane, which shared memory serves and constant memory would serialise.
+#define FB_EXP2_TABLE                                                                                   \
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,               \
+    1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469,  \
+    1.241857812073484, 1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, \
+    1.383909881963832, 1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, \
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,  \
+    1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,    \
+    1.9152065613971474, 1.9571441241754002
+#ifdef __CUDACC__
+extern __shared__ __align__(16) double fb_smem[];
+#endif
+static const double fb_exp2_table_host[32] = {FB_EXP2_TABLE};
+#ifdef __CUDA_ARCH__
+#define FB_EXP2_TAB(j) fb_smem[j]
+#else
+#define FB_EXP2_TAB(j) fb_exp2_table_host[j]
+#endif
+
+// exp(x) for -700 <= x <= 709 for the Planck function, ~1 ulp with 11 FP64 operations: n = rint(32 x / ln2),
+// exp(x) = 2^(n >> 5) * 2^((n & 31)/32) * exp(r), |r| <= ln2/64, expm1(r) by a 6th-degree polynomial (truncation 4e-18).
+FB_HD double fb_exp_tab(double x) {
+    const double shift = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma(x, 46.16624130844683, shift);  // 32 / ln2
+    const double n = t - shift;
+#ifdef __CUDA_ARCH__
+    const int ni = __double2loint(t);
+#else
+    union { double d; long long i; } u;
+    u.d = t;
+    const int ni = (int)(u.i & 0xffffffffLL);
+#endif
+    double r = fma(n, -0.021660849392446835, x);     // ln2/32, leading 37 bits (n * hi is exact)
+    r = fma(n, -5.145609244655338e-14, r);           // ln2/32, tail
+    double q = fma(r, 1.388888888888889e-03, 8.333333333333333e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    const double p = fma(q * r, r, r);               // expm1(r)
+    const double tj = FB_EXP2_TAB(ni & 31);
+    return fb_scale2(fma(tj, p, tj), ni >> 5);
+}
+
 // 1/y for normal positive y, ~1 ulp (device: hardware seed + two Newton steps; host: IEEE division)
 FB_HD double fb_rcp(double y) {
 #ifdef __CUDA_ARCH__

@@ -130,6 +130,37 @@ FB_HD double fb_scale2(double p, int k) {  // p * 2^k for p in [0.5, 2) and a re
 #endif
 }
 
+// 2^(j/32), j = 0..31, correctly rounded.  On the device the table lives in the first 32 doubles of the CTA's
+// dynamic shared memory (64 doubles with the tails; every kernel of the library fills it at start, gpu_exec.cuh: stage_cfg): the index
+// differs from lane to lane, which shared memory serves and constant memory would serialise.
+#define FB_EXP2_TABLE                                                                                   \
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,               \
+    1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469,  \
+    1.241857812073484, 1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, \
+    1.383909881963832, 1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, \
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,  \
+    1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,    \
+    1.9152065613971474, 1.9571441241754002
+// 2^(j/32) - (double)2^(j/32): the tail that brings the table product back to ~0.5 ulp (used by fb_pow_pos)
+#define FB_EXP2_TABLE_LO \
+    0.0, 5.109225028973444e-17, 8.551889705537965e-17, -7.899853966841582e-17, \
+    -3.046782079812471e-17, 1.0410278456845571e-16, 8.912812676025408e-17, 3.8292048369240935e-17, \
+    3.982015231465646e-17, -7.712630692681488e-17, 4.658027591836937e-17, 2.667932131342186e-18, \
+    2.5382502794888315e-17, -2.8587312100388614e-17, 7.70094837980299e-17, -6.770511658794786e-17, \
+    -9.667293313452913e-17, -3.0237581349939873e-17, -3.483994556892796e-17, -1.016455327754295e-16, \
+    7.949834809697621e-17, -1.0136916471278304e-17, 2.4707192569797888e-17, -1.0125679913674773e-16, \
+    8.199010020581497e-17, -1.851380418263111e-17, 2.960140695448873e-17, 1.8227458427912087e-17, \
+    3.283107224245627e-17, -6.122763413004143e-17, -1.0619946056195963e-16, 8.960767791036668e-17
+#ifdef __CUDACC__
+extern __shared__ __align__(16) double fb_smem[];
+#endif
+static const double fb_exp2_table_host[64] = {FB_EXP2_TABLE, FB_EXP2_TABLE_LO};
+#ifdef __CUDA_ARCH__
+#define FB_EXP2_TAB(j) fb_smem[j]
+#else
+#define FB_EXP2_TAB(j) fb_exp2_table_host[j]
+#endif
+
 // exp(x) for -700 <= x <= 709, within ~1 ulp: k = rint(x log2 e), r = x - k ln2 (two-piece ln2), 13th-degree
 // Taylor polynomial on |r| <= 0.347 (truncation 4e-18), scaling through the exponent field.
 FB_HD double fb_exp(double x) {
@@ -161,27 +192,6 @@ FB_HD double fb_exp(double x) {
     p = fma(p, r, 1.0);
     return fb_scale2(p, ki);
 }
-
-// 2^(j/32), j = 0..31, correctly rounded.  On the device the table lives in the first 32 doubles of the CTA's
-// dynamic shared memory (every kernel of the library fills it at start, gpu_exec.cuh: stage_cfg): the index
-// differs from lane to lane, which shared memory serves and constant memory would serialise.
-#define FB_EXP2_TABLE                                                                                   \
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,               \
-    1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469,  \
-    1.241857812073484, 1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, \
-    1.383909881963832, 1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, \
-    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,  \
-    1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,    \
-    1.9152065613971474, 1.9571441241754002
-#ifdef __CUDACC__
-extern __shared__ __align__(16) double fb_smem[];
-#endif
-static const double fb_exp2_table_host[32] = {FB_EXP2_TABLE};
-#ifdef __CUDA_ARCH__
-#define FB_EXP2_TAB(j) fb_smem[j]
-#else
-#define FB_EXP2_TAB(j) fb_exp2_table_host[j]
-#endif
 
 // exp(x) for -700 <= x <= 709 for the Planck function, ~1 ulp with 11 FP64 operations: n = rint(32 x / ln2),
 // exp(x) = 2^(n >> 5) * 2^((n & 31)/32) * exp(r), |r| <= ln2/64, expm1(r) by a 6th-degree polynomial (truncation 4e-18).
@@ -280,33 +290,26 @@ FB_HD double fb_pow_pos(double x, double a) {
     // y = a log2 x
     const double y_hi = a * l_hi;
     const double y_lo = fma(a, l_hi, -y_hi) + a * l_lo;
+    // 2^y = 2^(n >> 5) * 2^((n & 31)/32) * exp(f ln2), n = rint(32 y), |f| <= 1/64
     const double shift = 6755399441055744.0;
-    const double tk = y_hi + shift;
-    const double k = tk - shift;
+    const double tk = fma(y_hi, 32.0, shift);
+    const double nk = tk - shift;
 #ifdef __CUDA_ARCH__
-    const int ki = __double2loint(tk);
+    const int ni = __double2loint(tk);
 #else
     u_.d = tk;
-    const int ki = (int)(u_.i & 0xffffffffLL);
+    const int ni = (int)(u_.i & 0xffffffffLL);
 #endif
-    if (ki > 1000 || ki < -1000) return pow(x, a);
-    const double f = (y_hi - k) + y_lo;
-    const double g = f * 0.6931471805599453 + f * 2.3190468138462996e-17;
-    double w = 1.6059043836821613e-10;
-    w = fma(w, g, 2.08767569878681e-09);
-    w = fma(w, g, 2.505210838544172e-08);
-    w = fma(w, g, 2.755731922398589e-07);
-    w = fma(w, g, 2.7557319223985893e-06);
-    w = fma(w, g, 2.48015873015873e-05);
-    w = fma(w, g, 1.984126984126984e-04);
-    w = fma(w, g, 1.388888888888889e-03);
-    w = fma(w, g, 8.333333333333333e-03);
+    if (ni > 32000 || ni < -32000) return pow(x, a);
+    const double f = fma(nk, -0.03125, y_hi) + y_lo;   // exact subtraction, then the low part
+    const double g = fma(f, 0.6931471805599453, f * 2.3190468138462996e-17);
+    double w = fma(g, 1.388888888888889e-03, 8.333333333333333e-03);
     w = fma(w, g, 4.1666666666666664e-02);
     w = fma(w, g, 1.6666666666666666e-01);
     w = fma(w, g, 0.5);
-    w = fma(w, g, 1.0);
-    w = fma(w, g, 1.0);
-    return fb_scale2(w, ki);
+    const double pm1 = fma(w * g, g, g);               // expm1(g)
+    const double tj = FB_EXP2_TAB(ni & 31);
+    return fb_scale2(tj + fma(tj, pm1, FB_EXP2_TAB(32 + (ni & 31))), ni >> 5);  // small terms first: one final rounding
 }
 
 // base^p for base in [1e-5, 1e300], |p| <= 1/3, relative accuracy ~1e-12: only steers the step size of the

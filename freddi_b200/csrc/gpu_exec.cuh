@@ -36,16 +36,16 @@ static_assert(kNT * kPPT == FB200_NX_MAX && kNW >= 1 && kNW <= 32, "FB_NT must d
 
 // The CTA's dynamic shared memory.  Every kernel of this library declares the same window; all array
 // accessors below index it with compile-time offsets, so the compiler emits LDS/STS with immediate offsets.
-// (declared in fb200_math.h; its first 32 doubles hold the 2^(j/32) table of fb_exp_tab)
-__constant__ double c_exp2_table[32] = {FB_EXP2_TABLE};
+// (declared in fb200_math.h; its first 64 doubles hold the 2^(j/32) table (values, then tails) of fb_exp_tab / fb_pow_pos)
+__constant__ double c_exp2_table[64] = {FB_EXP2_TABLE, FB_EXP2_TABLE_LO};
 
 // Shared memory per CTA: reduced-system PCR ping-pong, F, hn, s_cc, s_frac (plain index), s_l, s_u, s_d, s_rhs,
 // p_a, p_c, p_g (padded index), then the reduction scratch, the model constants and the output configuration.
 // Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb (9 point arrays, read once per step).
 struct SmemLayout {
     static constexpr int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
-    static constexpr int o_exptab = 0;  // fixed: fb200_math.h reads the table at fb_smem[0..31]
-    static constexpr int o_lu0 = 32, o_lu1 = o_lu0 + 2 * NR, o_rr0 = o_lu1 + 2 * NR, o_rr1 = o_rr0 + NR;
+    static constexpr int o_exptab = 0;  // fixed: fb200_math.h reads the table at fb_smem[0..63]
+    static constexpr int o_lu0 = 64, o_lu1 = o_lu0 + 2 * NR, o_rr0 = o_lu1 + 2 * NR, o_rr1 = o_rr0 + NR;
     static constexpr int o_F = o_rr1 + NR, o_hn = o_F + N, o_cc = o_hn + N, o_frac = o_cc + N, o_K = o_frac + N;
     static constexpr int o_l = o_K + N, o_u = o_l + NP, o_d = o_u + NP, o_rhs = o_d + NP;
     static constexpr int o_pa = o_rhs + NP, o_pc = o_pa + NP, o_pg = o_pc + NP;
@@ -215,7 +215,7 @@ struct GpuEx {
 // parameter dynamically would make the compiler spill the whole parameter block to local memory.
 __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E) {
     OutCfg* c = smem_cfg();
-    if (threadIdx.x < 32) fb_smem[SmemLayout::o_exptab + threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (threadIdx.x < 64) fb_smem[SmemLayout::o_exptab + threadIdx.x] = c_exp2_table[threadIdx.x];
     if (threadIdx.x == 0) {
         c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
         c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows; c->lx_prune = E.cfg.lx_prune;

@@ -219,3 +219,24 @@ def test_reset_replays_the_ensemble_bit_for_bit():
     np.testing.assert_array_equal(F1, F2)
     for a, b in zip(st1, st2):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('Nx', [8, 33, 255, 1024])
+def test_grid_sizes_from_tiny_to_maximum(ref, Nx):
+    """Nx = 1024 is the largest grid the kernels take (one CTA holds the model); tiny grids exercise partial
+    blocks of the partitioned solve (block of 1, 2, ... rows) and partial warps."""
+    args = [cm.ini_args(Nx=Nx, initialcond='quasistat', time=5), cm.ini_args(Nx=Nx, time=5),
+            cm.ini_args(Nx=Nx, initialcond='quasistat', Thot=1e4, Cirr=3e-4, boundcond='Tirr', time=5)]
+    g = run_gpu(args, cm.LAM3)
+    for k, a in enumerate(args):
+        check_model(g, k, ref.run(a, cm.LAM3), 'Nx={}[{}]'.format(Nx, k))
+
+
+def test_zero_steps_and_single_step_runs(ref):
+    """time = 0 gives Nt = 0: one row (the initial state) and no step; time = tau gives exactly one step."""
+    args = [cm.ini_args(time=0.0, tau=0.25), cm.ini_args(time=0.25, tau=0.25, initialcond='quasistat')]
+    g = run_gpu(args, cm.LAM3)
+    assert g['valid'].tolist() == [1, 2]
+    for k, a in enumerate(args):
+        r = ref.run(a, cm.LAM3)
+        cm.assert_rows_close(g['rows'][k, :g['valid'][k]], r['rows'][:r['rows_valid']], g['columns'], what='short[{}]'.format(k))

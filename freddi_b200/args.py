@@ -57,6 +57,7 @@ class FB200Args(C.Structure):
 
 
 FB200_MAX_LAMBDAS = 16
+FB200_MAX_PASSBANDS = 4
 
 
 class FB200Config(C.Structure):
@@ -66,6 +67,9 @@ class FB200Config(C.Structure):
         ('lambdas', C.c_double * FB200_MAX_LAMBDAS),
         ('cold_disk', C.c_int32), ('record_F', C.c_int32), ('compute_lx', C.c_int32), ('host_threads', C.c_int32),
         ('threads_per_model', C.c_int32), ('exact_lx_walk', C.c_int32),
+        ('n_passbands', C.c_int32), ('passband_len', C.c_int32 * FB200_MAX_PASSBANDS),
+        ('passband_lambdas', C.POINTER(C.c_double) * FB200_MAX_PASSBANDS),
+        ('passband_transmissions', C.POINTER(C.c_double) * FB200_MAX_PASSBANDS),
     ]
 
 

@@ -146,6 +146,13 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     fb200_config_t cfg;
     if (cfg_in) cfg = *cfg_in; else fb200_config_default(&cfg);
     if (cfg.n_lambdas < 0 || cfg.n_lambdas > FB200_MAX_LAMBDAS) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_lambdas out of range");
+    if (cfg.n_passbands < 0 || cfg.n_passbands > FB200_MAX_PASSBANDS) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_passbands out of range");
+    std::vector<PassbandTable> passbands(cfg.n_passbands);
+    for (int p = 0; p < cfg.n_passbands; ++p) {
+        std::string msg;
+        const int rc = prepare_passband(cfg.passband_lambdas[p], cfg.passband_transmissions[p], cfg.passband_len[p], passbands[p], msg);
+        if (rc != FB200_OK) return set_err(rc, "passband " + std::to_string(p) + ": " + msg);
+    }
 
     // ---- resolve every model on the host ----
     std::vector<Resolved> res(n_models);
@@ -204,13 +211,14 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     auto guard_fail = [&](int code) { fb200_ensemble_destroy(e); return code; };
     e->device = cfg.device;
     e->cfg = cfg;
+    for (int p = 0; p < FB200_MAX_PASSBANDS; ++p) { e->cfg.passband_lambdas[p] = nullptr; e->cfg.passband_transmissions[p] = nullptr; }  // caller-owned, read above
     e->n = n_models;
     e->Nx = Nx;
     e->is_ns = is_ns;
     e->n_rows = max_Nt + 1;
     e->max_Nt = max_Nt;
     if (const char* c = getenv("FB200_CHUNK_STEPS")) e->chunk_steps = atoi(c) > 0 ? atoi(c) : 0x3fffffff;
-    e->n_cols = FB200_N_BH_COLS + cfg.n_lambdas * (cfg.cold_disk ? 2 : 1) + (is_ns ? FB200_N_NS_COLS : 0);
+    e->n_cols = FB200_N_BH_COLS + (cfg.n_lambdas + cfg.n_passbands) * (cfg.cold_disk ? 2 : 1) + (is_ns ? FB200_N_NS_COLS : 0);
     e->info.resize(n_models);
     for (size_t i = 0; i < n_models; ++i) e->info[i] = res[i].info;
     {
@@ -239,6 +247,29 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     D.cfg.n_cols = e->n_cols;
     D.cfg.n_rows = e->n_rows;
     for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) D.cfg.lambdas[k] = (k < cfg.n_lambdas) ? cfg.lambdas[k] : 0.;
+
+    D.cfg.n_passbands = cfg.n_passbands;
+    D.cfg.pb_a = nullptr;
+    D.cfg.pb_w = nullptr;
+    for (int k = 0; k < FB200_MAX_PASSBANDS + 2; ++k) D.cfg.pb_off[k] = 0;
+    for (int k = 0; k < FB200_MAX_PASSBANDS; ++k) D.cfg.pb_tdnu[k] = 1.;
+    if (cfg.n_passbands > 0) {  // all tables back to back: a_j, then w_j
+        std::vector<double> ha, hw;
+        for (int p = 0; p < cfg.n_passbands; ++p) {
+            D.cfg.pb_off[p] = int(ha.size());
+            ha.insert(ha.end(), passbands[p].a.begin(), passbands[p].a.end());
+            hw.insert(hw.end(), passbands[p].w.begin(), passbands[p].w.end());
+            D.cfg.pb_tdnu[p] = passbands[p].t_dnu;
+        }
+        for (int p = cfg.n_passbands; p < FB200_MAX_PASSBANDS + 2; ++p) D.cfg.pb_off[p] = int(ha.size());
+        double *d_a = nullptr, *d_w = nullptr;
+        FB_TRY(dev_alloc(e, &d_a, ha.size()));
+        FB_TRY(dev_alloc(e, &d_w, hw.size()));
+        FB_TRYC(cudaMemcpy(d_a, ha.data(), sizeof(double) * ha.size(), cudaMemcpyHostToDevice));
+        FB_TRYC(cudaMemcpy(d_w, hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice));
+        D.cfg.pb_a = d_a;
+        D.cfg.pb_w = d_w;
+    }
 
     const size_t NN = n_models * size_t(Nx);
     fb200_model_dev_t* d_models = nullptr;

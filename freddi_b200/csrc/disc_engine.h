@@ -35,7 +35,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 namespace fb200 {
 
 #define FB200_LX_PRUNE 100.0 /* see structure_and_row: rings fainter than exp(-100) of the hottest one in the X-ray band */
-#define FB200_MAXQ 40 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], Lx trial count, spare */
+#define FB200_MAXQ 44 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], passbands[4], passbands_cold[4], Lx trial count */
 
 // Ensemble-wide output configuration (device copy of fb200_config_t's output part)
 struct OutCfg {
@@ -46,8 +46,13 @@ struct OutCfg {
     int n_cols;
     int n_rows;  // rows allocated per model
     int lx_prune;  // 1: skip the Lx quadrature of rings that cannot contribute (bound in structure_and_row)
-    int _pad;
+    int n_passbands;
     double lambdas[FB200_MAX_LAMBDAS];
+    // tabulated passbands (resolve.hpp PassbandTable), samples of passband p at [pb_off[p], pb_off[p+1]) of pb_a / pb_w
+    int pb_off[FB200_MAX_PASSBANDS + 2];
+    double pb_tdnu[FB200_MAX_PASSBANDS];
+    const double* pb_a;
+    const double* pb_w;
 };
 
 // Mutable per-model state carried between evolve calls (FreddiState::CurrentState, cpp/include/freddi_state.hpp:242-258)
@@ -107,6 +112,30 @@ FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
     const double a = FB_CH_OVER_KB * fb_rcp(lambda * T);
     const double b = pref * fb_rcp(fb_exp_tab((a < 700.) ? a : 700.) - 1.);
     return (a < 700.) ? b : 0.;  // beyond exp(700) the value is < 1e-300 of the Rayleigh-Jeans level
+}
+
+// sum_j w_j / (exp(a_j / T) - 1) over the samples of one tabulated passband: the lambda-trapezoid of
+// B_lambda(T, lambda_j) * transmission_j (cpp/include/freddi_state.hpp:408-417) for ONE ring, so that the radial and
+// the wavelength trapezoids can be exchanged (both are plain weighted sums; all terms are >= 0) and a ring's
+// temperature stays in a register for the whole passband.  0 when !(T > 0), as Planck_lambda (spectrum.cpp:17-22).
+FB_HD double passband_ring_sum(double T, const double* __restrict__ a, const double* __restrict__ w, int n) {
+    if (!(T > 0.)) return 0.;
+    const double invT = fb_rcp(T);
+    double s0 = 0., s1 = 0.;
+    int j = 0;
+    for (; j + 1 < n; j += 2) {  // two independent exp/reciprocal chains in flight
+        const double x0 = a[j] * invT, x1 = a[j + 1] * invT;
+        const double b0 = w[j] * fb_rcp(fb_exp_tab((x0 < 700.) ? x0 : 700.) - 1.);
+        const double b1 = w[j + 1] * fb_rcp(fb_exp_tab((x1 < 700.) ? x1 : 700.) - 1.);
+        s0 += (x0 < 700.) ? b0 : 0.;
+        s1 += (x1 < 700.) ? b1 : 0.;
+    }
+    if (j < n) {
+        const double x0 = a[j] * invT;
+        const double b0 = w[j] * fb_rcp(fb_exp_tab((x0 < 700.) ? x0 : 700.) - 1.);
+        s0 += (x0 < 700.) ? b0 : 0.;
+    }
+    return s0 + s1;
 }
 
 // integral of B_nu over [nu1, nu2]: boost::numeric::odeint::integrate_adaptive with
@@ -772,8 +801,12 @@ struct DiscEngine {
         const double T_prune = (cfg.lx_prune && TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / (a_hot + FB200_LX_PRUNE) : 0.;
 
         // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
-        const int nl = cfg.n_lambdas;
-        const int nq = 2 + nl * (cfg.cold_disk ? 2 : 1);
+        // slots: 0 Mdisk, 1 Lx, [2, 2+nl) Fnu hot, [2+nl, 2+2nl) Fnu cold, [q_pb, q_pb+npb) passbands hot,
+        //        [q_pb+npb, q_pb+2npb) passbands cold, nq: Lx trial count
+        const int nl = cfg.n_lambdas, npb = cfg.n_passbands;
+        const int per = cfg.cold_disk ? 2 : 1;
+        const int q_pb = 2 + nl * per;
+        const int nq = q_pb + npb * per;
         double cold_K = 0.;
         const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
@@ -781,11 +814,15 @@ struct DiscEngine {
             if (i >= Nx) return 0.;
             if (q == 1) S.aux[i] = 0.;
             if (q == nq) return S.aux[i];  // this point's Lx trial-step count, parked by q == 1
-            if (q < 2 + nl) {  // hot zone [first, last]: weights prepared above (0 outside)
+            const bool hot_pb = (q >= q_pb && q < q_pb + npb);
+            if (q < 2 + nl || hot_pb) {  // hot zone [first, last]: weights prepared above (0 outside)
                 const double wq = S.wq[i];
                 if (wq == 0.) return 0.;
                 double y;
-                if (q == 0) {
+                if (hot_pb) {
+                    const int p = q - q_pb;
+                    y = passband_ring_sum(S.Tph[i], cfg.pb_a + cfg.pb_off[p], cfg.pb_w + cfg.pb_off[p], cfg.pb_off[p + 1] - cfg.pb_off[p]);
+                } else if (q == 0) {
                     y = S.Sigma[i];
                 } else if (q == 1) {
                     if (!cfg.compute_lx) return 0.;
@@ -806,14 +843,21 @@ struct DiscEngine {
             if (i == rf) w = S.R[i + 1] - R;
             else if (i == rl) w = R - S.R[i - 1];
             else w = S.R[i + 1] - S.R[i - 1];
-            const int kl = q - 2 - nl;
             double Qx;
             if (M.is_ns)
                 Qx = cold_K * (sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, cold_mu)) /
                      (4. * FB_PI * p2(R));
             else
                 Qx = cold_K * sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) / (4. * FB_PI * p2(R));
-            const double y = planck_lambda_pref(pow025(Qx / FB_SIGMA_SB), cfg.lambdas[kl], ex.lambda_pref(kl));
+            const double Tcold = pow025(Qx / FB_SIGMA_SB);  // Tirr of the cold zone, freddi_state.cpp:221-231
+            double y;
+            if (q >= q_pb) {
+                const int p = q - q_pb - npb;
+                y = passband_ring_sum(Tcold, cfg.pb_a + cfg.pb_off[p], cfg.pb_w + cfg.pb_off[p], cfg.pb_off[p + 1] - cfg.pb_off[p]);
+            } else {
+                const int kl = q - 2 - nl;
+                y = planck_lambda_pref(Tcold, cfg.lambdas[kl], ex.lambda_pref(kl));
+            }
             return 2 * FB_PI * R * y * w;
         });
         ex.tick(4);
@@ -846,15 +890,20 @@ struct DiscEngine {
                 case FB200_COL_FBOL: v = sc.Lbol_disk * psi / d2; break;
                 default: {
                     const int k = i - FB200_N_BH_COLS;
-                    const int per = cfg.cold_disk ? 2 : 1;
                     if (k < nl * per) {
                         const int kl = k / per;
                         const bool cold = (k % per) == 1;
                         const double lam = cfg.lambdas[kl];
                         const double I = 0.5 * ex.sum(cold ? 2 + nl + kl : 2 + kl);
                         v = I * p2(lam) / FB_C_LIGHT * M.cosiOverD2;  // freddi_state.hpp:405-407
+                    } else if (k < (nl + npb) * per) {
+                        const int kp = (k - nl * per) / per;
+                        const bool cold = ((k - nl * per) % per) == 1;
+                        // the two nested trapezoids (radius, wavelength) each carry a factor 1/2
+                        const double intens = 0.5 * (0.5 * ex.sum(cold ? q_pb + npb + kp : q_pb + kp));
+                        v = intens * M.cosiOverD2 / cfg.pb_tdnu[kp];  // freddi_state.hpp:408-417
                     } else {
-                        v = ns_column(k - nl * per, sc);
+                        v = ns_column(k - (nl + npb) * per, sc);
                     }
                 }
             }

@@ -646,4 +646,33 @@ int resolve(const fb200_args_t& a, Resolved& out, std::string& err) {
     }
 }
 
+int prepare_passband(const double* lam, const double* tr, int n, PassbandTable& out, std::string& err) {
+    if (!lam || !tr || n < 2 || n > FB200_MAX_PASSBAND_SAMPLES) {
+        err = "a passband needs between 2 and " + std::to_string(FB200_MAX_PASSBAND_SAMPLES) + " tabulated points";
+        return FB200_ERR_INVALID_ARGUMENT;
+    }
+    for (int j = 0; j < n; ++j) {
+        if (!(lam[j] > 0.) || !(tr[j] == tr[j])) {
+            err = "passband wavelengths must be positive and transmissions not NaN";
+            return FB200_ERR_INVALID_ARGUMENT;
+        }
+    }
+    out.a.resize(n);
+    out.w.resize(n);
+    const double ch_over_kb = FB_C_LIGHT * (FB_H_PLANCK / FB_K_BOLTZ);
+    const double double_h_c2 = 2. * FB_H_PLANCK * FB_C_LIGHT * FB_C_LIGHT;
+    auto f_dnu = [&](int j) { return tr[j] * FB_C_LIGHT / (lam[j] * lam[j]); };
+    // trapz(x, f, 0, n-1), util.cpp:21-30: both ends first, then the interior left to right
+    double s = f_dnu(0) * (lam[1] - lam[0]) + f_dnu(n - 1) * (lam[n - 1] - lam[n - 2]);
+    for (int j = 1; j <= n - 2; ++j) s += f_dnu(j) * (lam[j + 1] - lam[j - 1]);
+    out.t_dnu = 0.5 * s;
+    for (int j = 0; j < n; ++j) {
+        const double dl = (j == 0) ? lam[1] - lam[0] : (j == n - 1) ? lam[n - 1] - lam[n - 2] : lam[j + 1] - lam[j - 1];
+        const double l2 = lam[j] * lam[j];
+        out.a[j] = ch_over_kb / lam[j];
+        out.w[j] = dl * tr[j] * (double_h_c2 / (l2 * l2 * lam[j]));  // pow<5>(x) = x * (x*x) * (x*x)
+    }
+    return FB200_OK;
+}
+
 }  // namespace fb200

@@ -21,6 +21,18 @@ struct Resolved {
     std::vector<double> Fmagn, dFmagn_dh, d2Fmagn_dh2;  // NS [Nx]; empty for BH
 };
 
+// One tabulated passband prepared for the kernels (EnergyPassband, cpp/include/passband.hpp:26-47): per sample
+//   a_j = (c h / k_B) / lambda_j                    the exponent of B_lambda is a_j / T
+//   w_j = dlambda_j * transmission_j * 2 h c^2 / lambda_j^5,  dlambda_j = the trapezoid weight of util.cpp:21-30
+//         (lambda_1 - lambda_0, lambda_{j+1} - lambda_{j-1}, lambda_{n-1} - lambda_{n-2}; the two factors 1/2 of the
+//          nested trapezoids are applied once at the end)
+// and t_dnu = trapz(lambdas, transmission * c / lambda^2) (cpp/src/passband.cpp:64-68, passband.hpp:41-42).
+struct PassbandTable {
+    std::vector<double> a, w;
+    double t_dnu = 0.;
+};
+int prepare_passband(const double* lambdas, const double* transmissions, int n, PassbandTable& out, std::string& err);
+
 // Returns FB200_OK or the error class the reference's constructor would have thrown, message in err.
 int resolve(const fb200_args_t& a, Resolved& out, std::string& err);
 

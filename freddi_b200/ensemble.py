@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .args import FB200Args, FB200Config, FB200ModelInfo, FB200_MAX_LAMBDAS, args_array
+from .args import FB200Args, FB200Config, FB200ModelInfo, FB200_MAX_LAMBDAS, FB200_MAX_PASSBANDS, args_array
 
 N_BH_COLS = 15
 N_NS_COLS = 10
@@ -17,12 +17,53 @@ FIELDS = {'h': 0, 'R': 1, 'F': 2, 'W': 3, 'Sigma': 4, 'Tph': 5, 'Tph_vis': 6, 'T
           'd2Fmagn_dh2': 17}
 
 
-def column_names(n_lambdas=0, cold_disk=False, is_ns=False):
+class Passband:
+    """One tabulated passband as the reference's ``EnergyPassband`` holds it (cpp/include/passband.hpp:26-47):
+    ``lambdas`` [cm] and ``transmissions`` (for a photon counter already multiplied by the wavelength)."""
+
+    def __init__(self, name, lambdas, transmissions):
+        self.name = str(name)
+        self.lambdas = np.ascontiguousarray(lambdas, dtype=np.float64).ravel()
+        self.transmissions = np.ascontiguousarray(transmissions, dtype=np.float64).ravel()
+        if self.lambdas.shape != self.transmissions.shape:
+            raise ValueError('passband {}: lambdas and transmissions differ in length'.format(name))
+
+    @classmethod
+    def from_file(cls, path, detector='photon-counter'):
+        """Two whitespace-separated columns, wavelength [Angstrom] and transmission, read until the first token that
+        is not a number (EnergyPassband::dataFromFile, cpp/src/passband.cpp:16-43).  The CLI always builds
+        photon-counter passbands (cpp/src/options.cpp:316): transmission *= lambda[cm]."""
+        import os
+        vals = []
+        with open(path) as f:
+            for tok in f.read().split():
+                try:
+                    vals.append(float(tok))
+                except ValueError:
+                    break
+        vals = vals[:len(vals) // 2 * 2]
+        lam = np.array(vals[0::2]) * 1e-8  # angstromToCm, cpp/include/unit_transformation.hpp:30-32
+        tr = np.array(vals[1::2])
+        if detector == 'photon-counter':
+            tr = tr * lam
+        elif detector != 'energy':
+            raise ValueError('detector must be "photon-counter" or "energy"')
+        name = str(path)  # EnergyPassband::nameFromPath: `for (; !path.extension().empty(); path = path.stem());`
+        while os.path.splitext(os.path.basename(name))[1]:
+            name = os.path.splitext(os.path.basename(name))[0]
+        return cls(name, lam, tr)
+
+
+def column_names(n_lambdas=0, cold_disk=False, is_ns=False, passbands=()):
     cols = list(BH_COLS)
     for k in range(n_lambdas):
         cols.append('Fnu{}'.format(k))
         if cold_disk:
             cols.append('Fnu{}_cold'.format(k))
+    for name in passbands:
+        cols.append('Fnu{}'.format(name))
+        if cold_disk:
+            cols.append('Fnu{}_cold'.format(name))
     if is_ns:
         cols += NS_COLS
     return cols
@@ -43,6 +84,7 @@ class Ensemble:
 
     args      : sequence of FB200Args (freddi_b200.args.make_args) or a ctypes array of them
     lambdas   : wavelengths [cm] of the Fnu columns every row carries (FluxArguments::lambdas)
+    passbands : sequence of Passband: one Fnu<name> column each (FluxArguments::passbands)
     cold_disk : add the Fnu_cold columns (--colddiskflux)
     record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
     exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip rings that are
@@ -50,7 +92,7 @@ class Ensemble:
     """
 
     def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0,
-                 exact_lx_walk=False):
+                 exact_lx_walk=False, passbands=()):
         self._h = None
         arr = args if isinstance(args, C.Array) else args_array(list(args))
         cfg = FB200Config()
@@ -67,6 +109,15 @@ class Ensemble:
         cfg.compute_lx = int(bool(compute_lx))
         cfg.host_threads = int(host_threads)
         cfg.exact_lx_walk = int(bool(exact_lx_walk))
+        passbands = list(passbands)
+        if len(passbands) > FB200_MAX_PASSBANDS:
+            raise ValueError('at most {} passbands per ensemble'.format(FB200_MAX_PASSBANDS))
+        cfg.n_passbands = len(passbands)
+        dp = C.POINTER(C.c_double)
+        for k, pb in enumerate(passbands):
+            cfg.passband_len[k] = pb.lambdas.size
+            cfg.passband_lambdas[k] = pb.lambdas.ctypes.data_as(dp)
+            cfg.passband_transmissions[k] = pb.transmissions.ctypes.data_as(dp)
         handle = C.c_void_p()
         bad = C.c_size_t()
         rc = _lib.lib.fb200_ensemble_create(arr, len(arr), C.byref(cfg), C.byref(handle), C.byref(bad))
@@ -81,7 +132,8 @@ class Ensemble:
         self.n_rows = int(_lib.lib.fb200_ensemble_n_rows(handle))
         self.n_cols = int(_lib.lib.fb200_ensemble_n_cols(handle))
         self.Nx = int(_lib.lib.fb200_ensemble_nx(handle))
-        self.columns = column_names(len(lambdas), cold_disk, self.is_ns)
+        self.passbands = passbands
+        self.columns = column_names(len(lambdas), cold_disk, self.is_ns, [pb.name for pb in passbands])
         self._info = None
 
     # -- life cycle --

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 1
+#define FB200_ABI_VERSION 2
 
 /* ---- return codes ---- */
 enum {
@@ -133,6 +133,8 @@ typedef struct fb200_args {
 
 /* Ensemble-wide configuration: the outputs every model of the ensemble produces. */
 #define FB200_MAX_LAMBDAS 16
+#define FB200_MAX_PASSBANDS 4
+#define FB200_MAX_PASSBAND_SAMPLES 2048 /* tabulated points per passband */
 typedef struct fb200_config {
     int32_t device;         /* CUDA device ordinal                                                        */
     int32_t n_lambdas;      /* Fnu columns, FluxArguments::lambdas (cpp/include/arguments.hpp:286)        */
@@ -145,9 +147,19 @@ typedef struct fb200_config {
     int32_t exact_lx_walk;  /* 0 (default): rings whose X-ray band emission is < exp(-100) of the hottest
                              * ring's are not integrated (changes Lx by < 1e-31 relative); 1: integrate every
                              * ring like the reference does                                                 */
+    /* Tabulated passbands, FluxArguments::passbands (cpp/include/arguments.hpp:287): one Fnu<name> column each
+     * (+ Fnu<name>_cold with cold_disk) after the Fnu{k} columns, cpp/src/output.cpp:258-271.  The arrays are what
+     * EnergyPassband holds (cpp/include/passband.hpp:33-36): wavelengths [cm] and transmission factors, for the
+     * photon-counter detector of the CLI already multiplied by the wavelength (cpp/src/passband.cpp:35-37).  They are
+     * read during fb200_ensemble_create only. */
+    int32_t n_passbands;
+    int32_t passband_len[FB200_MAX_PASSBANDS];
+    const double* passband_lambdas[FB200_MAX_PASSBANDS];
+    const double* passband_transmissions[FB200_MAX_PASSBANDS];
 } fb200_config_t;
 
-/* Row layout: cpp/src/output.cpp:197-214, then Fnu columns, then cpp/src/ns/ns_output.cpp:6-19 for NS. */
+/* Row layout: cpp/src/output.cpp:197-214, then the Fnu{k}[, Fnu{k}_cold] columns of the wavelengths, then the
+ * Fnu<passband>[, Fnu<passband>_cold] columns (cpp/src/output.cpp:219-271), then cpp/src/ns/ns_output.cpp:6-19 for NS. */
 enum {
     FB200_COL_T = 0,        /* days */
     FB200_COL_MDOT = 1, FB200_COL_MDISK = 2,

@@ -34,12 +34,16 @@ def build(target='all'):
     subprocess.run(['make', '-s', '-C', HERE, target], check=True)
 
 
-def column_names(n_lambdas=0, cold_disk=False, is_ns=False):
+def column_names(n_lambdas=0, cold_disk=False, is_ns=False, passbands=()):
     cols = list(BH_COLS)
     for k in range(n_lambdas):
         cols.append('Fnu{}'.format(k))
         if cold_disk:
             cols.append('Fnu{}_cold'.format(k))
+    for name in passbands:
+        cols.append('Fnu{}'.format(name))
+        if cold_disk:
+            cols.append('Fnu{}_cold'.format(name))
     if is_ns:
         cols += NS_COLS
     return cols
@@ -87,12 +91,34 @@ class _Checker:
         return getattr(self.lib, self.prefix + name)
 
     # ---- whole light curve ----
-    def run(self, args, lambdas=(), cold_disk=False, snapshots=True):
+    def set_passbands(self, passbands=()):
+        """Passbands (objects with .lambdas [cm] and .transmissions) of the models built afterwards; () clears.
+        Returns EnergyPassband::t_dnu of each."""
+        passbands = list(passbands)
+        f = self._fn('set_passbands')
+        f.restype = None
+        dp = C.POINTER(C.c_double)
+        f.argtypes = [C.c_int, C.POINTER(C.c_int), dp, dp, dp]
+        lens = (C.c_int * max(1, len(passbands)))(*[pb.lambdas.size for pb in passbands])
+        lam = np.concatenate([pb.lambdas for pb in passbands]) if passbands else np.zeros(1)
+        tr = np.concatenate([pb.transmissions for pb in passbands]) if passbands else np.zeros(1)
+        tdnu = np.zeros(max(1, len(passbands)))
+        f(len(passbands), lens, lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), tdnu.ctypes.data_as(dp))
+        return tdnu[:len(passbands)]
+
+    def run(self, args, lambdas=(), cold_disk=False, snapshots=True, passbands=()):
         """Returns dict(rows [(Nt+1) x ncol, NaN after collapse], rows_valid, F, first, last, picard)."""
+        if passbands:
+            self.set_passbands(passbands)
+            try:
+                return self.run(args, lambdas, cold_disk, snapshots)
+            finally:
+                self.set_passbands(())
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
-        info = self.model(args, lambdas).info()
+        m = self.model(args, lambdas)
+        info = m.info()
         Nt, Nx = int(info.Nt), int(info.Nx)
-        ncol = N_BH_COLS + len(lam) * (2 if cold_disk else 1) + (N_NS_COLS if args.is_ns else 0)
+        ncol = m.n_cols(cold_disk)
         rows = np.full((Nt + 1, ncol), np.nan)
         F = np.full((Nt + 1, Nx), np.nan) if snapshots else None
         first = np.full(Nt + 1, -1, dtype=np.int64)
@@ -154,6 +180,9 @@ class _Model:
             self._info = FB200ModelInfo()
             self.c._fn('info')(self.h, C.byref(self._info))
         return self._info
+
+    def n_cols(self, cold_disk=False):
+        return int(self.c._fn('n_cols')(self.h, int(cold_disk)))
 
     def step(self):
         return self.c._fn('step')(self.h)

@@ -84,19 +84,25 @@ struct Model {
     std::shared_ptr<Counting<FreddiEvolution>> bh;
     std::shared_ptr<Counting<FreddiNeutronStarEvolution>> ns;
     std::vector<double> lambdas;
+    size_t n_passbands = 0;
     long last_picard = 0;
     FreddiEvolution* ev() const { return is_ns ? static_cast<FreddiEvolution*>(ns.get()) : static_cast<FreddiEvolution*>(bh.get()); }
 };
 
+// Passbands of the models built next (FluxArguments::passbands, cpp/include/arguments.hpp:287): set by
+// ref_set_passbands, read-only while models are built and run.
+std::vector<EnergyPassband> g_passbands;
+
 FluxArguments* make_flux(const fb200_args_t& a, const std::vector<double>& lambdas) {
     return new FluxArguments(a.colourfactor, a.emin, a.emax, a.staralbedo, a.inclination, a.ephemerist0, a.distance,
-                             false, false, lambdas, std::vector<EnergyPassband>());
+                             false, false, lambdas, g_passbands);
 }
 
 Model* build(const fb200_args_t& a, const double* lambdas, int n_lambdas) {
     auto m = std::make_unique<Model>();
     m->is_ns = a.is_ns != 0;
     m->lambdas.assign(lambdas, lambdas + n_lambdas);
+    m->n_passbands = g_passbands.size();
     const std::string opacity = pick(kOpacity, 2, a.opacity), bound = pick(kBound, 2, a.boundcond),
                       ic = pick(kIC, 7, a.initialcond), wind = pick(kWind, 12, a.windtype);
     const double Tirr2Tvishot = std::pow(a.Qirr2Qvishot, 0.25);  // cpp/pywrap/pywrap_freddi_evolution.cpp:148
@@ -148,7 +154,7 @@ Model* build(const fb200_args_t& a, const double* lambdas, int n_lambdas) {
 }
 
 int n_cols(const Model& m, int cold_disk) {
-    return FB200_N_BH_COLS + static_cast<int>(m.lambdas.size()) * (cold_disk ? 2 : 1) + (m.is_ns ? FB200_N_NS_COLS : 0);
+    return FB200_N_BH_COLS + static_cast<int>(m.lambdas.size() + m.n_passbands) * (cold_disk ? 2 : 1) + (m.is_ns ? FB200_N_NS_COLS : 0);
 }
 
 // cpp/src/output.cpp:197-214,219-233 and cpp/src/ns/ns_output.cpp:6-19, same evaluation order.
@@ -173,6 +179,10 @@ void fill_row(Model& m, int cold_disk, double* out) {
     for (double lambda : m.lambdas) {
         out[k++] = f->flux(lambda);
         if (cold_disk) out[k++] = f->flux_region<FreddiState::ColdRegion>(lambda);
+    }
+    for (const auto& pb : f->args().flux->passbands) {  // cpp/src/output.cpp:258-271
+        out[k++] = f->flux(pb);
+        if (cold_disk) out[k++] = f->flux_region<FreddiState::ColdRegion>(pb);
     }
     if (m.is_ns) {
         auto* n = m.ns.get();
@@ -214,6 +224,20 @@ int do_step(Model& m) {
 }  // namespace
 
 extern "C" {
+
+// Tabulated passbands for the models created afterwards: n tables, lens[p] samples each, wavelengths [cm] and
+// transmissions back to back.  n = 0 clears.  t_dnu[p] (optional) returns EnergyPassband::t_dnu.
+void ref_set_passbands(int n, const int* lens, const double* lambdas, const double* transmissions, double* t_dnu) {
+    g_passbands.clear();
+    size_t off = 0;
+    for (int p = 0; p < n; ++p) {
+        std::vector<EnergyPassband::PassbandPoint> data;
+        for (int j = 0; j < lens[p]; ++j) data.emplace_back(lambdas[off + j], transmissions[off + j]);
+        off += lens[p];
+        g_passbands.emplace_back("pb" + std::to_string(p), data);
+        if (t_dnu) t_dnu[p] = g_passbands.back().t_dnu;
+    }
+}
 
 void* ref_create(const fb200_args_t* a, const double* lambdas, int n_lambdas, int* err_code, char* err, size_t err_len) {
     try {

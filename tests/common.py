@@ -22,6 +22,13 @@ def golden_files():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, '*.dat')))
 
 
+def golden_passbands(paths):
+    """The `passband=` entries of a golden header (relative to the golden directory) as Passband objects,
+    read the way the reference's CLI does (photon counter)."""
+    from freddi_b200.ensemble import Passband
+    return [Passband.from_file(os.path.join(GOLDEN_DIR, p)) for p in paths]
+
+
 from freddi_b200.workloads import (INI, NS_CI, WOODS, ini_args, config2_args, config3_args, config4_args,  # noqa: F401,E402
                                    config5_args)
 
@@ -39,9 +46,28 @@ class HostEmu:
         self.lib.emu_planck_nu1_nu2.restype = C.c_double
         self.lib.emu_planck_nu1_nu2.argtypes = [C.c_double] * 4 + [C.POINTER(C.c_int)]
 
-    def run(self, args, Nt, Nx, lambdas=(), cold_disk=False):
+    def set_passbands(self, passbands=()):
+        passbands = list(passbands)
+        dp = C.POINTER(C.c_double)
+        self.lib.emu_set_passbands.argtypes = [C.c_int, C.POINTER(C.c_int), dp, dp, dp]
+        lens = (C.c_int * max(1, len(passbands)))(*[pb.lambdas.size for pb in passbands])
+        lam = np.concatenate([pb.lambdas for pb in passbands]) if passbands else np.zeros(1)
+        tr = np.concatenate([pb.transmissions for pb in passbands]) if passbands else np.zeros(1)
+        tdnu = np.zeros(max(1, len(passbands)))
+        rc = self.lib.emu_set_passbands(len(passbands), lens, lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), tdnu.ctypes.data_as(dp))
+        if rc != 0:
+            raise ValueError('emu_set_passbands: {}'.format(rc))
+        return tdnu[:len(passbands)]
+
+    def run(self, args, Nt, Nx, lambdas=(), cold_disk=False, passbands=()):
+        if passbands:
+            self.set_passbands(passbands)
+            try:
+                return self.run(args, Nt, Nx, lambdas, cold_disk)
+            finally:
+                self.set_passbands(())
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
-        ncol = 15 + len(lam) * (2 if cold_disk else 1) + (10 if args.is_ns else 0)
+        ncol = 15 + (len(lam) + self.n_passbands()) * (2 if cold_disk else 1) + (10 if args.is_ns else 0)
         rows = np.full((Nt + 1, ncol), np.nan)
         F = np.full((Nt + 1, Nx), np.nan)
         first = np.full(Nt + 1, -1, dtype=np.int64)
@@ -55,6 +81,9 @@ class HostEmu:
         if n < 0:
             raise RuntimeError('[{}] {}'.format(n, err.value.decode()))
         return dict(rows=rows, rows_valid=int(n), F=F, first=first, last=last, picard=pic)
+
+    def n_passbands(self):
+        return int(self.lib.emu_n_passbands())
 
     def planck(self, T, nu1, nu2, tol=1e-4):
         n = C.c_int()

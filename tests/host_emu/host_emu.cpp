@@ -55,8 +55,25 @@ struct HostEx {
 }  // namespace
 
 static long long g_last_lx_trials = 0;
+static std::vector<PassbandTable> g_passbands;  // set by emu_set_passbands for the runs that follow
 
 extern "C" {
+
+// Same contract as ref_set_passbands (oracle/ref_driver.cpp); returns 0 or the resolver's error code.
+int emu_set_passbands(int n, const int* lens, const double* lambdas, const double* transmissions, double* t_dnu) {
+    g_passbands.clear();
+    size_t off = 0;
+    for (int p = 0; p < n; ++p) {
+        PassbandTable t;
+        std::string msg;
+        const int rc = prepare_passband(lambdas + off, transmissions + off, lens[p], t, msg);
+        if (rc != FB200_OK) { g_passbands.clear(); return rc; }
+        off += lens[p];
+        if (t_dnu) t_dnu[p] = t.t_dnu;
+        g_passbands.push_back(t);
+    }
+    return 0;
+}
 
 // Same contract as ref_run (oracle/ref_driver.cpp): returns the number of valid rows, <0 on a resolve error.
 int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int cold_disk, double* rows, int64_t rows_cap,
@@ -75,7 +92,19 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     cfg.cold_disk = cold_disk;
     cfg.compute_lx = 1;
     cfg.lx_prune = 1;
-    cfg.n_cols = FB200_N_BH_COLS + n_lambdas * (cold_disk ? 2 : 1) + (M.is_ns ? FB200_N_NS_COLS : 0);
+    const int npb = int(g_passbands.size());
+    std::vector<double> pb_a, pb_w;
+    cfg.n_passbands = npb;
+    for (int p = 0; p < npb; ++p) {
+        cfg.pb_off[p] = int(pb_a.size());
+        pb_a.insert(pb_a.end(), g_passbands[p].a.begin(), g_passbands[p].a.end());
+        pb_w.insert(pb_w.end(), g_passbands[p].w.begin(), g_passbands[p].w.end());
+        cfg.pb_tdnu[p] = g_passbands[p].t_dnu;
+    }
+    for (int p = npb; p < FB200_MAX_PASSBANDS + 2; ++p) cfg.pb_off[p] = int(pb_a.size());
+    cfg.pb_a = pb_a.data();
+    cfg.pb_w = pb_w.data();
+    cfg.n_cols = FB200_N_BH_COLS + (n_lambdas + npb) * (cold_disk ? 2 : 1) + (M.is_ns ? FB200_N_NS_COLS : 0);
     cfg.n_rows = M.Nt + 1;
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
 
@@ -133,6 +162,8 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     g_last_lx_trials = eng.st.lx_trials;
     return r;
 }
+
+int emu_n_passbands() { return int(g_passbands.size()); }
 
 long long emu_last_lx_trials() { return g_last_lx_trials; }
 

@@ -10,9 +10,9 @@ from tests import common as cm
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(args_list, lambdas=(), cold_disk=False, record_F=True):
+def run_gpu(args_list, lambdas=(), cold_disk=False, record_F=True, passbands=()):
     from freddi_b200 import Ensemble
-    with Ensemble(args_list, lambdas=lambdas, cold_disk=cold_disk, record_F=record_F) as ens:
+    with Ensemble(args_list, lambdas=lambdas, cold_disk=cold_disk, record_F=record_F, passbands=passbands) as ens:
         ens.evolve(-1)
         out = dict(rows=ens.rows(), columns=ens.columns)
         out['status'], out['valid'], out['picard'] = ens.status()
@@ -41,12 +41,16 @@ def check_model(g, k, r, what, snapshot_rows=None):
 @pytest.mark.parametrize('path', cm.golden_files(), ids=lambda p: p.split('/')[-1])
 def test_golden_configurations(ref, path):
     """The reference's 8 regression configurations (python/test/data/*.dat): every row, F at every row."""
-    kw, lam, _pb, data = pyoracle.load_golden(path)
+    kw, lam, pb, data = pyoracle.load_golden(path)
     from freddi_b200.args import make_args
     a = make_args(False, **kw)
-    g = run_gpu([a], lam)
-    r = ref.run(a, lam)
+    passbands = cm.golden_passbands(pb)
+    g = run_gpu([a], lam, passbands=passbands)
+    assert g['columns'] == list(data.dtype.names)
+    r = ref.run(a, lam, passbands=passbands)
     check_model(g, 0, r, path.split('/')[-1])
+    for pbn in passbands:  # the golden's own passband columns (6 printed digits)
+        np.testing.assert_allclose(g['rows'][0, :len(data), g['columns'].index('Fnu' + pbn.name)], data['Fnu' + pbn.name], rtol=6e-6)
     # and the reference's own criterion against the golden file (python/test/test_regression.py:64-98)
     n = min(len(data), r['rows_valid'])
     for col in ('Mdot', 'Mdisk', 'Sigmaout', 'Teffout', 'Tirrout', 'Lx', 'Fx'):
@@ -118,6 +122,24 @@ def test_edge_cases(ref, name):
     a = cm.ini_args(is_ns, **kw)
     g = run_gpu([a], lam, cold_disk=cold)
     check_model(g, 0, ref.run(a, lam, cold_disk=cold), name)
+
+
+def test_passbands_with_cold_disk_and_neutron_star(ref):
+    """Fnu<passband>[_cold] columns (cpp/src/output.cpp:258-271) in a sweep with a shrinking hot zone, and ahead of the NS columns."""
+    pbs = cm.golden_passbands(['passbands/Swift_V.dat', 'passbands/Swift_B.dat'])
+    base = dict(initialcond='quasistat', Thot=1e4, Cirrcold=1e-4, h2rcold=0.03, irrindex=0.5, irrindexcold=0.2, boundcond='Tirr',
+                angulardistdisk='plane', inclination=30, time=25)
+    args = [cm.ini_args(False, **dict(base, Cirr=c, alpha=al)) for c in (1e-4, 3e-4) for al in (0.25, 0.7)]
+    g = run_gpu(args, cm.LAM3[:2], cold_disk=True, passbands=pbs)
+    assert g['columns'][15:] == ['Fnu0', 'Fnu0_cold', 'Fnu1', 'Fnu1_cold', 'FnuSwift_V', 'FnuSwift_V_cold', 'FnuSwift_B', 'FnuSwift_B_cold']
+    for k, a in enumerate(args):
+        r = ref.run(a, cm.LAM3[:2], cold_disk=True, passbands=pbs)
+        check_model(g, k, r, 'passbands_cold[{}]'.format(k), snapshot_rows=(0, 50, 100))
+    assert (g['rows'][:, -1, -1] > 0).all()  # the cold zone exists and shines in Swift_B
+    a = cm.ini_args(True, **dict(cm.NS_CI, time=10))
+    g = run_gpu([a], (), passbands=pbs[:1])
+    assert g['columns'][15:17] == ['FnuSwift_V', 'Rin']
+    check_model(g, 0, ref.run(a, (), passbands=pbs[:1]), 'passbands_ns')
 
 
 def test_mixed_lengths_and_incremental_evolve(ref):

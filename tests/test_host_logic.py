@@ -21,7 +21,7 @@ def test_c_abi_exports_every_declared_symbol(built):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.fb200_abi_version() == 1
+    assert _lib.lib.fb200_abi_version() == 2
 
 
 def test_args_struct_layout_matches_the_header(built):
@@ -115,10 +115,10 @@ def test_resolver_error_classes(ref, built, kw, exc):
     assert (ei.value.code == -1) == (exc is ValueError)
 
 
-def emu_vs_ref(ref, emu, a, lam=(), cold=False):
-    r = ref.run(a, lam, cold_disk=cold)
-    e = emu.run(a, r['Nt'], r['Nx'], lam, cold)
-    names = pyoracle.column_names(len(lam), cold, bool(a.is_ns))
+def emu_vs_ref(ref, emu, a, lam=(), cold=False, passbands=()):
+    r = ref.run(a, lam, cold_disk=cold, passbands=passbands)
+    e = emu.run(a, r['Nt'], r['Nx'], lam, cold, passbands=passbands)
+    names = pyoracle.column_names(len(lam), cold, bool(a.is_ns), [p.name for p in passbands])
     n = r['rows_valid']
     assert e['rows_valid'] == n
     np.testing.assert_array_equal(e['picard'][:n], r['picard'][:n])
@@ -132,8 +132,24 @@ def emu_vs_ref(ref, emu, a, lam=(), cold=False):
 
 @pytest.mark.parametrize('path', cm.golden_files(), ids=os.path.basename)
 def test_engine_host_policy_matches_oracle_on_golden_configurations(ref, emu, path):
-    kw, lam, _pb, _data = pyoracle.load_golden(path)
-    emu_vs_ref(ref, emu, make_args(False, **kw), lam)
+    kw, lam, pb, _data = pyoracle.load_golden(path)
+    emu_vs_ref(ref, emu, make_args(False, **kw), lam, passbands=cm.golden_passbands(pb))
+
+
+def test_passbands_hot_and_cold_regions(ref, emu):
+    """Fnu<passband> and Fnu<passband>_cold (cpp/src/output.cpp:258-271) next to the wavelength columns, NS rows after
+    them; t_dnu of the prepared table equals EnergyPassband::t_dnu bit for bit."""
+    pbs = cm.golden_passbands(['passbands/Swift_V.dat', 'passbands/Swift_B.dat'])
+    assert [p.name for p in pbs] == ['Swift_V', 'Swift_B']
+    np.testing.assert_array_equal(emu.set_passbands(pbs), ref.set_passbands(pbs))
+    emu.set_passbands(())
+    ref.set_passbands(())
+    kw = dict(initialcond='quasistat', Thot=1e4, Cirr=3e-4, Cirrcold=1e-4, h2rcold=0.03, irrindex=0.5, irrindexcold=0.2,
+              boundcond='Tirr', angulardistdisk='plane', inclination=30, time=25)
+    r, e = emu_vs_ref(ref, emu, cm.ini_args(False, **kw), cm.LAM3[:1], True, pbs)
+    assert r['rows'].shape[1] == 15 + 2 + 4
+    assert r['last'][r['rows_valid'] - 1] < r['Nx'] - 2 and r['rows'][r['rows_valid'] - 1, -1] > 0  # a cold zone exists and shines
+    emu_vs_ref(ref, emu, cm.ini_args(True, **dict(cm.NS_CI, time=5)), (), False, pbs[:1])
 
 
 ENGINE_CASES = {

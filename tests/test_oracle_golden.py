@@ -14,14 +14,16 @@ from freddi_b200.args import make_args
 
 @pytest.mark.parametrize('path', cm.golden_files(), ids=os.path.basename)
 def test_reference_build_reproduces_golden_light_curves(ref, path):
-    kw, lam, _pb, data = pyoracle.load_golden(path)
+    kw, lam, pb, data = pyoracle.load_golden(path)
     a = make_args(False, **kw)
-    r = ref.run(a, lam, snapshots=False)
+    passbands = cm.golden_passbands(pb)
+    r = ref.run(a, lam, snapshots=False, passbands=passbands)
     assert r['rows_valid'] == len(data)  # "Number of lines"
-    names = pyoracle.column_names(len(lam))
+    names = pyoracle.column_names(len(lam), passbands=[p.name for p in passbands])
+    assert names == list(data.dtype.names)
     np.testing.assert_allclose(r['rows'][:, 0], data['t'], rtol=1e-12)
     for col in ['Mdot', 'Mdisk', 'Rhot', 'Sigmaout', 'Kirrout', 'H2R', 'Teffout', 'Tirrout', 'Qirr2Qvisout', 'TphXmax', 'Lx', 'Lbol',
-                'Fx', 'Fbol'] + ['Fnu{}'.format(k) for k in range(len(lam))]:
+                'Fx', 'Fbol'] + ['Fnu{}'.format(k) for k in range(len(lam))] + ['Fnu' + p.name for p in passbands]:
         v = r['rows'][:, names.index(col)]
         g = data[col]
         # 6 significant digits in the file: half a unit of the last printed digit

@@ -135,7 +135,7 @@ def test_passbands_with_cold_disk_and_neutron_star(ref):
     for k, a in enumerate(args):
         r = ref.run(a, cm.LAM3[:2], cold_disk=True, passbands=pbs)
         check_model(g, k, r, 'passbands_cold[{}]'.format(k), snapshot_rows=(0, 50, 100))
-    assert (g['rows'][:, -1, -1] > 0).all()  # the cold zone exists and shines in Swift_B
+    assert all(g['rows'][k, g['valid'][k] - 1, -1] > 0 for k in range(len(args)))  # the cold zone exists and shines in Swift_B
     a = cm.ini_args(True, **dict(cm.NS_CI, time=10))
     g = run_gpu([a], (), passbands=pbs[:1])
     assert g['columns'][15:17] == ['FnuSwift_V', 'Rin']

@@ -453,6 +453,10 @@ FB_HD int pidx(int i) { return i ^ ((i >> 4) & 7); }
 
 FB_HD bool fb_isfinite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 FB_HD bool fb_isnan(double x) { return x != x; }
+// The NaN an invalid operation produces on the reference's platform (x86-64 SSE2: the default QNaN has the sign bit
+// set; glibc's pow(negative, 0.25) returns (x - x) / (x - x)).  The value is the same NaN either way; the sign only
+// shows in text output ("-nan"), which the freddi.dat writer reproduces byte for byte.
+#define FB_NAN_INVALID (-NAN)
 
 // ------------------------------------------------------------------------------------------------
 // The engine.  Execution policy `Ex` provides:
@@ -769,7 +773,7 @@ struct DiscEngine {
             if (i >= first && i <= last) {
                 double x = S.c1[i] * F_first;
                 const double g = KM * S.Gb[i];  // = T_GR^4 sigma; T_GR = pow(., 0.25) is NaN for a negative argument
-                x += (g < 0.) ? NAN : g;
+                x += (g < 0.) ? FB_NAN_INVALID : g;
                 T = M.colourfactor * pow025(x / FB_SIGMA_SB);
                 // weight of this ring in the radial trapezoid of the hot zone: 2 pi R_i (R_{i+1} - R_{i-1}) (ends one-sided)
                 if (first < last) {
@@ -792,7 +796,7 @@ struct DiscEngine {
             return -INFINITY;
         });
         double TphXmax = TphX_hottest;
-        if (fb_isnan(S.TphX[first])) TphXmax = NAN;
+        if (fb_isnan(S.TphX[first])) TphXmax = S.TphX[first];  // max_element returns the first element
         // Rings whose X-ray band emission is below exp(-FB200_LX_PRUNE) = 4e-44 of the hottest ring's are not
         // integrated: B_nu(T_i)/B_nu(T_hot) <= exp(-(a_i - a_hot)) for every nu of the band (a = h nu1 / k T), and
         // Lx >= the hottest ring's share, so even with an area ratio of 1e12 the omitted rings change Lx by

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
                         const double KM = 3. * fabs(sc.Mdot_plain) * p6(FB_C_LIGHT) / (8. * FB_PI * p2(M.GM));
                         double x = S.c1[i] * S.F[first];
                         const double g = KM * S.Gb[i];
-                        x += (g < 0.) ? NAN : g;
+                        x += (g < 0.) ? FB_NAN_INVALID : g;
                         v = M.colourfactor * pow025(x / FB_SIGMA_SB);
                     }
                     break;

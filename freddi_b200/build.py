@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['capi.cu', 'evolve.cu', 'fields.cu', 'resolve.cpp']
+SOURCES = ['capi.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'resolve.cpp']
 HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp',
            os.path.join('..', '..', 'include', 'freddi_b200.h')]
 OUT = os.path.join(HERE, 'libfreddi_b200.so')

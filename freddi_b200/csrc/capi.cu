@@ -16,6 +16,19 @@
 
 using namespace fb200;
 
+// the large-grid build of the kernels (evolve_big.cu, fields_big.cu)
+extern "C" {
+size_t fb200_big_evolve_smem_bytes();
+size_t fb200_big_evolve_scratch_doubles_per_cta();
+int fb200_big_evolve_ctas_per_sm();
+int fb200_big_evolve_resident_ctas_per_sm();
+cudaError_t fb200_big_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+cudaError_t fb200_big_launch_field(const void* E, int field, long long row, double* out, cudaStream_t stream);
+cudaError_t fb200_big_launch_flux(const void* E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
+                                  cudaStream_t stream);
+cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
+}
+
 namespace {
 thread_local std::string g_err;
 int set_err(int code, const std::string& msg) {
@@ -40,6 +53,7 @@ struct fb200_ensemble {
     size_t n = 0;
     int Nx = 0, n_rows = 0, n_cols = 0, sm_count = 0, max_Nt = 0, chunk_steps = 25;
     bool is_ns = false;
+    bool big = false;  // Nx > 1024: the large-grid build of the kernels
     fb200_config_t cfg{};
     std::vector<fb200_model_info_t> info;
     EnsembleDev dev{};
@@ -228,7 +242,9 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, e->device) != cudaSuccess) return guard_fail(set_err(FB200_ERR_CUDA, "cudaGetDeviceProperties"));
     e->sm_count = prop.multiProcessorCount;
-    if (size_t(prop.sharedMemPerBlockOptin) < evolve_smem_bytes())
+    e->big = Nx > 1024;
+    const bool big = e->big;
+    if (size_t(prop.sharedMemPerBlockOptin) < (big ? fb200_big_evolve_smem_bytes() : evolve_smem_bytes()))
         return guard_fail(set_err(FB200_ERR_UNSUPPORTED, "device offers too little shared memory per block for the sm_100a kernels"));
 #define FB_TRY(x) do { int _rc = (x); if (_rc != FB200_OK) return guard_fail(_rc); } while (0)
 #define FB_TRYC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return guard_fail(cuda_fail(_e, #call)); } while (0)
@@ -284,16 +300,20 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     FB_TRY(dev_alloc(e, &D.queue, 4));
     {
         // the chunked scheduler lets a CTA wait for another one: never launch more CTAs than can be resident
-        int resident = evolve_resident_ctas_per_sm();
+        int resident = big ? fb200_big_evolve_resident_ctas_per_sm() : evolve_resident_ctas_per_sm();
         if (resident < 1) return guard_fail(set_err(FB200_ERR_UNSUPPORTED, "the evolve kernel does not fit on this device"));
-        if (resident > evolve_ctas_per_sm()) resident = evolve_ctas_per_sm();
+        const int designed = big ? fb200_big_evolve_ctas_per_sm() : evolve_ctas_per_sm();
+        if (resident > designed) resident = designed;
+        if (big && size_t(e->sm_count) * resident > n_models) {  // 3 MB of scratch per CTA: no more CTAs than models
+            resident = int((n_models + e->sm_count - 1) / e->sm_count);
+        }
         D.max_ctas = e->sm_count * resident;
     }
     FB_TRY(dev_alloc(e, &D.progress, n_models));
     if (getenv("FB200_DEBUG"))
         fprintf(stderr, "[fb200] smem/CTA %zu B, CTAs/SM designed %d, resident %d, SMs %d\n", evolve_smem_bytes(), evolve_ctas_per_sm(),
                 evolve_resident_ctas_per_sm(), e->sm_count);
-    FB_TRY(dev_alloc(e, &D.cta_scratch, size_t(D.max_ctas) * evolve_scratch_doubles_per_cta()));
+    FB_TRY(dev_alloc(e, &D.cta_scratch, size_t(D.max_ctas) * (big ? fb200_big_evolve_scratch_doubles_per_cta() : evolve_scratch_doubles_per_cta())));
     FB_TRY(dev_alloc(e, &D.prof, 8));
     FB_TRYC(cudaMemset(D.prof, 0, 8 * sizeof(long long)));
     {
@@ -427,7 +447,7 @@ int fb200_ensemble_evolve_async(fb200_ensemble_t* e, int64_t n_steps) {
     }
     FB_CUDA(cudaEventRecord(e->ev0, e->stream));
     const int n_ctas = int(std::min<size_t>(e->n, size_t(e->dev.max_ctas)));
-    cudaError_t ce = launch_evolve(e->dev, n_ctas, e->stream);
+    cudaError_t ce = e->big ? fb200_big_launch_evolve(&e->dev, n_ctas, e->stream) : launch_evolve(e->dev, n_ctas, e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_evolve_kernel launch");
     FB_CUDA(cudaEventRecord(e->ev1, e->stream));
     e->last_launches = 1;
@@ -568,7 +588,8 @@ int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* ou
     if (rc != FB200_OK) return rc;
     rc = select_device(e);
     if (rc != FB200_OK) return rc;
-    cudaError_t ce = launch_field(e->dev, field, row, e->scratch, e->stream);
+    cudaError_t ce = e->big ? fb200_big_launch_field(&e->dev, field, row, e->scratch, e->stream)
+                            : launch_field(e->dev, field, row, e->scratch, e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_field_kernel launch");
     FB_CUDA(cudaMemcpyAsync(out, e->scratch, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FB_CUDA(cudaStreamSynchronize(e->stream));
@@ -590,7 +611,9 @@ int fb200_ensemble_flux(fb200_ensemble_t* e, int region, int64_t row, const doub
     cudaError_t ce = cudaMalloc(&d_o, e->n * n_lambdas * sizeof(double));
     if (ce != cudaSuccess) { cudaFree(d_l); return cuda_fail(ce, "cudaMalloc"); }
     ce = cudaMemcpyAsync(d_l, lambdas, n_lambdas * sizeof(double), cudaMemcpyHostToDevice, e->stream);
-    if (ce == cudaSuccess) ce = launch_flux(e->dev, region, row, d_l, int(n_lambdas), d_o, e->stream);
+    if (ce == cudaSuccess)
+        ce = e->big ? fb200_big_launch_flux(&e->dev, region, row, d_l, int(n_lambdas), d_o, e->stream)
+                    : launch_flux(e->dev, region, row, d_l, int(n_lambdas), d_o, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, e->n * n_lambdas * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     cudaFree(d_l);
@@ -606,7 +629,8 @@ int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size
     if (rc != FB200_OK) return rc;
     rc = select_device(e);
     if (rc != FB200_OK) return rc;
-    cudaError_t ce = launch_mdot_wind(e->dev, row, e->scratch, e->stream);
+    cudaError_t ce = e->big ? fb200_big_launch_mdot_wind(&e->dev, row, e->scratch, e->stream)
+                            : launch_mdot_wind(e->dev, row, e->scratch, e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_mdot_wind_kernel launch");
     FB_CUDA(cudaMemcpyAsync(out, e->scratch, e->n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FB_CUDA(cudaStreamSynchronize(e->stream));

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 
     GpuEx ex;
     ex.init();
+    ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
 #ifdef FB_PROFILE
     for (int p = 0; p < 8; ++p) ex.prof[p] = 0;
@@ -129,3 +130,17 @@ cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream)
 }
 
 }  // namespace fb200
+
+#ifdef FB_BIG
+// The large-grid build is a second compilation of this file (evolve_big.cu) in its own namespace; capi.cu reaches it
+// through these plain-C names.  EnsembleDev has the same layout in both builds (nothing in it depends on FB200_NX_MAX).
+extern "C" {
+size_t fb200_big_evolve_smem_bytes() { return fb200::evolve_smem_bytes(); }
+size_t fb200_big_evolve_scratch_doubles_per_cta() { return fb200::evolve_scratch_doubles_per_cta(); }
+int fb200_big_evolve_ctas_per_sm() { return fb200::evolve_ctas_per_sm(); }
+int fb200_big_evolve_resident_ctas_per_sm() { return fb200::evolve_resident_ctas_per_sm(); }
+cudaError_t fb200_big_launch_evolve(const void* E, int n_ctas, cudaStream_t stream) {
+    return fb200::launch_evolve(*static_cast<const fb200::EnsembleDev*>(E), n_ctas, stream);
+}
+}
+#endif

@@ -12,7 +12,14 @@
 
 #include <stdint.h>
 
-#define FB200_NX_MAX 1024 /* one radial point per thread of a 1024-thread CTA */
+/* Radial points a kernel build handles.  The product library holds two builds of the same engine: the shared-memory
+ * resident one (1024: every BASELINE configuration) and, compiled with -DFB_BIG, a large-grid one whose per-point
+ * arrays live in an L2-resident global scratch slot (FB200_NX_LIMIT: the reference's analytical tests run Nx = 10^4,
+ * python/test/test_analytical.py:84,113,216). */
+#ifndef FB200_NX_MAX
+#define FB200_NX_MAX 1024
+#endif
+#define FB200_NX_LIMIT 16384
 
 /* physical constants: cpp/include/gsl_const_cgsm.h:24-38,107,113-114 (GSL 2009 CGSM values) */
 #define FB_C_LIGHT 2.99792458e10

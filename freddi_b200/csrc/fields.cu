@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
     GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
     ex.init();
+    ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
     GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
     ex.init();
+    ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
     GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
     ex.init();
+    ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
     for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
@@ -305,3 +308,18 @@ cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, c
 }
 
 }  // namespace fb200
+
+#ifdef FB_BIG
+extern "C" {  // see evolve.cu
+cudaError_t fb200_big_launch_field(const void* E, int field, long long row, double* out, cudaStream_t stream) {
+    return fb200::launch_field(*static_cast<const fb200::EnsembleDev*>(E), field, row, out, stream);
+}
+cudaError_t fb200_big_launch_flux(const void* E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
+                                  cudaStream_t stream) {
+    return fb200::launch_flux(*static_cast<const fb200::EnsembleDev*>(E), region, row, lambdas_dev, n_lambdas, out, stream);
+}
+cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream) {
+    return fb200::launch_mdot_wind(*static_cast<const fb200::EnsembleDev*>(E), row, out, stream);
+}
+}
+#endif

@@ -29,10 +29,14 @@ namespace fb200 {
 #define FB_PRAGMA(x) _Pragma(#x)
 #define FB_UNROLL(n) FB_PRAGMA(unroll n)
 constexpr int kNT = FB_NT;                 // threads per CTA
-constexpr int kPPT = FB200_NX_MAX / kNT;   // radial points per thread
+constexpr int kPPT = FB200_NX_MAX / kNT;   // radial points per thread (FB_BIG builds: the upper bound, see GpuEx::n_slots)
 constexpr int kNW = kNT / 32;              // warps per CTA
 constexpr int kCtasPerSm = FB_CTAS_PER_SM;
 static_assert(kNT * kPPT == FB200_NX_MAX && kNW >= 1 && kNW <= 32, "FB_NT must divide FB200_NX_MAX");
+// FB_BIG: the large-grid build (Nx up to FB200_NX_MAX = 16384).  Same engine, same kernels; the per-point arrays do not
+// fit into shared memory (22 arrays x 128 KB), so they all live in the CTA's global scratch slot (L2-resident for the
+// small ensembles such grids are used with) and every per-thread slot loop has a run-time trip count ceil(Nx / kNT).
+// Shared memory keeps the exp table, the reduction scratch, the model constants and the output configuration.
 
 // The CTA's dynamic shared memory.  Every kernel of this library declares the same window; all array
 // accessors below index it with compile-time offsets, so the compiler emits LDS/STS with immediate offsets.
@@ -49,7 +53,11 @@ struct SmemLayout {
     static constexpr int o_F = o_rr1 + NR, o_hn = o_F + N, o_cc = o_hn + N, o_frac = o_cc + N, o_K = o_frac + N;
     static constexpr int o_l = o_K + N, o_u = o_l + NP, o_d = o_u + NP, o_rhs = o_d + NP;
     static constexpr int o_pa = o_rhs + NP, o_pc = o_pa + NP, o_pg = o_pc + NP;
+#ifdef FB_BIG
+    static constexpr int kPointDoubles = 64;  // only the exp table; o_lu0..o_pg above are unused
+#else
     static constexpr int kPointDoubles = o_pg + NP;
+#endif
     // reduction scratch
     static constexpr int o_redA = kPointDoubles, o_redQ = o_redA + 2 * 32, o_sums = o_redQ + kNW * FB200_MAXQ;
     static constexpr int o_scal = o_sums + FB200_MAXQ, o_lampref = o_scal + 8, o_model = o_lampref + FB200_MAX_LAMBDAS;
@@ -58,8 +66,14 @@ struct SmemLayout {
     static constexpr int kCfgDoubles = int((sizeof(OutCfg) + 7) / 8);
     static constexpr int kTotalDoubles = o_cfg + kCfgDoubles + 2;
     static constexpr size_t bytes() { return sizeof(double) * size_t(kTotalDoubles); }
+#ifdef FB_BIG
+    // R ca cb cc frac c1 hm175 hotR Gb | F hn s_cc s_frac s_K | s_l s_u s_d s_rhs p_a p_c p_g | lu0 lu1 (2 NR each) rr0 rr1
+    static constexpr int kScratchArrays = 21;
+    static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX + 6 * size_t(NR);
+#else
     static constexpr int kScratchArrays = 9;
     static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX;
+#endif
     static constexpr size_t scratch_doubles_per_cta() { return kScratchDoublesPerCta; }
 };
 
@@ -75,6 +89,26 @@ struct ShDyn2 {
     __device__ __forceinline__ double2& operator[](int i) const { return reinterpret_cast<double2*>(fb_smem + off)[i]; }
 };
 
+#ifdef FB_BIG
+typedef PtrArrays GpuArrays;  // every array a plain pointer into the CTA's global scratch slot
+
+__device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double* h_global) {
+    GpuArrays S;
+    const size_t N = FB200_NX_MAX, NR = FB200_NRED_MAX;
+    double* p = gscratch;
+    auto take = [&](size_t n) { double* q = p; p += n; return q; };
+    S.h = h_global;
+    S.R = take(N); S.ca = take(N); S.cb = take(N); S.cc = take(N); S.frac = take(N);
+    S.c1 = take(N); S.hm175 = take(N); S.hotR = take(N); S.Gb = take(N);
+    S.F = take(N); S.hn = take(N); S.s_cc = take(N); S.s_frac = take(N); S.s_K = take(N);
+    S.s_l = take(N); S.s_u = take(N); S.s_d = take(N); S.s_rhs = take(N); S.p_a = take(N); S.p_c = take(N); S.p_g = take(N);
+    S.lu[0] = reinterpret_cast<double2*>(take(2 * NR)); S.lu[1] = reinterpret_cast<double2*>(take(2 * NR));
+    S.rr[0] = take(NR); S.rr[1] = take(NR);
+    S.Tph = S.s_l; S.Tirr = S.s_u; S.Sigma = S.s_d; S.Tvis = S.s_rhs; S.TphX = S.p_a; S.aux = S.p_c; S.wq = S.p_g;
+    return S;
+}
+
+#else
 struct GpuArrays {
     typedef SmemLayout L;
     const double* h;                                   // the ensemble's grid array of this model (global)
@@ -99,6 +133,8 @@ __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double
     return S;
 }
 
+#endif
+
 __device__ __forceinline__ fb200_model_dev_t* smem_model() { return reinterpret_cast<fb200_model_dev_t*>(fb_smem + SmemLayout::o_model); }
 __device__ __forceinline__ OutCfg* smem_cfg() { return reinterpret_cast<OutCfg*>(fb_smem + SmemLayout::o_cfg); }
 
@@ -110,20 +146,33 @@ struct GpuEx {
     // per-model global arrays (already offset to this model), null when absent
     const double *gA, *gB, *gCs, *gFm, *gdFm;
 
+#ifdef FB_BIG
+    int n_slots;  // ceil(Nx / kNT)
+    __device__ __forceinline__ void set_nx(int Nx) { n_slots = (Nx + kNT - 1) / kNT; }
+    __device__ __forceinline__ int slots() const { return n_slots; }
+#else
+    __device__ __forceinline__ void set_nx(int) {}
+    __device__ __forceinline__ static constexpr int slots() { return kPPT; }
+#endif
     __device__ __forceinline__ void init() {
         tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; flip = 0;
         gA = gB = gCs = gFm = gdFm = nullptr;
+        set_nx(FB200_NX_MAX);
     }
     // f(i, k): point index i, register slot k (a compile-time constant after unrolling)
     // The slot loops are deliberately NOT unrolled: the kernel is large and unrolling every per-point lambda
     // kPPT times costs more in instruction-cache misses than it gains in ILP (profiles/r01_v3_ncu_full_metrics.txt).
     template <class F> __device__ __forceinline__ void points(F&& f) {
         FB_UNROLL(FB_UNROLL_POINTS)
-        for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
+        for (int k = 0; k < slots(); ++k) f(tid + k * kNT, k);
     }
     // one thread per block / per reduced unknown of the tridiagonal solve
     template <class F> __device__ __forceinline__ void blocks(int n, F&& f) {
+#ifdef FB_BIG
+        for (int b = tid; b < n; b += kNT) f(b);
+#else
         if (tid < n) f(tid);
+#endif
     }
     template <class F> __device__ __forceinline__ void reduced(int n, F&& f) {
         for (int q = tid; q < n; q += kNT) f(q);
@@ -153,7 +202,7 @@ struct GpuEx {
     template <class F> __device__ __forceinline__ double reduce_max(F&& f) {
         double v = -INFINITY;
         FB_UNROLL(FB_UNROLL_MAX)
-        for (int k = 0; k < kPPT; ++k) {
+        for (int k = 0; k < slots(); ++k) {
             const double x = f(tid + k * kNT, k);
             v = fmax(v, x);  // fmax skips a NaN like `if (x > max)` does
         }
@@ -171,7 +220,7 @@ struct GpuEx {
     template <class F> __device__ __forceinline__ int reduce_max_int(F&& f) {
         int v = 0x80000000;
 #pragma unroll 1
-        for (int k = 0; k < kPPT; ++k) v = max(v, f(tid + k * kNT, k));
+        for (int k = 0; k < slots(); ++k) v = max(v, f(tid + k * kNT, k));
         v = __reduce_max_sync(0xffffffffu, v);
         int* row = reinterpret_cast<int*>(fb_smem + L::o_redA + flip * 32);
         flip ^= 1;
@@ -182,7 +231,7 @@ struct GpuEx {
     template <class F> __device__ __forceinline__ int reduce_min_int(F&& f) {
         int v = 0x7fffffff;
 #pragma unroll 1
-        for (int k = 0; k < kPPT; ++k) v = min(v, f(tid + k * kNT, k));
+        for (int k = 0; k < slots(); ++k) v = min(v, f(tid + k * kNT, k));
         v = __reduce_min_sync(0xffffffffu, v);
         int* row = reinterpret_cast<int*>(fb_smem + L::o_redA + flip * 32);
         flip ^= 1;
@@ -195,7 +244,7 @@ struct GpuEx {
         for (int q = 0; q < nq; ++q) {
             double v = 0.;
             FB_UNROLL(FB_UNROLL_SUMS)
-            for (int k = 0; k < kPPT; ++k) v += f(tid + k * kNT, k, q);
+            for (int k = 0; k < slots(); ++k) v += f(tid + k * kNT, k, q);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) fb_smem[L::o_redQ + warp * FB200_MAXQ + q] = v;
@@ -246,8 +295,11 @@ __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, cons
     }
     const int Nx = E.Nx;
     const size_t off = size_t(model) * Nx;
+    ex.set_nx(Nx);
+#ifndef FB_BIG
 #pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
+#endif
+    for (int k = 0; k < ex.slots(); ++k) {
         const int i = tid + k * kNT;
         S.F[i] = (i < Nx) ? __ldcg(F_src + i) : 0.;  // L2: another SM may have written it in the previous round
         if (i >= Nx) S.R[i] = 0.;

@@ -393,8 +393,8 @@ int resolve_impl(const fb200_args_t& a, Resolved& out) {
     // ---- CalculationArguments, cpp/include/arguments.hpp:323-332 ----
     const double tau = opt(a.tau) ? a.tau : a.time / 200;
     const unsigned Nx = a.Nx;
-    if (Nx < 4 || Nx > FB200_NX_MAX) {
-        fail(FB200_ERR_UNSUPPORTED, "Nx must be in [4, " + std::to_string(FB200_NX_MAX) + "] for the sm_100a kernels");
+    if (Nx < 4 || Nx > FB200_NX_LIMIT) {
+        fail(FB200_ERR_UNSUPPORTED, "Nx must be in [4, " + std::to_string(FB200_NX_LIMIT) + "] for the sm_100a kernels");
     }
 
     // ---- FreddiState::DiskStructure, cpp/src/freddi_state.cpp:13-53 ----

@@ -36,8 +36,8 @@ from freddi_b200.workloads import (INI, NS_CI, WOODS, ini_args, config2_args, co
 class HostEmu:
     """tests/host_emu/libhost_emu.so: DiscEngine under the sequential host policy (test infrastructure)."""
 
-    def __init__(self):
-        self.lib = C.CDLL(EMU_SO)
+    def __init__(self, big=False):
+        self.lib = C.CDLL(EMU_SO.replace('libhost_emu.so', 'libhost_emu_big.so') if big else EMU_SO)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
         self.lib.emu_run.restype = C.c_int64
         self.lib.emu_run.argtypes = [C.POINTER(FB200Args), dp, C.c_int, C.c_int, dp, C.c_int64, dp, ip, ip, ip, C.c_char_p,

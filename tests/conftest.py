@@ -30,3 +30,10 @@ def ref(built):
 def emu(built):
     from tests.common import HostEmu
     return HostEmu()
+
+
+@pytest.fixture(scope='session')
+def emu_big(built):
+    """DiscEngine under the host policy compiled for the large-grid build (Nx up to 16384)."""
+    from tests.common import HostEmu
+    return HostEmu(big=True)

@@ -206,3 +206,12 @@ def test_planck_band_integral_controller(emu):
         assert abs(v / exact - 1) < 2e-3, (T, v, exact)
         assert v > prev and n >= 4
         prev = v
+
+
+def test_large_grid_engine_build_matches_oracle(ref, emu_big):
+    """DiscEngine compiled for the large-grid build (FB200_NX_MAX = 16384: more blocks than threads in the solver's block
+    elimination, run-time slot counts) against the oracle at Nx = 2500: irradiated shrinking disc and a static wind on a linear grid."""
+    emu_vs_ref(ref, emu_big, cm.ini_args(False, initialcond='quasistat', Thot=1e4, boundcond='Tirr', angulardistdisk='isotropic',
+                                         Cirr=3e-4, Nx=2500, time=6), cm.LAM3)
+    emu_vs_ref(ref, emu_big, cm.ini_args(False, windtype='__testA__', windparams={'kA': 1.0}, Mdotout=1e18, initialcond='sineF',
+                                         Mdot0=1e18, F0=None, Nx=2500, gridscale='linear', time=20, tau=1), ())

@@ -108,6 +108,7 @@ int main(int ac, char** av) {
         for (double l : s0.lambdas) cfg.lambda(l);
         cfg.cold_disk = s0.cold_disk ? 1 : 0;
         cfg.record_F = s0.fulldata ? 1 : 0;
+        cfg.star_flux = s0.star_flux ? 1 : 0;
         if (passbands.size() > FB200_MAX_PASSBANDS) throw OptionError("at most " + std::to_string(FB200_MAX_PASSBANDS) + " --passband files");
         cfg.n_passbands = int(passbands.size());
         std::vector<std::string> passband_names;
@@ -128,7 +129,7 @@ int main(int ac, char** av) {
         const FreddiEnsemble::Status st = ens.status();
         const size_t ncol = ens.n_cols(), nrows = ens.n_rows(), Nx = ens.Nx();
 
-        const std::vector<FieldMeta> fields = short_fields(ns, s0.cold_disk, s0.lambdas, passband_names);
+        const std::vector<FieldMeta> fields = short_fields(ns, s0.cold_disk, s0.lambdas, passband_names, s0.star_flux);
         if (fields.size() != ncol) throw std::logic_error("column count of the engine and of the writer differ");
         const std::vector<LongField> long_fields = disk_structure_fields(ns);
 

@@ -354,7 +354,7 @@ struct RunSetup {
     unsigned precision = 12, tempsparsity = 1;
     bool fulldata = false, to_stdout = false;
     // FluxArguments' ensemble-wide parts
-    bool cold_disk = false;
+    bool cold_disk = false, star_flux = false;
     std::vector<double> lambdas;            // cm
     std::vector<std::string> passband_files;
 };
@@ -363,8 +363,10 @@ inline RunSetup make_setup(const VariablesMap& vm, bool ns) {
     RunSetup s;
     fb200_args_t& a = s.args;
     fb200_args_default(&a, ns ? 1 : 0);
-    if (vm.count("starflux"))
-        throw OptionError("--starflux is not supported: the irradiated companion star is outside the B200 hot path");
+    // FreddiOptions ctor, cpp/src/options.cpp:383-386
+    if (vm.count("starflux") && (!vm.count("Mx") || !vm.count("Topt") || !vm.count("Mopt") || !vm.count("period")))
+        throw OptionError("--starflux requires --Mx, --Mopt and --period to be specified");
+    s.star_flux = vm.count("starflux") > 0;
     // GeneralOptions, cpp/src/options.cpp:11-18
     s.prefix = vm.at("prefix").s; s.dir = vm.at("dir").s; s.precision = vm.at("precision").u; s.tempsparsity = vm.at("tempsparsity").u;
     s.fulldata = vm.count("fulldata") > 0; s.to_stdout = vm.count("stdout") > 0;

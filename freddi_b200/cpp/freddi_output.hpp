@@ -8,7 +8,7 @@
 //   shortDump / diskStructureDump        cpp/src/output.cpp:134-162 (tab-separated, stream precision = --precision)
 //   field names, units, descriptions     cpp/src/output.cpp:197-305, cpp/src/ns/ns_output.cpp:6-27
 // Numbers are printed as a C++ ostream prints a double with precision(p) and default float format, i.e. "%.{p}g".
-// The `_star*` columns and the star dump are not produced (the companion star is outside the hot path).
+// The star dump of --fulldata --starflux (PREFIX_<i_t>_star.dat, cpp/src/output.cpp:164-181) is not produced.
 #pragma once
 #include <cstdio>
 #include <ostream>
@@ -32,7 +32,7 @@ inline std::string format_double(double v, unsigned precision) {
 
 // FreddiFileOutput::initializeShortFields (cpp/src/output.cpp:197-292) + FreddiNeutronStarFileOutput (ns_output.cpp:6-19)
 inline std::vector<FieldMeta> short_fields(bool ns, bool cold_disk, const std::vector<double>& lambdas_cm,
-                                           const std::vector<std::string>& passband_names) {
+                                           const std::vector<std::string>& passband_names, bool star = false) {
     std::vector<FieldMeta> f = {
         {"t", "days", "Time moment"},
         {"Mdot", "g/s", "Accretion rate onto central object"},
@@ -55,11 +55,23 @@ inline std::vector<FieldMeta> short_fields(bool ns, bool cold_disk, const std::v
         f.push_back({"Fnu" + std::to_string(i), "erg/s/cm^2/Hz", "Spectral flux density of the hot disk at wavelength of " + aa});
         if (cold_disk)
             f.push_back({"Fnu" + std::to_string(i) + "_cold", "erg/s/cm^2/Hz", "Spectral flux density of the cold disk at wavelength of " + aa});
+        if (star) {
+            const std::string n = "Fnu" + std::to_string(i), d = "Spectral flux density of the optical star at wavelength of " + aa;
+            f.push_back({n + "_star", "erg/s/cm^2/Hz", d + " with respect to an orbital phase"});
+            f.push_back({n + "_star_min", "erg/s/cm^2/Hz", d + " on the phase of inferior conjunction of the star"});
+            f.push_back({n + "_star_max", "erg/s/cm^2/Hz", d + " on the phase of superior conjunction of the star"});
+        }
     }
     for (const std::string& pb : passband_names) {
         f.push_back({"Fnu" + pb, "erg/s/cm^2/Hz", "Spectral flux density of the hot disk in passband " + pb});
         // unit and description are swapped in the reference (cpp/src/output.cpp:266-267); kept for byte compatibility
         if (cold_disk) f.push_back({"Fnu" + pb + "_cold", "Spectral flux density of the cold disk in passband " + pb, "erg/s/cm^2/Hz"});
+        if (star) {
+            const std::string d = "Spectral flux density of the optical star in passband " + pb;
+            f.push_back({"Fnu" + pb + "_star", "erg/s/cm^2/Hz", d + " with respect to an orbital phase"});
+            f.push_back({"Fnu" + pb + "_star_min", "erg/s/cm^2/Hz", d + " on the phase of inferior conjunction of the star"});
+            f.push_back({"Fnu" + pb + "_star_max", "erg/s/cm^2/Hz", d + " on the phase of superior conjunction of the star"});
+        }
     }
     if (ns) {
         const std::vector<FieldMeta> n = {

@@ -13,6 +13,7 @@
 
 #include "evolve.cuh"
 #include "resolve.hpp"
+#include "star.hpp"
 
 using namespace fb200;
 
@@ -232,7 +233,8 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     e->n_rows = max_Nt + 1;
     e->max_Nt = max_Nt;
     if (const char* c = getenv("FB200_CHUNK_STEPS")) e->chunk_steps = atoi(c) > 0 ? atoi(c) : 0x3fffffff;
-    e->n_cols = FB200_N_BH_COLS + (cfg.n_lambdas + cfg.n_passbands) * (cfg.cold_disk ? 2 : 1) + (is_ns ? FB200_N_NS_COLS : 0);
+    e->n_cols = FB200_N_BH_COLS + (cfg.n_lambdas + cfg.n_passbands) * ((cfg.cold_disk ? 2 : 1) + (cfg.star_flux ? 3 : 0)) +
+                (is_ns ? FB200_N_NS_COLS : 0);
     e->info.resize(n_models);
     for (size_t i = 0; i < n_models; ++i) e->info[i] = res[i].info;
     {
@@ -287,6 +289,43 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
         D.cfg.pb_w = d_w;
     }
 
+    // ---- companion star (--starflux): one triangle table per distinct (semi-axis, mass ratio, fill factor, starlod) ----
+    D.cfg.star_flux = cfg.star_flux ? 1 : 0;
+    D.cfg.star_data = nullptr;
+    D.star_T = nullptr;
+    D.star_ntri_max = 0;
+    if (cfg.star_flux) {
+        struct Key { double semiaxis, q, fill; int lod; long long off; int ntri; };
+        std::vector<Key> keys;
+        std::vector<double> table;
+        for (size_t i = 0; i < n_models; ++i) {
+            const double q = args[i].Mopt / args[i].Mx;
+            const Key* hit = nullptr;
+            for (const Key& k : keys)
+                if (k.semiaxis == res[i].dev.star_semiaxis && k.q == q && k.fill == args[i].rochelobefill && k.lod == args[i].starlod) { hit = &k; break; }
+            if (!hit) {
+                StarGeometry g;
+                std::string msg;
+                const int rc = build_star_geometry(res[i].dev.star_semiaxis, q, args[i].rochelobefill, args[i].starlod, g, msg);
+                if (rc != FB200_OK) {
+                    if (bad_model) *bad_model = i;
+                    return guard_fail(set_err(rc, msg));
+                }
+                keys.push_back(Key{res[i].dev.star_semiaxis, q, args[i].rochelobefill, args[i].starlod, (long long)table.size(), g.n_tri});
+                const std::vector<double> packed = g.packed();
+                table.insert(table.end(), packed.begin(), packed.end());
+                hit = &keys.back();
+            }
+            res[i].dev.star_off = hit->off;
+            res[i].dev.star_ntri = hit->ntri;
+            D.star_ntri_max = std::max(D.star_ntri_max, hit->ntri);
+        }
+        double* d_star = nullptr;
+        FB_TRY(dev_alloc(e, &d_star, table.size()));
+        FB_TRYC(cudaMemcpy(d_star, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+        D.cfg.star_data = d_star;
+    }
+
     const size_t NN = n_models * size_t(Nx);
     fb200_model_dev_t* d_models = nullptr;
     ModelState* d_state = nullptr;
@@ -314,6 +353,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
         fprintf(stderr, "[fb200] smem/CTA %zu B, CTAs/SM designed %d, resident %d, SMs %d\n", evolve_smem_bytes(), evolve_ctas_per_sm(),
                 evolve_resident_ctas_per_sm(), e->sm_count);
     FB_TRY(dev_alloc(e, &D.cta_scratch, size_t(D.max_ctas) * (big ? fb200_big_evolve_scratch_doubles_per_cta() : evolve_scratch_doubles_per_cta())));
+    if (D.star_ntri_max > 0) FB_TRY(dev_alloc(e, &D.star_T, size_t(D.max_ctas) * D.star_ntri_max));
     FB_TRY(dev_alloc(e, &D.prof, 8));
     FB_TRYC(cudaMemset(D.prof, 0, 8 * sizeof(long long)));
     {

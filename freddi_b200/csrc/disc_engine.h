@@ -53,6 +53,10 @@ struct OutCfg {
     double pb_tdnu[FB200_MAX_PASSBANDS];
     const double* pb_a;
     const double* pb_w;
+    // companion star (--starflux): triangle tables of all geometries back to back (star.hpp StarGeometry::packed)
+    const double* star_data;
+    int star_flux;
+    int _pad;
 };
 
 // Mutable per-model state carried between evolve calls (FreddiState::CurrentState, cpp/include/freddi_state.hpp:242-258)
@@ -471,6 +475,9 @@ FB_HD bool fb_isnan(double x) { return x != x; }
 //   blocks(n, f)         run f(b) for b < n, one thread per b (the in-thread block elimination of the solve)
 //   reduced(n, f)        run f(q) for q < n, one thread per q (reduced-system PCR)
 //   tick(p)              phase boundary marker (cycle accounting in FB_PROFILE builds, otherwise a no-op)
+//   tri_points(n, f)     run f(t) for t < n (the triangles of the companion star), spread over the threads
+//   reduce_sums3(n, f)   sums over t < n of the three values f(t, a, b, c) produces; results via sum(0..2)
+//   star_T(t), star_sum(k)   per-triangle effective temperature; the 3 x (n_lambdas + n_passbands) star sums
 // ------------------------------------------------------------------------------------------------
 template <class Ex>
 struct DiscEngine {
@@ -721,6 +728,7 @@ struct DiscEngine {
                 const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i]);
                 Tph = q.Tph; Tirr = q.Tirr; Sigma = q.Sigma; Tvis = q.Tvis;
                 if (i == last) { ex.scalar(0) = q.Kirr; ex.scalar(1) = q.Height / S.R[i]; }
+                if (cfg.star_flux) S.aux[i] = q.Height / S.R[i];  // for Height2R of the star's irradiation sources
             }
             S.Tph[i] = Tph; S.Tirr[i] = Tirr; S.Sigma[i] = Sigma; S.Tvis[i] = Tvis;
         });
@@ -762,6 +770,20 @@ struct DiscEngine {
         }
         ex.tick(3);
         if (!row) return true;
+        // BasicFreddiIrradiationSource::Height2R (cpp/src/freddi_state.cpp:663-671): max of Height/R over [first, Nx); the cold
+        // zone has Height = h2rcold R (freddi_state.cpp:271-273).  Taken here, before S.aux is reused below.
+        double star_h2r = 0.;
+        if (cfg.star_flux) {
+            star_h2r = ex.reduce_max([&](int i, int k) -> double {
+                if (i < first || i >= Nx) return 0.;
+                if (i <= last) return S.aux[i];
+                return (M.h2rcold * S.R[i]) / S.R[i];
+            });
+            if (!(star_h2r > 0.)) star_h2r = 0.;  // std::max(H/R, 0.0) chain: NaN and negatives leave 0
+            ex.sync();
+            // before the radial sums below: star_row reuses the reduction slots sum(0..2)
+            star_row(sc, star_h2r, do_truncate);  // the state at t0 has no sources yet (freddi_state.cpp:79, freddi_evolution.cpp:28)
+        }
 
         // ---- Tph_X over the hot zone, freddi_state.cpp:292-312 ----
         const double absMdot = fabs(sc.Mdot_plain);
@@ -893,21 +915,28 @@ struct DiscEngine {
                 case FB200_COL_FX: v = Lx * psi / d2; break;
                 case FB200_COL_FBOL: v = sc.Lbol_disk * psi / d2; break;
                 default: {
+                    // per wavelength / passband: hot, [cold], [star, star_min, star_max]  (output.cpp:219-291)
                     const int k = i - FB200_N_BH_COLS;
-                    if (k < nl * per) {
-                        const int kl = k / per;
-                        const bool cold = (k % per) == 1;
-                        const double lam = cfg.lambdas[kl];
-                        const double I = 0.5 * ex.sum(cold ? 2 + nl + kl : 2 + kl);
-                        v = I * p2(lam) / FB_C_LIGHT * M.cosiOverD2;  // freddi_state.hpp:405-407
-                    } else if (k < (nl + npb) * per) {
-                        const int kp = (k - nl * per) / per;
-                        const bool cold = ((k - nl * per) % per) == 1;
-                        // the two nested trapezoids (radius, wavelength) each carry a factor 1/2
-                        const double intens = 0.5 * (0.5 * ex.sum(cold ? q_pb + npb + kp : q_pb + kp));
-                        v = intens * M.cosiOverD2 / cfg.pb_tdnu[kp];  // freddi_state.hpp:408-417
+                    const int percol = per + (cfg.star_flux ? 3 : 0);
+                    if (k < (nl + npb) * percol) {
+                        const int kl = k / percol;          // wavelength kl < nl, else passband kl - nl
+                        const int sub = k % percol;
+                        if (sub >= per) {
+                            v = ex.star_sum(3 * kl + (sub - per));
+                        } else if (kl < nl) {
+                            const bool cold = (sub == 1);
+                            const double lam = cfg.lambdas[kl];
+                            const double I = 0.5 * ex.sum(cold ? 2 + nl + kl : 2 + kl);
+                            v = I * p2(lam) / FB_C_LIGHT * M.cosiOverD2;  // freddi_state.hpp:405-407
+                        } else {
+                            const int kp = kl - nl;
+                            const bool cold = (sub == 1);
+                            // the two nested trapezoids (radius, wavelength) each carry a factor 1/2
+                            const double intens = 0.5 * (0.5 * ex.sum(cold ? q_pb + npb + kp : q_pb + kp));
+                            v = intens * M.cosiOverD2 / cfg.pb_tdnu[kp];  // freddi_state.hpp:408-417
+                        }
                     } else {
-                        v = ns_column(k - (nl + npb) * per, sc);
+                        v = ns_column(k - (nl + npb) * percol, sc);
                     }
                 }
             }
@@ -922,6 +951,76 @@ struct DiscEngine {
         ex.sync();
         ex.tick(5);
         return true;
+    }
+
+    // ---- companion star (--starflux) ----
+    // IrradiatedStar::Qirr / Star::Teff (cpp/src/star.cpp:68-80,246-258) with the sources FreddiState::star_irr_sources sets
+    // at the end of every step (cpp/src/freddi_state.cpp:348-352,656-690; NS adds its own, ns_evolution.cpp:480-484), then
+    // flux_star(lambda | passband, phase) for the current phase and the two conjunctions (freddi_state.cpp:355-361,
+    // star.cpp:100-111, output.cpp:234-255,272-291).  Results in ex.star_sum(3 l + d).
+    FB_HD void star_row(const StateScalars& sc, double h2r_max, bool with_sources) {
+        const int nt = M.star_ntri;
+        const double* G = cfg.star_data + M.star_off;
+        const double *cx = G, *cy = G + nt, *cz = G + 2 * nt, *nx = G + 3 * nt, *ny = G + 4 * nt, *nz = G + 5 * nt, *ar = G + 6 * nt;
+        const double h2r2 = p2(h2r_max);  // DiskShadowSource, star.cpp:190-196
+        const double sx = -M.star_semiaxis, albedo = M.star_albedo;
+        const double Tth4 = p4(M.star_Topt);
+        const double L_disk = sc.Lbol_disk, L_ns = sc.Lbol_ns;
+        const bool two = M.is_ns != 0;
+        ex.tri_points(nt, [&](int t) {
+            double Q = 0.;
+            if (with_sources) {
+                const double dx = cx[t] - sx, dy = cy[t] - 0.0, dz = cz[t] - 0.0;  // PointLikeSource::irr_flux, star.cpp:128-136
+                const double len = sqrt(dx * dx + dy * dy + dz * dz);
+                const double inv = 1.0 / len;
+                const double ux = dx * inv, uy = dy * inv, uz = dz * inv;
+                const double rho2 = p2(ux) + p2(uy);
+                if (!((p2(uz) / rho2) < h2r2)) {
+                    double cos_obj = -(ux * nx[t] + uy * ny[t] + uz * nz[t]);
+                    if (cos_obj <= 0.0) cos_obj = 0.0;
+                    const double cos_source = fabs(0.0 * ux + 0.0 * uy + 1.0 * uz);  // plain_normal = UnitVec3(0, 0)
+                    const double lum_d = (M.angdist_disk == FB200_ANGDIST_ISOTROPIC) ? L_disk : L_disk * 2.0 * cos_source;
+                    Q += lum_d * (1.0 - albedo) / (4. * FB_PI * p2(len)) * cos_obj;
+                    if (two) {
+                        const double lum_n = (M.angdist_ns == FB200_ANGDIST_ISOTROPIC) ? L_ns : L_ns * 2.0 * cos_source;
+                        Q += lum_n * (1.0 - albedo) / (4. * FB_PI * p2(len)) * cos_obj;
+                    }
+                }
+            }
+            ex.star_T(t) = pow(Q / FB_SIGMA_SB + Tth4, 0.25);
+        });
+        ex.sync();
+        // observer directions UnitVec3(inclination, phase): the current phase (freddi_state.cpp:166-168), 0 and pi
+        const double phase = 2.0 * FB_PI * (st.t - M.star_t0) / M.star_period;
+        const double si = M.star_sini, ci = M.star_cosi;
+        const double d0x = si * cos(phase), d0y = si * sin(phase);
+        const double d1x = si * 1.0, d1y = si * 0.0;
+        const double d2x = si * -1.0, d2y = si * 1.2246467991473532e-16;  // cos(M_PI), sin(M_PI) in IEEE double
+        const int nl = cfg.n_lambdas, npb = cfg.n_passbands;
+        const double over_d2 = 4. * FB_PI * p2(M.distance);
+        for (int l = 0; l < nl + npb; ++l) {
+            const double lam = (l < nl) ? cfg.lambdas[l] : 0.;
+            const double pref = (l < nl) ? ex.lambda_pref(l) : 0.;
+            const int p = l - nl;
+            ex.reduce_sums3(nt, [&](int t, double& a, double& b, double& c) {
+                const double T = ex.star_T(t);
+                double y;
+                if (l < nl) {
+                    y = planck_lambda_pref(T, lam, pref) * p2(lam) / FB_C_LIGHT;
+                } else {  // EnergyPassband::bb_nu, passband.hpp:43
+                    y = (0.5 * passband_ring_sum(T, cfg.pb_a + cfg.pb_off[p], cfg.pb_w + cfg.pb_off[p], cfg.pb_off[p + 1] - cfg.pb_off[p])) / cfg.pb_tdnu[p];
+                }
+                const double nxt = nx[t], nyt = ny[t], nzc = nz[t] * ci, area = ar[t];
+                const double c0 = d0x * nxt + d0y * nyt + nzc, c1 = d1x * nxt + d1y * nyt + nzc, c2 = d2x * nxt + d2y * nyt + nzc;
+                a = (c0 <= 0.) ? 0. : area * c0 * y;  // Triangle::area_cos, geometry.cpp:201-207
+                b = (c1 <= 0.) ? 0. : area * c1 * y;
+                c = (c2 <= 0.) ? 0. : area * c2 * y;
+            });
+            ex.points([&](int i, int k) {
+                if (i < 3) ex.star_sum(3 * l + i) = ex.sum(i) * (4. * FB_PI) / over_d2;
+            });
+            ex.sync();
+        }
     }
 
     // NS columns (ns_output.cpp:6-19); each evaluated by one thread

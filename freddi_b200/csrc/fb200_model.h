@@ -68,6 +68,13 @@ typedef struct fb200_model_dev {
     double R_x, redshift, R_m_min, mu_magn, R_cor, R_dead, inverse_beta, epsilon_Alfven, hot_spot_area, freqx, risco;
     double kappat[4]; /* value | in,out | in,out,par1,par2 */
     double fpparams[2]; /* romanova: par1,par2 ; geometrical: chi [rad] */
+    /* --- companion star, --starflux (cpp/src/freddi_state.cpp:17-21,78-79,166-168,348-361,656-690) --- */
+    double star_semiaxis;    /* the irradiation sources sit at (-semiaxis, 0, 0) */
+    double star_Topt, star_albedo;
+    double star_sini, star_cosi; /* of the inclination: UnitVec3(inclination, phase), cpp/src/geometry.cpp:117-124 */
+    double star_t0, star_period; /* ephemeris T0 [s], orbital period [s]: phase = 2 pi (t - t0) / period */
+    long long star_off;      /* offset [doubles] of this model's triangle table in the ensemble's star array */
+    int32_t star_ntri, _pad2;
 } fb200_model_dev_t;
 
 #endif

@@ -60,7 +60,8 @@ struct SmemLayout {
 #endif
     // reduction scratch
     static constexpr int o_redA = kPointDoubles, o_redQ = o_redA + 2 * 32, o_sums = o_redQ + kNW * FB200_MAXQ;
-    static constexpr int o_scal = o_sums + FB200_MAXQ, o_lampref = o_scal + 8, o_model = o_lampref + FB200_MAX_LAMBDAS;
+    static constexpr int o_scal = o_sums + FB200_MAXQ, o_lampref = o_scal + 8, o_starsum = o_lampref + FB200_MAX_LAMBDAS;
+    static constexpr int o_model = o_starsum + 3 * (FB200_MAX_LAMBDAS + FB200_MAX_PASSBANDS);
     static constexpr int kModelDoubles = int((sizeof(fb200_model_dev_t) + 7) / 8);
     static constexpr int o_cfg = o_model + kModelDoubles;
     static constexpr int kCfgDoubles = int((sizeof(OutCfg) + 7) / 8);
@@ -145,6 +146,7 @@ struct GpuEx {
     int flip;
     // per-model global arrays (already offset to this model), null when absent
     const double *gA, *gB, *gCs, *gFm, *gdFm;
+    double* gStarT;  // per-triangle effective temperature of the companion star (the CTA's slice of EnsembleDev::star_T)
 
 #ifdef FB_BIG
     int n_slots;  // ceil(Nx / kNT)
@@ -157,6 +159,7 @@ struct GpuEx {
     __device__ __forceinline__ void init() {
         tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; flip = 0;
         gA = gB = gCs = gFm = gdFm = nullptr;
+        gStarT = nullptr;
         set_nx(FB200_NX_MAX);
     }
     // f(i, k): point index i, register slot k (a compile-time constant after unrolling)
@@ -191,6 +194,39 @@ struct GpuEx {
     __device__ __forceinline__ double& scalar(int k) { return fb_smem[L::o_scal + k]; }
     __device__ __forceinline__ double sum(int q) const { return fb_smem[L::o_sums + q]; }
     __device__ __forceinline__ double lambda_pref(int k) const { return fb_smem[L::o_lampref + k]; }
+    __device__ __forceinline__ double& star_T(int t) const { return gStarT[t]; }
+    __device__ __forceinline__ double& star_sum(int k) const { return fb_smem[L::o_starsum + k]; }
+    template <class F> __device__ __forceinline__ void tri_points(int n, F&& f) {
+        for (int t = tid; t < n; t += kNT) f(t);
+    }
+    // sums over t < n of the three values f(t, a, b, c) produces -> sum(0), sum(1), sum(2)
+    template <class F> __device__ __forceinline__ void reduce_sums3(int n, F&& f) {
+        double v0 = 0., v1 = 0., v2 = 0.;
+        for (int t = tid; t < n; t += kNT) {
+            double a, b, c;
+            f(t, a, b, c);
+            v0 += a; v1 += b; v2 += c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if (lane == 0) {
+            fb_smem[L::o_redQ + warp * FB200_MAXQ + 0] = v0;
+            fb_smem[L::o_redQ + warp * FB200_MAXQ + 1] = v1;
+            fb_smem[L::o_redQ + warp * FB200_MAXQ + 2] = v2;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double s = 0.;
+#pragma unroll
+            for (int w = 0; w < kNW; ++w) s += fb_smem[L::o_redQ + w * FB200_MAXQ + tid];
+            fb_smem[L::o_sums + tid] = s;
+        }
+        __syncthreads();
+    }
     __device__ __forceinline__ double windA(int i) const { return gA ? __ldg(gA + i) : 0.; }
     __device__ __forceinline__ double windB(int i) const { return gB ? __ldg(gB + i) : 0.; }
     __device__ __forceinline__ double windC_static(int i) const { return gCs ? __ldg(gCs + i) : 0.; }
@@ -269,6 +305,7 @@ __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E) {
         c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
         c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows; c->lx_prune = E.cfg.lx_prune;
         c->n_passbands = E.cfg.n_passbands; c->pb_a = E.cfg.pb_a; c->pb_w = E.cfg.pb_w;
+        c->star_flux = E.cfg.star_flux; c->star_data = E.cfg.star_data;
 #pragma unroll
         for (int k = 0; k < FB200_MAX_PASSBANDS + 2; ++k) c->pb_off[k] = E.cfg.pb_off[k];
 #pragma unroll
@@ -310,6 +347,7 @@ __device__ __forceinline__ void load_model(const EnsembleDev& E, int model, cons
     ex.gCs = E.wCs ? E.wCs + off : nullptr;
     ex.gFm = E.Fmagn ? E.Fmagn + off : nullptr;
     ex.gdFm = E.dFmagn_dh ? E.dFmagn_dh + off : nullptr;
+    ex.gStarT = E.star_T ? E.star_T + size_t(blockIdx.x) * E.star_ntri_max : nullptr;
     __syncthreads();
 }
 

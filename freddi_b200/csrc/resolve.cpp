@@ -405,6 +405,13 @@ int resolve_impl(const fb200_args_t& a, Resolved& out) {
     d.R_g = FB_G_GRAV * Mx / p2(FB_C_LIGHT);
     d.eta = efficiency_of_accretion(kerr);
     d.cosi = std::cos(a.inclination / 180.0 * M_PI);
+    // companion star (the geometry itself is built by capi.cu only when the ensemble asks for --starflux)
+    d.star_semiaxis = semiaxis(Mx + a.Mopt, a.period);     // cpp/src/freddi_state.cpp:20, cpp/include/orbit.hpp:24-29
+    d.star_Topt = a.Topt; d.star_albedo = a.staralbedo;
+    d.star_sini = std::sin(a.inclination / 180.0 * M_PI);  // cpp/src/freddi_state.cpp:21, cpp/src/geometry.cpp:117-124
+    d.star_cosi = std::cos(a.inclination / 180.0 * M_PI);
+    d.star_t0 = a.ephemerist0; d.star_period = a.period;
+    d.star_off = 0; d.star_ntri = 0;
     d.distance = a.distance;
     d.cosiOverD2 = d.cosi / p2(a.distance);
     out.h.resize(Nx);

@@ -54,16 +54,14 @@ class Passband:
         return cls(name, lam, tr)
 
 
-def column_names(n_lambdas=0, cold_disk=False, is_ns=False, passbands=()):
+def column_names(n_lambdas=0, cold_disk=False, is_ns=False, passbands=(), star_flux=False):
     cols = list(BH_COLS)
-    for k in range(n_lambdas):
-        cols.append('Fnu{}'.format(k))
-        if cold_disk:
-            cols.append('Fnu{}_cold'.format(k))
-    for name in passbands:
+    for name in [str(k) for k in range(n_lambdas)] + list(passbands):  # cpp/src/output.cpp:219-291
         cols.append('Fnu{}'.format(name))
         if cold_disk:
             cols.append('Fnu{}_cold'.format(name))
+        if star_flux:
+            cols += ['Fnu{}_star'.format(name), 'Fnu{}_star_min'.format(name), 'Fnu{}_star_max'.format(name)]
     if is_ns:
         cols += NS_COLS
     return cols
@@ -86,13 +84,14 @@ class Ensemble:
     lambdas   : wavelengths [cm] of the Fnu columns every row carries (FluxArguments::lambdas)
     passbands : sequence of Passband: one Fnu<name> column each (FluxArguments::passbands)
     cold_disk : add the Fnu_cold columns (--colddiskflux)
+    star_flux : add the Fnu_star, _star_min, _star_max columns of the irradiated companion star (--starflux)
     record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
     exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip rings that are
                     > 43 decades fainter than the hottest one in the X-ray band; changes Lx by < 1e-31 relative)
     """
 
     def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0,
-                 exact_lx_walk=False, passbands=()):
+                 exact_lx_walk=False, passbands=(), star_flux=False):
         self._h = None
         arr = args if isinstance(args, C.Array) else args_array(list(args))
         cfg = FB200Config()
@@ -112,6 +111,7 @@ class Ensemble:
         passbands = list(passbands)
         if len(passbands) > FB200_MAX_PASSBANDS:
             raise ValueError('at most {} passbands per ensemble'.format(FB200_MAX_PASSBANDS))
+        cfg.star_flux = int(bool(star_flux))
         cfg.n_passbands = len(passbands)
         dp = C.POINTER(C.c_double)
         for k, pb in enumerate(passbands):
@@ -133,7 +133,8 @@ class Ensemble:
         self.n_cols = int(_lib.lib.fb200_ensemble_n_cols(handle))
         self.Nx = int(_lib.lib.fb200_ensemble_nx(handle))
         self.passbands = passbands
-        self.columns = column_names(len(lambdas), cold_disk, self.is_ns, [pb.name for pb in passbands])
+        self.star_flux = bool(star_flux)
+        self.columns = column_names(len(lambdas), cold_disk, self.is_ns, [pb.name for pb in passbands], star_flux)
         self._info = None
 
     # -- life cycle --

@@ -122,7 +122,7 @@ typedef struct fb200_args {
     double inittime, time, tau /*opt*/, eps;
     uint32_t Nx;
     int32_t gridscale;
-    int32_t starlod; /* accepted and ignored: the companion star is outside the hot path */
+    int32_t starlod; /* level of detail of the companion star (20 * 4^starlod triangles), used with fb200_config_t::star_flux */
     int32_t nsprop;
     /* NeutronStarArguments, cpp/include/ns/ns_arguments.hpp:16-67 (ignored when !is_ns) */
     double freqx /*opt*/, Rx /*opt*/, Bx, hotspotarea, epsilonAlfven, inversebeta, Rdead;
@@ -156,10 +156,16 @@ typedef struct fb200_config {
     int32_t passband_len[FB200_MAX_PASSBANDS];
     const double* passband_lambdas[FB200_MAX_PASSBANDS];
     const double* passband_transmissions[FB200_MAX_PASSBANDS];
+    /* --starflux (cpp/src/options.cpp:333): after every Fnu column (and its _cold one) add Fnu*_star, Fnu*_star_min,
+     * Fnu*_star_max — the irradiated companion star at the current orbital phase and at the two conjunctions
+     * (cpp/src/output.cpp:234-255,272-291).  The Roche-lobe surface is triangulated on the host at create
+     * (20 * 4^starlod triangles per distinct Mopt/Mx, rochelobefill, semi-axis). */
+    int32_t star_flux;
+    int32_t _pad_cfg;
 } fb200_config_t;
 
-/* Row layout: cpp/src/output.cpp:197-214, then the Fnu{k}[, Fnu{k}_cold] columns of the wavelengths, then the
- * Fnu<passband>[, Fnu<passband>_cold] columns (cpp/src/output.cpp:219-271), then cpp/src/ns/ns_output.cpp:6-19 for NS. */
+/* Row layout: cpp/src/output.cpp:197-214, then per wavelength Fnu{k}[, Fnu{k}_cold][, Fnu{k}_star, _star_min, _star_max],
+ * then the same group per passband (cpp/src/output.cpp:219-291), then cpp/src/ns/ns_output.cpp:6-19 for NS. */
 enum {
     FB200_COL_T = 0,        /* days */
     FB200_COL_MDOT = 1, FB200_COL_MDISK = 2,

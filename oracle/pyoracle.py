@@ -34,16 +34,14 @@ def build(target='all'):
     subprocess.run(['make', '-s', '-C', HERE, target], check=True)
 
 
-def column_names(n_lambdas=0, cold_disk=False, is_ns=False, passbands=()):
+def column_names(n_lambdas=0, cold_disk=False, is_ns=False, passbands=(), star_flux=False):
     cols = list(BH_COLS)
-    for k in range(n_lambdas):
-        cols.append('Fnu{}'.format(k))
-        if cold_disk:
-            cols.append('Fnu{}_cold'.format(k))
-    for name in passbands:
+    for name in [str(k) for k in range(n_lambdas)] + list(passbands):
         cols.append('Fnu{}'.format(name))
         if cold_disk:
             cols.append('Fnu{}_cold'.format(name))
+        if star_flux:
+            cols += ['Fnu{}_star'.format(name), 'Fnu{}_star_min'.format(name), 'Fnu{}_star_max'.format(name)]
     if is_ns:
         cols += NS_COLS
     return cols
@@ -106,14 +104,19 @@ class _Checker:
         f(len(passbands), lens, lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), tdnu.ctypes.data_as(dp))
         return tdnu[:len(passbands)]
 
-    def run(self, args, lambdas=(), cold_disk=False, snapshots=True, passbands=()):
+    def set_star_flux(self, on):
+        self._fn('set_star_flux')(int(bool(on)))
+
+    def run(self, args, lambdas=(), cold_disk=False, snapshots=True, passbands=(), star_flux=False):
         """Returns dict(rows [(Nt+1) x ncol, NaN after collapse], rows_valid, F, first, last, picard)."""
-        if passbands:
+        if passbands or star_flux:
             self.set_passbands(passbands)
+            self.set_star_flux(star_flux)
             try:
                 return self.run(args, lambdas, cold_disk, snapshots)
             finally:
                 self.set_passbands(())
+                self.set_star_flux(False)
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         m = self.model(args, lambdas)
         info = m.info()
@@ -183,6 +186,16 @@ class _Model:
 
     def n_cols(self, cold_disk=False):
         return int(self.c._fn('n_cols')(self.h, int(cold_disk)))
+
+    def star_triangles(self):
+        """(n, 7): centre, unit normal, area of every triangle of the companion star."""
+        f = self.c._fn('star_triangles')
+        f.restype = C.c_long
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        n = f(self.h, None)
+        out = np.empty((n, 7))
+        f(self.h, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
 
     def step(self):
         return self.c._fn('step')(self.h)

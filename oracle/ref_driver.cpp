@@ -85,6 +85,7 @@ struct Model {
     std::shared_ptr<Counting<FreddiNeutronStarEvolution>> ns;
     std::vector<double> lambdas;
     size_t n_passbands = 0;
+    int star_flux = 0;
     long last_picard = 0;
     FreddiEvolution* ev() const { return is_ns ? static_cast<FreddiEvolution*>(ns.get()) : static_cast<FreddiEvolution*>(bh.get()); }
 };
@@ -92,6 +93,7 @@ struct Model {
 // Passbands of the models built next (FluxArguments::passbands, cpp/include/arguments.hpp:287): set by
 // ref_set_passbands, read-only while models are built and run.
 std::vector<EnergyPassband> g_passbands;
+int g_star_flux = 0;  // ref_set_star_flux: add the Fnu*_star, _star_min, _star_max columns (--starflux, cpp/src/output.cpp:234-255,272-291)
 
 FluxArguments* make_flux(const fb200_args_t& a, const std::vector<double>& lambdas) {
     return new FluxArguments(a.colourfactor, a.emin, a.emax, a.staralbedo, a.inclination, a.ephemerist0, a.distance,
@@ -103,6 +105,7 @@ Model* build(const fb200_args_t& a, const double* lambdas, int n_lambdas) {
     m->is_ns = a.is_ns != 0;
     m->lambdas.assign(lambdas, lambdas + n_lambdas);
     m->n_passbands = g_passbands.size();
+    m->star_flux = g_star_flux;
     const std::string opacity = pick(kOpacity, 2, a.opacity), bound = pick(kBound, 2, a.boundcond),
                       ic = pick(kIC, 7, a.initialcond), wind = pick(kWind, 12, a.windtype);
     const double Tirr2Tvishot = std::pow(a.Qirr2Qvishot, 0.25);  // cpp/pywrap/pywrap_freddi_evolution.cpp:148
@@ -154,7 +157,8 @@ Model* build(const fb200_args_t& a, const double* lambdas, int n_lambdas) {
 }
 
 int n_cols(const Model& m, int cold_disk) {
-    return FB200_N_BH_COLS + static_cast<int>(m.lambdas.size() + m.n_passbands) * (cold_disk ? 2 : 1) + (m.is_ns ? FB200_N_NS_COLS : 0);
+    return FB200_N_BH_COLS + static_cast<int>(m.lambdas.size() + m.n_passbands) * ((cold_disk ? 2 : 1) + (m.star_flux ? 3 : 0)) +
+           (m.is_ns ? FB200_N_NS_COLS : 0);
 }
 
 // cpp/src/output.cpp:197-214,219-233 and cpp/src/ns/ns_output.cpp:6-19, same evaluation order.
@@ -179,10 +183,20 @@ void fill_row(Model& m, int cold_disk, double* out) {
     for (double lambda : m.lambdas) {
         out[k++] = f->flux(lambda);
         if (cold_disk) out[k++] = f->flux_region<FreddiState::ColdRegion>(lambda);
+        if (m.star_flux) {
+            out[k++] = f->flux_star(lambda);
+            out[k++] = f->flux_star(lambda, 0.0);
+            out[k++] = f->flux_star(lambda, M_PI);
+        }
     }
-    for (const auto& pb : f->args().flux->passbands) {  // cpp/src/output.cpp:258-271
+    for (const auto& pb : f->args().flux->passbands) {  // cpp/src/output.cpp:258-291
         out[k++] = f->flux(pb);
         if (cold_disk) out[k++] = f->flux_region<FreddiState::ColdRegion>(pb);
+        if (m.star_flux) {
+            out[k++] = f->flux_star(pb);
+            out[k++] = f->flux_star(pb, 0.0);
+            out[k++] = f->flux_star(pb, M_PI);
+        }
     }
     if (m.is_ns) {
         auto* n = m.ns.get();
@@ -237,6 +251,21 @@ void ref_set_passbands(int n, const int* lens, const double* lambdas, const doub
         g_passbands.emplace_back("pb" + std::to_string(p), data);
         if (t_dnu) t_dnu[p] = g_passbands.back().t_dnu;
     }
+}
+
+void ref_set_star_flux(int on) { g_star_flux = on; }
+
+// Companion-star triangles of a model: centre (3), normal (3), area per triangle, [n][7]; returns n (out may be NULL).
+long ref_star_triangles(void* h, double* out) {
+    const auto& tr = static_cast<Model*>(h)->ev()->star().triangles();
+    if (out)
+        for (size_t i = 0; i < tr.size(); ++i) {
+            double* o = out + 7 * i;
+            o[0] = tr[i].center().x(); o[1] = tr[i].center().y(); o[2] = tr[i].center().z();
+            o[3] = tr[i].normal().x(); o[4] = tr[i].normal().y(); o[5] = tr[i].normal().z();
+            o[6] = tr[i].area();
+        }
+    return static_cast<long>(tr.size());
 }
 
 void* ref_create(const fb200_args_t* a, const double* lambdas, int n_lambdas, int* err_code, char* err, size_t err_len) {

@@ -59,15 +59,18 @@ class HostEmu:
             raise ValueError('emu_set_passbands: {}'.format(rc))
         return tdnu[:len(passbands)]
 
-    def run(self, args, Nt, Nx, lambdas=(), cold_disk=False, passbands=()):
-        if passbands:
+    def run(self, args, Nt, Nx, lambdas=(), cold_disk=False, passbands=(), star_flux=False):
+        if passbands or star_flux:
             self.set_passbands(passbands)
+            self.lib.emu_set_star_flux(int(bool(star_flux)))
             try:
                 return self.run(args, Nt, Nx, lambdas, cold_disk)
             finally:
                 self.set_passbands(())
+                self.lib.emu_set_star_flux(0)
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
-        ncol = 15 + (len(lam) + self.n_passbands()) * (2 if cold_disk else 1) + (10 if args.is_ns else 0)
+        ncol = (15 + (len(lam) + self.n_passbands()) * ((2 if cold_disk else 1) + (3 if self.lib.emu_star_flux() else 0))
+                + (10 if args.is_ns else 0))
         rows = np.full((Nt + 1, ncol), np.nan)
         F = np.full((Nt + 1, Nx), np.nan)
         first = np.full(Nt + 1, -1, dtype=np.int64)
@@ -81,6 +84,15 @@ class HostEmu:
         if n < 0:
             raise RuntimeError('[{}] {}'.format(n, err.value.decode()))
         return dict(rows=rows, rows_valid=int(n), F=F, first=first, last=last, picard=pic)
+
+    def star_triangles(self, args, cap=100000):
+        out = np.empty((cap, 7))
+        self.lib.emu_star_triangles.restype = C.c_long
+        self.lib.emu_star_triangles.argtypes = [C.POINTER(FB200Args), C.POINTER(C.c_double), C.c_long]
+        n = self.lib.emu_star_triangles(C.byref(args), out.ctypes.data_as(C.POINTER(C.c_double)), cap)
+        if n < 0:
+            raise RuntimeError('emu_star_triangles: {}'.format(n))
+        return out[:n].copy()
 
     def n_passbands(self):
         return int(self.lib.emu_n_passbands())

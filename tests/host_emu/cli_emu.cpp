@@ -51,7 +51,7 @@ long cli_render_dat(int ns, int argc, const char* const* argv, const char* const
         if (!parse_options(ns != 0, argc, argv, vm, nullptr, "/nonexistent")) return -2;
         const RunSetup s = make_setup(vm, ns != 0);
         std::vector<std::string> names(passband_names, passband_names + n_passband_names);
-        const std::vector<FieldMeta> fields = short_fields(ns != 0, s.cold_disk, s.lambdas, names);
+        const std::vector<FieldMeta> fields = short_fields(ns != 0, s.cold_disk, s.lambdas, names, s.star_flux);
         std::ostringstream os;
         const double alphacold = std::isnan(s.args.alphacold) ? s.args.alpha / 10.0 : s.args.alphacold;
         write_dat_header(os, fields, vm, s.precision, alphacold, rout_cm, risco_cm, tau_s);

@@ -13,6 +13,7 @@
 
 #include "../../freddi_b200/csrc/disc_engine.h"
 #include "../../freddi_b200/csrc/resolve.hpp"
+#include "../../freddi_b200/csrc/star.hpp"
 
 using namespace fb200;
 
@@ -40,6 +41,16 @@ struct HostEx {
     double windC_static(int i) const { return gCs ? gCs[i] : 0.; }
     double Fmagn(int i) const { return gFm ? gFm[i] : 0.; }
     double dFmagn_dh(int i) const { return gdFm ? gdFm[i] : 0.; }
+    std::vector<double> starT;
+    double starsum[3 * (FB200_MAX_LAMBDAS + FB200_MAX_PASSBANDS)] = {0};
+    double& star_T(int t) { return starT[t]; }
+    double& star_sum(int k) { return starsum[k]; }
+    template <class F> void tri_points(int n, F&& f) { for (int t = 0; t < n; ++t) f(t); }
+    template <class F> void reduce_sums3(int n, F&& f) {
+        double s0 = 0., s1 = 0., s2 = 0.;
+        for (int t = 0; t < n; ++t) { double a, b, c; f(t, a, b, c); s0 += a; s1 += b; s2 += c; }
+        sums[0] = s0; sums[1] = s1; sums[2] = s2;
+    }
     template <class F> double reduce_max(F&& f) {
         double m = -INFINITY;
         for (int i = 0; i < NT; ++i) { cur = i; const double v = f(i, 0); if (v == v) m = std::fmax(m, v); }
@@ -56,6 +67,7 @@ struct HostEx {
 
 static long long g_last_lx_trials = 0;
 static std::vector<PassbandTable> g_passbands;  // set by emu_set_passbands for the runs that follow
+static int g_star_flux = 0;                      // set by emu_set_star_flux for the runs that follow
 
 extern "C" {
 
@@ -104,7 +116,19 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     for (int p = npb; p < FB200_MAX_PASSBANDS + 2; ++p) cfg.pb_off[p] = int(pb_a.size());
     cfg.pb_a = pb_a.data();
     cfg.pb_w = pb_w.data();
-    cfg.n_cols = FB200_N_BH_COLS + (n_lambdas + npb) * (cold_disk ? 2 : 1) + (M.is_ns ? FB200_N_NS_COLS : 0);
+    cfg.star_flux = g_star_flux;
+    StarGeometry geom;
+    std::vector<double> star_packed;
+    if (g_star_flux) {
+        std::string serr;
+        const int src = build_star_geometry(res.dev.star_semiaxis, a->Mopt / a->Mx, a->rochelobefill, a->starlod, geom, serr);
+        if (src != FB200_OK) { if (err && err_len) std::snprintf(err, err_len, "%s", serr.c_str()); return src; }
+        star_packed = geom.packed();
+        res.dev.star_off = 0;
+        res.dev.star_ntri = geom.n_tri;
+        cfg.star_data = star_packed.data();
+    }
+    cfg.n_cols = FB200_N_BH_COLS + (n_lambdas + npb) * ((cold_disk ? 2 : 1) + (g_star_flux ? 3 : 0)) + (M.is_ns ? FB200_N_NS_COLS : 0);
     cfg.n_rows = M.Nt + 1;
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
 
@@ -125,6 +149,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     for (int i = 0; i < Nx; ++i) { hbuf[i] = res.h[i]; S.F[i] = res.F[i]; }
 
     HostEx ex;
+    ex.starT.assign(size_t(geom.n_tri) + 1, 0.);
     for (int k = 0; k < n_lambdas; ++k) ex.lampref[k] = FB_DOUBLE_H_C2 / p5(lambdas[k]);
     std::vector<double> wCs;
     if (!res.wC.empty() || (M.is_ns && M.inverse_beta != 0.)) {
@@ -163,7 +188,23 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     return r;
 }
 
+// Companion-star triangles as the product's host code builds them (star.cpp): [n][7] centre, normal, area; returns n or <0.
+long emu_star_triangles(const fb200_args_t* a, double* out, long cap) {
+    Resolved res;
+    std::string msg;
+    if (resolve(*a, res, msg) != FB200_OK) return -1;
+    StarGeometry g;
+    if (build_star_geometry(res.dev.star_semiaxis, a->Mopt / a->Mx, a->rochelobefill, a->starlod, g, msg) != FB200_OK) return -2;
+    for (long i = 0; i < g.n_tri && i < cap; ++i) {
+        double* o = out + 7 * i;
+        o[0] = g.cx[i]; o[1] = g.cy[i]; o[2] = g.cz[i]; o[3] = g.nx[i]; o[4] = g.ny[i]; o[5] = g.nz[i]; o[6] = g.area[i];
+    }
+    return g.n_tri;
+}
+
 int emu_n_passbands() { return int(g_passbands.size()); }
+void emu_set_star_flux(int on) { g_star_flux = on; }
+int emu_star_flux() { return g_star_flux; }
 
 long long emu_last_lx_trials() { return g_last_lx_trials; }
 

@@ -10,9 +10,9 @@ from tests import common as cm
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(args_list, lambdas=(), cold_disk=False, record_F=True, passbands=()):
+def run_gpu(args_list, lambdas=(), cold_disk=False, record_F=True, passbands=(), star_flux=False):
     from freddi_b200 import Ensemble
-    with Ensemble(args_list, lambdas=lambdas, cold_disk=cold_disk, record_F=record_F, passbands=passbands) as ens:
+    with Ensemble(args_list, lambdas=lambdas, cold_disk=cold_disk, record_F=record_F, passbands=passbands, star_flux=star_flux) as ens:
         ens.evolve(-1)
         out = dict(rows=ens.rows(), columns=ens.columns)
         out['status'], out['valid'], out['picard'] = ens.status()
@@ -140,6 +140,26 @@ def test_passbands_with_cold_disk_and_neutron_star(ref):
     g = run_gpu([a], (), passbands=pbs[:1])
     assert g['columns'][15:17] == ['FnuSwift_V', 'Rin']
     check_model(g, 0, ref.run(a, (), passbands=pbs[:1]), 'passbands_ns')
+
+
+def test_star_flux_columns(ref):
+    """--starflux: the irradiated companion star at the current phase and the two conjunctions, for
+    wavelengths and a passband, BH (two mass ratios = two triangle tables in one ensemble, isotropic and plane disc emission,
+    cold disc) and NS (second source, plane NS emission)."""
+    pbs = cm.golden_passbands(['passbands/Swift_V.dat'])
+    star = dict(initialcond='quasistat', Thot=1e4, boundcond='Tirr', Cirr=3e-4, Topt=4000, inclination=40, staralbedo=0.3, h2rcold=0.03,
+                Cirrcold=1e-4, ephemerist0=0.1, time=12)
+    args = [cm.ini_args(False, angulardistdisk='isotropic', **star), cm.ini_args(False, angulardistdisk='plane', **dict(star, Mopt=2.0, starlod=2)),
+            cm.ini_args(False, angulardistdisk='plane', **dict(star, rochelobefill=0.7, Topt=0))]
+    g = run_gpu(args, cm.LAM3[:2], cold_disk=True, passbands=pbs, star_flux=True)
+    assert g['columns'][15:20] == ['Fnu0', 'Fnu0_cold', 'Fnu0_star', 'Fnu0_star_min', 'Fnu0_star_max']
+    assert g['columns'][25:30] == ['FnuSwift_V', 'FnuSwift_V_cold', 'FnuSwift_V_star', 'FnuSwift_V_star_min', 'FnuSwift_V_star_max']
+    for k, a in enumerate(args):
+        check_model(g, k, ref.run(a, cm.LAM3[:2], cold_disk=True, passbands=pbs, star_flux=True), 'star[{}]'.format(k), snapshot_rows=(0, 20))
+    assert g['rows'][2, 0, 17] == 0 and g['rows'][2, 5, 17] > 0   # Topt = 0: dark until the disc's irradiation sources are set
+    a = cm.ini_args(True, **dict(cm.NS_CI, Topt=3500, inclination=60, staralbedo=0.5, angulardistns='plane', Cirr=1e-3, time=5))
+    g = run_gpu([a], cm.LAM3[:1], star_flux=True)
+    check_model(g, 0, ref.run(a, cm.LAM3[:1], star_flux=True), 'star_ns')
 
 
 def test_mixed_lengths_and_incremental_evolve(ref):

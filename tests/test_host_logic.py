@@ -115,10 +115,10 @@ def test_resolver_error_classes(ref, built, kw, exc):
     assert (ei.value.code == -1) == (exc is ValueError)
 
 
-def emu_vs_ref(ref, emu, a, lam=(), cold=False, passbands=()):
-    r = ref.run(a, lam, cold_disk=cold, passbands=passbands)
-    e = emu.run(a, r['Nt'], r['Nx'], lam, cold, passbands=passbands)
-    names = pyoracle.column_names(len(lam), cold, bool(a.is_ns), [p.name for p in passbands])
+def emu_vs_ref(ref, emu, a, lam=(), cold=False, passbands=(), star_flux=False):
+    r = ref.run(a, lam, cold_disk=cold, passbands=passbands, star_flux=star_flux)
+    e = emu.run(a, r['Nt'], r['Nx'], lam, cold, passbands=passbands, star_flux=star_flux)
+    names = pyoracle.column_names(len(lam), cold, bool(a.is_ns), [p.name for p in passbands], star_flux)
     n = r['rows_valid']
     assert e['rows_valid'] == n
     np.testing.assert_array_equal(e['picard'][:n], r['picard'][:n])
@@ -215,3 +215,37 @@ def test_large_grid_engine_build_matches_oracle(ref, emu_big):
                                          Cirr=3e-4, Nx=2500, time=6), cm.LAM3)
     emu_vs_ref(ref, emu_big, cm.ini_args(False, windtype='__testA__', windparams={'kA': 1.0}, Mdotout=1e18, initialcond='sineF',
                                          Mdot0=1e18, F0=None, Nx=2500, gridscale='linear', time=20, tau=1), ())
+
+
+STAR = dict(initialcond='quasistat', Thot=1e4, boundcond='Tirr', Cirr=3e-4, Topt=4000, inclination=40, staralbedo=0.3, h2rcold=0.03,
+            ephemerist0=0.1, time=4)
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(Mx=9, Mopt=12, period=1.5, rochelobefill=0.8, starlod=2), dict(starlod=0, Mopt=5)],
+                         ids=['default', 'heavy_donor_underfilled_lod2', 'equal_mass_lod0'])
+def test_star_geometry_matches_reference(ref, emu, kw):
+    """The triangulated Roche-lobe surface (star.cpp) against the reference's Star::triangles(): centres, normals, areas."""
+    a = cm.ini_args(False, **kw)
+    want = ref.model(a).star_triangles()
+    got = emu.star_triangles(a)
+    assert got.shape == want.shape == (20 * 4 ** int(a.starlod), 7)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    np.testing.assert_allclose(got[:, 6], want[:, 6], rtol=1e-11)
+
+
+@pytest.mark.parametrize('name', ['bh_isotropic', 'bh_plane_cold_passband', 'ns_two_sources'])
+def test_star_flux_columns(ref, emu, name):
+    """--starflux: Fnu*_star, _star_min, _star_max (cpp/src/output.cpp:234-255,272-291).  The state at t0 has no irradiation
+    sources yet (they are set at the end of step(), cpp/src/freddi_evolution.cpp:28), later rows do."""
+    if name == 'bh_isotropic':
+        r, e = emu_vs_ref(ref, emu, cm.ini_args(False, angulardistdisk='isotropic', **STAR), cm.LAM3, star_flux=True)
+        k = 15 + 1
+        np.testing.assert_allclose(r['rows'][0, k + 1:k + 3], r['rows'][0, k], rtol=1e-6)  # unirradiated: Topt only, (almost) the same from every side
+        assert r['rows'][3, k + 2] > 3 * r['rows'][3, k + 1]                            # superior conjunction shows the heated side
+    elif name == 'bh_plane_cold_passband':
+        pbs = cm.golden_passbands(['passbands/Swift_V.dat'])
+        emu_vs_ref(ref, emu, cm.ini_args(False, angulardistdisk='plane', Cirrcold=1e-4, irrindex=0.5, **dict(STAR, time=12)), cm.LAM3[:1],
+                   True, pbs, star_flux=True)
+    else:
+        emu_vs_ref(ref, emu, cm.ini_args(True, **dict(cm.NS_CI, Topt=3500, inclination=60, staralbedo=0.5, angulardistns='plane',
+                                                      Cirr=1e-3, time=3)), cm.LAM3[:2], star_flux=True)

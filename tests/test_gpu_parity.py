@@ -240,7 +240,7 @@ def test_invalid_arguments_raise_reference_error_classes():
     with pytest.raises(ValueError):
         Ensemble([cm.ini_args(opacity='nope')])
     with pytest.raises(NotImplementedError):
-        Ensemble([cm.ini_args(Nx=5000)])
+        Ensemble([cm.ini_args(Nx=50000)])  # beyond the large-grid build (16384)
 
 
 def test_reset_replays_the_ensemble_bit_for_bit():

@@ -479,7 +479,9 @@ FB_HD bool fb_isnan(double x) { return x != x; }
 //   reduce_sums3(n, f)   sums over t < n of the three values f(t, a, b, c) produces; results via sum(0..2)
 //   star_T(t), star_sum(k)   per-triangle effective temperature; the 3 x (n_lambdas + n_passbands) star sums
 // ------------------------------------------------------------------------------------------------
-template <class Ex>
+// kExtras = false compiles the passband and companion-star columns out (they cost registers and ~2 % of the kernel
+// even when unused): the evolve kernel is instantiated both ways and launched by what the ensemble asks for.
+template <class Ex, bool kExtras = true>
 struct DiscEngine {
     Ex& ex;
     const fb200_model_dev_t& M;
@@ -728,7 +730,7 @@ struct DiscEngine {
                 const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i]);
                 Tph = q.Tph; Tirr = q.Tirr; Sigma = q.Sigma; Tvis = q.Tvis;
                 if (i == last) { ex.scalar(0) = q.Kirr; ex.scalar(1) = q.Height / S.R[i]; }
-                if (cfg.star_flux) S.aux[i] = q.Height / S.R[i];  // for Height2R of the star's irradiation sources
+                if (kExtras && cfg.star_flux) S.aux[i] = q.Height / S.R[i];  // for Height2R of the star's irradiation sources
             }
             S.Tph[i] = Tph; S.Tirr[i] = Tirr; S.Sigma[i] = Sigma; S.Tvis[i] = Tvis;
         });
@@ -773,7 +775,7 @@ struct DiscEngine {
         // BasicFreddiIrradiationSource::Height2R (cpp/src/freddi_state.cpp:663-671): max of Height/R over [first, Nx); the cold
         // zone has Height = h2rcold R (freddi_state.cpp:271-273).  Taken here, before S.aux is reused below.
         double star_h2r = 0.;
-        if (cfg.star_flux) {
+        if (kExtras && cfg.star_flux) {
             star_h2r = ex.reduce_max([&](int i, int k) -> double {
                 if (i < first || i >= Nx) return 0.;
                 if (i <= last) return S.aux[i];
@@ -829,7 +831,7 @@ struct DiscEngine {
         // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
         // slots: 0 Mdisk, 1 Lx, [2, 2+nl) Fnu hot, [2+nl, 2+2nl) Fnu cold, [q_pb, q_pb+npb) passbands hot,
         //        [q_pb+npb, q_pb+2npb) passbands cold, nq: Lx trial count
-        const int nl = cfg.n_lambdas, npb = cfg.n_passbands;
+        const int nl = cfg.n_lambdas, npb = kExtras ? cfg.n_passbands : 0;
         const int per = cfg.cold_disk ? 2 : 1;
         const int q_pb = 2 + nl * per;
         const int nq = q_pb + npb * per;
@@ -917,7 +919,7 @@ struct DiscEngine {
                 default: {
                     // per wavelength / passband: hot, [cold], [star, star_min, star_max]  (output.cpp:219-291)
                     const int k = i - FB200_N_BH_COLS;
-                    const int percol = per + (cfg.star_flux ? 3 : 0);
+                    const int percol = per + ((kExtras && cfg.star_flux) ? 3 : 0);
                     if (k < (nl + npb) * percol) {
                         const int kl = k / percol;          // wavelength kl < nl, else passband kl - nl
                         const int sub = k % percol;

@@ -6,6 +6,7 @@
 
 namespace fb200 {
 
+template <bool kExtras>
 __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const EnsembleDev E) {
     GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     __shared__ int s_model;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
             load_model(E, model, S, ex, E.F + size_t(model) * Nx);
             const fb200_model_dev_t& M = *smem_model();
 
-            DiscEngine<GpuEx> eng(ex, M, cfg, S, st);
+            DiscEngine<GpuEx, kExtras> eng(ex, M, cfg, S, st);
             eng.init_points();
 
             double* rows = E.rows + size_t(model) * nrows * ncol;
@@ -112,20 +113,25 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 
 size_t evolve_smem_bytes() { return SmemLayout::bytes(); }
 int evolve_resident_ctas_per_sm() {
-    int n = 0;
-    cudaFuncSetAttribute(fb200_evolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fb200_evolve_kernel, kNT, SmemLayout::bytes()) != cudaSuccess) return -1;
-    return n;
+    int n = 0, m = 0;
+    cudaFuncSetAttribute(fb200_evolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
+    cudaFuncSetAttribute(fb200_evolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fb200_evolve_kernel<false>, kNT, SmemLayout::bytes()) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, fb200_evolve_kernel<true>, kNT, SmemLayout::bytes()) != cudaSuccess) return -1;
+    return n < m ? n : m;
 }
 size_t evolve_scratch_doubles_per_cta() { return SmemLayout::scratch_doubles_per_cta(); }
 int evolve_ctas_per_sm() { return kCtasPerSm; }
 
 cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream) {
     // per device and cheap: set on every launch so that several devices in one process all get it
-    cudaError_t e = cudaFuncSetAttribute(fb200_evolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
+    const bool extras = E.cfg.star_flux || E.cfg.n_passbands > 0;  // passband / companion-star columns: the second instantiation
+    cudaError_t e = extras ? cudaFuncSetAttribute(fb200_evolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()))
+                           : cudaFuncSetAttribute(fb200_evolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SmemLayout::bytes()));
     if (e != cudaSuccess) return e;
     if (n_ctas > E.max_ctas) n_ctas = E.max_ctas;
-    fb200_evolve_kernel<<<n_ctas, kNT, SmemLayout::bytes(), stream>>>(E);
+    if (extras) fb200_evolve_kernel<true><<<n_ctas, kNT, SmemLayout::bytes(), stream>>>(E);
+    else fb200_evolve_kernel<false><<<n_ctas, kNT, SmemLayout::bytes(), stream>>>(E);
     return cudaGetLastError();
 }
 

@@ -59,7 +59,15 @@ struct SmemLayout {
     static constexpr int kPointDoubles = o_pg + NP;
 #endif
     // reduction scratch
+#ifdef FB_BIG
     static constexpr int o_redA = kPointDoubles, o_redQ = o_redA + 2 * 32, o_sums = o_redQ + kNW * FB200_MAXQ;
+#else
+    // The cross-warp partial sums of reduce_sums / reduce_sums3 ([kNW][FB200_MAXQ]) alias the first PCR ping-pong buffer:
+    // sums are only taken in the row phase and in the read-out kernels, when the reduced system is dead (the next solve
+    // rebuilds it from scratch).  This keeps the CTA at <= 113 KB so that two CTAs fit into the SM's 228 KB.
+    static constexpr int o_redA = kPointDoubles, o_redQ = o_lu0, o_sums = o_redA + 2 * 32;
+    static_assert(kNW * FB200_MAXQ <= 2 * NR, "reduce_sums scratch must fit into the first PCR buffer");
+#endif
     static constexpr int o_scal = o_sums + FB200_MAXQ, o_lampref = o_scal + 8, o_starsum = o_lampref + FB200_MAX_LAMBDAS;
     static constexpr int o_model = o_starsum + 3 * (FB200_MAX_LAMBDAS + FB200_MAX_PASSBANDS);
     static constexpr int kModelDoubles = int((sizeof(fb200_model_dev_t) + 7) / 8);
@@ -67,6 +75,11 @@ struct SmemLayout {
     static constexpr int kCfgDoubles = int((sizeof(OutCfg) + 7) / 8);
     static constexpr int kTotalDoubles = o_cfg + kCfgDoubles + 2;
     static constexpr size_t bytes() { return sizeof(double) * size_t(kTotalDoubles); }
+#ifndef FB_BIG
+    // B200: 233,472 B of shared memory per SM, 1 KB reserved per CTA -> two resident CTAs need <= 115,712 B each.
+    // (One CTA per SM costs 38 % of the throughput: measured 59 ms -> 95 ms per launch of the bench.)
+    static_assert(FB_CTAS_PER_SM != 2 || sizeof(double) * size_t(kTotalDoubles) <= 115712, "shared memory per CTA too large for 2 CTAs/SM");
+#endif
 #ifdef FB_BIG
     // R ca cb cc frac c1 hm175 hotR Gb | F hn s_cc s_frac s_K | s_l s_u s_d s_rhs p_a p_c p_g | lu0 lu1 (2 NR each) rr0 rr1
     static constexpr int kScratchArrays = 21;

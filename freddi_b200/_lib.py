@@ -24,6 +24,7 @@ SYMBOLS = (
     'fb200_ensemble_evolve_async', 'fb200_ensemble_reset', 'fb200_ensemble_sync', 'fb200_ensemble_last_evolve_ms', 'fb200_ensemble_last_launches',
     'fb200_ensemble_rows', 'fb200_ensemble_rows_device', 'fb200_ensemble_status', 'fb200_ensemble_state',
     'fb200_ensemble_row_bounds', 'fb200_ensemble_field', 'fb200_ensemble_flux', 'fb200_ensemble_mdot_wind',
+    'fb200_ensemble_field_rows', 'fb200_ensemble_flux_rows',
 )
 
 
@@ -80,6 +81,8 @@ def _load():
     lib.fb200_ensemble_field.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t]
     lib.fb200_ensemble_flux.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t, dp, C.c_size_t]
     lib.fb200_ensemble_mdot_wind.argtypes = [vp, C.c_int64, dp, C.c_size_t]
+    lib.fb200_ensemble_field_rows.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_int, dp, C.c_size_t]
+    lib.fb200_ensemble_flux_rows.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, dp, C.c_size_t, dp, dp, C.c_size_t]
     return lib
 
 

@@ -24,9 +24,9 @@ size_t fb200_big_evolve_scratch_doubles_per_cta();
 int fb200_big_evolve_ctas_per_sm();
 int fb200_big_evolve_resident_ctas_per_sm();
 cudaError_t fb200_big_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
-cudaError_t fb200_big_launch_field(const void* E, int field, long long row, double* out, cudaStream_t stream);
-cudaError_t fb200_big_launch_flux(const void* E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
-                                  cudaStream_t stream);
+cudaError_t fb200_big_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t fb200_big_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                  const double* phases_dev, double* out, cudaStream_t stream);
 cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
 }
 
@@ -233,7 +233,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     e->n_rows = max_Nt + 1;
     e->max_Nt = max_Nt;
     if (const char* c = getenv("FB200_CHUNK_STEPS")) e->chunk_steps = atoi(c) > 0 ? atoi(c) : 0x3fffffff;
-    e->n_cols = FB200_N_BH_COLS + (cfg.n_lambdas + cfg.n_passbands) * ((cfg.cold_disk ? 2 : 1) + (cfg.star_flux ? 3 : 0)) +
+    e->n_cols = FB200_N_BH_COLS + (cfg.n_lambdas + cfg.n_passbands) * ((cfg.cold_disk ? 2 : 1) + (cfg.star_flux == 1 ? 3 : 0)) +
                 (is_ns ? FB200_N_NS_COLS : 0);
     e->info.resize(n_models);
     for (size_t i = 0; i < n_models; ++i) e->info[i] = res[i].info;
@@ -290,7 +290,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     }
 
     // ---- companion star (--starflux): one triangle table per distinct (semi-axis, mass ratio, fill factor, starlod) ----
-    D.cfg.star_flux = cfg.star_flux ? 1 : 0;
+    D.cfg.star_flux = (cfg.star_flux == 1) ? 1 : 0;  // 2: geometry for fb200_ensemble_flux_rows(region 2) only, no columns
     D.cfg.star_data = nullptr;
     D.star_T = nullptr;
     D.star_ntri_max = 0;
@@ -619,47 +619,90 @@ static int check_row(fb200_ensemble_t* e, int64_t row) {
     return FB200_OK;
 }
 
-int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* out, size_t out_len) {
+// field of rows row0 .. row0 + n_sel - 1 of every model -> host out[model][n_sel][Nx]
+static int field_rows(fb200_ensemble_t* e, int field, int64_t row0, int n_sel, int pad_nan, double* out, size_t out_len) {
     if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
     if (field < 0 || field >= FB200_N_FIELDS) return set_err(FB200_ERR_INVALID_ARGUMENT, "unknown field");
-    const size_t need = e->n * size_t(e->Nx);
+    if (n_sel < 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_rows must be positive");
+    const size_t need = e->n * size_t(n_sel) * size_t(e->Nx);
     if (out_len < need) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
-    int rc = check_row(e, row);
+    int rc = check_row(e, row0);
     if (rc != FB200_OK) return rc;
+    if (row0 >= 0 && row0 + n_sel > e->n_rows) return set_err(FB200_ERR_INVALID_ARGUMENT, "row range out of bounds");
+    if (row0 < 0 && n_sel != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "the current state is a single row");
     rc = select_device(e);
     if (rc != FB200_OK) return rc;
-    cudaError_t ce = e->big ? fb200_big_launch_field(&e->dev, field, row, e->scratch, e->stream)
-                            : launch_field(e->dev, field, row, e->scratch, e->stream);
-    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_field_kernel launch");
-    FB_CUDA(cudaMemcpyAsync(out, e->scratch, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    FB_CUDA(cudaStreamSynchronize(e->stream));
+    double* d_o = e->scratch;
+    bool own = false;
+    if (need > e->scratch_len) {
+        FB_CUDA(cudaMalloc(&d_o, need * sizeof(double)));
+        own = true;
+    }
+    cudaError_t ce = e->big ? fb200_big_launch_field(&e->dev, field, row0, n_sel, pad_nan, d_o, e->stream)
+                            : launch_field(e->dev, field, row0, n_sel, pad_nan, d_o, e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (own) cudaFree(d_o);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_field_kernel");
     return FB200_OK;
 }
 
-int fb200_ensemble_flux(fb200_ensemble_t* e, int region, int64_t row, const double* lambdas, size_t n_lambdas, double* out,
-                        size_t out_len) {
+int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* out, size_t out_len) {
+    return field_rows(e, field, row, 1, 0, out, out_len);
+}
+
+int fb200_ensemble_field_rows(fb200_ensemble_t* e, int field, int64_t row_begin, int64_t n_rows, int pad_nan, double* out, size_t out_len) {
+    if (row_begin < 0) return set_err(FB200_ERR_INVALID_ARGUMENT, "row_begin must be a recorded row");
+    if (n_rows < 1 || n_rows > 0x7fffffff) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_rows out of range");
+    return field_rows(e, field, row_begin, int(n_rows), pad_nan, out, out_len);
+}
+
+// region 0 hot, 1 cold, 2 companion star (needs phases[n_sel] and an ensemble created with star_flux)
+static int flux_rows(fb200_ensemble_t* e, int region, int64_t row0, int n_sel, const double* lambdas, size_t n_lambdas,
+                     const double* phases, double* out, size_t out_len) {
     if (!e || !out || !lambdas) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
-    if (region != 0 && region != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "region must be 0 (hot) or 1 (cold)");
+    if (region < 0 || region > 2) return set_err(FB200_ERR_INVALID_ARGUMENT, "region must be 0 (hot), 1 (cold) or 2 (star)");
+    if (region == 2 && (!e->dev.cfg.star_data || !phases))
+        return set_err(FB200_ERR_LOGIC, "the star flux needs an ensemble created with star_flux and a phase per row");
     if (n_lambdas == 0) return FB200_OK;
-    if (out_len < e->n * n_lambdas) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
-    int rc = check_row(e, row);
+    if (n_sel < 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_rows must be positive");
+    const size_t need = e->n * size_t(n_sel) * n_lambdas;
+    if (out_len < need) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    int rc = check_row(e, row0);
     if (rc != FB200_OK) return rc;
+    if (row0 >= 0 && row0 + n_sel > e->n_rows) return set_err(FB200_ERR_INVALID_ARGUMENT, "row range out of bounds");
+    if (row0 < 0 && n_sel != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "the current state is a single row");
     rc = select_device(e);
     if (rc != FB200_OK) return rc;
-    double *d_l = nullptr, *d_o = nullptr;
-    FB_CUDA(cudaMalloc(&d_l, n_lambdas * sizeof(double)));
-    cudaError_t ce = cudaMalloc(&d_o, e->n * n_lambdas * sizeof(double));
+    double *d_l = nullptr, *d_o = nullptr, *d_p = nullptr;
+    FB_CUDA(cudaMalloc(&d_l, (n_lambdas + size_t(n_sel)) * sizeof(double)));
+    d_p = d_l + n_lambdas;
+    cudaError_t ce = cudaMalloc(&d_o, need * sizeof(double));
     if (ce != cudaSuccess) { cudaFree(d_l); return cuda_fail(ce, "cudaMalloc"); }
     ce = cudaMemcpyAsync(d_l, lambdas, n_lambdas * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess && phases) ce = cudaMemcpyAsync(d_p, phases, size_t(n_sel) * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess)
-        ce = e->big ? fb200_big_launch_flux(&e->dev, region, row, d_l, int(n_lambdas), d_o, e->stream)
-                    : launch_flux(e->dev, region, row, d_l, int(n_lambdas), d_o, e->stream);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, e->n * n_lambdas * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        ce = e->big ? fb200_big_launch_flux(&e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream)
+                    : launch_flux(e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     cudaFree(d_l);
     cudaFree(d_o);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_flux_kernel");
     return FB200_OK;
+}
+
+int fb200_ensemble_flux(fb200_ensemble_t* e, int region, int64_t row, const double* lambdas, size_t n_lambdas, double* out,
+                        size_t out_len) {
+    if (region == 2) return set_err(FB200_ERR_INVALID_ARGUMENT, "use fb200_ensemble_flux_rows for the star (it needs a phase)");
+    return flux_rows(e, region, row, 1, lambdas, n_lambdas, nullptr, out, out_len);
+}
+
+int fb200_ensemble_flux_rows(fb200_ensemble_t* e, int region, int64_t row_begin, int64_t n_rows, const double* lambdas, size_t n_lambdas,
+                             const double* phases, double* out, size_t out_len) {
+    if (n_rows < 1 || n_rows > 0x7fffffff) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_rows out of range");
+    if (row_begin < 0 && n_rows != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "the current state is a single row");
+    return flux_rows(e, region, row_begin, int(n_rows), lambdas, n_lambdas, phases, out, out_len);
 }
 
 int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size_t out_len) {

@@ -961,9 +961,25 @@ struct DiscEngine {
     // flux_star(lambda | passband, phase) for the current phase and the two conjunctions (freddi_state.cpp:355-361,
     // star.cpp:100-111, output.cpp:234-255,272-291).  Results in ex.star_sum(3 l + d).
     FB_HD void star_row(const StateScalars& sc, double h2r_max, bool with_sources) {
+        star_teff(sc, h2r_max, with_sources);
+        const double phase = 2.0 * FB_PI * (st.t - M.star_t0) / M.star_period;  // phase_opt, freddi_state.cpp:166-168
+        const int nl = cfg.n_lambdas, npb = cfg.n_passbands;
+        const double over_d2 = 4. * FB_PI * p2(M.distance);
+        for (int l = 0; l < nl + npb; ++l) {
+            if (l < nl) star_dir_sums(cfg.lambdas[l], ex.lambda_pref(l), -1, phase);
+            else star_dir_sums(0., 0., l - nl, phase);
+            ex.points([&](int i, int k) {
+                if (i < 3) ex.star_sum(3 * l + i) = ex.sum(i) * (4. * FB_PI) / over_d2;
+            });
+            ex.sync();
+        }
+    }
+
+    // Effective temperature of every triangle -> ex.star_T (IrradiatedStar::Qirr, Star::Teff)
+    FB_HD void star_teff(const StateScalars& sc, double h2r_max, bool with_sources) {
         const int nt = M.star_ntri;
         const double* G = cfg.star_data + M.star_off;
-        const double *cx = G, *cy = G + nt, *cz = G + 2 * nt, *nx = G + 3 * nt, *ny = G + 4 * nt, *nz = G + 5 * nt, *ar = G + 6 * nt;
+        const double *cx = G, *cy = G + nt, *cz = G + 2 * nt, *nx = G + 3 * nt, *ny = G + 4 * nt, *nz = G + 5 * nt;
         const double h2r2 = p2(h2r_max);  // DiskShadowSource, star.cpp:190-196
         const double sx = -M.star_semiaxis, albedo = M.star_albedo;
         const double Tth4 = p4(M.star_Topt);
@@ -992,37 +1008,33 @@ struct DiscEngine {
             ex.star_T(t) = pow(Q / FB_SIGMA_SB + Tth4, 0.25);
         });
         ex.sync();
-        // observer directions UnitVec3(inclination, phase): the current phase (freddi_state.cpp:166-168), 0 and pi
-        const double phase = 2.0 * FB_PI * (st.t - M.star_t0) / M.star_period;
+    }
+
+    // Star::integrate(func, direction) (star.cpp:58-64) for the observer directions UnitVec3(inclination, phi) with
+    // phi = phase, 0 and pi -> ex.sum(0..2).  func = B_lambda lambda^2 / c at wavelength lam (star.cpp:100-105), or
+    // EnergyPassband::bb_nu of passband p >= 0 (star.cpp:107-111).
+    FB_HD void star_dir_sums(double lam, double pref, int p, double phase) {
+        const int nt = M.star_ntri;
+        const double* G = cfg.star_data + M.star_off;
+        const double *nx = G + 3 * nt, *ny = G + 4 * nt, *nz = G + 5 * nt, *ar = G + 6 * nt;
         const double si = M.star_sini, ci = M.star_cosi;
         const double d0x = si * cos(phase), d0y = si * sin(phase);
         const double d1x = si * 1.0, d1y = si * 0.0;
         const double d2x = si * -1.0, d2y = si * 1.2246467991473532e-16;  // cos(M_PI), sin(M_PI) in IEEE double
-        const int nl = cfg.n_lambdas, npb = cfg.n_passbands;
-        const double over_d2 = 4. * FB_PI * p2(M.distance);
-        for (int l = 0; l < nl + npb; ++l) {
-            const double lam = (l < nl) ? cfg.lambdas[l] : 0.;
-            const double pref = (l < nl) ? ex.lambda_pref(l) : 0.;
-            const int p = l - nl;
-            ex.reduce_sums3(nt, [&](int t, double& a, double& b, double& c) {
-                const double T = ex.star_T(t);
-                double y;
-                if (l < nl) {
-                    y = planck_lambda_pref(T, lam, pref) * p2(lam) / FB_C_LIGHT;
-                } else {  // EnergyPassband::bb_nu, passband.hpp:43
-                    y = (0.5 * passband_ring_sum(T, cfg.pb_a + cfg.pb_off[p], cfg.pb_w + cfg.pb_off[p], cfg.pb_off[p + 1] - cfg.pb_off[p])) / cfg.pb_tdnu[p];
-                }
-                const double nxt = nx[t], nyt = ny[t], nzc = nz[t] * ci, area = ar[t];
-                const double c0 = d0x * nxt + d0y * nyt + nzc, c1 = d1x * nxt + d1y * nyt + nzc, c2 = d2x * nxt + d2y * nyt + nzc;
-                a = (c0 <= 0.) ? 0. : area * c0 * y;  // Triangle::area_cos, geometry.cpp:201-207
-                b = (c1 <= 0.) ? 0. : area * c1 * y;
-                c = (c2 <= 0.) ? 0. : area * c2 * y;
-            });
-            ex.points([&](int i, int k) {
-                if (i < 3) ex.star_sum(3 * l + i) = ex.sum(i) * (4. * FB_PI) / over_d2;
-            });
-            ex.sync();
-        }
+        ex.reduce_sums3(nt, [&](int t, double& a, double& b, double& c) {
+            const double T = ex.star_T(t);
+            double y;
+            if (p < 0) {
+                y = planck_lambda_pref(T, lam, pref) * p2(lam) / FB_C_LIGHT;
+            } else {  // EnergyPassband::bb_nu, passband.hpp:43
+                y = (0.5 * passband_ring_sum(T, cfg.pb_a + cfg.pb_off[p], cfg.pb_w + cfg.pb_off[p], cfg.pb_off[p + 1] - cfg.pb_off[p])) / cfg.pb_tdnu[p];
+            }
+            const double nxt = nx[t], nyt = ny[t], nzc = nz[t] * ci, area = ar[t];
+            const double c0 = d0x * nxt + d0y * nyt + nzc, c1 = d1x * nxt + d1y * nyt + nzc, c2 = d2x * nxt + d2y * nyt + nzc;
+            a = (c0 <= 0.) ? 0. : area * c0 * y;  // Triangle::area_cos, geometry.cpp:201-207
+            b = (c1 <= 0.) ? 0. : area * c1 * y;
+            c = (c2 <= 0.) ? 0. : area * c2 * y;
+        });
     }
 
     // NS columns (ns_output.cpp:6-19); each evaluated by one thread

@@ -47,9 +47,9 @@ cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream)
 cudaError_t measure_fp64_peak(double* tflops);
 
 // field / flux read-out kernels (fields.cu)
-cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream);
-cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
-                        cudaStream_t stream);
+cudaError_t launch_field(const EnsembleDev& E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t launch_flux(const EnsembleDev& E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                        const double* phases_dev, double* out, cudaStream_t stream);
 cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, cudaStream_t stream);
 
 }  // namespace fb200

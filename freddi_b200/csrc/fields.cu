@@ -33,14 +33,19 @@ __device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long lo
     return L;
 }
 
-__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const EnsembleDev E, int field, long long row, double* out) {
+// Work items are (model, row) pairs: rows row0 .. row0 + n_sel - 1 of every model (n_sel = 1, row0 < 0: the current
+// state).  out[model][n_sel][Nx]; pad_nan: NaN outside [first, last] like EvolutionResult (python/freddi/evolution_result.py:55-71).
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const EnsembleDev E, int field, long long row0, int n_sel, int pad_nan,
+                                                             double* out) {
     GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
     ex.init();
     ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
-    for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
+    for (long long item = blockIdx.x; item < (long long)E.n_models * n_sel; item += gridDim.x) {
+        const int model = int(item / n_sel);
+        const long long row = row0 + (item - (long long)model * n_sel);
         __syncthreads();
         const Loaded L = stage(E, model, row, S, ex);
         const fb200_model_dev_t& M = *smem_model();
@@ -110,21 +115,26 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
                 case FB200_FIELD_D2FMAGN_DH2: v = E.d2Fmagn_dh2 ? E.d2Fmagn_dh2[size_t(model) * Nx + i] : 0.; break;
                 default: v = NAN;
             }
-            out[size_t(model) * Nx + i] = L.valid ? v : NAN;
+            if (pad_nan && !(i >= first && i <= last)) v = NAN;
+            out[size_t(item) * Nx + i] = L.valid ? v : NAN;
         }
     }
 }
 
 // out[model][k] = flux_region<region>(lambdas[k]); region 0 hot (Tph over [first,last]), 1 cold (Tirr over [last+1,Nx-1])
-__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const EnsembleDev E, int region, long long row, const double* lambdas,
-                                                            int n_lambdas, double* out) {
+// region 2: the irradiated companion star seen at orbital phase phases[row - row0] (FreddiState::flux_star(lambda, phase),
+// cpp/src/freddi_state.cpp:355-357).  Work items (model, row) as in fb200_field_kernel; out[model][n_sel][n_lambdas].
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const EnsembleDev E, int region, long long row0, int n_sel,
+                                                            const double* lambdas, int n_lambdas, const double* phases, double* out) {
     GpuArrays S = carve_arrays(E.cta_scratch + size_t(blockIdx.x) * SmemLayout::kScratchDoublesPerCta, E.h);
     GpuEx ex;
     ex.init();
     ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
     const int Nx = E.Nx;
-    for (int model = blockIdx.x; model < E.n_models; model += gridDim.x) {
+    for (long long item = blockIdx.x; item < (long long)E.n_models * n_sel; item += gridDim.x) {
+        const int model = int(item / n_sel);
+        const long long row = row0 + (item - (long long)model * n_sel);
         __syncthreads();
         const Loaded L = stage(E, model, row, S, ex);
         const fb200_model_dev_t& M = *smem_model();
@@ -134,6 +144,28 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
         eng.init_points();
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, true);
+        if (region == 2) {
+            // Height2R of the irradiation sources (freddi_state.cpp:663-671), then Teff of every triangle, then one
+            // directional sum per wavelength.  The sources exist from the first step on (freddi_evolution.cpp:28).
+            const double h2r = ex.reduce_max([&](int i, int) -> double {
+                if (i < first || i >= Nx) return 0.;
+                const double R = S.R[i];
+                if (i <= last) return hot_structure(M, sc, S.h[i], R, S.hn[i], S.hm175[i], S.hotR[i], S.F[i]).Height / R;
+                return (M.h2rcold * R) / R;
+            });
+            const bool with_sources = (row >= 0) ? (row > 0) : (E.state[model].i_t > 0);
+            __syncthreads();
+            eng.star_teff(sc, (h2r > 0.) ? h2r : 0., with_sources);
+            const double phase = phases[item - (long long)model * n_sel];
+            for (int k = 0; k < n_lambdas; ++k) {
+                const double lam = lambdas[k];
+                eng.star_dir_sums(lam, FB_DOUBLE_H_C2 / p5(lam), -1, phase);
+                if (threadIdx.x == 0)
+                    out[size_t(item) * n_lambdas + k] = L.valid ? ex.sum(0) * (4. * FB_PI) / (4. * FB_PI * p2(M.distance)) : NAN;
+                __syncthreads();
+            }
+            continue;
+        }
         // temperature of the region at every point
         ex.points([&](int i, int) {
             double T = 0.;
@@ -170,7 +202,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
             });
             if (threadIdx.x < nq) {
                 const double lam = lambdas[k0 + threadIdx.x];
-                out[size_t(model) * n_lambdas + k0 + threadIdx.x] =
+                out[size_t(item) * n_lambdas + k0 + threadIdx.x] =
                     L.valid ? 0.5 * ex.sum(threadIdx.x) * p2(lam) / FB_C_LIGHT * M.cosiOverD2 : NAN;
             }
             __syncthreads();
@@ -282,20 +314,22 @@ cudaError_t measure_fp64_peak(double* tflops) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_field(const EnsembleDev& E, int field, long long row, double* out, cudaStream_t stream) {
+cudaError_t launch_field(const EnsembleDev& E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_field_kernel));
     if (e != cudaSuccess) return e;
-    const int grid = E.n_models < E.max_ctas ? E.n_models : E.max_ctas;
-    fb200_field_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, field, row, out);
+    const long long items = (long long)E.n_models * n_sel;
+    const int grid = items < E.max_ctas ? int(items) : E.max_ctas;
+    fb200_field_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, field, row0, n_sel, pad_nan, out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_flux(const EnsembleDev& E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
-                        cudaStream_t stream) {
+cudaError_t launch_flux(const EnsembleDev& E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                        const double* phases_dev, double* out, cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_flux_kernel));
     if (e != cudaSuccess) return e;
-    const int grid = E.n_models < E.max_ctas ? E.n_models : E.max_ctas;
-    fb200_flux_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, region, row, lambdas_dev, n_lambdas, out);
+    const long long items = (long long)E.n_models * n_sel;
+    const int grid = items < E.max_ctas ? int(items) : E.max_ctas;
+    fb200_flux_kernel<<<grid, kNT, SmemLayout::bytes(), stream>>>(E, region, row0, n_sel, lambdas_dev, n_lambdas, phases_dev, out);
     return cudaGetLastError();
 }
 
@@ -311,12 +345,12 @@ cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, c
 
 #ifdef FB_BIG
 extern "C" {  // see evolve.cu
-cudaError_t fb200_big_launch_field(const void* E, int field, long long row, double* out, cudaStream_t stream) {
-    return fb200::launch_field(*static_cast<const fb200::EnsembleDev*>(E), field, row, out, stream);
+cudaError_t fb200_big_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream) {
+    return fb200::launch_field(*static_cast<const fb200::EnsembleDev*>(E), field, row0, n_sel, pad_nan, out, stream);
 }
-cudaError_t fb200_big_launch_flux(const void* E, int region, long long row, const double* lambdas_dev, int n_lambdas, double* out,
-                                  cudaStream_t stream) {
-    return fb200::launch_flux(*static_cast<const fb200::EnsembleDev*>(E), region, row, lambdas_dev, n_lambdas, out, stream);
+cudaError_t fb200_big_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                  const double* phases_dev, double* out, cudaStream_t stream) {
+    return fb200::launch_flux(*static_cast<const fb200::EnsembleDev*>(E), region, row0, n_sel, lambdas_dev, n_lambdas, phases_dev, out, stream);
 }
 cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream) {
     return fb200::launch_mdot_wind(*static_cast<const fb200::EnsembleDev*>(E), row, out, stream);

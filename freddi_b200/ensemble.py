@@ -84,7 +84,8 @@ class Ensemble:
     lambdas   : wavelengths [cm] of the Fnu columns every row carries (FluxArguments::lambdas)
     passbands : sequence of Passband: one Fnu<name> column each (FluxArguments::passbands)
     cold_disk : add the Fnu_cold columns (--colddiskflux)
-    star_flux : add the Fnu_star, _star_min, _star_max columns of the irradiated companion star (--starflux)
+    star_flux : add the Fnu_star, _star_min, _star_max columns of the irradiated companion star (--starflux);
+                'readout': only triangulate the star so that flux_rows(region='star') works
     record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
     exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip rings that are
                     > 43 decades fainter than the hottest one in the X-ray band; changes Lx by < 1e-31 relative)
@@ -111,7 +112,7 @@ class Ensemble:
         passbands = list(passbands)
         if len(passbands) > FB200_MAX_PASSBANDS:
             raise ValueError('at most {} passbands per ensemble'.format(FB200_MAX_PASSBANDS))
-        cfg.star_flux = int(bool(star_flux))
+        cfg.star_flux = 2 if star_flux == 'readout' else int(bool(star_flux))
         cfg.n_passbands = len(passbands)
         dp = C.POINTER(C.c_double)
         for k, pb in enumerate(passbands):
@@ -133,8 +134,8 @@ class Ensemble:
         self.n_cols = int(_lib.lib.fb200_ensemble_n_cols(handle))
         self.Nx = int(_lib.lib.fb200_ensemble_nx(handle))
         self.passbands = passbands
-        self.star_flux = bool(star_flux)
-        self.columns = column_names(len(lambdas), cold_disk, self.is_ns, [pb.name for pb in passbands], star_flux)
+        self.star_flux = bool(star_flux) and star_flux != 'readout'
+        self.columns = column_names(len(lambdas), cold_disk, self.is_ns, [pb.name for pb in passbands], self.star_flux)
         self._info = None
 
     # -- life cycle --
@@ -245,6 +246,29 @@ class Ensemble:
         dp = C.POINTER(C.c_double)
         _lib.check(_lib.lib.fb200_ensemble_flux(self._h, reg, int(row), lam.ctypes.data_as(dp), lam.size,
                                                 out.ctypes.data_as(dp), out.size))
+        return out
+
+    def field_rows(self, name, row_begin=0, n_rows=None, pad_nan=True):
+        """(n_models, n_rows, Nx) in one launch; pad_nan: NaN outside [first, last] (the EvolutionResult layout)."""
+        n_rows = self.n_rows - row_begin if n_rows is None else int(n_rows)
+        out = np.empty((self.n_models, n_rows, self.Nx))
+        _lib.check(_lib.lib.fb200_ensemble_field_rows(self._h, FIELDS[name], int(row_begin), n_rows, int(bool(pad_nan)),
+                                                      out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out
+
+    def flux_rows(self, lambdas, region='hot', row_begin=0, n_rows=None, phases=None):
+        """(n_models, n_rows, len(lambdas)) in one launch; region 'star' needs one orbital phase [rad] per row."""
+        n_rows = self.n_rows - row_begin if n_rows is None else int(n_rows)
+        lam = np.ascontiguousarray(np.atleast_1d(lambdas), dtype=np.float64).ravel()
+        out = np.empty((self.n_models, n_rows, lam.size))
+        reg = {'hot': 0, 'cold': 1, 'star': 2}[region]
+        dp = C.POINTER(C.c_double)
+        ph = None
+        if phases is not None:
+            ph = np.ascontiguousarray(np.broadcast_to(np.asarray(phases, dtype=np.float64), (n_rows,)))
+        _lib.check(_lib.lib.fb200_ensemble_flux_rows(self._h, reg, int(row_begin), n_rows, lam.ctypes.data_as(dp), lam.size,
+                                                     ph.ctypes.data_as(dp) if ph is not None else None,
+                                                     out.ctypes.data_as(dp), out.size))
         return out
 
     def mdot_wind(self, row=-1):

@@ -3,8 +3,8 @@
 cpp/pywrap/pywrap_freddi_evolution.cpp:303-325), implemented over the C ABI: one model = an ensemble of one,
 evolved by a single persistent-kernel launch with F(h) of every row recorded in HBM.
 
-Differences from the reference, all forced by the star being outside the hot path: ``_flux_star`` / region
-``star`` / ``all`` raise NotImplementedError.
+``EvolutionResult`` serves its (Nt+1, Nx) arrays and ``flux()`` from ONE batched read-out launch over all recorded rows
+(``fb200_ensemble_field_rows`` / ``fb200_ensemble_flux_rows``) instead of one call per state.
 """
 import numpy as np
 
@@ -24,7 +24,7 @@ class _Run:
     def __init__(self, args, is_ns, device):
         self.args = args
         self.is_ns = is_ns
-        self.ens = Ensemble([args], record_F=True, device=device)
+        self.ens = Ensemble([args], record_F=True, device=device, star_flux='readout')
         self.ens.evolve(0)  # row 0 = the initial state
         self.info = self.ens.info()[0]
         self.evolved = False
@@ -178,7 +178,8 @@ class _BaseFreddi:
         return self._run.ens.flux(np.atleast_1d(lmbd), 'cold', self._row)[0]
 
     def _flux_star(self, lmbd, phase=None):
-        raise NotImplementedError('the irradiated companion star is outside the accelerated path')
+        self._run.ensure(self._row)
+        return self._run.ens.flux_rows(np.atleast_1d(lmbd), 'star', self._row, 1, [float(phase)])[0, 0]
 
     def flux(self, lmbd, region='hot', phase=None):
         region = region.lower()
@@ -190,10 +191,14 @@ class _BaseFreddi:
             out = self._flux_cold(flat)
         elif 'disk'.startswith(region):
             out = self._flux_hot(flat) + self._flux_cold(flat)
-        elif 'star'.startswith(region) or 'all'.startswith(region):
+        elif 'star'.startswith(region):
             if phase is None:
                 raise ValueError('Phase must be specified if star flux is required')
-            return self._flux_star(flat, phase)
+            out = self._flux_star(flat, phase)
+        elif 'all'.startswith(region):
+            if phase is None:
+                raise ValueError('Phase must be specified if star flux is required')
+            out = self._flux_hot(flat) + self._flux_cold(flat) + self._flux_star(flat, phase)
         else:
             raise ValueError(f'Zone {region} is not supported')
         return out.reshape(lmbd.shape)
@@ -250,6 +255,17 @@ class EvolutionResult:
         self.__states = tuple(states)
         self.__len_states = len(self.__states)
 
+    def __batched(self):
+        """(run, first row) when the states are consecutive recorded rows of one run, else None."""
+        st = self.__states
+        if not st or not all(isinstance(s, _BaseFreddi) for s in st):
+            return None
+        run, r0 = st[0]._run, st[0]._row
+        if any(s._run is not run or s._row != r0 + i for i, s in enumerate(st)):
+            return None
+        run.ensure(r0 + len(st) - 1)
+        return run, r0
+
     def flux(self, lmbd, region='hot', phase=None):
         from collections.abc import Iterable
         if isinstance(phase, Iterable):
@@ -259,12 +275,32 @@ class EvolutionResult:
         else:
             phase = [phase] * self.__len_states
         lmbd = np.asarray(lmbd)
+        b = self.__batched()
+        reg = region.lower()
+        if b is not None and reg and any(name.startswith(reg) for name in ('hot', 'cold', 'disk', 'star', 'all')):
+            run, r0 = b
+            n = self.__len_states
+            flat = np.asarray(lmbd, dtype=float).ravel()
+            parts = {'hot': ['hot'], 'cold': ['cold'], 'disk': ['hot', 'cold'], 'star': ['star'], 'all': ['hot', 'cold', 'star']}
+            key = next(name for name in ('hot', 'cold', 'disk', 'star', 'all') if name.startswith(reg))
+            if 'star' in parts[key] and any(p is None for p in phase):
+                raise ValueError('Phase must be specified if star flux is required')
+            total = 0.
+            for part in parts[key]:  # one launch per region for all rows
+                ph = np.asarray(phase, dtype=float) if part == 'star' else None
+                total = total + run.ens.flux_rows(flat, part, r0, n, ph)[0]
+            return total.reshape((n,) + lmbd.shape)
         arr = np.empty((self.__len_states,) + lmbd.shape, dtype=float)
         for i in range(self.__len_states):
             arr[i] = self.__states[i].flux(lmbd, region, phase[i])
         return arr
 
     def __getattr__(self, attr):
+        if attr in _ARRAY_PROPS + _NS_ARRAY_PROPS:
+            b = self.__batched()
+            if b is not None:  # one launch for all rows, NaN padding done on the device
+                run, r0 = b
+                return run.ens.field_rows(attr, r0, self.__len_states, pad_nan=True)[0]
         first_val = np.asarray(getattr(self.__states[0], attr))
         if first_val.ndim == 0:
             arr = np.empty(self.__len_states, dtype=first_val.dtype)

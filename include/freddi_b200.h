@@ -159,7 +159,8 @@ typedef struct fb200_config {
     /* --starflux (cpp/src/options.cpp:333): after every Fnu column (and its _cold one) add Fnu*_star, Fnu*_star_min,
      * Fnu*_star_max — the irradiated companion star at the current orbital phase and at the two conjunctions
      * (cpp/src/output.cpp:234-255,272-291).  The Roche-lobe surface is triangulated on the host at create
-     * (20 * 4^starlod triangles per distinct Mopt/Mx, rochelobefill, semi-axis). */
+     * (20 * 4^starlod triangles per distinct Mopt/Mx, rochelobefill, semi-axis).
+     * 2: build the geometry only, for fb200_ensemble_flux_rows(region 2) — no columns, no per-row work. */
     int32_t star_flux;
     int32_t _pad_cfg;
 } fb200_config_t;
@@ -275,6 +276,15 @@ int fb200_ensemble_field(fb200_ensemble_t* e, int field, int64_t row, double* ou
  * out[model][n_lambdas], evaluated on the state of `row` (row<0: current). */
 int fb200_ensemble_flux(fb200_ensemble_t* e, int region, int64_t row, const double* lambdas, size_t n_lambdas,
                         double* out, size_t out_len);
+/* The same for a range of recorded rows in ONE launch (work items = (model, row) pairs): out[model][n_rows][Nx], with
+ * pad_nan != 0 NaN outside [first, last] — the (Nt+1, Nx) arrays of EvolutionResult (python/freddi/evolution_result.py:55-71)
+ * without a call per state.  Requires cfg.record_F. */
+int fb200_ensemble_field_rows(fb200_ensemble_t* e, int field, int64_t row_begin, int64_t n_rows, int pad_nan, double* out, size_t out_len);
+/* Spectral flux densities of a range of rows in one launch: out[model][n_rows][n_lambdas].  region 0 hot, 1 cold,
+ * 2 the irradiated companion star seen at orbital phase phases[row - row_begin] [rad] (FreddiState::flux_star(lambda, phase),
+ * cpp/src/freddi_state.cpp:355-357; needs cfg.star_flux).  row_begin < 0 with n_rows = 1: the current state. */
+int fb200_ensemble_flux_rows(fb200_ensemble_t* e, int region, int64_t row_begin, int64_t n_rows, const double* lambdas, size_t n_lambdas,
+                             const double* phases, double* out, size_t out_len);
 /* Mdot_wind of FreddiState::Mdot_wind (cpp/src/freddi_state.cpp:364-383), per model, on the state of `row`. */
 int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size_t out_len);
 

@@ -350,6 +350,8 @@ double ref_flux(void* h, int region, double lambda) {
     return region == 0 ? f->flux(lambda) : f->flux_region<FreddiState::ColdRegion>(lambda);
 }
 
+double ref_flux_star(void* h, double lambda, double phase) { return static_cast<Model*>(h)->ev()->flux_star(lambda, phase); }
+
 double ref_mdot_wind(void* h) { return static_cast<Model*>(h)->ev()->Mdot_wind(); }
 
 // A whole light curve the way the Python iterator produces it (cpp/include/freddi_evolution.hpp:34-39,56-57):

@@ -231,6 +231,55 @@ def test_freddi_python_surface(ref):
     assert cm.rel_err(result.last_Sigma, r['rows'][:, 4]).max() <= cm.RTOL
     fl = result.flux([5e-5, 8e-5])
     assert fl.shape == (fr.Nt + 1, 2)
+    # the batched read-out (one launch for all rows) equals the per-state getters, NaN padding included
+    states = list(fr)
+    for name in ('F', 'Sigma', 'Tph', 'Tirr', 'Height'):
+        batched = getattr(result, name)
+        for i in (0, 7, fr.Nt):
+            per_state = np.full(fr.Nx, np.nan)
+            sl = slice(states[i].first, states[i].last + 1)
+            per_state[sl] = getattr(states[i], name)[sl]
+            np.testing.assert_array_equal(batched[i], per_state)
+    np.testing.assert_array_equal(fl[5], states[5].flux([5e-5, 8e-5]))
+    m = ref.model(a)
+    for i in range(6):
+        m.step()
+    assert cm.rel_err(result.Tph[6, states[6].first:states[6].last + 1], m.field('Tph')[states[6].first:states[6].last + 1]).max() <= cm.RTOL
+    assert cm.rel_err(fl[6], [m.flux(5e-5), m.flux(8e-5)]).max() <= cm.RTOL
+
+
+def test_python_star_flux_and_regions(ref):
+    """Freddi.flux(lambda, region, phase) for star / disk / all (python/freddi/__init__.py:103-137) against the oracle's
+    flux_star(lambda, phase), per state and batched over the whole EvolutionResult."""
+    import ctypes as C
+    from freddi_b200 import Freddi
+    kw = dict(cm.INI, initialcond='quasistat', Thot=1e4, boundcond='Tirr', Cirr=3e-4, angulardistdisk='plane', Topt=4500, inclination=35,
+              staralbedo=0.2, h2rcold=0.03, Cirrcold=1e-4, time=5)
+    fr = Freddi(**kw)
+    res = fr.evolve()
+    a = cm.ini_args(**{k: v for k, v in kw.items() if k != '__cgs'})
+    m = ref.model(a)
+    f = ref.lib.ref_flux_star
+    f.restype = C.c_double
+    f.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lam = np.array([4e-5, 6e-5])
+    phases = np.linspace(0.3, 5.0, fr.Nt + 1)
+    want_star = np.empty((fr.Nt + 1, 2))
+    want_all = np.empty((fr.Nt + 1, 2))
+    for i in range(fr.Nt + 1):
+        for k, l in enumerate(lam):
+            want_star[i, k] = f(m.h, l, phases[i])
+            want_all[i, k] = want_star[i, k] + m.flux(l, 0) + m.flux(l, 1)
+        if i < fr.Nt:
+            m.step()
+    got = res.flux(lam, 'star', phases)
+    assert got.shape == (fr.Nt + 1, 2) and (got > 0).all()
+    assert cm.rel_err(got, want_star).max() <= cm.RTOL
+    assert cm.rel_err(res.flux(lam, 'all', phases), want_all).max() <= cm.RTOL
+    states = list(fr)
+    np.testing.assert_array_equal(states[3].flux(lam, 'star', phases[3]), got[3])
+    with pytest.raises(ValueError):
+        res.flux(lam, 'star')
 
 
 def test_invalid_arguments_raise_reference_error_classes():

@@ -50,6 +50,7 @@ typedef struct fb200_model_dev {
     double alpha, alphacold, mu;
     /* --- opacity closure, cpp/src/opacity_related.cpp:27-93 --- */
     double one_minus_m, n_op, D, Height_coef, Height_exp_F, Height_exp_R;
+    double m_binom[8]; /* binomial coefficients C(m, k), k = 1..8: (1 + x)^m - 1 for the incremental K update of the Picard loop */
     /* --- boundary / truncation --- */
     double Mdot_out, F_in0, Thot, Tirr2Tvishot;
     /* Sigma_minus/Sigma_plus/v_cooling_front (cpp/src/freddi_state.cpp:692-715): per-model factors */

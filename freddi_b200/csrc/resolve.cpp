@@ -521,6 +521,13 @@ int resolve_impl(const fb200_args_t& a, Resolved& out) {
     d.alphacold = alphacold;
     d.mu = mu;
     d.one_minus_m = 1. - oprel.m;
+    {
+        double c = 1.;
+        for (int k = 1; k <= 8; ++k) {  // C(m, k) = C(m, k-1) (m - k + 1) / k
+            c *= (oprel.m - (k - 1)) / k;
+            d.m_binom[k - 1] = c;
+        }
+    }
     d.n_op = oprel.n;
     d.D = oprel.D;
     d.Height_coef = oprel.Height_coef;

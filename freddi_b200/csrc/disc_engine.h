@@ -408,12 +408,14 @@ FB_HD double wunc_point(const fb200_model_dev_t& M, double F, double hnD) {
     return fb_pow_pos(fabs(F), M.one_minus_m) * hnD;
 }
 
+// W_known >= 0: the closure value is already known (see structure_and_row); need_height = false: Height (a pow per ring) is
+// neither output nor used — isotropic emitters with irrindex = 0 make Qx independent of H/R — and is left 0.
 FB_HD PointStructure hot_structure(const fb200_model_dev_t& M, const StateScalars& sc, double h, double R, double hn, double hm175,
-                                   double hotR, double F) {
+                                   double hotR, double F, double W_known = -1., bool need_height = true) {
     PointStructure q;
-    q.W = wunc_point(M, F, hn);
+    q.W = (W_known >= 0.) ? W_known : wunc_point(M, F, hn);
     q.Sigma = q.W * p2(M.GM) / (4. * FB_PI * p3(h));
-    q.Height = hotR * fb_pow_pos(F, M.Height_exp_F);
+    q.Height = need_height ? hotR * fb_pow_pos(F, M.Height_exp_F) : 0.;
     const double mu = q.Height / R;
     q.Kirr = M.Cirr * ((M.irrindex == 0.) ? 1.0 : pow(q.Height / (R * 0.05), M.irrindex));
     if (M.is_ns) {
@@ -561,6 +563,8 @@ struct DiscEngine {
         WindScalars ws{0, 0, 0, 0, 0};
         if (M.wind_dynamic) ws = wind_scalars(M, Mdot_in_for_wind, S.h[first], S.h[last], S.h[Nx - 1]);
         const bool janiuk = (M.windtype == FB200_WIND_JANIUK2015);
+        // the initial K holds the source term tau C (nonlinear_diffusion.cpp:61): only without one is it the pure closure
+        const bool has_C = M.wind_dynamic || ex.has_windC();
 
         if (janiuk) {  // B changes with Mdot_in: refresh the interior coefficients
             ex.points([&](int i, int k) {
@@ -684,7 +688,7 @@ struct DiscEngine {
                 cur ^= 1;
             }
             const auto z = S.rr[cur];
-            const bool incremental = iters > 0;
+            const bool incremental = iters > 0 || !has_C;
             ex.tick(1);
             // -- back-substitution fused with the y, W, K update and the convergence norm (nonlinear_diffusion.cpp:83-88) --
             maxrel = ex.reduce_max([&](int i, int k) -> double {
@@ -742,11 +746,19 @@ struct DiscEngine {
         const StateScalars sc = state_scalars(ex, M, S, first, true);
 
         // hot-zone structure of every point of [first, last]
+        // After a solve the closure value of an interior ring needs no pow: the last Picard iteration left
+        // K_i = frac_i W(y_i) / y_i for the final y (nonlinear_diffusion.cpp:85-87), so W_i = K_i y_i / frac_i (K[last] is
+        // frozen at its pre-step value and `first` is not part of the system: those two use the closure itself).
+        // Height is needed at every ring only if H/R enters Qx (plane emitters, irrindex != 0) or the star's shadow.
+        const bool height_everywhere = (M.irrindex != 0.) || M.angdist_disk != FB200_ANGDIST_ISOTROPIC ||
+                                       (M.is_ns && M.angdist_ns != FB200_ANGDIST_ISOTROPIC) || (kExtras && cfg.star_flux);
         ex.points([&](int i, int k) {
             if (i >= Nx) return;
             double Tph = 0., Tirr = 0., Sigma = 0., Tvis = 0.;
             if (i >= first && i <= last) {
-                const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i]);
+                const double Wk = (do_truncate && i > first && i < last) ? S.s_K[i] * S.F[i] * fb_rcp(S.s_frac[i]) : -1.;
+                const PointStructure q = hot_structure(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i], Wk,
+                                                       height_everywhere || i == last);
                 Tph = q.Tph; Tirr = q.Tirr; Sigma = q.Sigma; Tvis = q.Tvis;
                 if (i == last) { ex.scalar(0) = q.Kirr; ex.scalar(1) = q.Height / S.R[i]; }
                 if (kExtras && cfg.star_flux) S.aux[i] = q.Height / S.R[i];  // for Height2R of the star's irradiation sources

@@ -243,6 +243,7 @@ struct GpuEx {
     __device__ __forceinline__ double windA(int i) const { return gA ? __ldg(gA + i) : 0.; }
     __device__ __forceinline__ double windB(int i) const { return gB ? __ldg(gB + i) : 0.; }
     __device__ __forceinline__ double windC_static(int i) const { return gCs ? __ldg(gCs + i) : 0.; }
+    __device__ __forceinline__ bool has_windC() const { return gCs != nullptr; }
     __device__ __forceinline__ double Fmagn(int i) const { return gFm ? __ldg(gFm + i) : 0.; }
     __device__ __forceinline__ double dFmagn_dh(int i) const { return gdFm ? __ldg(gdFm + i) : 0.; }
 

@@ -39,6 +39,7 @@ struct HostEx {
     double windA(int i) const { return gA ? gA[i] : 0.; }
     double windB(int i) const { return gB ? gB[i] : 0.; }
     double windC_static(int i) const { return gCs ? gCs[i] : 0.; }
+    bool has_windC() const { return gCs != nullptr; }
     double Fmagn(int i) const { return gFm ? gFm[i] : 0.; }
     double dFmagn_dh(int i) const { return gdFm ? gdFm[i] : 0.; }
     std::vector<double> starT;

@@ -179,24 +179,17 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         ++n;
         const double xnew = 1. * x + (b1 * dt) * k1 + (b3 * dt) * k3 + (b4 * dt) * k4 + (b6 * dt) * k6;
         const double xerr = (db1 * dt) * k1 + (db3 * dt) * k3 + (db4 * dt) * k4 + (db5 * dt) * k5 + (db6 * dt) * k6;
-        // err = |xerr| / den feeds comparisons and the step factor only.  The comparisons are taken on the products
-        // (err > 1  <=>  |xerr| > den, ...), so the common case on the exponential tail of the band — accept at the
-        // growth limit — needs neither the division nor the power.  0/0 (identically zero integrand so far) compares
-        // false both ways like the reference's NaN: accepted, dt unchanged.
-        const double axerr = fabs(xerr);
-        const double den = tol * (fabs(x) + fabs(dt) * fabs(k1));
+        const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
         // Step-size controller.  Both adjustments are powers of the error, so one power evaluation serves the
         // rejecting and the accepting lanes of a warp alike:
         //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
         //   accept, err < 0.5:     dt *= 0.9 max(5^-5, err)^(-1/5)
-        const bool reject = axerr > den;
-        const bool grow = axerr < 0.5 * den;  // err < 0.5
+        const bool reject = err > 1.0;
         const double floor_ = 0.00032;  // pow(5.0, -5)
         double fac;
-        if (!reject && !(floor_ * den < axerr)) {
+        if (!reject && !(floor_ < err)) {
             fac = 4.5;  // 0.9 * (5^-5)^(-1/5): the growth limit — the common case on the exponential tail of the band
         } else {
-            const double err = axerr * fb_rcp(den);
             fac = 9. / 10. * fb_pow_coarse((err < 1e300) ? err : 1e300, reject ? -1. / 3. : -1. / 5.);
         }
         if (reject) {
@@ -206,7 +199,7 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
         }
         fails = 0;
         t += dt;  // == the abscissa of stage 5 (c5 = 1): the derivative at the new t is k5, bit for bit
-        if (grow) dt *= fac;
+        if (err < 0.5) dt *= fac;
         x = xnew;
         k1 = k5;
     }

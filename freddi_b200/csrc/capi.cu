@@ -330,6 +330,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     fb200_model_dev_t* d_models = nullptr;
     ModelState* d_state = nullptr;
     double *d_h = nullptr, *d_F = nullptr, *d_rows = nullptr;
+    FB_TRY(dev_alloc(e, &D.K, NN));
     FB_TRY(dev_alloc(e, &d_models, n_models));
     FB_TRY(dev_alloc(e, &d_state, n_models));
     FB_TRY(dev_alloc(e, &d_h, NN));

@@ -63,7 +63,8 @@ struct OutCfg {
 struct ModelState {
     double t, F_in, Mdot_in_prev;
     int first, last, i_t, status, rows_valid, row0_done;
-    int target_i_t, _pad;  // i_t this launch runs to (set by the first work item of the launch)
+    int target_i_t;  // i_t this launch runs to (set by the first work item of the launch)
+    int k_valid;     // EnsembleDev::K holds the closure K of the state in F (DiscEngine::k_valid carried between work items)
     long long picard_iters;
     long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
 };
@@ -490,6 +491,7 @@ struct DiscEngine {
     const OutCfg& cfg;
     typename Ex::Arrays S;
     ModelState st;  // uniform copy (every thread holds the same values)
+    bool k_valid = false;  // S.s_K holds the closure of the state in S.F for every interior ring (set by a completed solve)
 
     FB_HD DiscEngine(Ex& ex_, const fb200_model_dev_t& M_, const OutCfg& cfg_, const typename Ex::Arrays& S_, const ModelState& st_)
         : ex(ex_), M(M_), cfg(cfg_), S(S_), st(st_) {}
@@ -589,14 +591,23 @@ struct DiscEngine {
                 if (janiuk) B = Bd; else C = Cd + C;
             }
             const double y = S.F[i];
-            const double W = wunc_point(M, y, S.hn[i]);
             double lo, up, cc, frac, rhs;
-            if (!is_last) {
+            if (!is_last && k_valid) {
+                // An interior ring of this step was one in the previous step too (`first` only grows, `last` only shrinks), and
+                // s_K still holds K = frac W(y) / y of that step's last iteration for the very y in S.F: frac W = K y, no pow.
+                lo = S.ca[i]; up = S.cb[i]; cc = S.cc[i]; frac = S.frac[i];
+                const double Kp = S.s_K[i];
+                const double fW = Kp * y;
+                if (C == 0.) { K = Kp; rhs = fW; }
+                else { rhs = fW + frac * (tau * C); K = rhs / y; }
+            } else if (!is_last) {
+                const double W = wunc_point(M, y, S.hn[i]);
                 lo = S.ca[i]; up = S.cb[i]; cc = S.cc[i]; frac = S.frac[i];
                 const double f = frac * (W + tau * C);
                 K = f / y;                // nonlinear_diffusion.cpp:61 — includes tau*C
                 rhs = f;
             } else {
+                const double W = wunc_point(M, y, S.hn[i]);
                 const double d = h - S.h[i - 1];
                 const double aL = 1 - 0.5 * A * d;
                 lo = aL; up = 0.;
@@ -733,6 +744,7 @@ struct DiscEngine {
             if (iters >= 100000) return -1;
         } while (maxrel > M.eps);
         ex.sync();
+        k_valid = true;
         return iters;
     }
 

@@ -74,6 +74,11 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 
             DiscEngine<GpuEx, kExtras> eng(ex, M, cfg, S, st);
             eng.init_points();
+            if (st.k_valid) {  // the closure of the stored state: results do not depend on where a run is cut into work items
+                for (int i = tid; i < Nx; i += kNT) S.s_K[i] = __ldcg(E.K + size_t(model) * Nx + i);
+                eng.k_valid = true;
+                __syncthreads();
+            }
 
             double* rows = E.rows + size_t(model) * nrows * ncol;
             double* Fsnap = E.Fsnap ? E.Fsnap + size_t(model) * nrows * Nx : nullptr;
@@ -97,7 +102,10 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
             // write the state back for the next work item / evolve call / the read-out kernels
             __syncthreads();
             for (int i = tid; i < Nx; i += kNT) E.F[size_t(model) * Nx + i] = S.F[i];
+            if (eng.k_valid)
+                for (int i = tid; i < Nx; i += kNT) E.K[size_t(model) * Nx + i] = S.s_K[i];
             st = eng.st;
+            st.k_valid = eng.k_valid ? 1 : 0;
         }
         if (tid == 0 && (active || round == 0 || s_abort)) E.state[model] = st;
         __threadfence();   // F, rows and state are visible device-wide before the round is published

@@ -15,6 +15,7 @@ struct EnsembleDev {
     ModelState* state;                // [n_models]
     const double* h;                  // [n_models][Nx]
     double* F;                        // [n_models][Nx] current state
+    double* K;                        // [n_models][Nx] K of the last Picard iteration, carried between work items with F
     const double* wA;                 // [n_models][Nx] or null: static wind A
     const double* wB;                 // [n_models][Nx] or null
     const double* wCs;                // [n_models][Nx] or null: static wind C + d2Fmagn_dh2

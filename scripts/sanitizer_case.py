@@ -13,4 +13,17 @@ for args, cold in ((config2_args([0.3, 0.9], [1e-4], time=1.0), True), (config3_
         e.field('Tph', 2); e.flux([5e-5, 8e-5], 'hot', 3); e.mdot_wind()
         e.reset(); e.evolve(1)
         print(len(args), 'models', rows.shape, 'status', e.status()[0].tolist())
+# extras instantiation: passband + companion star columns, batched read-out, star flux at a phase; large-grid build
+from freddi_b200.ensemble import Passband
+pb = Passband('box', np.linspace(4e-5, 6e-5, 40), np.linspace(4e-5, 6e-5, 40) * 1.0)
+args = config2_args([0.3, 0.9], [3e-4], time=1.0, Topt=4000, inclination=40, h2rcold=0.03)
+with Ensemble(args, lambdas=LAM3[:2], cold_disk=True, record_F=True, passbands=[pb], star_flux=True) as e:
+    e.evolve(-1)
+    rows = e.rows()
+    e.field_rows('Sigma'); e.flux_rows([5e-5], 'hot'); e.flux_rows([5e-5], 'star', phases=0.5)
+    print('extras', rows.shape, 'status', e.status()[0].tolist())
+with Ensemble(config2_args([0.5], [1e-4], time=0.5, Nx=1500), lambdas=LAM3[:1], record_F=True) as e:
+    e.evolve(-1)
+    e.field('Tph', 1); e.mdot_wind()
+    print('large grid', e.rows().shape, 'status', e.status()[0].tolist())
 print('done')

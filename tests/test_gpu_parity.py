@@ -293,6 +293,22 @@ def test_invalid_arguments_raise_reference_error_classes():
         Ensemble([cm.ini_args(Nx=50000)])  # beyond the large-grid build (16384)
 
 
+def test_piecewise_evolve_is_bit_identical():
+    """evolve() cut at arbitrary steps gives the same bits as one call: the Picard state carried between work items (F and
+    the closure K of the last iteration) is complete."""
+    from freddi_b200 import Ensemble
+    args = cm.config2_args([0.2, 0.7], [1e-4, 1e-3], time=20) + [cm.ini_args(False, windtype='Woods1996', windparams={'Xi_max': 10, 'T_ic': 1e8, 'Pow': 1},
+                                                                        initialcond='quasistat', Cirr=1e-3, time=20)]
+    with Ensemble(args, lambdas=cm.LAM3) as ens:
+        ens.evolve(-1)
+        whole = ens.rows()
+    with Ensemble(args, lambdas=cm.LAM3) as ens:
+        for n in (1, 6, 13, 30):
+            ens.evolve(n)
+        ens.evolve(-1)
+        np.testing.assert_array_equal(ens.rows(), whole)
+
+
 def test_reset_replays_the_ensemble_bit_for_bit():
     """fb200_ensemble_reset: initial conditions copied again from pinned host memory; the replay is bit-identical."""
     from freddi_b200 import Ensemble

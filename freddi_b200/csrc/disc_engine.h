@@ -940,7 +940,11 @@ struct DiscEngine {
         const double psi = angular_dist(M.angdist_disk, M.cosi);
         const int ncol = cfg.n_cols;
         const double t_now = st.t;
-        ex.points([&](int i, int k) {
+        // One thread per column, columns dealt round-robin over 8 warps (column c -> lane c / 8 of warp c % 8): every case of the
+        // switch below is its own divergent path, and 18 of them in one warp cost more than the rest of the row phase.
+        ex.points([&](int ii, int k) {
+            if (ii >= 256) return;
+            const int i = (ii & 31) * 8 + (ii >> 5);
             if (i >= ncol) return;
             double v;
             switch (i) {

@@ -153,7 +153,9 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
     // Identically-zero integrand: T <= 0 or NaN (Planck_nu returns 0), or exp() overflows to +inf already at
     // nu1 so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros
     // (error 0/0 = NaN compares false both ways) and returns exactly 0; skip the walk.
-    if (!(T > 0.) || FB_H_OVER_KB * nu1 / T > 710.) return 0.;
+    if (!(T > 0.)) return 0.;
+    const double hkT = FB_H_OVER_KB * fb_rcp(T);
+    if (hkT * nu1 > 710.) return 0.;
     const double a21 = 1. / 5.;
     const double a31 = 3. / 40., a32 = 9. / 40.;
     const double a41 = 3. / 10., a42 = -9. / 10., a43 = 6. / 5.;
@@ -168,7 +170,6 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
     const double eps_mach = 2.220446049250313e-16;
     double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
     int fails = 0, n = 0;
-    const double hkT = FB_H_OVER_KB / T;
     double k1 = planck_nu_fast(hkT, t);
     while (nu2 - t > eps_mach) {
         if ((t + dt) - nu2 > eps_mach) dt = nu2 - t;  // less_with_sign(end, t + dt, dt)
@@ -873,7 +874,7 @@ struct DiscEngine {
                 double x = S.c1[i] * F_first;
                 const double g = KM * S.Gb[i];  // = T_GR^4 sigma; T_GR = pow(., 0.25) is NaN for a negative argument
                 x += (g < 0.) ? FB_NAN_INVALID : g;
-                T = M.colourfactor * pow025(x / FB_SIGMA_SB);
+                T = M.colourfactor * pow025(x * (1. / FB_SIGMA_SB));
                 // weight of this ring in the radial trapezoid of the hot zone: 2 pi R_i (R_{i+1} - R_{i-1}) (ends one-sided)
                 if (first < last) {
                     const double R = S.R[i];

@@ -523,6 +523,9 @@ struct DiscEngine {
     FB_HD DiscEngine(Ex& ex_, const fb200_model_dev_t& M_, const OutCfg& cfg_, const typename Ex::Arrays& S_, const ModelState& st_)
         : ex(ex_), M(M_), cfg(cfg_), S(S_), st(st_) {}
 
+    // storage position of reduced unknown q (see solve_step)
+    FB_HD static int rpos(int q) { return Ex::kWarpPcr ? ((q & 7) * 32 + (q >> 3)) : q; }
+
     // nonlinear_diffusion.cpp:46-51 for an interior point i (1 <= i <= Nx-2), wind terms A, B
     FB_HD void interior_coeffs(int i, double A, double B) const {
         const double xm = S.h[i - 1], x = S.h[i], xp = S.h[i + 1];
@@ -701,29 +704,73 @@ struct DiscEngine {
                     }
                 }
                 const double inv0 = fb_rcp(D0), inv1 = fb_rcp(D1);
-                S.lu[0][2 * b] = make_double2(L0 * inv0, U0 * inv0);
-                S.rr[0][2 * b] = R0 * inv0;
-                S.lu[0][2 * b + 1] = make_double2(L1 * inv1, U1 * inv1);
-                S.rr[0][2 * b + 1] = R1 * inv1;
+                // reduced row q is stored at rpos(q): the identity, or the warp-major order of the hybrid solver below
+                S.lu[0][rpos(2 * b)] = make_double2(L0 * inv0, U0 * inv0);
+                S.rr[0][rpos(2 * b)] = R0 * inv0;
+                S.lu[0][rpos(2 * b + 1)] = make_double2(L1 * inv1, U1 * inv1);
+                S.rr[0][rpos(2 * b + 1)] = R1 * inv1;
             });
             ex.sync();
             // -- reduced system (nred unknowns): parallel cyclic reduction, diagonal normalised to 1 --
             int cur = 0;
-            for (int s = 1; s < nred; s <<= 1) {
-                ex.reduced(nred, [&](int q) {
-                    const double2 me = S.lu[cur][q];
-                    const double rme = S.rr[cur][q];
+            if constexpr (Ex::kWarpPcr) {
+                // Hybrid: thread t owns unknown q = warp + 8 lane.  The strides 1, 2, 4 couple different warps and go
+                // through shared memory (two barriers; the third level stays in registers); after them the couplings are
+                // at distance 8 = the neighbouring LANE, and strides 8 .. 128 are warp shuffles without any barrier.
+                // Same arithmetic, level by level, as the plain loop below (levels beyond nred see no neighbour and
+                // leave a row unchanged bit for bit): 4 CTA barriers per Picard iteration instead of 9.
+                const int t = ex.thread(), lane = t & 31;
+                const int q = (t >> 5) + 8 * lane;
+                double lo = 0., up = 0., r = 0.;
+                for (int s = 1; s <= 4; s <<= 1) {
+                    const double2 me = S.lu[cur][t];
+                    const double rme = S.rr[cur][t];
                     const int qm = q - s, qp = q + s;
                     double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
                     double ra = 0., rb = 0.;
-                    if (qm >= 0) { a = S.lu[cur][qm]; ra = S.rr[cur][qm]; }
-                    if (qp < nred) { b = S.lu[cur][qp]; rb = S.rr[cur][qp]; }
+                    if (q < nred && qm >= 0) { a = S.lu[cur][rpos(qm)]; ra = S.rr[cur][rpos(qm)]; }
+                    if (qp < nred) { b = S.lu[cur][rpos(qp)]; rb = S.rr[cur][rpos(qp)]; }
                     const double inv = fb_rcp(1.0 - me.x * a.y - me.y * b.x);
-                    S.lu[cur ^ 1][q] = make_double2(-me.x * a.x * inv, -me.y * b.y * inv);
-                    S.rr[cur ^ 1][q] = (rme - me.x * ra - me.y * rb) * inv;
-                });
+                    lo = -me.x * a.x * inv; up = -me.y * b.y * inv; r = (rme - me.x * ra - me.y * rb) * inv;
+                    if (s < 4) {
+                        S.lu[cur ^ 1][t] = make_double2(lo, up);
+                        S.rr[cur ^ 1][t] = r;
+                        ex.sync();
+                        cur ^= 1;
+                    }
+                }
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double alo = ex.shfl_up(lo, d), aup = ex.shfl_up(up, d), ar = ex.shfl_up(r, d);
+                    const double blo = ex.shfl_down(lo, d), bup = ex.shfl_down(up, d), br = ex.shfl_down(r, d);
+                    const bool ha = lane >= d, hb = (lane + d < 32) && (q + 8 * d < nred);
+                    const double a_x = ha ? alo : 0., a_y = ha ? aup : 0., ra = ha ? ar : 0.;
+                    const double b_x = hb ? blo : 0., b_y = hb ? bup : 0., rb = hb ? br : 0.;
+                    const double inv = fb_rcp(1.0 - lo * a_y - up * b_x);
+                    const double nlo = -lo * a_x * inv, nup = -up * b_y * inv;
+                    r = (r - lo * ra - up * rb) * inv;
+                    lo = nlo; up = nup;
+                }
+                // buffer 1 was last read two barriers ago; buffer 0 may still be read by a warp at stride 4
+                if (q < nred) S.rr[1][q] = r;
                 ex.sync();
-                cur ^= 1;
+                cur = 1;
+            } else {
+                for (int s = 1; s < nred; s <<= 1) {
+                    ex.reduced(nred, [&](int q) {
+                        const double2 me = S.lu[cur][q];
+                        const double rme = S.rr[cur][q];
+                        const int qm = q - s, qp = q + s;
+                        double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
+                        double ra = 0., rb = 0.;
+                        if (qm >= 0) { a = S.lu[cur][qm]; ra = S.rr[cur][qm]; }
+                        if (qp < nred) { b = S.lu[cur][qp]; rb = S.rr[cur][qp]; }
+                        const double inv = fb_rcp(1.0 - me.x * a.y - me.y * b.x);
+                        S.lu[cur ^ 1][q] = make_double2(-me.x * a.x * inv, -me.y * b.y * inv);
+                        S.rr[cur ^ 1][q] = (rme - me.x * ra - me.y * rb) * inv;
+                    });
+                    ex.sync();
+                    cur ^= 1;
+                }
             }
             const auto z = S.rr[cur];
             const bool incremental = iters > 0 || !has_C;

@@ -194,6 +194,15 @@ struct GpuEx {
         for (int q = tid; q < n; q += kNT) f(q);
     }
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    // hybrid reduced-system solver of DiscEngine::solve_step: needs one thread per reduced unknown, 8 warps
+#ifdef FB_BIG
+    static constexpr bool kWarpPcr = false;
+#else
+    static constexpr bool kWarpPcr = (kNT == 256 && FB200_NRED_MAX == 256);
+#endif
+    __device__ __forceinline__ int thread() const { return tid; }
+    __device__ __forceinline__ double shfl_up(double v, int d) const { return __shfl_up_sync(0xffffffffu, v, d); }
+    __device__ __forceinline__ double shfl_down(double v, int d) const { return __shfl_down_sync(0xffffffffu, v, d); }
 #ifdef FB_PROFILE
     // cycle accounting per phase (thread 0 only): phase p collects the cycles since the previous tick
     long long prof_last;

@@ -31,6 +31,10 @@ struct HostEx {
     template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) { cur = i; f(i, 0); } }
     void sync() {}
     void tick(int) {}
+    static constexpr bool kWarpPcr = false;  // the plain PCR loop; the device's hybrid does the same arithmetic level by level
+    int thread() const { return 0; }
+    double shfl_up(double v, int) const { return v; }
+    double shfl_down(double v, int) const { return v; }
     template <class F> void blocks(int n, F&& f) { for (int b = 0; b < n; ++b) f(b); }
     template <class F> void reduced(int n, F&& f) { for (int q = 0; q < n; ++q) f(q); }
     double& scalar(int k) { return scal[k]; }

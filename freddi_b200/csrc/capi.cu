@@ -355,8 +355,8 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
                 evolve_resident_ctas_per_sm(), e->sm_count);
     FB_TRY(dev_alloc(e, &D.cta_scratch, size_t(D.max_ctas) * (big ? fb200_big_evolve_scratch_doubles_per_cta() : evolve_scratch_doubles_per_cta())));
     if (D.star_ntri_max > 0) FB_TRY(dev_alloc(e, &D.star_T, size_t(D.max_ctas) * D.star_ntri_max));
-    FB_TRY(dev_alloc(e, &D.prof, 8));
-    FB_TRYC(cudaMemset(D.prof, 0, 8 * sizeof(long long)));
+    FB_TRY(dev_alloc(e, &D.prof, 16));
+    FB_TRYC(cudaMemset(D.prof, 0, 16 * sizeof(long long)));
     {
         std::vector<fb200_model_dev_t> hm(n_models);
         std::vector<ModelState> hs(n_models);
@@ -527,7 +527,7 @@ int fb200_debug_phase_cycles(fb200_ensemble_t* e, long long* out8) {
     if (!e || !out8) return FB200_ERR_BAD_HANDLE;
     if (select_device(e) != FB200_OK) return FB200_ERR_CUDA;
     cudaStreamSynchronize(e->stream);
-    return cudaMemcpy(out8, e->dev.prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? FB200_OK : FB200_ERR_CUDA;
+    return cudaMemcpy(out8, e->dev.prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? FB200_OK : FB200_ERR_CUDA;
 }
 
 int fb200_ensemble_rows(fb200_ensemble_t* e, double* out, size_t out_len) {

@@ -101,15 +101,6 @@ struct PtrArrays {
 #define FB_DOUBLE_H_C2 (2. * FB_H_PLANCK * FB_C_LIGHT * FB_C_LIGHT)
 #define FB_CH_OVER_KB (FB_C_LIGHT * (FB_H_PLANCK / FB_K_BOLTZ))
 
-// B_nu (cpp/src/spectrum.cpp:10-15) for T > 0 with the lean exp/reciprocal: hk_over_T = (h/k_B)/T.  For h nu / k T > 700 the value
-// (< 1e-295 of the peak) is returned as exactly 0.
-FB_HD double planck_nu_fast(double hk_over_T, double nu) {
-    const double a = hk_over_T * nu;
-    const double em1 = fb_exp_tab((a < 700.) ? a : 700.) - 1.;
-    const double b = FB_DOUBLE_H_OVER_C2 * p3(nu) * fb_rcp(em1);
-    return (a < 700.) ? b : 0.;
-}
-
 // B_lambda with the lambda-only factor pre-divided: pref = double_h_c2 / lambda^5 (same operation order
 // as `double_h_c2 / pow<5>(lambda) / (exp(...) - 1)`)
 FB_HD double planck_lambda_pref(double T, double lambda, double pref) {
@@ -143,41 +134,38 @@ FB_HD double passband_ring_sum(double T, const double* __restrict__ a, const dou
     return s0 + s1;
 }
 
-// integral of B_nu over [nu1, nu2]: boost::numeric::odeint::integrate_adaptive with
-// make_controlled(eps_abs = 0, eps_rel = tol, runge_kutta_cash_karp54<double>), initial step
-// 0.01 (nu2 - nu1) (cpp/src/spectrum.cpp:26-37).  Controller = odeint's default error checker
-// (a_x = a_dxdt = 1) and default step adjuster: reject when err > 1 with dt *= max(0.9 err^(-1/3), 0.2);
-// on acceptance grow when err < 0.5 with dt *= 0.9 max(5^-5, err)^(-1/5).  `trials` counts try_step calls.
-FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) {
-    if (trials) *trials = 0;
-    // Identically-zero integrand: T <= 0 or NaN (Planck_nu returns 0), or exp() overflows to +inf already at
-    // nu1 so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros
-    // (error 0/0 = NaN compares false both ways) and returns exactly 0; skip the walk.
-    if (!(T > 0.)) return 0.;
-    const double hkT = FB_H_OVER_KB * fb_rcp(T);
-    if (hkT * nu1 > 710.) return 0.;
-    const double a21 = 1. / 5.;
-    const double a31 = 3. / 40., a32 = 9. / 40.;
-    const double a41 = 3. / 10., a42 = -9. / 10., a43 = 6. / 5.;
-    const double a51 = -11. / 54., a52 = 5. / 2., a53 = -70. / 27., a54 = 35. / 27.;
-    const double a61 = 1631. / 55296., a62 = 175. / 512., a63 = 575. / 13824., a64 = 44275. / 110592., a65 = 253. / 4096.;
+// nu^3 / (exp(a) - 1), a = (h/k_B) nu / T: B_nu without its constant factor 2h/c^2, which planck_nu1_nu2 applies once to the
+// finished integral.  kClamp = false: the caller guarantees a < 700 over the whole band (no range checks: 2 DSETP and 7
+// integer-pipe instructions fewer per evaluation).
+template <bool kClamp>
+FB_HD double planck_nu_core(double hk_over_T, double nu) {
+    const double a = hk_over_T * nu;
+    if (kClamp) {
+        const double b = p3(nu) * fb_rcp(fb_exp_tab((a < 700.) ? a : 700.) - 1.);
+        return (a < 700.) ? b : 0.;
+    }
+    return p3(nu) * fb_rcp(fb_exp_tab(a) - 1.);
+}
+
+// The adaptive walk of planck_nu1_nu2 over the scaled integrand planck_nu_core.
+template <bool kClamp>
+FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* trials) {
     const double b1 = 37. / 378., b3 = 250. / 621., b4 = 125. / 594., b6 = 512. / 1771.;
     const double db1 = 37. / 378. - 2825. / 27648., db3 = 250. / 621. - 18575. / 48384., db4 = 125. / 594. - 13525. / 55296.,
                  db5 = -277. / 14336., db6 = 512. / 1771. - 1. / 4.;
-    const double c2 = 1. / 5., c3 = 3. / 10., c4 = 3. / 5., c5 = 1., c6 = 7. / 8.;
-    (void)a21; (void)a31; (void)a32; (void)a41; (void)a42; (void)a43; (void)a51; (void)a52; (void)a53; (void)a54;
-    (void)a61; (void)a62; (void)a63; (void)a64; (void)a65;  // the integrand does not depend on the state
+    const double c3 = 3. / 10., c4 = 3. / 5., c5 = 1., c6 = 7. / 8.;
     const double eps_mach = 2.220446049250313e-16;
     double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
     int fails = 0, n = 0;
-    double k1 = planck_nu_fast(hkT, t);
+    double k1 = planck_nu_core<kClamp>(hkT, t);
     while (nu2 - t > eps_mach) {
         if ((t + dt) - nu2 > eps_mach) dt = nu2 - t;  // less_with_sign(end, t + dt, dt)
-        const double k3 = planck_nu_fast(hkT, t + c3 * dt);
-        const double k4 = planck_nu_fast(hkT, t + c4 * dt);
-        const double k5 = planck_nu_fast(hkT, t + c5 * dt);
-        const double k6 = planck_nu_fast(hkT, t + c6 * dt);
-        (void)c2;  // stage 2 has zero weight in both the solution and the error estimate (b2 = db2 = 0)
+        // stage 2 has zero weight in both the solution and the error estimate (b2 = db2 = 0) and the integrand does not depend
+        // on the state: it is not evaluated
+        const double k3 = planck_nu_core<kClamp>(hkT, t + c3 * dt);
+        const double k4 = planck_nu_core<kClamp>(hkT, t + c4 * dt);
+        const double k5 = planck_nu_core<kClamp>(hkT, t + c5 * dt);
+        const double k6 = planck_nu_core<kClamp>(hkT, t + c6 * dt);
         ++n;
         // odeint forms x + (b1 dt) k1 + (b3 dt) k3 + ...; with dt factored out the two sums are 11 instead of 19 FP64
         // instructions (the kernel is FP64-throughput-bound here) and differ from that order by rounding only.
@@ -209,6 +197,31 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
     }
     if (trials) *trials = n;
     return x;
+}
+
+// integral of B_nu over [nu1, nu2]: boost::numeric::odeint::integrate_adaptive with
+// make_controlled(eps_abs = 0, eps_rel = tol, runge_kutta_cash_karp54<double>), initial step
+// 0.01 (nu2 - nu1) (cpp/src/spectrum.cpp:26-37).  Controller = odeint's default error checker
+// (a_x = a_dxdt = 1) and default step adjuster: reject when err > 1 with dt *= max(0.9 err^(-1/3), 0.2);
+// on acceptance grow when err < 0.5 with dt *= 0.9 max(5^-5, err)^(-1/5).  `trials` counts try_step calls.
+// The constant factor 2h/c^2 of B_nu is applied to the finished integral (the controller's error ratio does not see a
+// common factor of the integrand), and the walk is compiled twice: with and without the exp-overflow range checks.
+FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) {
+    if (trials) *trials = 0;
+    // Identically-zero integrand: T <= 0 or NaN (Planck_nu returns 0), or exp() overflows to +inf already at
+    // nu1 so every sample is h nu^3 / inf = 0.  The reference then accepts 100 constant steps of zeros
+    // (error 0/0 = NaN compares false both ways) and returns exactly 0; skip the walk.
+    if (!(T > 0.)) return 0.;
+    const double hkT = FB_H_OVER_KB * fb_rcp(T);
+    if (hkT * nu1 > 710.) return 0.;
+    // Both walks return the same bits where the unchecked one is valid, so the choice is free: on the device it is made per
+    // warp (a warp whose lanes disagreed would run the two walks one after the other).
+    bool unchecked = hkT * nu2 < 699.;
+#ifdef __CUDA_ARCH__
+    unchecked = __all_sync(__activemask(), unchecked);
+#endif
+    const double x = unchecked ? planck_walk<false>(hkT, nu1, nu2, tol, trials) : planck_walk<true>(hkT, nu1, nu2, tol, trials);
+    return FB_DOUBLE_H_OVER_C2 * x;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -673,17 +686,24 @@ struct DiscEngine {
                 } else {
                     // forward: row j becomes  a_j x_0 + x_j + c_j x_{j+1} = g_j ; rolling, results parked in p_a/p_c/p_g
                     double a, c, g;
+                    // The sweep carries the rows unnormalised, A x_0 + D x_j + C x_{j+1} = G (row j times D_{j-1} minus l_j times
+                    // row j-1): the recurrence is two dependent FP64 operations per row instead of seven — no reciprocal on the
+                    // critical path; the reciprocals that normalise the stored rows are independent of each other and pipeline.
+                    // |D| grows by a factor ~(2 + K) per row (K >= 0), 7 rows at most: far inside the double range.
                     {
-                        const int pj = pidx(i0 + 1);
-                        const double inv = fb_rcp(S.s_d[pj]);
-                        a = S.s_l[pj] * inv; c = S.s_u[pj] * inv; g = S.s_rhs[pj] * inv;
-                        S.p_a[pj] = a; S.p_c[pj] = c; S.p_g[pj] = g;
-                    }
-                    for (int j = 2; j < nb; ++j) {
-                        const int pj = pidx(i0 + j);
-                        const double l = S.s_l[pj];
-                        const double inv = fb_rcp(S.s_d[pj] - l * c);
-                        a = -l * a * inv; c = S.s_u[pj] * inv; g = (S.s_rhs[pj] - l * g) * inv;
+                        int pj = pidx(i0 + 1);
+                        double A = S.s_l[pj], D = S.s_d[pj], C = S.s_u[pj], G = S.s_rhs[pj];
+                        for (int j = 2; j < nb; ++j) {
+                            const int pn = pidx(i0 + j);
+                            const double l = S.s_l[pn], d = S.s_d[pn], u = S.s_u[pn], r = S.s_rhs[pn];
+                            const double inv = fb_rcp(D);
+                            S.p_a[pj] = A * inv; S.p_c[pj] = C * inv; S.p_g[pj] = G * inv;
+                            const double Dn = fma(d, D, -(l * C));
+                            G = fma(r, D, -(l * G)); C = u * D; A = -l * A; D = Dn;
+                            pj = pn;
+                        }
+                        const double inv = fb_rcp(D);
+                        a = A * inv; c = C * inv; g = G * inv;
                         S.p_a[pj] = a; S.p_c[pj] = c; S.p_g[pj] = g;
                     }
                     L1 = a; D1 = 1.; U1 = c; R1 = g;      // row nb-1:  a x_0 + x_last + c x_next = g
@@ -711,6 +731,7 @@ struct DiscEngine {
                 S.rr[0][rpos(2 * b + 1)] = R1 * inv1;
             });
             ex.sync();
+            ex.tick(8);
             // -- reduced system (nred unknowns): parallel cyclic reduction, diagonal normalised to 1 --
             int cur = 0;
             if constexpr (Ex::kWarpPcr) {
@@ -739,6 +760,7 @@ struct DiscEngine {
                         cur ^= 1;
                     }
                 }
+                ex.tick(9);
                 for (int d = 1; d < 32; d <<= 1) {
                     const double alo = ex.shfl_up(lo, d), aup = ex.shfl_up(up, d), ar = ex.shfl_up(r, d);
                     const double blo = ex.shfl_down(lo, d), bup = ex.shfl_down(up, d), br = ex.shfl_down(r, d);
@@ -776,43 +798,85 @@ struct DiscEngine {
             const bool incremental = iters > 0 || !has_C;
             ex.tick(1);
             // -- back-substitution fused with the y, W, K update and the convergence norm (nonlinear_diffusion.cpp:83-88) --
-            maxrel = ex.reduce_max([&](int i, int k) -> double {
-                if (i == first) S.F[i] = F_in;
-                if (!(i > first && i <= last)) return 0.;
-                const int un = i - first - 1, b = un / FB200_BLK, j = un - b * FB200_BLK;
-                const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
-                const int pi = pidx(i);
-                double y;
-                if (j == 0) y = z[2 * b];
-                else if (j == nb - 1) y = z[2 * b + 1];
-                else y = S.p_g[pi] - S.p_a[pi] * z[2 * b] - S.p_c[pi] * z[2 * b + 1];
-                const double y_old = S.F[i];
-                S.F[i] = y;
-                if (i == last) return 0.;  // K[last] stays at its pre-step value
-                const double K0 = S.s_K[i];
-                const double inv = fb_rcp(y);
-                // K = frac W / y = (frac h^n / ((1-m) D)) |y|^(1-m) / y  is a pure power of y, so from the second iteration on
-                // (the first K holds the wind term tau C, nonlinear_diffusion.cpp:61 vs :86)  K1 = K0 (y_old / y)^m.
-                // With x = y_old / y - 1 small, (1 + x)^m - 1 is an 8-term binomial series (|x| < 2^-6: truncation < 1e-18),
-                // 10 FP64 operations instead of the 60 of a pow; |K1 - K0| / |K1| = |s| / (1 + s) follows from the same s.
-                const double x = (y_old - y) * inv;
-                double K1, rel;
-                if (incremental && fabs(x) < 0.015625) {
-                    double s = M.m_binom[7];
-                    s = fma(s, x, M.m_binom[6]); s = fma(s, x, M.m_binom[5]); s = fma(s, x, M.m_binom[4]); s = fma(s, x, M.m_binom[3]);
-                    s = fma(s, x, M.m_binom[2]); s = fma(s, x, M.m_binom[1]); s = fma(s, x, M.m_binom[0]);
-                    s *= x;
-                    K1 = fma(K0, s, K0);
-                    rel = fabs(s) * (1. - s);  // |s| / (1 + s) to O(s^2); only compared with eps
-                } else {
-                    const double W = wunc_point(M, y, S.hn[i]);
-                    K1 = S.s_frac[i] * W * inv;  // d = c0 + K absorbs far more than the last ulp of K
-                    rel = fabs((K1 - K0) * fb_rcp(fabs(K1)));  // only compared with eps
+            // K = frac W / y = (frac h^n / ((1-m) D)) |y|^(1-m) / y  is a pure power of y, so from the second iteration on
+            // (the first K holds the wind term tau C, nonlinear_diffusion.cpp:61 vs :86)  K1 = K0 (y_old / y)^m.
+            // With x = y_old / y - 1 small, (1 + x)^m - 1 is an 8-term binomial series (|x| < 2^-6: truncation < 1e-18),
+            // 10 FP64 operations instead of the 60 of a pow; |K1 - K0| / |K1| = |s| / (1 + s) follows from the same s.
+            if (incremental) {
+                // Pass 1 is branch-free (loads at the thread's own, always valid indices; selects and predicated stores), so the
+                // chains of a thread's four rings — reciprocal, series — interleave instead of running one after the other; the
+                // rings whose change is too large for the series are marked (NaN diagonal) and redone with the pow in pass 2.
+                double vmax = 0.;
+                bool anybad = false;
+                const double b0 = M.m_binom[0], b1 = M.m_binom[1], b2 = M.m_binom[2], b3 = M.m_binom[3], b4 = M.m_binom[4],
+                             b5 = M.m_binom[5], b6 = M.m_binom[6], b7 = M.m_binom[7];
+                ex.points_ilp([&](int i, int k) {
+                    const bool in = (i > first) && (i <= last);
+                    const int un = i - first - 1;
+                    int b = ((un < 0) ? 0 : un) / FB200_BLK;
+                    b = (b > nblk - 1) ? nblk - 1 : b;
+                    const int j = un - b * FB200_BLK;
+                    const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
+                    const int pi = pidx(i);
+                    const double z0 = z[2 * b], z1 = z[2 * b + 1];
+                    const double yg = S.p_g[pi] - S.p_a[pi] * z0 - S.p_c[pi] * z1;
+                    const double y = (j == 0) ? z0 : ((j == nb - 1) ? z1 : yg);
+                    const double y_old = S.F[i];
+                    const double K0 = S.s_K[i];
+                    const double inv = fb_rcp(y);
+                    const double x = (y_old - y) * inv;
+                    double sr = b7;
+                    sr = fma(sr, x, b6); sr = fma(sr, x, b5); sr = fma(sr, x, b4); sr = fma(sr, x, b3);
+                    sr = fma(sr, x, b2); sr = fma(sr, x, b1); sr = fma(sr, x, b0);
+                    sr *= x;
+                    const double K1 = fma(K0, sr, K0);
+                    const double rel = fabs(sr) * (1. - sr);  // |s| / (1 + s) to O(s^2); only compared with eps
+                    const bool upd = in && (i != last);       // K[last] stays at its pre-step value
+                    const bool ok = fabs(x) < 0.015625;
+                    if (i == first) S.F[i] = F_in;
+                    if (in) S.F[i] = y;
+                    if (upd) {
+                        S.s_K[i] = ok ? K1 : K0;
+                        S.s_d[pi] = ok ? S.s_cc[i] + K1 : NAN;
+                    }
+                    vmax = fmax(vmax, (upd && ok) ? rel : 0.);  // fmax skips a NaN, as `x > max` does in max_dif_rel
+                    anybad = anybad || (upd && !ok);
+                });
+                if (anybad) {
+                    ex.points([&](int i, int k) {
+                        if (!(i > first && i < last)) return;
+                        const int pi = pidx(i);
+                        if (!fb_isnan(S.s_d[pi])) return;
+                        const double y = S.F[i], K0 = S.s_K[i];
+                        const double W = wunc_point(M, y, S.hn[i]);
+                        const double K1 = S.s_frac[i] * W * fb_rcp(y);
+                        S.s_K[i] = K1;
+                        S.s_d[pi] = S.s_cc[i] + K1;
+                        vmax = fmax(vmax, fabs((K1 - K0) * fb_rcp(fabs(K1))));
+                    });
                 }
-                S.s_K[i] = K1;
-                S.s_d[pi] = S.s_cc[i] + K1;
-                return rel;  // a NaN is skipped by the reduction, as `x > max` does in max_dif_rel
-            });
+                maxrel = ex.reduce_max_of(vmax);
+            } else {
+                maxrel = ex.reduce_max([&](int i, int k) -> double {
+                    if (i == first) S.F[i] = F_in;
+                    if (!(i > first && i <= last)) return 0.;
+                    const int un = i - first - 1, b = un / FB200_BLK, j = un - b * FB200_BLK;
+                    const int nb = (m - b * FB200_BLK < FB200_BLK) ? m - b * FB200_BLK : FB200_BLK;
+                    const int pi = pidx(i);
+                    double y;
+                    if (j == 0) y = z[2 * b];
+                    else if (j == nb - 1) y = z[2 * b + 1];
+                    else y = S.p_g[pi] - S.p_a[pi] * z[2 * b] - S.p_c[pi] * z[2 * b + 1];
+                    S.F[i] = y;
+                    if (i == last) return 0.;  // K[last] stays at its pre-step value
+                    const double K0 = S.s_K[i];
+                    const double W = wunc_point(M, y, S.hn[i]);
+                    const double K1 = S.s_frac[i] * W * fb_rcp(y);  // d = c0 + K absorbs far more than the last ulp of K
+                    S.s_K[i] = K1;
+                    S.s_d[pi] = S.s_cc[i] + K1;
+                    return fabs((K1 - K0) * fb_rcp(fabs(K1)));  // only compared with eps; a NaN is skipped by the reduction
+                });
+            }
             ex.tick(2);
             ++iters;
             if (iters >= 100000) return -1;
@@ -936,6 +1000,7 @@ struct DiscEngine {
             S.wq[i] = wq;
         });
         ex.sync();
+        ex.tick(10);
 
         // max Tph_X over [first, last] with std::max_element's NaN behaviour (output.cpp:208)
         const double TphX_hottest = ex.reduce_max([&](int i, int k) -> double {

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
     ex.set_nx(E.Nx);
     const OutCfg& cfg = stage_cfg(E);
 #ifdef FB_PROFILE
-    for (int p = 0; p < 8; ++p) ex.prof[p] = 0;
+    for (int p = 0; p < 16; ++p) ex.prof[p] = 0;
     ex.prof_last = clock64();
 #endif
     const int tid = threadIdx.x;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
     }
 #ifdef FB_PROFILE
     if (tid == 0 && E.prof)
-        for (int p = 0; p < 8; ++p) atomicAdd(reinterpret_cast<unsigned long long*>(E.prof + p), (unsigned long long)ex.prof[p]);
+        for (int p = 0; p < 16; ++p) atomicAdd(reinterpret_cast<unsigned long long*>(E.prof + p), (unsigned long long)ex.prof[p]);
 #endif
 }
 

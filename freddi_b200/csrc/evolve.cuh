@@ -31,7 +31,7 @@ struct EnsembleDev {
     int n_rounds;                     // work items per model in this launch
     double* cta_scratch;              // [max_ctas][scratch_doubles_per_cta()] once-per-step arrays of the model a CTA holds
     int max_ctas;                     // CTAs the scratch was sized for (2 per SM)
-    long long* prof;                  // [8] per-phase cycle sums (FB_PROFILE builds only), else null
+    long long* prof;                  // [16] per-phase cycle sums (FB_PROFILE builds only), else null
     double* star_T;                   // [max_ctas][star_ntri_max] companion-star triangle temperatures (--starflux), else null
     int star_ntri_max;
     int _pad_star;

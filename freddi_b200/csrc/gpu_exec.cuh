@@ -182,6 +182,15 @@ struct GpuEx {
         FB_UNROLL(FB_UNROLL_POINTS)
         for (int k = 0; k < slots(); ++k) f(tid + k * kNT, k);
     }
+    // the same with the slot loop fully unrolled: for branch-free lambdas whose per-ring dependency chains should interleave
+    template <class F> __device__ __forceinline__ void points_ilp(F&& f) {
+#ifdef FB_BIG
+        for (int k = 0; k < slots(); ++k) f(tid + k * kNT, k);
+#else
+#pragma unroll
+        for (int k = 0; k < kPPT; ++k) f(tid + k * kNT, k);
+#endif
+    }
     // one thread per block / per reduced unknown of the tridiagonal solve
     template <class F> __device__ __forceinline__ void blocks(int n, F&& f) {
 #ifdef FB_BIG
@@ -206,7 +215,7 @@ struct GpuEx {
 #ifdef FB_PROFILE
     // cycle accounting per phase (thread 0 only): phase p collects the cycles since the previous tick
     long long prof_last;
-    long long prof[8];
+    long long prof[16];
     __device__ __forceinline__ void tick(int p) {
         if (tid == 0) { const long long c = clock64(); prof[p] += c - prof_last; prof_last = c; }
     }
@@ -265,6 +274,10 @@ struct GpuEx {
             const double x = f(tid + k * kNT, k);
             v = fmax(v, x);  // fmax skips a NaN like `if (x > max)` does
         }
+        return reduce_max_of(v);
+    }
+    // CTA maximum of one value per thread (NaN-skipping), returned to every thread
+    __device__ __forceinline__ double reduce_max_of(double v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         double* row = fb_smem + L::o_redA + flip * 32;

@@ -29,6 +29,8 @@ struct HostEx {
 
     int cur = 0;  // point the lambda is running for: the host policy has one register slot per point
     template <class F> void points(F&& f) { for (int i = 0; i < NT; ++i) { cur = i; f(i, 0); } }
+    template <class F> void points_ilp(F&& f) { points(f); }
+    double reduce_max_of(double v) const { return v; }  // the sequential policy accumulated it over all points already
     void sync() {}
     void tick(int) {}
     static constexpr bool kWarpPcr = false;  // the plain PCR loop; the device's hybrid does the same arithmetic level by level

@@ -150,10 +150,9 @@ FB_HD double planck_nu_core(double hk_over_T, double nu) {
 // The adaptive walk of planck_nu1_nu2 over the scaled integrand planck_nu_core.
 template <bool kClamp>
 FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* trials) {
-    const double b1 = 37. / 378., b3 = 250. / 621., b4 = 125. / 594., b6 = 512. / 1771.;
-    const double db1 = 37. / 378. - 2825. / 27648., db3 = 250. / 621. - 18575. / 48384., db4 = 125. / 594. - 13525. / 55296.,
-                 db5 = -277. / 14336., db6 = 512. / 1771. - 1. / 4.;
-    const double c3 = 3. / 10., c4 = 3. / 5., c5 = 1., c6 = 7. / 8.;
+    const double b1 = FB_KC(CK_B1), b3 = FB_KC(CK_B3), b4 = FB_KC(CK_B4), b6 = FB_KC(CK_B6);
+    const double db1 = FB_KC(CK_DB1), db3 = FB_KC(CK_DB3), db4 = FB_KC(CK_DB4), db5 = FB_KC(CK_DB5), db6 = FB_KC(CK_DB6);
+    const double c3 = FB_KC(CK_C3), c4 = FB_KC(CK_C4), c5 = 1., c6 = 7. / 8.;
     const double eps_mach = 2.220446049250313e-16;
     double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
     int fails = 0, n = 0;
@@ -177,15 +176,15 @@ FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* tr
         //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
         //   accept, err < 0.5:     dt *= 0.9 max(5^-5, err)^(-1/5)
         const bool reject = err > 1.0;
-        const double floor_ = 0.00032;  // pow(5.0, -5)
+        const double floor_ = FB_KL(CK_FLOOR);  // pow(5.0, -5)
         double fac;
         if (!reject && !(floor_ < err)) {
             fac = 4.5;  // 0.9 * (5^-5)^(-1/5): the growth limit — the common case on the exponential tail of the band
         } else {
-            fac = 9. / 10. * fb_pow_coarse((err < 1e300) ? err : 1e300, reject ? -1. / 3. : -1. / 5.);
+            fac = FB_KL(CK_NINE_TENTHS) * fb_pow_coarse((err < FB_KL(CK_HUGE)) ? err : FB_KL(CK_HUGE), reject ? FB_KL(CK_M_THIRD) : FB_KL(CK_M_FIFTH));
         }
         if (reject) {
-            dt *= (fac < 1. / 5.) ? 1. / 5. : fac;
+            dt *= (fac < FB_KL(CK_FIFTH)) ? FB_KL(CK_FIFTH) : fac;
             if (++fails >= 500) break;  // odeint throws here; unreachable for a Planck integrand
             continue;
         }
@@ -1039,7 +1038,7 @@ struct DiscEngine {
                     if (!cfg.compute_lx) return 0.;
                     int trials = 0;
                     const double T = S.TphX[i];
-                    y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, 1e-4, &trials);
+                    y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, FB_KL(CK_TOL), &trials);
                     S.aux[i] = double(trials);
                 } else {
                     y = planck_lambda_pref(S.Tph[i], cfg.lambdas[q - 2], ex.lambda_pref(q - 2));
@@ -1235,7 +1234,7 @@ struct DiscEngine {
             case FB200_NSCOL_FXNS: {  // ns_evolution.cpp:398-422
                 const double T = pow025(sc.Lbol_ns_rest / (area * FB_SIGMA_SB));
                 const double intensity =
-                    cfg.compute_lx ? planck_nu1_nu2(T, M.emin / M.redshift, M.emax / M.redshift, 1e-4, nullptr) : NAN;
+                    cfg.compute_lx ? planck_nu1_nu2(T, M.emin / M.redshift, M.emax / M.redshift, FB_KL(CK_TOL), nullptr) : NAN;
                 const double Lx_ns = M.redshift * (area * FB_PI * intensity);
                 if (k == FB200_NSCOL_LXNS) return Lx_ns;
                 return Lx_ns * angular_dist(M.angdist_ns, M.cosi) / (4.0 * FB_PI * p2(M.distance));

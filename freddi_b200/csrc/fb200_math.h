@@ -193,11 +193,62 @@ FB_HD double fb_exp(double x) {
     return fb_scale2(p, ki);
 }
 
+// Full-precision FP64 literals cost two UMOV / IMAD.MOV each on sm_100a every time they are used (DFMA takes no 64-bit immediate
+// and ptxas rematerialises them); from __constant__ memory one LDCU.128 fetches two.  FB_KC(name) is the table entry on the
+// device and the literal on the host — one list, so the two cannot drift apart.
+#define FB_KC_LIST(X)                                                                                                     \
+    X(EXP_32_LN2, 46.16624130844683) X(EXP_LN2_32_HI, -0.021660849392446835)                                             \
+    X(EXP_LN2_32_LO, -5.145609244655338e-14) X(EXP_Q6, 1.388888888888889e-03)                                            \
+    X(EXP_Q5, 8.333333333333333e-03) X(EXP_Q4, 4.1666666666666664e-02)                                                   \
+    X(EXP_Q3, 1.6666666666666666e-01) X(CK_B1, 37. / 378.)                                                               \
+    X(CK_B3, 250. / 621.) X(CK_B4, 125. / 594.)                                                                          \
+    X(CK_B6, 512. / 1771.) X(CK_DB1, 37. / 378. - 2825. / 27648.)                                                        \
+    X(CK_DB3, 250. / 621. - 18575. / 48384.) X(CK_DB4, 125. / 594. - 13525. / 55296.)                                    \
+    X(CK_DB5, -277. / 14336.) X(CK_DB6, 512. / 1771. - 1. / 4.)                                                          \
+    X(CK_C3, 3. / 10.) X(CK_C4, 3. / 5.)                                                                                 \
+    X(CK_FLOOR, 0.00032) X(CK_NINE_TENTHS, 9. / 10.)                                                                     \
+    X(CK_M_THIRD, -1. / 3.) X(CK_M_FIFTH, -1. / 5.)                                                                      \
+    X(CK_FIFTH, 1. / 5.) X(CK_HUGE, 1e300)                                                                               \
+    X(ATH_21, 0.047619047619047616) X(ATH_19, 0.05263157894736842)                                                       \
+    X(ATH_17, 0.058823529411764705) X(ATH_15, 0.06666666666666667)                                                       \
+    X(ATH_13, 0.07692307692307693) X(ATH_11, 0.09090909090909091)                                                        \
+    X(ATH_9, 0.1111111111111111) X(ATH_7, 0.14285714285714285)                                                           \
+    X(ATH_5, 0.2) X(ATH_3, 0.3333333333333333)                                                                           \
+    X(TWO_OVER_LN2_HI, 2.8853900817779268) X(TWO_OVER_LN2_LO, 4.0710547481862066e-17)                                    \
+    X(LN2_HI, 0.6931471805599453) X(LN2_LO, 2.3190468138462996e-17)                                                      \
+    X(INVFACT_11, 2.505210838544172e-08) X(INVFACT_10, 2.755731922398589e-07)                                            \
+    X(INVFACT_9, 2.7557319223985893e-06) X(INVFACT_8, 2.48015873015873e-05)                                              \
+    X(INVFACT_7, 1.984126984126984e-04) X(CK_TOL, 1e-4)
+enum {
+#define FB_KC_ENUM(n, v) FBK_##n,
+    FB_KC_LIST(FB_KC_ENUM)
+#undef FB_KC_ENUM
+    FBK_COUNT
+};
+#ifdef __CUDACC__
+static __constant__ __align__(16) double fb_kc[FBK_COUNT] = {
+#define FB_KC_VAL(n, v) v,
+    FB_KC_LIST(FB_KC_VAL)
+#undef FB_KC_VAL
+};
+#endif
+#define FB_KC_HOST(n, v) static const double FBKV_##n = v;
+FB_KC_LIST(FB_KC_HOST)
+#undef FB_KC_HOST
+#ifdef __CUDA_ARCH__
+#define FB_KC(n) fb_kc[FBK_##n]
+#else
+#define FB_KC(n) FBKV_##n
+#endif
+// FB_KL(name): the literal on both sides — for the places where the table entry measured slower than the immediates (the step-size
+// power of the quadrature controller and the controller's own constants: 3.82 -> 3.80 M model-steps/s)
+#define FB_KL(n) FBKV_##n
+
 // exp(x) for -700 <= x <= 709 for the Planck function, ~1 ulp with 11 FP64 operations: n = rint(32 x / ln2),
 // exp(x) = 2^(n >> 5) * 2^((n & 31)/32) * exp(r), |r| <= ln2/64, expm1(r) by a 6th-degree polynomial (truncation 4e-18).
 FB_HD double fb_exp_tab(double x) {
     const double shift = 6755399441055744.0;  // 1.5 * 2^52
-    const double t = fma(x, 46.16624130844683, shift);  // 32 / ln2
+    const double t = fma(x, FB_KC(EXP_32_LN2), shift);  // 32 / ln2
     const double n = t - shift;
 #ifdef __CUDA_ARCH__
     const int ni = __double2loint(t);
@@ -206,11 +257,11 @@ FB_HD double fb_exp_tab(double x) {
     u.d = t;
     const int ni = (int)(u.i & 0xffffffffLL);
 #endif
-    double r = fma(n, -0.021660849392446835, x);     // ln2/32, leading 37 bits (n * hi is exact)
-    r = fma(n, -5.145609244655338e-14, r);           // ln2/32, tail
-    double q = fma(r, 1.388888888888889e-03, 8.333333333333333e-03);
-    q = fma(q, r, 4.1666666666666664e-02);
-    q = fma(q, r, 1.6666666666666666e-01);
+    double r = fma(n, FB_KC(EXP_LN2_32_HI), x);      // ln2/32, leading 37 bits (n * hi is exact)
+    r = fma(n, FB_KC(EXP_LN2_32_LO), r);             // ln2/32, tail
+    double q = fma(r, FB_KC(EXP_Q6), FB_KC(EXP_Q5));
+    q = fma(q, r, FB_KC(EXP_Q4));
+    q = fma(q, r, FB_KC(EXP_Q3));
     q = fma(q, r, 0.5);
     const double p = fma(q * r, r, r);               // expm1(r)
     const double tj = FB_EXP2_TAB(ni & 31);
@@ -268,19 +319,19 @@ FB_HD double fb_pow_pos(double x, double a) {
     const double s_lo = t * r;
     // atanh(s) = s + s (s^2/3 + s^4/5 + ... + s^20/21), |s| <= 0.1716
     const double s2 = s_hi * s_hi;
-    double q = 0.047619047619047616;
-    q = fma(q, s2, 0.05263157894736842);
-    q = fma(q, s2, 0.058823529411764705);
-    q = fma(q, s2, 0.06666666666666667);
-    q = fma(q, s2, 0.07692307692307693);
-    q = fma(q, s2, 0.09090909090909091);
-    q = fma(q, s2, 0.1111111111111111);
-    q = fma(q, s2, 0.14285714285714285);
-    q = fma(q, s2, 0.2);
-    q = fma(q, s2, 0.3333333333333333);
+    double q = FB_KC(ATH_21);
+    q = fma(q, s2, FB_KC(ATH_19));
+    q = fma(q, s2, FB_KC(ATH_17));
+    q = fma(q, s2, FB_KC(ATH_15));
+    q = fma(q, s2, FB_KC(ATH_13));
+    q = fma(q, s2, FB_KC(ATH_11));
+    q = fma(q, s2, FB_KC(ATH_9));
+    q = fma(q, s2, FB_KC(ATH_7));
+    q = fma(q, s2, FB_KC(ATH_5));
+    q = fma(q, s2, FB_KC(ATH_3));
     const double a_lo = fma(s_hi * s2, q, s_lo);        // tail + s_lo
     // log2 m = (2/ln2) (s_hi + a_lo), double-double product
-    const double c_hi = 2.8853900817779268, c_lo = 4.0710547481862066e-17;
+    const double c_hi = FB_KC(TWO_OVER_LN2_HI), c_lo = FB_KC(TWO_OVER_LN2_LO);
     const double p_hi = s_hi * c_hi;
     const double p_lo = fma(s_hi, c_hi, -p_hi) + fma(s_hi, c_lo, a_lo * c_hi);
     // log2 x = e + p_hi + p_lo
@@ -302,10 +353,10 @@ FB_HD double fb_pow_pos(double x, double a) {
 #endif
     if (ni > 32000 || ni < -32000) return pow(x, a);
     const double f = fma(nk, -0.03125, y_hi) + y_lo;   // exact subtraction, then the low part
-    const double g = fma(f, 0.6931471805599453, f * 2.3190468138462996e-17);
-    double w = fma(g, 1.388888888888889e-03, 8.333333333333333e-03);
-    w = fma(w, g, 4.1666666666666664e-02);
-    w = fma(w, g, 1.6666666666666666e-01);
+    const double g = fma(f, FB_KC(LN2_HI), f * FB_KC(LN2_LO));
+    double w = fma(g, FB_KC(EXP_Q6), FB_KC(EXP_Q5));
+    w = fma(w, g, FB_KC(EXP_Q4));
+    w = fma(w, g, FB_KC(EXP_Q3));
     w = fma(w, g, 0.5);
     const double pm1 = fma(w * g, g, g);               // expm1(g)
     const double tj = FB_EXP2_TAB(ni & 31);
@@ -336,15 +387,15 @@ FB_HD double fb_pow_coarse(double base, double p) {
     // log2(m) = (2/ln2) atanh(s), s = (m-1)/(m+1), |s| <= 0.1716
     const double s = (m - 1.0) * fb_rcp(m + 1.0);
     const double s2 = s * s;
-    double q = 1. / 15.;
-    q = fma(q, s2, 1. / 13.);
-    q = fma(q, s2, 1. / 11.);
-    q = fma(q, s2, 1. / 9.);
-    q = fma(q, s2, 1. / 7.);
-    q = fma(q, s2, 1. / 5.);
-    q = fma(q, s2, 1. / 3.);
+    double q = FB_KL(ATH_15);
+    q = fma(q, s2, FB_KL(ATH_13));
+    q = fma(q, s2, FB_KL(ATH_11));
+    q = fma(q, s2, FB_KL(ATH_9));
+    q = fma(q, s2, FB_KL(ATH_7));
+    q = fma(q, s2, FB_KL(ATH_5));
+    q = fma(q, s2, FB_KL(ATH_3));
     q = fma(q * s2, s, s);
-    const double lg = fma(q, 2.8853900817779268, (double)e);  // 2/ln2
+    const double lg = fma(q, FB_KL(TWO_OVER_LN2_HI), (double)e);  // 2/ln2
     // 2^(p lg)
     const double y = p * lg;
     const double shift = 6755399441055744.0;
@@ -356,16 +407,16 @@ FB_HD double fb_pow_coarse(double base, double p) {
     u.d = t;
     const int ki = (int)(u.i & 0xffffffffLL);
 #endif
-    const double f = (y - k) * 0.6931471805599453;  // ln2
-    double w = 2.505210838544172e-08;            // 1/11!
-    w = fma(w, f, 2.755731922398589e-07);
-    w = fma(w, f, 2.7557319223985893e-06);
-    w = fma(w, f, 2.48015873015873e-05);
-    w = fma(w, f, 1.984126984126984e-04);
-    w = fma(w, f, 1.388888888888889e-03);
-    w = fma(w, f, 8.333333333333333e-03);
-    w = fma(w, f, 4.1666666666666664e-02);
-    w = fma(w, f, 1.6666666666666666e-01);
+    const double f = (y - k) * FB_KL(LN2_HI);  // ln2
+    double w = FB_KL(INVFACT_11);            // 1/11!
+    w = fma(w, f, FB_KL(INVFACT_10));
+    w = fma(w, f, FB_KL(INVFACT_9));
+    w = fma(w, f, FB_KL(INVFACT_8));
+    w = fma(w, f, FB_KL(INVFACT_7));
+    w = fma(w, f, FB_KL(EXP_Q6));
+    w = fma(w, f, FB_KL(EXP_Q5));
+    w = fma(w, f, FB_KL(EXP_Q4));
+    w = fma(w, f, FB_KL(EXP_Q3));
     w = fma(w, f, 0.5);
     w = fma(w, f, 1.0);
     w = fma(w, f, 1.0);

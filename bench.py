@@ -274,7 +274,8 @@ def run_gpu(opts):
                         frac=(achieved_tf / peak) if peak else None, traffic=traffic,
                         peak_source='DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)',
                         flop_model='SURVEY.md 8(d) op counts x SASS-counted FP64 flop per call (pow 100, exp 31, log 45, div 20, sqrt 20); '
-                                   'measured P={:.2f} Picard iterations/step, S={:.2f} quadrature trial steps/point/row'.format(P, S),
+                                   'measured P={:.2f} Picard iterations/step, S={:.2f} quadrature trial steps/point/row (the trial steps the kernel '
+                                   'executes: rings it prunes are not counted)'.format(P, S),
                         flops_per_model_step=fl,
                         hbm=dict(achieved=per_gpu_rate * hbm_bytes_per_step / 1e9, peak=peaks.get('hbm_gbs'), unit='GB/s',
                                  note='algorithmic HBM traffic is one {}-byte row per model-step: irrelevant to this path'.format(

@@ -34,7 +34,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace fb200 {
 
-#define FB200_LX_PRUNE 100.0 /* see structure_and_row: rings fainter than exp(-100) of the hottest one in the X-ray band */
+#define FB200_LX_PRUNE 100.0 /* see structure_and_row: upper limit of the per-row pruning exponent of the Lx quadrature */
 #define FB200_MAXQ 44 /* reduction slots: Mdisk, Lx, Fnu[16], Fnu_cold[16], passbands[4], passbands_cold[4], Lx trial count */
 
 // Ensemble-wide output configuration (device copy of fb200_config_t's output part)
@@ -1003,12 +1003,24 @@ struct DiscEngine {
         });
         double TphXmax = TphX_hottest;
         if (fb_isnan(S.TphX[first])) TphXmax = S.TphX[first];  // max_element returns the first element
-        // Rings whose X-ray band emission is below exp(-FB200_LX_PRUNE) = 4e-44 of the hottest ring's are not
-        // integrated: B_nu(T_i)/B_nu(T_hot) <= exp(-(a_i - a_hot)) for every nu of the band (a = h nu1 / k T), and
-        // Lx >= the hottest ring's share, so even with an area ratio of 1e12 the omitted rings change Lx by
-        // < 1e-31 relative — twenty orders below the 1e-10 parity tolerance.  (The reference walks them all.)
+        // Rings that cannot contribute to Lx are not integrated (the reference walks them all).  With a = h nu1 / k T,
+        // B_nu(T_i) / B_nu(T_hot) <= exp(-(a_i - a_hot)) for every nu of the band, and Lx >= the hottest ring's share
+        // 1/2 wq_hot I(T_hot), so the rings with a_i - a_hot > P change Lx by less than
+        //     exp(-P) * sum_i wq_i / wq_hot  <=  exp(-P) * 4 pi R_last^2 / wq[first]
+        // relative (sum_i wq_i = 2 pi sum R_i (R_{i+1} - R_{i-1}) <= 4 pi R_last^2; wq[first], the one-sided weight of the
+        // innermost ring, is the smallest weight of the hot zone on the log and the linear grid alike).  P is chosen per row so
+        // that this bound is 1e-16 — six orders below the 1e-10 parity tolerance, below the rounding of the sum itself — and
+        // never above the fixed FB200_LX_PRUNE = 100.
         const double a_hot = (TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / TphX_hottest : 0.;
-        const double T_prune = (cfg.lx_prune && TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / (a_hot + FB200_LX_PRUNE) : 0.;
+        double prune = FB200_LX_PRUNE;
+        {
+            const double ratio = 4. * FB_PI * p2(S.R[last]) * fb_rcp(S.wq[first]);
+            if (ratio > 1. && ratio < 1e25) {
+                const double P = log(ratio) + 36.85;  // -ln(1e-16) = 36.84
+                prune = (P < FB200_LX_PRUNE) ? P : FB200_LX_PRUNE;
+            }
+        }
+        const double T_prune = (cfg.lx_prune && TphX_hottest > 0.) ? FB_H_OVER_KB * M.emin / (a_hot + prune) : 0.;
 
         // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
         // slots: 0 Mdisk, 1 Lx, [2, 2+nl) Fnu hot, [2+nl, 2+2nl) Fnu cold, [q_pb, q_pb+npb) passbands hot,

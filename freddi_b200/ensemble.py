@@ -87,8 +87,8 @@ class Ensemble:
     star_flux : add the Fnu_star, _star_min, _star_max columns of the irradiated companion star (--starflux);
                 'readout': only triangulate the star so that flux_rows(region='star') works
     record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
-    exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip rings that are
-                    > 43 decades fainter than the hottest one in the X-ray band; changes Lx by < 1e-31 relative)
+    exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip the rings that are
+                    provably negligible against the hottest one in the X-ray band; changes Lx by < 1e-16 relative)
     """
 
     def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0,

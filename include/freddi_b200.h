@@ -144,9 +144,9 @@ typedef struct fb200_config {
     int32_t compute_lx;     /* 1 (reference behaviour): Lx/Fx by the adaptive quadrature; 0: columns NaN  */
     int32_t host_threads;   /* threads for host-side argument resolution, 0 = all cores                   */
     int32_t threads_per_model; /* reserved (the CTA size is a build-time constant)                       */
-    int32_t exact_lx_walk;  /* 0 (default): rings whose X-ray band emission is < exp(-100) of the hottest
-                             * ring's are not integrated (changes Lx by < 1e-31 relative); 1: integrate every
-                             * ring like the reference does                                                 */
+    int32_t exact_lx_walk;  /* 0 (default): rings whose X-ray band emission is provably negligible against the
+                             * hottest ring's are not integrated (changes Lx by < 1e-16 relative, bound per row);
+                             * 1: integrate every ring like the reference does                              */
     /* Tabulated passbands, FluxArguments::passbands (cpp/include/arguments.hpp:287): one Fnu<name> column each
      * (+ Fnu<name>_cold with cold_disk) after the Fnu{k} columns, cpp/src/output.cpp:258-271.  The arrays are what
      * EnergyPassband holds (cpp/include/passband.hpp:33-36): wavelengths [cm] and transmission factors, for the

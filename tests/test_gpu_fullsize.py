@@ -80,8 +80,8 @@ def test_full_sweep_sample_against_oracle(full_run, ref):
 
 
 def test_exact_lx_walk_agrees_with_pruned_lx(full_run):
-    """The pruned Lx (rings > 43 decades fainter than the hottest one skipped) equals the ring-by-ring walk to far
-    better than the parity tolerance."""
+    """The pruned Lx (rings skipped whose total share is bounded by 1e-16 of Lx, disc_engine.h structure_and_row) equals the
+    ring-by-ring walk to far better than the parity tolerance."""
     from freddi_b200 import Ensemble
     r = full_run
     pick = list(range(0, 1000, 125))

@@ -755,12 +755,14 @@ struct DiscEngine {
                     }
                 }
                 ex.tick(9);
+                // No selects on the neighbours' values in the shuffle levels: a row without a lower (upper) neighbour at the
+                // current stride has lo (up) == +-0 exactly — the guards of the levels above made it a product with 0, and
+                // every later level multiplies it on — so whatever finite value the shuffle delivers (the lane's own one at the
+                // warp's edge, the zeros of a padding row) drops out as 0 * finite.
+                if (q >= nred) { lo = 0.; up = 0.; r = 0.; }  // padding rows: finite, and they stay 0 / 0 / 0
                 for (int d = 1; d < 32; d <<= 1) {
-                    const double alo = ex.shfl_up(lo, d), aup = ex.shfl_up(up, d), ar = ex.shfl_up(r, d);
-                    const double blo = ex.shfl_down(lo, d), bup = ex.shfl_down(up, d), br = ex.shfl_down(r, d);
-                    const bool ha = lane >= d, hb = (lane + d < 32) && (q + 8 * d < nred);
-                    const double a_x = ha ? alo : 0., a_y = ha ? aup : 0., ra = ha ? ar : 0.;
-                    const double b_x = hb ? blo : 0., b_y = hb ? bup : 0., rb = hb ? br : 0.;
+                    const double a_x = ex.shfl_up(lo, d), a_y = ex.shfl_up(up, d), ra = ex.shfl_up(r, d);
+                    const double b_x = ex.shfl_down(lo, d), b_y = ex.shfl_down(up, d), rb = ex.shfl_down(r, d);
                     const double inv = fb_rcp(1.0 - lo * a_y - up * b_x);
                     const double nlo = -lo * a_x * inv, nup = -up * b_y * inv;
                     r = (r - lo * ra - up * rb) * inv;

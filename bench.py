@@ -109,21 +109,22 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
-def cpu_baseline(n_models_cap=None, cores=None):
+def cpu_baseline(n_models_cap=None, cores=None, args=None, sweep='alpha x Cirr'):
     """The reference's own CPU implementation (oracle/_ref: unmodified sources + Boost shim), one model per
-    thread across all host cores, on a bounded sample of the N=1 workload."""
+    thread across all host cores, on a bounded sample of the N=1 workload (or of `args`: scripts/sweep_1e5.py)."""
     from oracle import pyoracle
     ref = pyoracle.Ref()
     cores = cores or os.cpu_count() or 1
-    args = workload_args(1)
+    if args is None:
+        args = workload_args(1)
     n = min(len(args), n_models_cap or max(8, 8 * cores))
     idx = np.linspace(0, len(args) - 1, n).round().astype(int)  # stride-sampled over the sweep
     sample = [args[i] for i in idx]
     out = ref.run_ensemble(sample, LAMBDAS, n_threads=cores)
     value = out['steps'] / out['evolve_s']
     return dict(value=value, unit=UNIT, cores=cores, kind='reference',
-                sample='{} of {} models (every {:.1f}-th of the alpha x Cirr sweep), all {} steps each; evolve {:.2f} s, '
-                       'model construction {:.2f} s excluded'.format(n, len(args), len(args) / n, out['steps'] // n,
+                sample='{} of {} models (every {:.1f}-th of the {} sweep), all {} steps each; evolve {:.2f} s, '
+                       'model construction {:.2f} s excluded'.format(n, len(args), len(args) / n, sweep, out['steps'] // n,
                                                                       out['evolve_s'], out['construct_s']),
                 steps=out['steps'], evolve_s=out['evolve_s'], construct_s=out['construct_s'])
 

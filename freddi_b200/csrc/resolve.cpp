@@ -137,7 +137,7 @@ struct GridMemo {
     std::vector<double> h;
 };
 struct FfMemo {
-    double key[9];  // h.front(), h[1], h.back(), N, a0, a1, a2, k, l
+    double key[10];  // h.front(), h[1], h[N/2], h.back(), N, a0, a1, a2, k, l (the grids are log or linear: these points fix them)
     std::vector<double> fF;
     bool valid = false;
 };
@@ -305,7 +305,7 @@ void initial_F(const InitialF& ic, const Oprel& oprel, const std::vector<double>
             break;
         case FB200_IC_QUASISTAT: {
             static thread_local FfMemo memo;
-            const double key[9] = {h.front(), h[N > 1 ? 1 : 0], h.back(), double(N), oprel.a0, oprel.a1, oprel.a2, oprel.k, oprel.l};
+            const double key[10] = {h.front(), h[N > 1 ? 1 : 0], h[N / 2], h.back(), double(N), oprel.a0, oprel.a1, oprel.a2, oprel.k, oprel.l};
             if (!(memo.valid && std::memcmp(memo.key, key, sizeof(key)) == 0)) {
                 memo.fF.resize(N);
                 for (size_t i = 0; i < N; ++i) memo.fF[i] = oprel.f_F(h[i] / h.back());

@@ -93,6 +93,27 @@ def test_resolver_reproduces_reference_constructors(ref, built, name):
             assert getattr(info, f) == getattr(ri, f), f
 
 
+def test_resolver_memos_are_transparent(ref, built):
+    """The per-thread memos of the resolver (grid, quasistat normalisation integral, f_F on the grid: resolve.cpp) return the
+    same bits whether they hit or miss, in any order of the models of a sweep — and those bits are the reference's."""
+    from freddi_b200.ensemble import resolve
+    mk = lambda **kw: cm.ini_args(False, initialcond='quasistat', F0=None, Thot=1e4, boundcond='Tirr', Cirr=1e-4, **kw)  # noqa: E731
+    sweep = [mk(Mx=5, alpha=0.3, Mdisk0=1e26), mk(Mx=5, alpha=0.7, Mdisk0=3e25),       # same grid: hits
+             mk(Mx=9, alpha=0.3, Mdisk0=1e26), mk(Mx=9, alpha=0.3, Mdisk0=1e26, opacity='OPAL'),
+             mk(Mx=9, alpha=0.3, Mdisk0=1e26, gridscale='linear'), mk(Mx=9, alpha=0.3, Mdisk0=1e26, Nx=300)]
+    first = [resolve(a) for a in sweep]
+    for order in (range(len(sweep)), reversed(range(len(sweep))), (0, 0, 2, 1, 3, 3, 5, 4, 0)):
+        for k in order:
+            info, h, F = resolve(sweep[k])
+            np.testing.assert_array_equal(h, first[k][1])
+            np.testing.assert_array_equal(F, first[k][2])
+            assert info.first0 == first[k][0].first0
+    for a, (info, h, F) in zip(sweep, first):
+        m = ref.model(a)
+        np.testing.assert_array_equal(h, m.field('h'))
+        np.testing.assert_array_equal(F, m.field('F'))
+
+
 @pytest.mark.parametrize('kw,exc', [
     (dict(F0=None), RuntimeError),                       # One of F0, Mdisk0 or Mdot0 must be specified
     (dict(Mdot0=1e18), RuntimeError),                    # Set Mdisk0 or F0 instead of Mdot0 if initialcond=powerF

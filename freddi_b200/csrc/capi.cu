@@ -1,6 +1,8 @@
 // extern "C" layer of include/freddi_b200.h: owns device memory, resolves arguments on the host, launches
 // the kernels.  No CPU implementation of the path lives here: without a CUDA device every compute call fails.
 #include <atomic>
+#include <memory>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -64,7 +66,7 @@ struct fb200_ensemble {
     double* scratch = nullptr;  // [n * Nx] read-out staging
     size_t scratch_len = 0;
     // initial conditions kept on the host for fb200_ensemble_reset (pinned staging is allocated on first use)
-    std::vector<double> host_F0;
+    std::unique_ptr<double[]> host_F0;  // [n * Nx]
     std::vector<ModelState> host_state0;
     double* pinned_F0 = nullptr;
     ModelState* pinned_state0 = nullptr;
@@ -158,6 +160,14 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
                           size_t* bad_model) {
     if (bad_model) *bad_model = 0;
     if (!args || !out || n_models == 0) return set_err(FB200_ERR_INVALID_ARGUMENT, "null argument or empty ensemble");
+    const bool dbg_time = getenv("FB200_DEBUG") != nullptr;  // FB200_DEBUG: where the time of a create goes, on stderr
+    auto dbg_t0 = std::chrono::steady_clock::now();
+    auto dbg_lap = [&](const char* what) {
+        if (!dbg_time) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fb200] create: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - dbg_t0).count());
+        dbg_t0 = t;
+    };
     fb200_config_t cfg;
     if (cfg_in) cfg = *cfg_in; else fb200_config_default(&cfg);
     if (cfg.n_lambdas < 0 || cfg.n_lambdas > FB200_MAX_LAMBDAS) return set_err(FB200_ERR_INVALID_ARGUMENT, "n_lambdas out of range");
@@ -173,13 +183,14 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     std::vector<Resolved> res(n_models);
     std::vector<int> codes(n_models, FB200_OK);
     std::vector<std::string> errs(n_models);
-    {
+    // body(i) for every model, on the host threads of the configuration (models are handed out one by one: their cost varies)
+    auto for_each_model = [&](auto&& body) {
         unsigned nt = cfg.host_threads > 0 ? unsigned(cfg.host_threads) : std::thread::hardware_concurrency();
         if (nt == 0) nt = 1;
         if (nt > n_models) nt = unsigned(n_models);
         std::atomic<size_t> next{0};
         auto work = [&] {
-            for (size_t i; (i = next.fetch_add(1)) < n_models;) codes[i] = resolve(args[i], res[i], errs[i]);
+            for (size_t i; (i = next.fetch_add(1)) < n_models;) body(i);
         };
         if (nt <= 1) {
             work();
@@ -188,7 +199,9 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
             for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work);
             for (auto& th : pool) th.join();
         }
-    }
+    };
+    for_each_model([&](size_t i) { codes[i] = resolve(args[i], res[i], errs[i]); });
+    dbg_lap("host resolve");
     for (size_t i = 0; i < n_models; ++i) {
         if (codes[i] != FB200_OK) {
             if (bad_model) *bad_model = i;
@@ -326,6 +339,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
         D.cfg.star_data = d_star;
     }
 
+    dbg_lap("context, stream, tables");
     const size_t NN = n_models * size_t(Nx);
     fb200_model_dev_t* d_models = nullptr;
     ModelState* d_state = nullptr;
@@ -357,11 +371,14 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     if (D.star_ntri_max > 0) FB_TRY(dev_alloc(e, &D.star_T, size_t(D.max_ctas) * D.star_ntri_max));
     FB_TRY(dev_alloc(e, &D.prof, 16));
     FB_TRYC(cudaMemset(D.prof, 0, 16 * sizeof(long long)));
+    dbg_lap("device allocations");
     {
         std::vector<fb200_model_dev_t> hm(n_models);
         std::vector<ModelState> hs(n_models);
-        std::vector<double> hh(NN), hF(NN);
-        for (size_t i = 0; i < n_models; ++i) {
+        // 16 KB per model: packed by the host threads into buffers that are not value-initialised first (a single thread zeroing and
+        // filling 200 MB for 12,500 models took 104 ms of a 170 ms create)
+        std::unique_ptr<double[]> hh(new double[NN]), hF(new double[NN]);
+        for_each_model([&](size_t i) {
             hm[i] = res[i].dev;
             ModelState& s = hs[i];
             std::memset(&s, 0, sizeof(s));
@@ -372,15 +389,18 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
             s.last = Nx - 1;
             std::memcpy(&hh[i * Nx], res[i].h.data(), sizeof(double) * Nx);
             std::memcpy(&hF[i * Nx], res[i].F.data(), sizeof(double) * Nx);
-        }
+        });
+        dbg_lap("pack h, F, state");
         FB_TRYC(cudaMemcpy(d_models, hm.data(), sizeof(fb200_model_dev_t) * n_models, cudaMemcpyHostToDevice));
         FB_TRYC(cudaMemcpy(d_state, hs.data(), sizeof(ModelState) * n_models, cudaMemcpyHostToDevice));
-        FB_TRYC(cudaMemcpy(d_h, hh.data(), sizeof(double) * NN, cudaMemcpyHostToDevice));
-        FB_TRYC(cudaMemcpy(d_F, hF.data(), sizeof(double) * NN, cudaMemcpyHostToDevice));
+        FB_TRYC(cudaMemcpy(d_h, hh.get(), sizeof(double) * NN, cudaMemcpyHostToDevice));
+        FB_TRYC(cudaMemcpy(d_F, hF.get(), sizeof(double) * NN, cudaMemcpyHostToDevice));
         e->host_F0.swap(hF);
         e->host_state0.swap(hs);
+        dbg_lap("H2D models, state, h, F");
     }
     FB_TRYC(cudaMemset(d_rows, 0xFF, rows_len * sizeof(double)));  // all-ones = NaN: rows never written stay NaN
+    dbg_lap("memset rows");
     D.models = d_models; D.state = d_state; D.h = d_h; D.F = d_F; D.rows = d_rows;
 
     auto upload_opt = [&](bool any, const double** dst, auto getter) -> int {
@@ -425,6 +445,7 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
     e->scratch_len = NN > n_models * 64 ? NN : n_models * 64;
 #undef FB_TRY
 #undef FB_TRYC
+    dbg_lap("optional arrays, scratch");
     *out = e;
     return FB200_OK;
 }
@@ -461,7 +482,7 @@ int fb200_ensemble_reset(fb200_ensemble_t* e) {
     if (!e->pinned_F0) {
         FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->pinned_F0), NN * sizeof(double)));
         FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->pinned_state0), e->n * sizeof(ModelState)));
-        std::memcpy(e->pinned_F0, e->host_F0.data(), NN * sizeof(double));
+        std::memcpy(e->pinned_F0, e->host_F0.get(), NN * sizeof(double));
         std::memcpy(e->pinned_state0, e->host_state0.data(), e->n * sizeof(ModelState));
     }
     FB_CUDA(cudaMemcpyAsync(e->dev.F, e->pinned_F0, NN * sizeof(double), cudaMemcpyHostToDevice, e->stream));

@@ -24,7 +24,7 @@ SYMBOLS = (
     'fb200_ensemble_evolve_async', 'fb200_ensemble_reset', 'fb200_ensemble_sync', 'fb200_ensemble_last_evolve_ms', 'fb200_ensemble_last_launches',
     'fb200_ensemble_rows', 'fb200_ensemble_rows_device', 'fb200_ensemble_status', 'fb200_ensemble_state',
     'fb200_ensemble_row_bounds', 'fb200_ensemble_field', 'fb200_ensemble_flux', 'fb200_ensemble_mdot_wind',
-    'fb200_ensemble_field_rows', 'fb200_ensemble_flux_rows',
+    'fb200_ensemble_field_rows', 'fb200_ensemble_flux_rows', 'fb200_ensemble_work_counters', 'fb200_selftest_trapz',
 )
 
 
@@ -76,7 +76,9 @@ def _load():
     lib.fb200_ensemble_status.argtypes = [vp, i32p, i32p, ip]
     lib.fb200_ensemble_state.argtypes = [vp, dp, ip, ip, ip]
     lib.fb200_ensemble_counters.argtypes = [vp, ip, ip]
+    lib.fb200_ensemble_work_counters.argtypes = [vp, ip, C.c_size_t]
     lib.fb200_measure_fp64_peak.argtypes = [C.c_int, dp]
+    lib.fb200_selftest_trapz.argtypes = [C.c_int, dp, dp, C.c_size_t, C.c_size_t, C.c_size_t, dp]
     lib.fb200_ensemble_row_bounds.argtypes = [vp, C.c_int64, ip, ip]
     lib.fb200_ensemble_field.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t]
     lib.fb200_ensemble_flux.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t, dp, C.c_size_t]

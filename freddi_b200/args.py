@@ -70,7 +70,7 @@ class FB200Config(C.Structure):
         ('n_passbands', C.c_int32), ('passband_len', C.c_int32 * FB200_MAX_PASSBANDS),
         ('passband_lambdas', C.POINTER(C.c_double) * FB200_MAX_PASSBANDS),
         ('passband_transmissions', C.POINTER(C.c_double) * FB200_MAX_PASSBANDS),
-        ('star_flux', C.c_int32), ('_pad_cfg', C.c_int32),
+        ('star_flux', C.c_int32), ('wait_timeout_ms', C.c_int32),
     ]
 
 

@@ -88,6 +88,13 @@ int select_device(const fb200_ensemble* e) {
     return FB200_OK;
 }
 
+int readout_scratch_init(fb200_ensemble* e, size_t len, double** p) {
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->scratch), len * sizeof(double)));
+    e->scratch_len = len;
+    *p = e->scratch;
+    return FB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -112,6 +119,22 @@ int fb200_measure_fp64_peak(int device, double* tflops) {
     cudaError_t ce = fb200::measure_fp64_peak(&tf);
     if (ce != cudaSuccess) return cuda_fail(ce, "fp64 peak kernel");
     *tflops = tf;
+    return FB200_OK;
+}
+
+int fb200_selftest_trapz(int device, const double* x, const double* y, size_t n, size_t first, size_t last, double* out) {
+    if (!x || !y || !out) return set_err(FB200_ERR_INVALID_ARGUMENT, "null argument");
+    if (n < 2 || n > 1024 || last >= n) return set_err(FB200_ERR_INVALID_ARGUMENT, "need 2 <= n <= 1024 points and last < n");
+    FB_CUDA(cudaSetDevice(device));
+    double* d = nullptr;
+    const size_t slot = evolve_scratch_doubles_per_cta();
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), (2 * n + 1 + slot) * sizeof(double)));
+    cudaError_t ce = cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d + n, y, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = selftest_trapz(d, d + n, int(n), int(first), int(last), d + 2 * n, d + 2 * n + 1, nullptr);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, d + 2 * n, sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fb200_trapz_kernel");
     return FB200_OK;
 }
 
@@ -364,6 +387,22 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
         D.max_ctas = e->sm_count * resident;
     }
     FB_TRY(dev_alloc(e, &D.progress, n_models));
+    FB_TRY(dev_alloc(e, &D.failed, n_models));
+    FB_TRYC(cudaMemset(D.failed, 0, sizeof(int) * n_models));
+    {
+        long long ms = cfg.wait_timeout_ms > 0 ? cfg.wait_timeout_ms : 10000;
+        if (const char* c = getenv("FB200_WAIT_TIMEOUT_US")) D.wait_timeout_ns = 1000ll * atoll(c);  // test hook: forces the give-up path
+        else D.wait_timeout_ns = ms * 1000000ll;
+    }
+    D.wind_rec = nullptr;
+    {
+        bool any_dyn = false;
+        for (size_t i = 0; i < n_models; ++i) any_dyn |= res[i].dev.wind_dynamic != 0;
+        if (any_dyn) {  // 16 B per row: which update() the wind getters of a row reflect (read-out kernels)
+            FB_TRY(dev_alloc(e, &D.wind_rec, n_models * size_t(e->n_rows)));
+            FB_TRYC(cudaMemset(D.wind_rec, 0, n_models * size_t(e->n_rows) * sizeof(WindRecord)));
+        }
+    }
     if (getenv("FB200_DEBUG"))
         fprintf(stderr, "[fb200] smem/CTA %zu B, CTAs/SM designed %d, resident %d, SMs %d\n", evolve_smem_bytes(), evolve_ctas_per_sm(),
                 evolve_resident_ctas_per_sm(), e->sm_count);
@@ -441,8 +480,10 @@ int fb200_ensemble_create(const fb200_args_t* args, size_t n_models, const fb200
         FB_TRYC(cudaMemset(D.Fsnap, 0xFF, n_models * size_t(e->n_rows) * Nx * sizeof(double)));
         FB_TRYC(cudaMemset(D.bounds, 0xFF, n_models * size_t(e->n_rows) * 2 * sizeof(int)));
     }
-    FB_TRY(dev_alloc(e, &e->scratch, NN > n_models * 64 ? NN : n_models * 64));
-    e->scratch_len = NN > n_models * 64 ? NN : n_models * 64;
+    {
+        double* p = nullptr;
+        FB_TRY(readout_scratch_init(e, NN > n_models * 64 ? NN : n_models * 64, &p));
+    }
 #undef FB_TRY
 #undef FB_TRYC
     dbg_lap("optional arrays, scratch");
@@ -455,6 +496,7 @@ void fb200_ensemble_destroy(fb200_ensemble_t* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void* p : e->allocs) cudaFree(p);
+    if (e->scratch) cudaFree(e->scratch);
     if (e->pinned_F0) cudaFreeHost(e->pinned_F0);
     if (e->pinned_state0) cudaFreeHost(e->pinned_state0);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -488,6 +530,7 @@ int fb200_ensemble_reset(fb200_ensemble_t* e) {
     FB_CUDA(cudaMemcpyAsync(e->dev.F, e->pinned_F0, NN * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     FB_CUDA(cudaMemcpyAsync(e->dev.state, e->pinned_state0, e->n * sizeof(ModelState), cudaMemcpyHostToDevice, e->stream));
     FB_CUDA(cudaMemsetAsync(e->dev.rows, 0xFF, e->n * size_t(e->n_rows) * e->n_cols * sizeof(double), e->stream));
+    FB_CUDA(cudaMemsetAsync(e->dev.failed, 0, e->n * sizeof(int), e->stream));
     if (e->dev.Fsnap) {
         FB_CUDA(cudaMemsetAsync(e->dev.Fsnap, 0xFF, e->n * size_t(e->n_rows) * e->Nx * sizeof(double), e->stream));
         FB_CUDA(cudaMemsetAsync(e->dev.bounds, 0xFF, e->n * size_t(e->n_rows) * 2 * sizeof(int), e->stream));
@@ -572,8 +615,13 @@ static int fetch_state(fb200_ensemble_t* e, std::vector<ModelState>& hs) {
     int rc = select_device(e);
     if (rc != FB200_OK) return rc;
     hs.resize(e->n);
+    std::vector<int> failed(e->n);
     FB_CUDA(cudaMemcpyAsync(hs.data(), e->dev.state, sizeof(ModelState) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaMemcpyAsync(failed.data(), e->dev.failed, sizeof(int) * e->n, cudaMemcpyDeviceToHost, e->stream));
     FB_CUDA(cudaStreamSynchronize(e->stream));
+    // a model whose work item gave up waiting (evolve.cu) keeps the rows its producers finished and is reported FAILED
+    for (size_t i = 0; i < e->n; ++i)
+        if (failed[i] && hs[i].status == FB200_MODEL_OK) hs[i].status = FB200_MODEL_FAILED;
     return FB200_OK;
 }
 
@@ -598,6 +646,23 @@ int fb200_ensemble_counters(fb200_ensemble_t* e, int64_t* picard_iters, int64_t*
     for (size_t i = 0; i < e->n; ++i) {
         if (picard_iters) picard_iters[i] = hs[i].picard_iters;
         if (lx_trial_steps) lx_trial_steps[i] = hs[i].lx_trials;
+    }
+    return FB200_OK;
+}
+
+int fb200_ensemble_work_counters(fb200_ensemble_t* e, int64_t* out, size_t out_len) {
+    if (!e || !out) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (out_len < e->n * size_t(FB200_N_WORK_COUNTERS)) return set_err(FB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    std::vector<ModelState> hs;
+    int rc = fetch_state(e, hs);
+    if (rc != FB200_OK) return rc;
+    for (size_t i = 0; i < e->n; ++i) {
+        int64_t* o = out + i * FB200_N_WORK_COUNTERS;
+        o[FB200_WORK_PICARD_ITERS] = hs[i].picard_iters;
+        o[FB200_WORK_LX_TRIALS] = hs[i].lx_trials;
+        o[FB200_WORK_RING_STEPS] = hs[i].ring_steps;
+        o[FB200_WORK_RING_ITERS] = hs[i].ring_iters;
+        o[FB200_WORK_POW_EVALS] = hs[i].pow_evals;
     }
     return FB200_OK;
 }
@@ -633,6 +698,22 @@ int fb200_ensemble_row_bounds(fb200_ensemble_t* e, int64_t row, int64_t* first, 
     return FB200_OK;
 }
 
+// The read-out staging buffer of the ensemble, at least `need` doubles: allocated once, grown when a larger request
+// comes, freed by fb200_ensemble_destroy (no cudaMalloc / cudaFree per call).
+static int readout_scratch(fb200_ensemble_t* e, size_t need, double** p) {
+    if (need > e->scratch_len) {
+        FB_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->scratch) FB_CUDA(cudaFree(e->scratch));
+        e->scratch = nullptr;
+        e->scratch_len = 0;
+        const size_t len = need + need / 4;
+        FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->scratch), len * sizeof(double)));
+        e->scratch_len = len;
+    }
+    *p = e->scratch;
+    return FB200_OK;
+}
+
 static int check_row(fb200_ensemble_t* e, int64_t row) {
     if (row >= 0) {
         if (!e->dev.Fsnap) return set_err(FB200_ERR_LOGIC, "reading a recorded row needs an ensemble created with record_F");
@@ -654,17 +735,13 @@ static int field_rows(fb200_ensemble_t* e, int field, int64_t row0, int n_sel, i
     if (row0 < 0 && n_sel != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "the current state is a single row");
     rc = select_device(e);
     if (rc != FB200_OK) return rc;
-    double* d_o = e->scratch;
-    bool own = false;
-    if (need > e->scratch_len) {
-        FB_CUDA(cudaMalloc(&d_o, need * sizeof(double)));
-        own = true;
-    }
+    double* d_o = nullptr;
+    rc = readout_scratch(e, need, &d_o);
+    if (rc != FB200_OK) return rc;
     cudaError_t ce = e->big ? fb200_big_launch_field(&e->dev, field, row0, n_sel, pad_nan, d_o, e->stream)
                             : launch_field(e->dev, field, row0, n_sel, pad_nan, d_o, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-    if (own) cudaFree(d_o);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_field_kernel");
     return FB200_OK;
 }
@@ -696,20 +773,19 @@ static int flux_rows(fb200_ensemble_t* e, int region, int64_t row0, int n_sel, c
     if (row0 < 0 && n_sel != 1) return set_err(FB200_ERR_INVALID_ARGUMENT, "the current state is a single row");
     rc = select_device(e);
     if (rc != FB200_OK) return rc;
+    // one persistent scratch buffer (grown on demand, freed with the ensemble): wavelengths, phases, then the result
     double *d_l = nullptr, *d_o = nullptr, *d_p = nullptr;
-    FB_CUDA(cudaMalloc(&d_l, (n_lambdas + size_t(n_sel)) * sizeof(double)));
+    rc = readout_scratch(e, n_lambdas + size_t(n_sel) + need, &d_l);
+    if (rc != FB200_OK) return rc;
     d_p = d_l + n_lambdas;
-    cudaError_t ce = cudaMalloc(&d_o, need * sizeof(double));
-    if (ce != cudaSuccess) { cudaFree(d_l); return cuda_fail(ce, "cudaMalloc"); }
-    ce = cudaMemcpyAsync(d_l, lambdas, n_lambdas * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    d_o = d_p + n_sel;
+    cudaError_t ce = cudaMemcpyAsync(d_l, lambdas, n_lambdas * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess && phases) ce = cudaMemcpyAsync(d_p, phases, size_t(n_sel) * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess)
         ce = e->big ? fb200_big_launch_flux(&e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream)
                     : launch_flux(e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-    cudaFree(d_l);
-    cudaFree(d_o);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_flux_kernel");
     return FB200_OK;
 }

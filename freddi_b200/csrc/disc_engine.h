@@ -67,7 +67,28 @@ struct ModelState {
     int k_valid;     // EnsembleDev::K holds the closure K of the state in F (DiscEngine::k_valid carried between work items)
     long long picard_iters;
     long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
+    long long ring_steps; // sum over the solves of (last - first): the unknowns the implicit solves really had (roofline bookkeeping)
+    long long ring_iters; // sum over the solves of (last - first) x Picard iterations
+    long long pow_evals;  // closure pow() calls the Picard loops really made (set-up, first iterations with a source term, series fall-backs)
+    // What the last BasicWind::update() of a dynamic wind saw (cpp/src/freddi_state.cpp:147-153,457-654): the reference's
+    // windB()/windC() getters and Mdot_wind() return the arrays that update left, i.e. values of the state BEFORE the solve.
+    double wind_Mdot;
+    int wind_first, wind_last;
 };
+
+// One per (model, row) of an ensemble with dynamic winds: the arguments of the update() whose values the reference's wind
+// getters hold at that row.  Row 0 holds the constructor's update (BH Mdot_in formula on the unshifted initial F, T12 of
+// SURVEY.md 9).  update() rewrites the rings of [first, last] only, so a ring outside keeps the value of the last update
+// that covered it: the read-out kernels walk the records backwards (fields.cu).
+struct WindRecord {
+    double Mdot;
+    int first, last;
+};
+
+// Bookkeeping the engine reports through its execution policy (ex.count / ex.note_*) instead of carrying it in the
+// per-thread copy of ModelState: on the GPU that copy lives in registers for the whole step loop, and 14 registers of
+// counters cost spills in the Lx walk.  The policy adds them to ModelState when the work item ends.
+enum { FB_CNT_PICARD = 0, FB_CNT_LX_TRIALS, FB_CNT_RING_STEPS, FB_CNT_RING_ITERS, FB_CNT_POW_EVALS, FB_CNT_POW_FALLBACKS, FB_CNT_N };
 
 
 // Per-point arrays of one model (length FB200_NX_MAX).  The engine only needs `S.name[i]`; each execution
@@ -486,6 +507,23 @@ FB_HD double v_cooling_front(const fb200_model_dev_t& M, double r, double Sigma_
 }
 
 
+// Weight of point i in trapz(x, y, first, last) without its factor 1/2 (cpp/src/util.cpp:9-19): one-sided at the two ends.
+// The kernels take every radial integral (Mdisk, Lx, Fnu, Mdot_wind) as a CTA-wide sum of y_i times this weight.
+template <class X>
+FB_HD double trapz_weight(const X& x, int i, int first, int last) {
+    if (i == first) return x[i + 1] - x[i];
+    if (i == last) return x[i] - x[i - 1];
+    return x[i + 1] - x[i - 1];
+}
+
+// trapz(x, y, first, last) of cpp/src/util.cpp:9-19 the way the kernels evaluate it: reduce_sums over the points.
+template <class Ex, class X, class Y>
+FB_HD double policy_trapz(Ex& ex, const X& x, const Y& y, int first, int last) {
+    if (first >= last) return 0.;
+    ex.reduce_sums(1, [&](int i, int k, int q) -> double { return (i < first || i > last) ? 0. : y[i] * trapz_weight(x, i, first, last); });
+    return 0.5 * ex.sum(0);
+}
+
 // The tridiagonal solve is block-partitioned: FB200_BLK consecutive unknowns are eliminated sequentially by
 // one thread (Thomas-style, in registers), which leaves a tridiagonal "reduced" system in the first and last
 // unknown of every block (2 per block, <= FB200_NRED_MAX) that is solved by parallel cyclic reduction.
@@ -516,6 +554,9 @@ FB_HD bool fb_isnan(double x) { return x != x; }
 //   lambda_pref(k)       double_h_c2 / lambda_k^5
 //   blocks(n, f)         run f(b) for b < n, one thread per b (the in-thread block elimination of the solve)
 //   reduced(n, f)        run f(q) for q < n, one thread per q (reduced-system PCR)
+//   count(c, v)          add v (a uniform value) to bookkeeping counter c (FB_CNT_*)
+//   note_pow_fallbacks(n)  n rings of this thread left the binomial series of the incremental K update (bookkeeping only)
+//   note_wind_update(Mdot, first, last)   arguments of the dynamic wind's update() of this step (read-out of windB/windC/Mdot_wind)
 //   tick(p)              phase boundary marker (cycle accounting in FB_PROFILE builds, otherwise a no-op)
 //   tri_points(n, f)     run f(t) for t < n (the triangles of the companion star), spread over the threads
 //   reduce_sums3(n, f)   sums over t < n of the three values f(t, a, b, c) produces; results via sum(0..2)
@@ -605,7 +646,12 @@ struct DiscEngine {
         const int Nx = M.Nx;
         const double tau = M.tau, F_in = st.F_in, rbc = M.Mdot_out;
         WindScalars ws{0, 0, 0, 0, 0};
-        if (M.wind_dynamic) ws = wind_scalars(M, Mdot_in_for_wind, S.h[first], S.h[last], S.h[Nx - 1]);
+        if (M.wind_dynamic) {
+            ws = wind_scalars(M, Mdot_in_for_wind, S.h[first], S.h[last], S.h[Nx - 1]);
+            ex.note_wind_update(Mdot_in_for_wind, first, last);  // what this update() saw
+        }
+        // closure pow() calls of this step (roofline bookkeeping): the outer ring always; the interior rings unless K is carried
+        ex.count(FB_CNT_POW_EVALS, k_valid ? 1 : m);
         const bool janiuk = (M.windtype == FB200_WIND_JANIUK2015);
         // the initial K holds the source term tau C (nonlinear_diffusion.cpp:61): only without one is it the pure closure
         const bool has_C = M.wind_dynamic || ex.has_windC();
@@ -839,10 +885,12 @@ struct DiscEngine {
                     anybad = anybad || (upd && !ok);
                 });
                 if (anybad) {
+                    int nbad = 0;
                     ex.points([&](int i, int k) {
                         if (!(i > first && i < last)) return;
                         const int pi = pidx(i);
                         if (!fb_isnan(S.s_d[pi])) return;
+                        ++nbad;
                         const double y = S.F[i], K0 = S.s_K[i];
                         const double W = wunc_point(M, y, S.hn[i]);
                         const double K1 = S.s_frac[i] * W * fb_rcp(y);
@@ -850,9 +898,11 @@ struct DiscEngine {
                         S.s_d[pi] = S.s_cc[i] + K1;
                         vmax = fmax(vmax, fabs((K1 - K0) * fb_rcp(fabs(K1))));
                     });
+                    ex.note_pow_fallbacks(nbad);
                 }
                 maxrel = ex.reduce_max_of(vmax);
             } else {
+                ex.count(FB_CNT_POW_EVALS, m - 1);
                 maxrel = ex.reduce_max([&](int i, int k) -> double {
                     if (i == first) S.F[i] = F_in;
                     if (!(i > first && i <= last)) return 0.;
@@ -879,6 +929,8 @@ struct DiscEngine {
         } while (maxrel > M.eps);
         ex.sync();
         k_valid = true;
+        ex.count(FB_CNT_RING_STEPS, m);
+        ex.count(FB_CNT_RING_ITERS, (long long)m * iters);
         return iters;
     }
 
@@ -983,14 +1035,7 @@ struct DiscEngine {
                 x += (g < 0.) ? FB_NAN_INVALID : g;
                 T = M.colourfactor * pow025(x * (1. / FB_SIGMA_SB));
                 // weight of this ring in the radial trapezoid of the hot zone: 2 pi R_i (R_{i+1} - R_{i-1}) (ends one-sided)
-                if (first < last) {
-                    const double R = S.R[i];
-                    double w;
-                    if (i == first) w = S.R[i + 1] - R;
-                    else if (i == last) w = R - S.R[i - 1];
-                    else w = S.R[i + 1] - S.R[i - 1];
-                    wq = 2 * FB_PI * R * w;
-                }
+                if (first < last) wq = 2 * FB_PI * S.R[i] * trapz_weight(S.R, i, first, last);
             }
             S.TphX[i] = T;
             S.wq[i] = wq;
@@ -1063,10 +1108,7 @@ struct DiscEngine {
             const int rf = last + 1, rl = Nx - 1;
             if (rf >= rl || i < rf || i > rl) return 0.;
             const double R = S.R[i];
-            double w;
-            if (i == rf) w = S.R[i + 1] - R;
-            else if (i == rl) w = R - S.R[i - 1];
-            else w = S.R[i + 1] - S.R[i - 1];
+            const double w = trapz_weight(S.R, i, rf, rl);
             double Qx;
             if (M.is_ns)
                 Qx = cold_K * (sc.Lbol_disk * angular_dist(M.angdist_disk, cold_mu) + sc.Lbol_ns * angular_dist(M.angdist_ns, cold_mu)) /
@@ -1086,7 +1128,7 @@ struct DiscEngine {
         });
         ex.tick(4);
         // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----
-        st.lx_trials += (long long)(ex.sum(nq) + 0.5);
+        ex.count(FB_CNT_LX_TRIALS, (long long)(ex.sum(nq) + 0.5));
         const double Mdisk = 0.5 * ex.sum(0);
         const double Lx = cfg.compute_lx ? (2. * FB_PI * (0.5 * ex.sum(1))) / p4(M.colourfactor) : NAN;
         const double d2 = 4.0 * FB_PI * p2(M.distance);
@@ -1278,7 +1320,7 @@ struct DiscEngine {
         const int it = solve_step(sc.Mdot);
         if (it < 0) { st.status = FB200_MODEL_FAILED; return false; }
         if (!structure_and_row(true, row, Fsnap_row, bounds_row)) { st.status = FB200_MODEL_COLLAPSED; return false; }
-        st.picard_iters += it;  // counted like rows_valid: completed steps only
+        ex.count(FB_CNT_PICARD, it);  // counted like rows_valid: completed steps only
         return true;
     }
 };

@@ -39,17 +39,30 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         const int model = item - round * E.n_models;
         if (tid == 0) {
             s_abort = 0;
+#pragma unroll
+            for (int c = 0; c < FB_CNT_N; ++c) GpuEx::counters()[c] = 0;  // bookkeeping of this work item (GpuEx::count)
             if (round > 0) {
+                // Wait for the producer of the previous round, by elapsed time (%globaltimer, ns).  A producer that never
+                // publishes (it can only be a CTA that died) must not hang the launch: after wait_timeout_ns the model is
+                // flagged in E.failed — a flag of its own, set with atomicExch: the state record belongs to the producer, which
+                // may still be writing it — and every later item of that model gives up at once.
                 const volatile int* p = E.progress + model;
-                long long spins = 0;
+                const volatile int* f = E.failed + model;
+                const unsigned long long t0 = fb_globaltimer();
                 while (*p < round) {
+                    if (*f) { s_abort = 1; break; }
                     __nanosleep(100);
-                    if (++spins > (1ll << 26)) { s_abort = 1; break; }  // seconds: the producer is gone, give up on this model
+                    if (fb_globaltimer() - t0 > (unsigned long long)E.wait_timeout_ns) {
+                        atomicExch(E.failed + model, 1);
+                        s_abort = 1;
+                        break;
+                    }
                 }
                 __threadfence();
             }
         }
         __syncthreads();
+        if (s_abort) continue;  // nothing of this model is touched: no state, no progress
 
         ModelState st;
         {
@@ -58,16 +71,17 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 #pragma unroll
             for (int w = 0; w < int(sizeof(ModelState) / 8); ++w) dst[w] = __ldcg(src + w);
         }
-        if (s_abort) st.status = FB200_MODEL_FAILED;
+        if (round == 0 && __ldcg(E.failed + model)) st.status = FB200_MODEL_FAILED;  // flagged in an earlier launch: stays failed
         bool active = (st.status == FB200_MODEL_OK);
         if (active && round == 0) {
             const int Nt_m = E.models[model].Nt;
             int target = Nt_m;
-            if (E.n_steps >= 0 && st.i_t + E.n_steps < Nt_m) target = st.i_t + E.n_steps;
+            if (E.n_steps >= 0 && (long long)st.i_t + E.n_steps < (long long)Nt_m) target = st.i_t + E.n_steps;
             st.target_i_t = target;
         }
         if (active && st.row0_done && st.i_t >= st.target_i_t) active = false;  // nothing left for this model in this launch
         if (active) {
+            if (tid == 0) GpuEx::wind_update() = WindRecord{st.wind_Mdot, st.wind_first, st.wind_last};
             S.h = E.h + size_t(model) * Nx;
             load_model(E, model, S, ex, E.F + size_t(model) * Nx);
             const fb200_model_dev_t& M = *smem_model();
@@ -84,11 +98,18 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
             double* Fsnap = E.Fsnap ? E.Fsnap + size_t(model) * nrows * Nx : nullptr;
             int* bounds = E.bounds ? E.bounds + size_t(model) * nrows * 2 : nullptr;
 
+            WindRecord* wrec = (E.wind_rec && M.wind_dynamic) ? E.wind_rec + size_t(model) * nrows : nullptr;
             if (!eng.st.row0_done) {
                 // the state at t0 is dumped before the first step (cpp/include/application.hpp:25-29)
                 eng.structure_and_row(false, rows, Fsnap, bounds);
                 eng.st.row0_done = 1;
                 eng.st.rows_valid = 1;
+                // the wind arrays at t0 are what the wind's constructor left: its own update() on the initial state, over
+                // [first, Nx - 1] — ShieldsOscil1986 has none (T12 of SURVEY.md 9): an empty range
+                if (wrec && tid == 0) {
+                    const bool ctor_update = (M.windtype != FB200_WIND_SHIELDSOSCIL1986);
+                    wrec[0] = WindRecord{M.wind_ctor_Mdot, ctor_update ? M.first0 : 1, ctor_update ? Nx - 1 : 0};
+                }
             }
             int todo = eng.st.target_i_t - eng.st.i_t;
             if (todo > E.chunk_steps) todo = E.chunk_steps;
@@ -98,6 +119,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
                                                  bounds ? bounds + size_t(r) * 2 : nullptr);
                 if (!ok) break;
                 eng.st.rows_valid = r + 1;
+                if (wrec && tid == 0) wrec[r] = GpuEx::wind_update();
             }
             // write the state back for the next work item / evolve call / the read-out kernels
             __syncthreads();
@@ -107,7 +129,26 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
             st = eng.st;
             st.k_valid = eng.k_valid ? 1 : 0;
         }
-        if (tid == 0 && (active || round == 0 || s_abort)) E.state[model] = st;
+        if (tid == 0 && (active || round == 0)) {
+            // Only what a work item changes is written back.  The bookkeeping fields are not carried through the step loop in the
+            // threads' registers: thread 0 owns them in shared memory (GpuEx::count) and adds them to the record here (the atomics
+            // of the other threads precede the barrier above).
+            ModelState* g = E.state + model;
+            g->t = st.t; g->F_in = st.F_in; g->Mdot_in_prev = st.Mdot_in_prev;
+            g->first = st.first; g->last = st.last; g->i_t = st.i_t; g->status = st.status; g->rows_valid = st.rows_valid;
+            g->row0_done = st.row0_done; g->target_i_t = st.target_i_t; g->k_valid = st.k_valid;
+            if (active) {
+                const long long* cnt = GpuEx::counters();
+                // (read through L2 like the rest of the record: another SM wrote it in the model's previous round)
+                g->picard_iters = __ldcg(&g->picard_iters) + cnt[FB_CNT_PICARD];
+                g->lx_trials = __ldcg(&g->lx_trials) + cnt[FB_CNT_LX_TRIALS];
+                g->ring_steps = __ldcg(&g->ring_steps) + cnt[FB_CNT_RING_STEPS];
+                g->ring_iters = __ldcg(&g->ring_iters) + cnt[FB_CNT_RING_ITERS];
+                g->pow_evals = __ldcg(&g->pow_evals) + cnt[FB_CNT_POW_EVALS] + cnt[FB_CNT_POW_FALLBACKS];
+                const WindRecord w = GpuEx::wind_update();
+                g->wind_Mdot = w.Mdot; g->wind_first = w.first; g->wind_last = w.last;
+            }
+        }
         __threadfence();   // F, rows and state are visible device-wide before the round is published
         __syncthreads();
         if (tid == 0) atomicExch(E.progress + model, round + 1);

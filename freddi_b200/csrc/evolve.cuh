@@ -27,6 +27,9 @@ struct EnsembleDev {
     int* bounds;                      // [n_models][n_rows][2] or null (first,last per row; record_F)
     int* queue;                       // work-queue counter
     int* progress;                    // [n_models] rounds completed in this launch (chunked scheduling)
+    int* failed;                      // [n_models] 1: a work item of the model gave up waiting for its producer (kept across launches)
+    long long wait_timeout_ns;        // how long a work item waits for the previous round of its model before giving up
+    WindRecord* wind_rec;             // [n_models][n_rows] or null: arguments of the wind update() behind every row (dynamic winds)
     int chunk_steps;                  // steps per work item; a model is handed back to the queue after that many
     int n_rounds;                     // work items per model in this launch
     double* cta_scratch;              // [max_ctas][scratch_doubles_per_cta()] once-per-step arrays of the model a CTA holds
@@ -46,6 +49,10 @@ cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream)
 
 // FP64 DFMA peak of the current device in TFLOP/s (fields.cu)
 cudaError_t measure_fp64_peak(double* tflops);
+
+// policy_trapz on caller data with one CTA (fields.cu): n <= FB200_NX_MAX points, scratch_dev = one CTA scratch slot
+cudaError_t selftest_trapz(const double* x_dev, const double* y_dev, int n, int first, int last, double* out_dev, double* scratch_dev,
+                           cudaStream_t stream);
 
 // field / flux read-out kernels (fields.cu)
 cudaError_t launch_field(const EnsembleDev& E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);

@@ -65,6 +65,9 @@ typedef struct fb200_model_dev {
     double tgr_rg, tgr_x0, tgr_x1, tgr_x2, tgr_x3;
     /* --- wind --- */
     double windparams[4];
+    /* Mdot_in the constructor of a dynamic wind sees: the BH formula on the initial F before the NS constructor shifts it
+     * (cpp/src/freddi_state.cpp:74-81,156-158; T12 of SURVEY.md 9).  Read-out of windB/windC/Mdot_wind at t0 only. */
+    double wind_ctor_Mdot;
     /* --- neutron star (cpp/include/ns/ns_evolution.hpp:42-67) --- */
     double R_x, redshift, R_m_min, mu_magn, R_cor, R_dead, inverse_beta, epsilon_Alfven, hot_spot_area, freqx, risco;
     double kappat[4]; /* value | in,out | in,out,par1,par2 */

@@ -33,6 +33,19 @@ __device__ __forceinline__ Loaded stage(const EnsembleDev& E, int model, long lo
     return L;
 }
 
+// The update() whose value ring i of a dynamic wind holds at `row` (cpp/src/freddi_state.cpp:457-654: update() rewrites the
+// rings of [first, last] only, so a ring outside keeps what the last update that covered it wrote; `first` only grows
+// and `last` only shrinks, so that is the latest record at or before `row` whose range holds i; record 0 is the
+// constructor's).  False: the ring was never written (BasicWind zero-initialises A, B, C).
+__device__ __forceinline__ bool wind_record_of(const EnsembleDev& E, int model, int row, int i, WindRecord* out) {
+    const WindRecord* rec = E.wind_rec + size_t(model) * E.cfg.n_rows;
+    for (int s = row; s >= 0; --s) {
+        const WindRecord r = rec[s];
+        if (i >= r.first && i <= r.last) { *out = r; return true; }
+    }
+    return false;
+}
+
 // Work items are (model, row) pairs: rows row0 .. row0 + n_sel - 1 of every model (n_sel = 1, row0 < 0: the current
 // state).  out[model][n_sel][Nx]; pad_nan: NaN outside [first, last] like EvolutionResult (python/freddi/evolution_result.py:55-71).
 __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const EnsembleDev E, int field, long long row0, int n_sel, int pad_nan,
@@ -99,13 +112,17 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_field_kernel(const Ense
                 case FB200_FIELD_WINDB:
                 case FB200_FIELD_WINDC: {
                     double B = ex.windB(i), C = ex.windC_static(i);
-                    if (M.wind_dynamic && hot) {
-                        // dynamic winds: value for the Mdot_in of THIS state (the reference holds the value of its
-                        // last update(), i.e. of the state before the last solve)
-                        const WindScalars ws = wind_scalars(M, sc.Mdot, S.h[first], S.h[last], S.h[Nx - 1]);
-                        double Bd = 0., Cd = 0.;
-                        wind_dynamic_point(M, ws, h, R, &Bd, &Cd);
-                        if (M.windtype == FB200_WIND_JANIUK2015) B = Bd; else C = Cd + C;
+                    if (M.wind_dynamic && E.wind_rec) {
+                        // dynamic winds: the reference's getters return what the last update() left — computed inside step()
+                        // BEFORE the solve, from the previous state's Mdot_in, and only for the rings of that update's [first, last]
+                        WindRecord rec;
+                        const int at = (row >= 0) ? int(row) : E.state[model].i_t;
+                        if (wind_record_of(E, model, at, i, &rec)) {
+                            const WindScalars ws = wind_scalars(M, rec.Mdot, S.h[rec.first], S.h[rec.last], S.h[Nx - 1]);
+                            double Bd = 0., Cd = 0.;
+                            wind_dynamic_point(M, ws, h, R, &Bd, &Cd);
+                            if (M.windtype == FB200_WIND_JANIUK2015) B = Bd; else C = Cd + C;
+                        }
                     }
                     v = (field == FB200_FIELD_WINDB) ? B : C;
                     break;
@@ -192,10 +209,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_flux_kernel(const Ensem
             const int nq = min(FB200_MAXQ, n_lambdas - k0);
             ex.reduce_sums(nq, [&](int i, int, int q) -> double {
                 if (rf >= rl || i < rf || i > rl) return 0.;
-                double w;
-                if (i == rf) w = S.R[i + 1] - S.R[i];
-                else if (i == rl) w = S.R[i] - S.R[i - 1];
-                else w = S.R[i + 1] - S.R[i - 1];
+                const double w = trapz_weight(S.R, i, rf, rl);
                 const double lam = lambdas[k0 + q];
                 const double y = planck_lambda_pref(S.Tph[i], lam, FB_DOUBLE_H_C2 / p5(lam));
                 return 2 * FB_PI * S.R[i] * y * w;
@@ -228,8 +242,16 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
         eng.init_points();
         const int first = L.first, last = L.last;
         const StateScalars sc = state_scalars(ex, M, S, first, false);
+        // the wind arrays behind Mdot_wind() are those of the last update(): the record of this row covers [first, last]
         WindScalars ws{0, 0, 0, 0, 0};
-        if (M.wind_dynamic) ws = wind_scalars(M, sc.Mdot, S.h[first], S.h[last], S.h[Nx - 1]);
+        bool dyn = false;
+        if (M.wind_dynamic && E.wind_rec) {
+            const WindRecord rec = E.wind_rec[size_t(model) * E.cfg.n_rows + ((row >= 0) ? int(row) : E.state[model].i_t)];
+            if (rec.first <= rec.last) {
+                dyn = true;
+                ws = wind_scalars(M, rec.Mdot, S.h[rec.first], S.h[rec.last], S.h[Nx - 1]);
+            }
+        }
         ex.reduce_sums(1, [&](int i, int, int) -> double {
             if (first >= last || i < first || i > last) return 0.;
             const double* h = S.h;
@@ -247,20 +269,32 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_mdot_wind_kernel(const 
                        (delta_0 * delta_1);
             }
             double A = ex.windA(i), B = ex.windB(i), C = ex.windC_static(i);
-            if (M.wind_dynamic) {
+            if (dyn) {
                 double Bd = 0., Cd = 0.;
                 wind_dynamic_point(M, ws, h[i], S.R[i], &Bd, &Cd);
                 if (M.windtype == FB200_WIND_JANIUK2015) B = Bd; else C = Cd + C;
             }
             const double y = -(A * dFdh + B * F[i] + C);
-            double w;
-            if (i == first) w = h[i + 1] - h[i];
-            else if (i == last) w = h[i] - h[i - 1];
-            else w = h[i + 1] - h[i - 1];
-            return y * w;
+            return y * trapz_weight(h, i, first, last);
         });
         if (threadIdx.x == 0) out[model] = L.valid ? 0.5 * ex.sum(0) : NAN;
     }
+}
+
+// fb200_selftest_trapz: the CTA-wide trapezoid of the kernels (policy_trapz) on caller data, x in S.R, y in S.F
+__global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_trapz_kernel(const double* x, const double* y, int n, int first, int last, double* out,
+                                                             double* gscratch) {
+    GpuArrays S = carve_arrays(gscratch, x);
+    GpuEx ex;
+    ex.init();
+    ex.set_nx(n);
+    for (int i = threadIdx.x; i < FB200_NX_MAX; i += kNT) {
+        S.R[i] = (i < n) ? x[i] : 0.;
+        S.F[i] = (i < n) ? y[i] : 0.;
+    }
+    __syncthreads();
+    const double v = policy_trapz(ex, S.R, S.F, first, last);
+    if (threadIdx.x == 0) out[0] = v;
 }
 
 // 16 independent DFMA chains per thread, 4096 iterations: 2 * 16 * 4096 flop per thread
@@ -313,6 +347,16 @@ cudaError_t measure_fp64_peak(double* tflops) {
     *tflops = flop / (best_ms * 1e-3) / 1e12;
     return cudaGetLastError();
 }
+
+#ifndef FB_BIG
+cudaError_t selftest_trapz(const double* x_dev, const double* y_dev, int n, int first, int last, double* out_dev, double* scratch_dev,
+                           cudaStream_t stream) {
+    cudaError_t e = prep(reinterpret_cast<const void*>(fb200_trapz_kernel));
+    if (e != cudaSuccess) return e;
+    fb200_trapz_kernel<<<1, kNT, SmemLayout::bytes(), stream>>>(x_dev, y_dev, n, first, last, out_dev, scratch_dev);
+    return cudaGetLastError();
+}
+#endif
 
 cudaError_t launch_field(const EnsembleDev& E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_field_kernel));

@@ -68,7 +68,8 @@ struct SmemLayout {
     static constexpr int o_redA = kPointDoubles, o_redQ = o_lu0, o_sums = o_redA + 2 * 32;
     static_assert(kNW * FB200_MAXQ <= 2 * NR, "reduce_sums scratch must fit into the first PCR buffer");
 #endif
-    static constexpr int o_scal = o_sums + FB200_MAXQ, o_lampref = o_scal + 8, o_starsum = o_lampref + FB200_MAX_LAMBDAS;
+    // o_count: FB_CNT_N bookkeeping counters (long long) of the current work item, then the wind-update record (Mdot, first|last)
+    static constexpr int o_scal = o_sums + FB200_MAXQ, o_count = o_scal + 8, o_lampref = o_count + FB_CNT_N + 2, o_starsum = o_lampref + FB200_MAX_LAMBDAS;
     static constexpr int o_model = o_starsum + 3 * (FB200_MAX_LAMBDAS + FB200_MAX_PASSBANDS);
     static constexpr int kModelDoubles = int((sizeof(fb200_model_dev_t) + 7) / 8);
     static constexpr int o_cfg = o_model + kModelDoubles;
@@ -152,6 +153,13 @@ __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double
 __device__ __forceinline__ fb200_model_dev_t* smem_model() { return reinterpret_cast<fb200_model_dev_t*>(fb_smem + SmemLayout::o_model); }
 __device__ __forceinline__ OutCfg* smem_cfg() { return reinterpret_cast<OutCfg*>(fb_smem + SmemLayout::o_cfg); }
 
+__device__ __forceinline__ int& fb_smem_int(int double_slot) { return *reinterpret_cast<int*>(fb_smem + double_slot); }
+__device__ __forceinline__ unsigned long long fb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct GpuEx {
     typedef GpuArrays Arrays;
     typedef SmemLayout L;
@@ -223,6 +231,17 @@ struct GpuEx {
     __device__ __forceinline__ void tick(int) {}
 #endif
     __device__ __forceinline__ double& scalar(int k) { return fb_smem[L::o_scal + k]; }
+    // bookkeeping (DiscEngine, FB_CNT_*): thread 0 owns the counters of the current work item in shared memory; only the rare
+    // pow fall-backs of the incremental K update are counted by every thread (atomically)
+    __device__ __forceinline__ static long long* counters() { return reinterpret_cast<long long*>(fb_smem + L::o_count); }
+    __device__ __forceinline__ void count(int c, long long v) { if (tid == 0) counters()[c] += v; }
+    __device__ __forceinline__ void note_pow_fallbacks(int n) {
+        if (n) atomicAdd(reinterpret_cast<unsigned long long*>(counters() + FB_CNT_POW_FALLBACKS), (unsigned long long)n);
+    }
+    __device__ __forceinline__ static WindRecord& wind_update() { return *reinterpret_cast<WindRecord*>(fb_smem + L::o_count + FB_CNT_N); }
+    __device__ __forceinline__ void note_wind_update(double Mdot, int first, int last) {
+        if (tid == 0) wind_update() = WindRecord{Mdot, first, last};
+    }
     __device__ __forceinline__ double sum(int q) const { return fb_smem[L::o_sums + q]; }
     __device__ __forceinline__ double lambda_pref(int k) const { return fb_smem[L::o_lampref + k]; }
     __device__ __forceinline__ double& star_T(int t) const { return gStarT[t]; }

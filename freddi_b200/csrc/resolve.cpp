@@ -473,6 +473,7 @@ int resolve_impl(const fb200_args_t& a, Resolved& out) {
     size_t first = 0;
     initial_F(ic, oprel, out.h, out.F, first);
     d.first0 = static_cast<int32_t>(first);
+    d.wind_ctor_Mdot = (first + 1 < Nx) ? (out.F[first + 1] - out.F[first]) / (out.h[first + 1] - out.h[first]) : 0.;  // FreddiState::Mdot_in on the unshifted F
     d.F_in0 = 0.0;
     d.t0 = a.inittime;
     d.Mdot_out = a.Mdotout;

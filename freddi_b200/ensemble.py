@@ -210,6 +210,16 @@ class Ensemble:
         _lib.check(_lib.lib.fb200_ensemble_counters(self._h, pi.ctypes.data_as(ip), lx.ctypes.data_as(ip)))
         return pi, lx
 
+    WORK_COUNTERS = ('picard_iters', 'lx_trials', 'ring_steps', 'ring_iters', 'pow_evals')
+
+    def work_counters(self):
+        """dict of per-model int64 arrays: what the kernels really did so far (roofline bookkeeping) — Picard iterations,
+        try_step calls of the Lx quadrature, sum of (last - first) over the solves, the same weighted by the Picard
+        iterations, closure pow() calls."""
+        out = np.empty((self.n_models, len(self.WORK_COUNTERS)), dtype=np.int64)
+        _lib.check(_lib.lib.fb200_ensemble_work_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size))
+        return {k: out[:, j].copy() for j, k in enumerate(self.WORK_COUNTERS)}
+
     def state(self):
         t = np.empty(self.n_models)
         i_t, first, last = (np.empty(self.n_models, dtype=np.int64) for _ in range(3))

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 2
+#define FB200_ABI_VERSION 3
 
 /* ---- return codes ---- */
 enum {
@@ -162,7 +162,10 @@ typedef struct fb200_config {
      * (20 * 4^starlod triangles per distinct Mopt/Mx, rochelobefill, semi-axis).
      * 2: build the geometry only, for fb200_ensemble_flux_rows(region 2) — no columns, no per-row work. */
     int32_t star_flux;
-    int32_t _pad_cfg;
+    /* A model's time steps are handed out in chunks to whichever CTA is free; a chunk waits for the model's previous chunk.
+     * If that one is not published within wait_timeout_ms (its CTA can only have died) the model is reported
+     * FB200_MODEL_FAILED with the rows finished so far, instead of hanging the launch.  0: 10 s. */
+    int32_t wait_timeout_ms;
 } fb200_config_t;
 
 /* Row layout: cpp/src/output.cpp:197-214, then per wavelength Fnu{k}[, Fnu{k}_cold][, Fnu{k}_star, _star_min, _star_max],
@@ -211,6 +214,11 @@ int fb200_device_count(void);       /* number of CUDA devices visible, <0 on dri
  * CUDA events.  It is the denominator of the roofline this path is reported against (the path is bound by
  * the FP64 pipe, not by HBM). */
 int fb200_measure_fp64_peak(int device, double* tflops);
+
+/* Self-test: trapz(x, y, first, last) of the reference (cpp/src/util.cpp:9-19) evaluated by the CTA-wide weighted sum the
+ * kernels use for every radial integral (Mdisk, Lx, Fnu, Mdot_wind), on caller data: 2 <= n <= 1024 host doubles.  The
+ * reference's known answer (cpp/test/util.cpp:31-41) is asserted through this entry. */
+int fb200_selftest_trapz(int device, const double* x, const double* y, size_t n, size_t first, size_t last, double* out);
 
 /* --- arguments --- */
 void fb200_args_default(fb200_args_t* args, int is_ns); /* defaults of pywrap_freddi_evolution.cpp:33-83,203-224 */
@@ -263,6 +271,13 @@ int fb200_ensemble_status(fb200_ensemble_t* e, int32_t* status, int32_t* rows_va
 /* Work counters per model, summed over the steps done so far: Picard iterations of the solver and try_step
  * calls of the Lx quadrature (6 Planck evaluations each in the reference).  For the roofline arithmetic. */
 int fb200_ensemble_counters(fb200_ensemble_t* e, int64_t* picard_iters, int64_t* lx_trial_steps);
+/* All work counters per model: out[model][FB200_N_WORK_COUNTERS].  RING_STEPS = sum over the implicit solves of the
+ * unknowns (last - first) they had, RING_ITERS = the same weighted by the Picard iterations of each solve, POW_EVALS =
+ * closure pow() calls the Picard loops made (the incremental K update replaces most): what the kernel really did, for
+ * the roofline arithmetic next to the reference's operation count. */
+enum { FB200_WORK_PICARD_ITERS = 0, FB200_WORK_LX_TRIALS = 1, FB200_WORK_RING_STEPS = 2, FB200_WORK_RING_ITERS = 3,
+       FB200_WORK_POW_EVALS = 4, FB200_N_WORK_COUNTERS = 5 };
+int fb200_ensemble_work_counters(fb200_ensemble_t* e, int64_t* out, size_t out_len);
 /* Current t [s], i_t, first, last per model (any pointer may be NULL). */
 int fb200_ensemble_state(fb200_ensemble_t* e, double* t, int64_t* i_t, int64_t* first, int64_t* last);
 /* State of a recorded row (requires record_F): first/last per model at that row. */

@@ -1,11 +1,10 @@
 """TEST INFRASTRUCTURE — ctypes access to the checkers.
 
-* ``Ref``    : ``oracle/_ref/libfreddi_ref.so`` — the unmodified reference sources + Boost shim (oracle/ref_driver.cpp).
-* ``Oracle`` : ``oracle/liboracle.so``          — the CPU restatement (oracle/freddi_oracle.cpp).
+``Ref`` : ``oracle/_ref/libfreddi_ref.so`` — the unmodified reference sources compiled in place against
+oracle/boost_shim, driven through the C functions of oracle/ref_driver.cpp (prefix ``ref_``) over ``fb200_args_t``.
 
-Both expose the same C functions (prefix ``ref_`` / ``orc_``) over ``fb200_args_t``.  Only ``tests/``,
-``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this module; nothing under
-``freddi_b200/`` does.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this module; nothing
+under ``freddi_b200/`` does.
 """
 import ctypes as C
 import os
@@ -18,7 +17,6 @@ from freddi_b200.args import FB200Args, FB200ModelInfo, args_array
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, '_ref', 'libfreddi_ref.so')
-ORACLE_SO = os.path.join(HERE, 'liboracle.so')
 
 N_BH_COLS = 15
 N_NS_COLS = 10
@@ -30,7 +28,7 @@ FIELDS = {'h': 0, 'R': 1, 'F': 2, 'W': 3, 'Sigma': 4, 'Tph': 5, 'Tph_vis': 6, 'T
           'd2Fmagn_dh2': 17}
 
 
-def build(target='all'):
+def build(target='ref'):
     subprocess.run(['make', '-s', '-C', HERE, target], check=True)
 
 
@@ -103,6 +101,24 @@ class _Checker:
         tdnu = np.zeros(max(1, len(passbands)))
         f(len(passbands), lens, lam.ctypes.data_as(dp), tr.ctypes.data_as(dp), tdnu.ctypes.data_as(dp))
         return tdnu[:len(passbands)]
+
+    def trapz(self, x, y, first=0, last=None):
+        """trapz(x, y, first, last) of cpp/src/util.cpp:9-19."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        f = self._fn('trapz')
+        f.restype = C.c_double
+        dp = C.POINTER(C.c_double)
+        f.argtypes = [dp, dp, C.c_size_t, C.c_size_t, C.c_size_t]
+        return f(x.ctypes.data_as(dp), y.ctypes.data_as(dp), x.size, int(first), x.size - 1 if last is None else int(last))
+
+    def define_mdot0(self, value=float('nan')):
+        """DiskStructureArguments::Mdot0 of the BH models built next: the reference leaves this member uninitialised
+        (cpp/src/arguments.cpp:42-55) although Cambier2013Wind reads it (cpp/src/freddi_state.cpp:408,411); NaN: untouched."""
+        f = self._fn('define_mdot0')
+        f.restype = None
+        f.argtypes = [C.c_double]
+        f(float(value))
 
     def set_star_flux(self, on):
         self._fn('set_star_flux')(int(bool(on)))
@@ -232,11 +248,6 @@ class _Model:
 class Ref(_Checker):
     prefix = 'ref_'
     path = REF_SO
-
-
-class Oracle(_Checker):
-    prefix = 'orc_'
-    path = ORACLE_SO
 
 
 # ---- the reference's golden light curves (python/test/data/*.dat) ----

@@ -28,6 +28,7 @@
 #include <ns/ns_arguments.hpp>
 #include <ns/ns_evolution.hpp>
 #include <unit_transformation.hpp>
+#include <util.hpp>
 
 #include "../include/freddi_b200.h"
 
@@ -93,6 +94,7 @@ struct Model {
 // Passbands of the models built next (FluxArguments::passbands, cpp/include/arguments.hpp:287): set by
 // ref_set_passbands, read-only while models are built and run.
 std::vector<EnergyPassband> g_passbands;
+double g_define_mdot0 = NAN;  // ref_define_mdot0: value of the member the reference leaves uninitialised (NaN: leave it)
 int g_star_flux = 0;  // ref_set_star_flux: add the Fnu*_star, _star_min, _star_max columns (--starflux, cpp/src/output.cpp:234-255,272-291)
 
 FluxArguments* make_flux(const fb200_args_t& a, const std::vector<double>& lambdas) {
@@ -118,6 +120,9 @@ Model* build(const fb200_args_t& a, const double* lambdas, int n_lambdas) {
         auto* disk = new DiskStructureArguments(*basic, opacity, a.Mdotout, bound, a.Thot, Tirr2Tvishot, ic, opt(a.F0),
                                                 opt(a.Mdisk0), opt(a.Mdot0), opt(a.powerorder), opt(a.gaussmu),
                                                 opt(a.gausssigma), wind, wind_params(a));
+        // DiskStructureArguments::Mdot0 is read by Cambier2013Wind (cpp/src/freddi_state.cpp:408,411) but no constructor ever
+        // sets it (cpp/src/arguments.cpp:42-55): ref_define_mdot0 gives the member a defined value for the models built next
+        if (g_define_mdot0 == g_define_mdot0) disk->Mdot0 = g_define_mdot0;
         auto* irr = new SelfIrradiationArguments(a.Cirr, a.irrindex, a.Cirrcold, a.irrindexcold, a.h2rcold,
                                                  pick(kAng, 2, a.angulardistdisk));
         FreddiArguments args(general, basic, disk, irr, make_flux(a, m->lambdas), calc);
@@ -351,6 +356,13 @@ double ref_flux(void* h, int region, double lambda) {
 }
 
 double ref_flux_star(void* h, double lambda, double phase) { return static_cast<Model*>(h)->ev()->flux_star(lambda, phase); }
+
+void ref_define_mdot0(double v) { g_define_mdot0 = v; }
+
+// trapz of the reference (cpp/src/util.cpp:9-19) on caller data
+double ref_trapz(const double* x, const double* y, size_t n, size_t first, size_t last) {
+    return trapz(std::vector<double>(x, x + n), std::vector<double>(y, y + n), first, last);
+}
 
 double ref_mdot_wind(void* h) { return static_cast<Model*>(h)->ev()->Mdot_wind(); }
 

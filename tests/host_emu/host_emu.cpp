@@ -40,6 +40,11 @@ struct HostEx {
     template <class F> void blocks(int n, F&& f) { for (int b = 0; b < n; ++b) f(b); }
     template <class F> void reduced(int n, F&& f) { for (int q = 0; q < n; ++q) f(q); }
     double& scalar(int k) { return scal[k]; }
+    long long counters[FB_CNT_N] = {0};
+    void count(int c, long long v) { counters[c] += v; }
+    void note_pow_fallbacks(int n) { counters[FB_CNT_POW_FALLBACKS] += n; }
+    WindRecord wind{0., 1, 0};
+    void note_wind_update(double Mdot, int first, int last) { wind = WindRecord{Mdot, first, last}; }
     double sum(int q) const { return sums[q]; }
     double lambda_pref(int k) const { return lampref[k]; }
     double windA(int i) const { return gA ? gA[i] : 0.; }
@@ -181,7 +186,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     int64_t r = 0;
     for (; r <= M.Nt && r < rows_cap; ++r) {
         bool ok;
-        const long long before = eng.st.picard_iters;
+        const long long before = ex.counters[FB_CNT_PICARD];
         if (r == 0) ok = eng.structure_and_row(false, rowbuf.data(), Fbuf.data(), bounds);
         else ok = eng.step_and_row(rowbuf.data(), Fbuf.data(), bounds);
         if (!ok) break;
@@ -189,9 +194,9 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
         if (Fsnap) std::memcpy(Fsnap + r * Nx, Fbuf.data(), sizeof(double) * Nx);
         if (first) first[r] = bounds[0];
         if (last) last[r] = bounds[1];
-        if (picard) picard[r] = eng.st.picard_iters - before;
+        if (picard) picard[r] = ex.counters[FB_CNT_PICARD] - before;
     }
-    g_last_lx_trials = eng.st.lx_trials;
+    g_last_lx_trials = ex.counters[FB_CNT_LX_TRIALS];
     return r;
 }
 
@@ -228,6 +233,14 @@ int emu_resolve(const fb200_args_t* a, fb200_model_info_t* info, double* h, doub
     if (h) std::memcpy(h, res.h.data(), sizeof(double) * res.h.size());
     if (F) std::memcpy(F, res.F.data(), sizeof(double) * res.F.size());
     return FB200_OK;
+}
+
+// policy_trapz (the radial trapezoid of the kernels) under the host policy, on caller data: n <= FB200_NX_MAX points
+double emu_trapz(const double* x, const double* y, int n, int first, int last) {
+    std::vector<double> xs(FB200_NX_MAX + 1, 0.), ys(FB200_NX_MAX + 1, 0.);
+    for (int i = 0; i < n; ++i) { xs[i] = x[i]; ys[i] = y[i]; }
+    HostEx ex;
+    return policy_trapz(ex, xs, ys, first, last);
 }
 
 double emu_planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) { return planck_nu1_nu2(T, nu1, nu2, tol, trials); }

@@ -97,17 +97,32 @@ def test_exact_lx_walk_agrees_with_pruned_lx(full_run):
         np.testing.assert_array_equal(r['rows'][k, :v][:, others], exact[j, :v][:, others])
 
 
-def test_ns_and_wind_sweeps_1000_models_invariants():
-    """10^3-model slices of configs #3 (NS, Bx x alpha) and #4 (Woods1996 wind + irradiation, 3 bands every row)."""
+SWEEPS_1000 = {
+    'config3_ns': lambda: cm.config3_args(np.geomspace(10 ** 7.5, 10 ** 8.5, 25), np.linspace(0.1, 1.0, 40)),
+    'config4_woods': lambda: cm.config4_args(np.linspace(0.1, 1.0, 40), np.geomspace(1e-5, 5e-3, 25)),
+}
+
+
+@pytest.mark.parametrize('name', sorted(SWEEPS_1000))
+def test_ns_and_wind_sweeps_1000_models(ref, name):
+    """10^3-model slices of configs #3 (NS, Bx x alpha) and #4 (Woods1996 wind + irradiation, 3 bands every row): invariants on
+    every model, and every 62nd model (17 models, corners included) against the reference's own code — all rows, all columns,
+    row counts and Picard iterations."""
     from freddi_b200 import Ensemble
-    for args in (cm.config3_args(np.geomspace(10 ** 7.5, 10 ** 8.5, 25), np.linspace(0.1, 1.0, 40)),
-                 cm.config4_args(np.linspace(0.1, 1.0, 40), np.geomspace(1e-5, 5e-3, 25))):
-        with Ensemble(args, lambdas=cm.LAM3) as ens:
-            ens.evolve(-1)
-            rows = ens.rows()
-            status, valid, picard = ens.status()
-        assert set(np.unique(status)) <= {0, 1}
-        for k in range(len(args)):
-            v = valid[k]
-            assert v >= 1 and np.isfinite(rows[k, :v, :3]).all() and np.isnan(rows[k, v:]).all(), k
-        assert (picard >= valid - 1).all()
+    args = SWEEPS_1000[name]()
+    with Ensemble(args, lambdas=cm.LAM3) as ens:
+        ens.evolve(-1)
+        rows = ens.rows()
+        status, valid, picard = ens.status()
+        cols = ens.columns
+    assert len(args) == 1000 and set(np.unique(status)) <= {0, 1}
+    for k in range(len(args)):
+        v = valid[k]
+        assert v >= 1 and np.isfinite(rows[k, :v, :3]).all() and np.isnan(rows[k, v:]).all(), k
+    assert (picard >= valid - 1).all()
+    for k in list(range(0, 1000, 62)) + [999]:
+        o = ref.run(args[k], cm.LAM3, snapshots=False)
+        n = o['rows_valid']
+        assert valid[k] == n, (name, k)
+        assert picard[k] == o['picard'].sum(), (name, k)
+        cm.assert_rows_close(rows[k, :n], o['rows'][:n], cols, what='{}[{}]'.format(name, k))

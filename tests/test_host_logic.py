@@ -21,7 +21,7 @@ def test_c_abi_exports_every_declared_symbol(built):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.fb200_abi_version() == 2
+    assert _lib.lib.fb200_abi_version() == 3
 
 
 def test_args_struct_layout_matches_the_header(built):
@@ -173,6 +173,11 @@ def test_passbands_hot_and_cold_regions(ref, emu):
     emu_vs_ref(ref, emu, cm.ini_args(True, **dict(cm.NS_CI, time=5)), (), False, pbs[:1])
 
 
+# python/test/test_ns.py:37-55 (moving inner radius), shortened to 300 steps for the CPU suite (the GPU suite runs the 2000)
+NS_MOVING = dict(Mx=1.4, alpha=0.25, Mopt=0.5, period=0.25, F0=None, Mdot0=1e16, initialcond='quasistat', Bx=1e8, freqx=500, Rx=1e6,
+                 rin=1.3e6 * 2.99792458e10 ** 2 / (6.673e-8 * 1.4 * 1.98892e33), rout=1e11 / 6.955e10, Rdead=5e6, time=30, tau=0.1,
+                 powerorder=None)
+
 ENGINE_CASES = {
     'woods1996_irr_opal': (False, dict(cm.WOODS), cm.LAM3, False),
     'shields1986': (False, dict(cm.WOODS, windtype='Shields1986', time=10), cm.LAM3, False),
@@ -191,6 +196,17 @@ ENGINE_CASES = {
                                                fptype='geometrical', fpparams={'chi': 30.0}, kappattype='corstep',
                                                kappatparams={'in': 0.3, 'out': 0.4}, time=20), cm.LAM3, False),
     'small_grid_nx64': (False, dict(Nx=64, initialcond='quasistat', time=10), cm.LAM3, False),
+    # branches without a test in round 1 (cpp/src/freddi_state.cpp:546-586, cpp/src/ns/ns_evolution.cpp:144-225)
+    'woods1996agn_strong': (False, dict(cm.WOODS, windtype='Woods1996AGN', windparams={'C_0': 100., 'T_ic': 1e8}, time=10), cm.LAM3, False),
+    'woods1996agn_shrinking': (False, dict(cm.WOODS, windtype='Woods1996AGN', windparams={'C_0': 10., 'T_ic': 1e7}, Thot=1e4,
+                                           boundcond='Tirr', time=10), cm.LAM3, False),
+    'woods1996agn_super_eddington': (False, dict(cm.WOODS, windtype='Woods1996AGN', windparams={'C_0': 1., 'T_ic': 1e9}, F0=6e38, time=5),
+                                     cm.LAM3, False),
+    'shields_oscil1986': (False, dict(windtype='ShieldsOscil1986', windparams={'C_w': 1.0, 'R_w': 0.5}, initialcond='quasistat', time=10), (), False),
+    'ns_propeller': (True, dict(NS_MOVING, fptype='propeller'), cm.LAM3, False),
+    'ns_corotation_block': (True, dict(NS_MOVING, fptype='corotation-block'), cm.LAM3, False),
+    'ns_no_outflow': (True, dict(NS_MOVING, fptype='no-outflow'), cm.LAM3, False),
+    'ns_geometrical_chi0': (True, dict(NS_MOVING, fptype='geometrical', fpparams={'chi': 0.}), cm.LAM3, False),
 }
 
 
@@ -207,6 +223,33 @@ def test_ns_moving_inner_radius(ref, emu):
               powerorder=None, fptype='eksi-kutlu2010')
     r, e = emu_vs_ref(ref, emu, cm.ini_args(True, **kw), cm.LAM3)
     assert r['first'][-1] > r['first'][0]
+
+
+def test_corotation_block_switches_off_beyond_the_corotation_radius(ref, emu):
+    """python/test/test_ns.py:74-80 on the engine (host policy): 2000 steps of 0.1 d, the inner radius crosses R_cor and
+    fp drops from 1 to 0 exactly there; rows against the oracle."""
+    from freddi_b200.ensemble import resolve
+    a = cm.ini_args(True, **dict(NS_MOVING, fptype='corotation-block', time=200))
+    r, e = emu_vs_ref(ref, emu, a, ())
+    cols = pyoracle.column_names(0, False, True)
+    info, _h, _F = resolve(a)
+    ratio = e['rows'][:, cols.index('Rin')] / info.R_cor
+    assert (ratio < 1).any() and (ratio > 1).any()
+    np.testing.assert_array_equal(ratio < 1, e['rows'][:, cols.index('fpin')] == 1)
+
+
+def test_cambier2013_with_the_uninitialised_member_defined(ref, emu):
+    """See tests/test_gpu_branches.py: the reference's Cambier2013 reads a member it never initialises; with the member
+    defined to the normalised Mdot0 (what this library uses) its code and the engine agree."""
+    from freddi_b200.ensemble import resolve
+    a = cm.ini_args(False, windtype='Cambier2013', windparams={'kC': 1.0, 'RIC': 1.0}, initialcond='quasistat', time=10)
+    info, _h, _F = resolve(a)
+    ref.define_mdot0(info.Mdot0)
+    try:
+        r, e = emu_vs_ref(ref, emu, a, cm.LAM3)
+    finally:
+        ref.define_mdot0()
+    assert r['picard'][1:].min() >= 2  # a static C term: T1 of SURVEY.md 9
 
 
 def test_planck_band_integral_controller(emu):

@@ -39,13 +39,24 @@ def test_mdisk0_normalisation_pins_the_odeint_shim(ref):
     assert '{:.6g}'.format(m.row()[2]) == '{:.6g}'.format(data['Mdisk'][0])
 
 
-def test_trapz_known_answer(emu):
-    """cpp/test/util.cpp:31-41: trapz of that data is 1.9829331321624648; the engine's radial trapezoid is
-    exercised through Mdisk instead (no free trapz in the C ABI) — here the raw known answer of the oracle's data."""
-    x = np.array([0.0, 0.1, 0.3, 0.35, 0.7, 0.9, 1.0])
-    y = np.sin(x) + 2 * x
-    s = 0.5 * (y[0] * (x[1] - x[0]) + y[-1] * (x[-1] - x[-2]) + np.sum(y[1:-1] * (x[2:] - x[:-2])))
-    assert abs(s - np.trapezoid(y, x)) < 1e-15
+def test_trapz_known_answer(ref, emu):
+    """cpp/test/util.cpp:31-41: trapz of sin(x) on 11 log-spaced points of [2 pi, 3 pi] is 1.9829331321624648 (scipy's value,
+    1e-12) and 2 analytically (1e-2).  Asserted on the reference's own trapz (oracle) and on the weighted point sum the engine
+    uses for every radial integral (policy_trapz under the host policy; the GPU test drives the same through the C ABI)."""
+    import ctypes as C
+    N = 11
+    x = 2 * np.pi * (3 * np.pi / (2 * np.pi)) ** (np.arange(N) / (N - 1.))
+    y = np.sin(x)
+    want = 1.9829331321624648
+    got_ref = ref.trapz(x, y, 0, N - 1)
+    assert abs(got_ref / want - 1) < 1e-12 and abs(got_ref / 2 - 1) < 1e-2
+    dp = C.POINTER(C.c_double)
+    emu.lib.emu_trapz.restype = C.c_double
+    emu.lib.emu_trapz.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int]
+    got = emu.lib.emu_trapz(x.ctypes.data_as(dp), y.ctypes.data_as(dp), N, 0, N - 1)
+    assert abs(got / want - 1) < 1e-12
+    assert emu.lib.emu_trapz(x.ctypes.data_as(dp), y.ctypes.data_as(dp), N, 4, 4) == 0.0 == ref.trapz(x, y, 4, 4)  # first >= last
+    assert abs(emu.lib.emu_trapz(x.ctypes.data_as(dp), y.ctypes.data_as(dp), N, 2, 9) / ref.trapz(x, y, 2, 9) - 1) < 1e-15
 
 
 def test_ss73_subcritical_steady_state(ref):

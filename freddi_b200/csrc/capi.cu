@@ -663,6 +663,7 @@ int fb200_ensemble_work_counters(fb200_ensemble_t* e, int64_t* out, size_t out_l
         o[FB200_WORK_RING_STEPS] = hs[i].ring_steps;
         o[FB200_WORK_RING_ITERS] = hs[i].ring_iters;
         o[FB200_WORK_POW_EVALS] = hs[i].pow_evals;
+        o[FB200_WORK_ROW_RINGS] = hs[i].row_rings;
     }
     return FB200_OK;
 }

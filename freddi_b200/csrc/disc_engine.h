@@ -69,6 +69,7 @@ struct ModelState {
     long long lx_trials;  // try_step calls of the Lx quadrature, summed over points and rows (roofline bookkeeping)
     long long ring_steps; // sum over the solves of (last - first): the unknowns the implicit solves really had (roofline bookkeeping)
     long long ring_iters; // sum over the solves of (last - first) x Picard iterations
+    long long row_rings;  // sum over the rows written of the hot-zone rings (last - first + 1) their columns were evaluated on
     long long pow_evals;  // closure pow() calls the Picard loops really made (set-up, first iterations with a source term, series fall-backs)
     // What the last BasicWind::update() of a dynamic wind saw (cpp/src/freddi_state.cpp:147-153,457-654): the reference's
     // windB()/windC() getters and Mdot_wind() return the arrays that update left, i.e. values of the state BEFORE the solve.
@@ -88,7 +89,7 @@ struct WindRecord {
 // Bookkeeping the engine reports through its execution policy (ex.count / ex.note_*) instead of carrying it in the
 // per-thread copy of ModelState: on the GPU that copy lives in registers for the whole step loop, and 14 registers of
 // counters cost spills in the Lx walk.  The policy adds them to ModelState when the work item ends.
-enum { FB_CNT_PICARD = 0, FB_CNT_LX_TRIALS, FB_CNT_RING_STEPS, FB_CNT_RING_ITERS, FB_CNT_POW_EVALS, FB_CNT_POW_FALLBACKS, FB_CNT_N };
+enum { FB_CNT_PICARD = 0, FB_CNT_LX_TRIALS, FB_CNT_RING_STEPS, FB_CNT_RING_ITERS, FB_CNT_POW_EVALS, FB_CNT_POW_FALLBACKS, FB_CNT_ROW_RINGS, FB_CNT_N };
 
 
 // Per-point arrays of one model (length FB200_NX_MAX).  The engine only needs `S.name[i]`; each execution
@@ -1035,7 +1036,18 @@ struct DiscEngine {
                 x += (g < 0.) ? FB_NAN_INVALID : g;
                 T = M.colourfactor * pow025(x * (1. / FB_SIGMA_SB));
                 // weight of this ring in the radial trapezoid of the hot zone: 2 pi R_i (R_{i+1} - R_{i-1}) (ends one-sided)
+#ifdef FB_OLD_WQ
+                if (first < last) {
+                    const double R = S.R[i];
+                    double w;
+                    if (i == first) w = S.R[i + 1] - R;
+                    else if (i == last) w = R - S.R[i - 1];
+                    else w = S.R[i + 1] - S.R[i - 1];
+                    wq = 2 * FB_PI * R * w;
+                }
+#else
                 if (first < last) wq = 2 * FB_PI * S.R[i] * trapz_weight(S.R, i, first, last);
+#endif
             }
             S.TphX[i] = T;
             S.wq[i] = wq;
@@ -1129,6 +1141,7 @@ struct DiscEngine {
         ex.tick(4);
         // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----
         ex.count(FB_CNT_LX_TRIALS, (long long)(ex.sum(nq) + 0.5));
+        ex.count(FB_CNT_ROW_RINGS, last - first + 1);
         const double Mdisk = 0.5 * ex.sum(0);
         const double Lx = cfg.compute_lx ? (2. * FB_PI * (0.5 * ex.sum(1))) / p4(M.colourfactor) : NAN;
         const double d2 = 4.0 * FB_PI * p2(M.distance);

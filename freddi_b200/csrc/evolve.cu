@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
                 g->lx_trials = __ldcg(&g->lx_trials) + cnt[FB_CNT_LX_TRIALS];
                 g->ring_steps = __ldcg(&g->ring_steps) + cnt[FB_CNT_RING_STEPS];
                 g->ring_iters = __ldcg(&g->ring_iters) + cnt[FB_CNT_RING_ITERS];
+                g->row_rings = __ldcg(&g->row_rings) + cnt[FB_CNT_ROW_RINGS];
                 g->pow_evals = __ldcg(&g->pow_evals) + cnt[FB_CNT_POW_EVALS] + cnt[FB_CNT_POW_FALLBACKS];
                 const WindRecord w = GpuEx::wind_update();
                 g->wind_Mdot = w.Mdot; g->wind_first = w.first; g->wind_last = w.last;

@@ -234,9 +234,15 @@ struct GpuEx {
     // bookkeeping (DiscEngine, FB_CNT_*): thread 0 owns the counters of the current work item in shared memory; only the rare
     // pow fall-backs of the incremental K update are counted by every thread (atomically)
     __device__ __forceinline__ static long long* counters() { return reinterpret_cast<long long*>(fb_smem + L::o_count); }
-    __device__ __forceinline__ void count(int c, long long v) { if (tid == 0) counters()[c] += v; }
+#ifndef FB_COUNT_MASK  // measurement variants: which counters are compiled in (bit c = FB_CNT_* c)
+#define FB_COUNT_MASK 0xff
+#endif
+    __device__ __forceinline__ void count(int c, long long v) { if (((FB_COUNT_MASK) >> c) & 1) { if (tid == 0) counters()[c] += v; } }
     __device__ __forceinline__ void note_pow_fallbacks(int n) {
-        if (n) atomicAdd(reinterpret_cast<unsigned long long*>(counters() + FB_CNT_POW_FALLBACKS), (unsigned long long)n);
+        // a 32-bit shared-memory atomic (native ATOMS.ADD; the 64-bit one is a compare-and-swap loop whose registers cost the
+        // Picard loop 7 % — measured, profiles/r02_counter_cost.txt); the slot's upper word stays 0 (< 2^31 rings per work item)
+        if (((FB_COUNT_MASK) >> FB_CNT_POW_FALLBACKS) & 1)
+            if (n) atomicAdd(reinterpret_cast<int*>(counters() + FB_CNT_POW_FALLBACKS), n);
     }
     __device__ __forceinline__ static WindRecord& wind_update() { return *reinterpret_cast<WindRecord*>(fb_smem + L::o_count + FB_CNT_N); }
     __device__ __forceinline__ void note_wind_update(double Mdot, int first, int last) {

@@ -210,7 +210,7 @@ class Ensemble:
         _lib.check(_lib.lib.fb200_ensemble_counters(self._h, pi.ctypes.data_as(ip), lx.ctypes.data_as(ip)))
         return pi, lx
 
-    WORK_COUNTERS = ('picard_iters', 'lx_trials', 'ring_steps', 'ring_iters', 'pow_evals')
+    WORK_COUNTERS = ('picard_iters', 'lx_trials', 'ring_steps', 'ring_iters', 'pow_evals', 'row_rings')
 
     def work_counters(self):
         """dict of per-model int64 arrays: what the kernels really did so far (roofline bookkeeping) — Picard iterations,

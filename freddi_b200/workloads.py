@@ -70,3 +70,50 @@ def config5_args(mxs, alphas, mdisks, cirrs, **kw):
                     out.append(ini_args(initialcond='quasistat', Thot=1e4, boundcond='Tirr', angulardistdisk='isotropic',
                                         Mx=float(m), alpha=float(a), Mdisk0=float(md), F0=None, Cirr=float(c), **kw))
     return out
+
+
+# ---- the same sweeps as packed argument arrays, built without a Python call per model (10^5 models in milliseconds) ----
+def sweep_array(base, n, **columns):
+    """ctypes array of `n` copies of `base` (an FB200Args) with the given double fields replaced column-wise (CGS values)."""
+    import ctypes as C
+    from .args import FB200Args
+    size = C.sizeof(FB200Args)
+    arr = (FB200Args * n)()
+    raw = np.frombuffer(arr, dtype=np.uint8).reshape(n, size)
+    raw[:] = np.frombuffer(bytes(base), dtype=np.uint8)
+    dbl = np.frombuffer(arr, dtype=np.float64).reshape(n, size // 8)
+    for name, values in columns.items():
+        off = getattr(FB200Args, name).offset
+        assert off % 8 == 0 and getattr(FB200Args, name).size == 8, name
+        dbl[:, off // 8] = np.asarray(values, dtype=np.float64)
+    return arr
+
+
+SOLAR_MASS_G = 1.98892e33  # cpp/include/constants.hpp (solar_mass), as freddi_b200.args applies it
+
+
+def config2_sweep(alphas, cirrs, indices=None):
+    """config2_args(alphas, cirrs) as a packed array; `indices` selects models of the flattened (alpha-major) sweep."""
+    alphas, cirrs = np.asarray(alphas, dtype=float), np.asarray(cirrs, dtype=float)
+    k = np.arange(alphas.size * cirrs.size) if indices is None else np.asarray(indices)
+    base = config2_args(alphas[:1], cirrs[:1])[0]
+    return sweep_array(base, k.size, alpha=alphas[k // cirrs.size], Cirr=cirrs[k % cirrs.size])
+
+
+def config4_sweep(alphas, cirrs, indices=None):
+    alphas, cirrs = np.asarray(alphas, dtype=float), np.asarray(cirrs, dtype=float)
+    k = np.arange(alphas.size * cirrs.size) if indices is None else np.asarray(indices)
+    base = config4_args(alphas[:1], cirrs[:1])[0]
+    return sweep_array(base, k.size, alpha=alphas[k // cirrs.size], Cirr=cirrs[k % cirrs.size])
+
+
+def config5_sweep(mxs, alphas, mdisks, cirrs, indices=None):
+    """config5_args(...) as a packed array: model k = ((i_Mx * n_alpha + i_alpha) * n_Mdisk + i_Mdisk) * n_Cirr + i_Cirr."""
+    mxs, alphas, mdisks, cirrs = (np.asarray(x, dtype=float) for x in (mxs, alphas, mdisks, cirrs))
+    k = np.arange(mxs.size * alphas.size * mdisks.size * cirrs.size) if indices is None else np.asarray(indices)
+    base = config5_args(mxs[:1], alphas[:1], mdisks[:1], cirrs[:1])[0]
+    ic = k % cirrs.size
+    imd = (k // cirrs.size) % mdisks.size
+    ia = (k // (cirrs.size * mdisks.size)) % alphas.size
+    im = k // (cirrs.size * mdisks.size * alphas.size)
+    return sweep_array(base, k.size, Mx=mxs[im] * SOLAR_MASS_G, alpha=alphas[ia], Mdisk0=mdisks[imd], Cirr=cirrs[ic])

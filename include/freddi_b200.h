@@ -276,7 +276,7 @@ int fb200_ensemble_counters(fb200_ensemble_t* e, int64_t* picard_iters, int64_t*
  * closure pow() calls the Picard loops made (the incremental K update replaces most): what the kernel really did, for
  * the roofline arithmetic next to the reference's operation count. */
 enum { FB200_WORK_PICARD_ITERS = 0, FB200_WORK_LX_TRIALS = 1, FB200_WORK_RING_STEPS = 2, FB200_WORK_RING_ITERS = 3,
-       FB200_WORK_POW_EVALS = 4, FB200_N_WORK_COUNTERS = 5 };
+       FB200_WORK_POW_EVALS = 4, FB200_WORK_ROW_RINGS = 5 /* sum over the rows of last - first + 1 */, FB200_N_WORK_COUNTERS = 6 };
 int fb200_ensemble_work_counters(fb200_ensemble_t* e, int64_t* out, size_t out_len);
 /* Current t [s], i_t, first, last per model (any pointer may be NULL). */
 int fb200_ensemble_state(fb200_ensemble_t* e, double* t, int64_t* i_t, int64_t* first, int64_t* last);

@@ -81,7 +81,7 @@ class _Checker:
         f.argtypes = [C.POINTER(FB200Args), dp, C.c_int, C.c_int, dp, C.c_int64, dp, ip, ip, ip, C.c_char_p, C.c_size_t]
         f = getattr(L, p + 'run_ensemble'); f.restype = C.c_int64
         f.argtypes = [C.POINTER(FB200Args), C.c_int64, dp, C.c_int, C.c_int, C.c_int, C.c_int64, dp, C.c_int64,
-                      C.POINTER(C.c_int32), dp, dp]
+                      C.POINTER(C.c_int32), dp, dp, ip]
 
     def _fn(self, name):
         return getattr(self.lib, self.prefix + name)
@@ -165,13 +165,14 @@ class _Checker:
         ncol = N_BH_COLS + len(lam) * (2 if cold_disk else 1) + (N_NS_COLS if arr[0].is_ns else 0)
         rows = np.full((n, rows_per_model, ncol), np.nan) if want_rows else None
         valid = np.zeros(n, dtype=np.int32)
+        picard = np.zeros(n, dtype=np.int64)
         tc = C.c_double()
         te = C.c_double()
         steps = self._fn('run_ensemble')(arr, n, lam.ctypes.data_as(dp), len(lam), int(cold_disk), int(n_threads),
                                          int(max_steps), rows.ctypes.data_as(dp) if want_rows else None,
                                          int(rows_per_model), valid.ctypes.data_as(C.POINTER(C.c_int32)),
-                                         C.byref(tc), C.byref(te))
-        return dict(steps=int(steps), construct_s=tc.value, evolve_s=te.value, rows=rows, rows_valid=valid)
+                                         C.byref(tc), C.byref(te), picard.ctypes.data_as(C.POINTER(C.c_int64)))
+        return dict(steps=int(steps), construct_s=tc.value, evolve_s=te.value, rows=rows, rows_valid=valid, picard=picard)
 
 
 class _Model:

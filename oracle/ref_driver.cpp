@@ -394,10 +394,11 @@ int64_t ref_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
 // CPU baseline: n_models light curves striped over n_threads std::threads, one reference instance per
 // model (instances share no mutable state).  Construction (incl. the companion-star triangulation,
 // cpp/src/freddi_state.cpp:78-79) is timed separately from the dump/step loop.
-// rows may be NULL (rows are still evaluated, into a scratch buffer).  Returns total model-steps done.
+// rows may be NULL (rows are still evaluated, into a scratch buffer); picard_total (optional) [n_models]: Picard iterations
+// summed over the completed steps of each model.  Returns total model-steps done.
 int64_t ref_run_ensemble(const fb200_args_t* args, int64_t n_models, const double* lambdas, int n_lambdas, int cold_disk,
                          int n_threads, int64_t max_steps, double* rows, int64_t rows_per_model, int32_t* rows_valid,
-                         double* construct_seconds, double* evolve_seconds) {
+                         double* construct_seconds, double* evolve_seconds, int64_t* picard_total) {
     if (n_threads <= 0) n_threads = static_cast<int>(std::thread::hardware_concurrency());
     if (n_threads <= 0) n_threads = 1;
     std::vector<Model*> models(static_cast<size_t>(n_models), nullptr);
@@ -427,15 +428,17 @@ int64_t ref_run_ensemble(const fb200_args_t* args, int64_t n_models, const doubl
                     scratch.resize(static_cast<size_t>(nc));
                     int64_t Nt = static_cast<int64_t>(m->ev()->Nt());
                     if (max_steps >= 0 && Nt > max_steps) Nt = max_steps;
-                    int64_t r = 0, steps = 0;
+                    int64_t r = 0, steps = 0, picard = 0;
                     for (; r <= Nt; ++r) {
                         double* dst = (rows && r < rows_per_model) ? rows + (i * rows_per_model + r) * nc : scratch.data();
                         fill_row(*m, cold_disk, dst);
                         if (r == Nt) { ++r; break; }
                         ++steps;
                         if (do_step(*m) != 0) { ++r; break; }
+                        picard += m->last_picard;  // completed steps only, like the kernels' counter
                     }
                     if (rows_valid) rows_valid[i] = static_cast<int32_t>(r);
+                    if (picard_total) picard_total[i] = picard;
                     steps_done += steps;
                 }
             });

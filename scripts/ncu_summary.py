@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""Compact summary of one `ncu --set full` capture: usage ncu_summary.py report.ncu-rep [label]"""
-import csv, subprocess, sys
+"""Compact summary of one `ncu --set full` capture: usage ncu_summary.py report.ncu-rep [--json out.json --model-steps N --source TEXT]
+With --json also writes the numbers bench.py's roofline object reads (profiles/roofline_ncu.json)."""
+import csv, json, subprocess, sys
 rep = sys.argv[1]
+def _opt(name, default=None):
+    return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else default
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -36,3 +39,14 @@ t = g('gpu__time_duration.sum')
 unit = m['gpu__time_duration.sum'][0]
 sec = t * {'ms': 1e-3, 'us': 1e-6, 's': 1, 'ns': 1e-9}.get(unit, 1e-3)
 print('executed FP64 flop (2*DFMA + DMUL + DADD): %.4e in %.4f s -> %.2f TFLOP/s executed' % (tot, sec, tot / sec / 1e12))
+
+if _opt('--json'):
+    dram = (g('dram__bytes_read.sum') * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(m['dram__bytes_read.sum'][0], 1) +
+            g('dram__bytes_write.sum') * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(m['dram__bytes_write.sum'][0], 1))
+    out = dict(dram_bytes_per_launch=int(dram), fp64_flop_per_launch=tot, model_steps_per_launch=int(float(_opt('--model-steps', '0'))),
+               fp64_pipe_active_pct=g('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed'),
+               issue_active_pct=g('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+               warps_active_pct=g('sm__warps_active.avg.pct_of_peak_sustained_active'), kernel_ms_under_ncu=sec * 1e3,
+               source=_opt('--source', rep) + ': one fb200_evolve_kernel launch under ncu --set full; fp64_flop = 2 x DFMA + DMUL + DADD executed '
+                      'thread-instructions; fp64_pipe_active = sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed')
+    json.dump(out, open(_opt('--json'), 'w'), indent=1)

@@ -86,7 +86,7 @@ def test_ns_fp_behaviour_like_the_reference_suite(fp_runs):
     assert (g['valid'] == 2001).all()
     np.testing.assert_array_equal(fp['no-outflow'], 1)
     np.testing.assert_array_equal(fp['propeller'], 0)
-    unity = Rin['propeller-unity-fp'] == 1e6   # fp must be unity if R_in <= Rx or R_in <= Risco
+    unity = Rin['propeller-unity-fp'] <= 1e6 * (1 + 1e-12)   # fp must be unity if R_in <= Rx or R_in <= Risco (R = h^2 / GM rounds)
     assert unity.any()
     np.testing.assert_array_equal(fp['propeller-unity-fp'][unity], 1)
     r = Rin['corotation-block'] / R_cor
@@ -118,7 +118,7 @@ def test_cambier2013_with_the_uninitialised_member_defined(ref):
     finally:
         ref.define_mdot0()
     check_model(g, 0, r, 'cambier2013')
-    assert (windC_ref < 0).all()  # the wind really acts
+    assert (windC_ref <= 0).all() and (windC_ref < 0).any()  # the wind really acts (exp underflows to -0 at the innermost rings)
     from freddi_b200 import Ensemble
     with Ensemble([a]) as ens:
         assert cm.rel_err(ens.field('windC')[0], windC_ref).max() <= cm.RTOL

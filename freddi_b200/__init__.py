@@ -4,14 +4,14 @@
 independent models at once.  Importing the compute classes loads ``libfreddi_b200.so``; there is no CPU
 fallback (``freddi_b200.args`` and ``freddi_b200.build`` are importable without it).
 """
-__all__ = ('Freddi', 'FreddiNeutronStar', 'EvolutionResult', 'Ensemble', 'make_args')
+__all__ = ('Freddi', 'FreddiNeutronStar', 'EvolutionResult', 'Ensemble', 'make_args', 'sweep', 'sweep_plan', 'pinned_empty')
 
 
 def __getattr__(name):
     if name in ('Freddi', 'FreddiNeutronStar', 'EvolutionResult'):
         from . import freddi
         return getattr(freddi, name)
-    if name in ('Ensemble', 'column_names', 'shard_indices'):
+    if name in ('Ensemble', 'column_names', 'shard_indices', 'sweep', 'sweep_plan', 'pinned_empty', 'SweepResult'):
         from . import ensemble
         return getattr(ensemble, name)
     if name == 'make_args':

@@ -25,7 +25,19 @@ SYMBOLS = (
     'fb200_ensemble_rows', 'fb200_ensemble_rows_device', 'fb200_ensemble_status', 'fb200_ensemble_state',
     'fb200_ensemble_row_bounds', 'fb200_ensemble_field', 'fb200_ensemble_flux', 'fb200_ensemble_mdot_wind',
     'fb200_ensemble_field_rows', 'fb200_ensemble_flux_rows', 'fb200_ensemble_work_counters', 'fb200_selftest_trapz',
+    'fb200_sharded_create', 'fb200_sharded_destroy', 'fb200_sharded_n_shards', 'fb200_sharded_shard', 'fb200_sharded_n_models',
+    'fb200_sharded_n_rows', 'fb200_sharded_n_cols', 'fb200_sharded_nx', 'fb200_sharded_info', 'fb200_sharded_reset',
+    'fb200_sharded_evolve', 'fb200_sharded_evolve_async', 'fb200_sharded_sync', 'fb200_sharded_last_evolve_ms',
+    'fb200_sharded_rows', 'fb200_sharded_status', 'fb200_sharded_state', 'fb200_sharded_work_counters', 'fb200_sharded_field',
+    'fb200_sharded_flux', 'fb200_sweep_plan', 'fb200_sweep_run', 'fb200_host_alloc', 'fb200_host_free', 'fb200_trim',
 )
+
+
+class FB200SweepStats(C.Structure):
+    """fb200_sweep_stats_t (include/freddi_b200.h)."""
+    _fields_ = [('total_ms', C.c_double), ('device_ms_max', C.c_double), ('first_launch_ms', C.c_double), ('resolve_ms', C.c_double),
+                ('uploads_ms', C.c_double), ('model_steps', C.c_int64), ('n_devices', C.c_int32), ('launches', C.c_int32),
+                ('n_rows', C.c_int32), ('n_cols', C.c_int32)]
 
 
 class FB200Error(Exception):
@@ -85,6 +97,39 @@ def _load():
     lib.fb200_ensemble_mdot_wind.argtypes = [vp, C.c_int64, dp, C.c_size_t]
     lib.fb200_ensemble_field_rows.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_int, dp, C.c_size_t]
     lib.fb200_ensemble_flux_rows.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, dp, C.c_size_t, dp, dp, C.c_size_t]
+    # in-process multi-GPU + one-shot sweep
+    szp = C.POINTER(C.c_size_t)
+    lib.fb200_sharded_create.argtypes = [C.POINTER(FB200Args), C.c_size_t, C.POINTER(FB200Config), i32p, C.c_int32, C.POINTER(vp), szp]
+    lib.fb200_sharded_destroy.argtypes = [vp]
+    lib.fb200_sharded_destroy.restype = None
+    lib.fb200_sharded_n_shards.argtypes = [vp]
+    lib.fb200_sharded_n_shards.restype = C.c_int32
+    lib.fb200_sharded_shard.argtypes = [vp, C.c_int32]
+    lib.fb200_sharded_shard.restype = vp
+    for name in ('n_models', 'n_cols', 'n_rows', 'nx'):
+        f = getattr(lib, 'fb200_sharded_' + name)
+        f.argtypes = [vp]
+        f.restype = C.c_size_t
+    lib.fb200_sharded_info.argtypes = [vp, C.POINTER(FB200ModelInfo)]
+    lib.fb200_sharded_reset.argtypes = [vp]
+    lib.fb200_sharded_evolve.argtypes = [vp, C.c_int64]
+    lib.fb200_sharded_evolve_async.argtypes = [vp, C.c_int64]
+    lib.fb200_sharded_sync.argtypes = [vp]
+    lib.fb200_sharded_last_evolve_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.fb200_sharded_rows.argtypes = [vp, dp, C.c_size_t]
+    lib.fb200_sharded_status.argtypes = [vp, i32p, i32p, ip]
+    lib.fb200_sharded_state.argtypes = [vp, dp, ip, ip, ip]
+    lib.fb200_sharded_work_counters.argtypes = [vp, ip, C.c_size_t]
+    lib.fb200_sharded_field.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t]
+    lib.fb200_sharded_flux.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t, dp, C.c_size_t]
+    lib.fb200_sweep_plan.argtypes = [C.POINTER(FB200Args), C.c_size_t, C.POINTER(FB200Config), szp, szp]
+    lib.fb200_sweep_run.argtypes = [C.POINTER(FB200Args), C.c_size_t, C.POINTER(FB200Config), i32p, C.c_int32, dp, C.c_size_t,
+                                    i32p, i32p, ip, C.POINTER(FB200SweepStats), szp]
+    lib.fb200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.fb200_host_free.argtypes = [vp]
+    lib.fb200_host_free.restype = None
+    lib.fb200_trim.argtypes = []
+    lib.fb200_trim.restype = None
     return lib
 
 

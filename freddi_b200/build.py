@@ -4,8 +4,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['capi.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'resolve.cpp', 'star.cpp']
-HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp', 'star.hpp',
+SOURCES = ['capi.cu', 'construct.cu', 'sharded.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'resolve.cpp', 'star.cpp']
+HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp', 'star.hpp', 'ensemble_impl.hpp',
            os.path.join('..', '..', 'include', 'freddi_b200.h')]
 OUT = os.path.join(HERE, 'libfreddi_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

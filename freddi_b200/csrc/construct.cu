@@ -1,0 +1,1106 @@
+// Construction pipeline of the ensembles (ensemble_impl.hpp): plan -> one device arena per GPU -> host workers resolve the
+// models into pinned staging slots -> chunked cudaMemcpyAsync uploads; for a streamed sweep the evolve kernel is already
+// running and picks every group up as its upload watermark arrives, and finished groups are read back meanwhile.
+// Replaces, per model, the constructors the reference's driver loop runs (cpp/include/application.hpp:17-24:
+// `Freddi freddi(args)`), the loop itself (`for (step...)`, :25-43) being the evolve kernel.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "ensemble_impl.hpp"
+#include "star.hpp"
+
+extern "C" {
+size_t fb200_big_evolve_smem_bytes();
+size_t fb200_big_evolve_scratch_doubles_per_cta();
+int fb200_big_evolve_ctas_per_sm();
+int fb200_big_evolve_resident_ctas_per_sm();
+cudaError_t fb200_big_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+}
+
+namespace fb200 {
+
+// ------------------------------------------------------------------------------------------------ errors
+namespace {
+thread_local std::string g_err;
+}
+int fb_set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int fb_cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? FB200_ERR_NO_DEVICE : FB200_ERR_CUDA;
+}
+const std::string& fb_err_msg() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ host workers
+struct HostPool::Impl {
+    std::mutex run_mutex;  // one job at a time
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::vector<std::thread> threads;
+    const std::function<void(unsigned)>* job = nullptr;
+    unsigned job_workers = 0;  // pool threads taking part in the current job (the caller is worker 0)
+    unsigned long long gen = 0;
+    unsigned running = 0;
+};
+
+HostPool& HostPool::instance() {
+    static HostPool* pool = new HostPool();  // never destroyed: its threads sleep until the process ends
+    return *pool;
+}
+
+unsigned HostPool::default_threads() {
+    if (const char* c = getenv("FB200_HOST_THREADS")) {
+        const int v = atoi(c);
+        if (v > 0) return unsigned(v);
+    }
+    const unsigned n = std::thread::hardware_concurrency();
+    return n ? n : 1;
+}
+
+void HostPool::run(unsigned n_workers, const std::function<void(unsigned)>& body) {
+    if (!impl_) {
+        static std::mutex init;
+        std::lock_guard<std::mutex> g(init);
+        if (!impl_) impl_ = new Impl();
+    }
+    Impl& I = *impl_;
+    if (n_workers <= 1) {
+        body(0);
+        return;
+    }
+    std::lock_guard<std::mutex> one(I.run_mutex);
+    {
+        std::unique_lock<std::mutex> lk(I.m);
+        while (I.threads.size() + 1 < n_workers) {
+            const unsigned idx = unsigned(I.threads.size());
+            const unsigned long long seen = I.gen;
+            I.threads.emplace_back([&I, idx, seen] {
+                unsigned long long last = seen;
+                for (;;) {
+                    const std::function<void(unsigned)>* job = nullptr;
+                    {
+                        std::unique_lock<std::mutex> lk(I.m);
+                        I.cv_job.wait(lk, [&] { return I.gen != last; });
+                        last = I.gen;
+                        if (idx < I.job_workers) job = I.job;
+                    }
+                    if (job) {
+                        (*job)(idx + 1);
+                        std::lock_guard<std::mutex> lk(I.m);
+                        if (--I.running == 0) I.cv_done.notify_all();
+                    }
+                }
+            });
+            I.threads.back().detach();
+        }
+        I.job = &body;
+        I.job_workers = n_workers - 1;
+        I.running = n_workers - 1;
+        ++I.gen;
+    }
+    I.cv_job.notify_all();
+    body(0);
+    std::unique_lock<std::mutex> lk(I.m);
+    I.cv_done.wait(lk, [&] { return I.running == 0; });
+    I.job = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ caches
+namespace {
+struct Block {
+    void* p;
+    size_t bytes;
+    bool in_use;
+    int device;  // arenas only
+};
+std::mutex g_cache_mutex;
+std::vector<Block> g_pinned, g_arenas;
+bool cache_disabled() {
+    static const bool off = getenv("FB200_NO_CACHE") != nullptr;
+    return off;
+}
+}  // namespace
+
+void* pinned_acquire(size_t bytes) {
+    size_t want = size_t(1) << 20;
+    while (want < bytes) want <<= 1;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mutex);
+        for (Block& b : g_pinned)
+            if (!b.in_use && b.bytes == want) {
+                b.in_use = true;
+                return b.p;
+            }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_cache_mutex);
+    g_pinned.push_back(Block{p, want, true, -1});
+    return p;
+}
+
+void pinned_release(void* block) {
+    if (!block) return;
+    std::lock_guard<std::mutex> g(g_cache_mutex);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+        if (g_pinned[i].p == block) {
+            if (cache_disabled()) {
+                cudaFreeHost(block);
+                g_pinned.erase(g_pinned.begin() + i);
+            } else {
+                g_pinned[i].in_use = false;
+            }
+            return;
+        }
+}
+
+// the calling thread has `device` selected
+int arena_acquire(int device, size_t bytes, void** p, size_t* got) {
+    {
+        std::lock_guard<std::mutex> g(g_cache_mutex);
+        Block* best = nullptr;
+        for (Block& b : g_arenas)
+            if (!b.in_use && b.device == device && b.bytes >= bytes && b.bytes <= 4 * bytes + (size_t(64) << 20) && (!best || b.bytes < best->bytes))
+                best = &b;
+        if (best) {
+            best->in_use = true;
+            *p = best->p;
+            *got = best->bytes;
+            return FB200_OK;
+        }
+    }
+    const size_t want = bytes + bytes / 8 + (size_t(1) << 20);
+    void* q = nullptr;
+    cudaError_t ce = cudaMalloc(&q, want);
+    if (ce != cudaSuccess) {  // give the cached blocks of this device back and try once more, without the head-room
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> g(g_cache_mutex);
+            for (size_t i = 0; i < g_arenas.size();)
+                if (!g_arenas[i].in_use && g_arenas[i].device == device) {
+                    cudaFree(g_arenas[i].p);
+                    g_arenas.erase(g_arenas.begin() + i);
+                } else {
+                    ++i;
+                }
+        }
+        ce = cudaMalloc(&q, bytes);
+        if (ce != cudaSuccess) return fb_cuda_fail(ce, "cudaMalloc (ensemble arena)");
+        *got = bytes;
+    } else {
+        *got = want;
+    }
+    *p = q;
+    std::lock_guard<std::mutex> g(g_cache_mutex);
+    g_arenas.push_back(Block{q, *got, true, device});
+    return FB200_OK;
+}
+
+void arena_release(int device, void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(g_cache_mutex);
+    int kept = 0;
+    for (const Block& b : g_arenas)
+        if (!b.in_use && b.device == device) ++kept;
+    for (size_t i = 0; i < g_arenas.size(); ++i)
+        if (g_arenas[i].p == p) {
+            if (cache_disabled() || kept >= 2) {  // at most two idle arenas per device
+                cudaFree(p);
+                g_arenas.erase(g_arenas.begin() + i);
+            } else {
+                g_arenas[i].in_use = false;
+            }
+            return;
+        }
+}
+
+void caches_trim() {
+    std::lock_guard<std::mutex> g(g_cache_mutex);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (size_t i = 0; i < g_arenas.size();)
+        if (!g_arenas[i].in_use) {
+            cudaSetDevice(g_arenas[i].device);
+            cudaFree(g_arenas[i].p);
+            g_arenas.erase(g_arenas.begin() + i);
+        } else {
+            ++i;
+        }
+    cudaSetDevice(cur);
+    for (size_t i = 0; i < g_pinned.size();)
+        if (!g_pinned[i].in_use) {
+            cudaFreeHost(g_pinned[i].p);
+            g_pinned.erase(g_pinned.begin() + i);
+        } else {
+            ++i;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+namespace {
+
+struct Plan {
+    int Nx = 0, n_rows = 0, n_cols = 0, max_Nt = 0;
+    bool is_ns = false, big = false, has_A = false, has_B = false, has_C = false, has_dyn = false;
+};
+
+int n_cols_of(const fb200_config_t& cfg, bool is_ns) {
+    return FB200_N_BH_COLS + (cfg.n_lambdas + cfg.n_passbands) * ((cfg.cold_disk ? 2 : 1) + (cfg.star_flux == 1 ? 3 : 0)) +
+           (is_ns ? FB200_N_NS_COLS : 0);
+}
+
+int make_plan(const fb200_args_t* args, size_t n, const fb200_config_t& cfg, Plan& P, size_t* bad_model) {
+    const ModelPlan p0 = plan_of(args[0]);
+    P.Nx = p0.Nx;
+    P.is_ns = p0.is_ns;
+    for (size_t i = 0; i < n; ++i) {
+        const ModelPlan p = plan_of(args[i]);
+        if (p.Nx != P.Nx || p.is_ns != P.is_ns) {
+            if (bad_model) *bad_model = i;
+            return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "all models of one ensemble must share Nx and the model class (BH / NS)");
+        }
+        P.max_Nt = std::max(P.max_Nt, p.Nt);
+        P.has_A |= p.has_A;
+        P.has_B |= p.has_B;
+        P.has_C |= p.has_C;
+        P.has_dyn |= p.dynamic;
+    }
+    P.n_rows = P.max_Nt + 1;
+    P.n_cols = n_cols_of(cfg, P.is_ns);
+    P.big = P.Nx > 1024;
+    return FB200_OK;
+}
+
+// scheduling groups / upload chunks: boundaries, every group but the last a multiple of 16 models (EnsembleDev::ready)
+std::vector<int> partition_groups(size_t n, int first, int size) {
+    std::vector<int> b{0};
+    if (n > size_t(first) + size / 2) {
+        b.push_back(first);
+        while (n - size_t(b.back()) > size_t(size) + size / 2) b.push_back(b.back() + size);
+    }
+    b.push_back(int(n));
+    return b;
+}
+
+struct SlotLayout {  // one staging slot: the arrays of up to `cap` models, back to back, 256-byte aligned
+    size_t cap = 0, o_models = 0, o_state = 0, o_h = 0, o_F = 0, o_A = 0, o_B = 0, o_C = 0, o_Fm = 0, o_dFm = 0, o_d2Fm = 0, bytes = 0;
+};
+
+SlotLayout slot_layout(const Plan& P, size_t cap) {
+    SlotLayout L;
+    L.cap = cap;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        off = (off + 255) & ~size_t(255);
+        const size_t o = off;
+        off += bytes;
+        return o;
+    };
+    const size_t arr = cap * size_t(P.Nx) * sizeof(double);
+    L.o_models = take(cap * sizeof(fb200_model_dev_t));
+    L.o_state = take(cap * sizeof(ModelState));
+    L.o_h = take(arr);
+    L.o_F = take(arr);
+    if (P.has_A) L.o_A = take(arr);
+    if (P.has_B) L.o_B = take(arr);
+    if (P.has_C) L.o_C = take(arr);
+    if (P.is_ns) {
+        L.o_Fm = take(arr);
+        L.o_dFm = take(arr);
+        L.o_d2Fm = take(arr);
+    }
+    L.bytes = off;
+    return L;
+}
+
+constexpr int kSlots = 3;
+
+struct DeviceBuild {
+    fb200_ensemble* e = nullptr;
+    int device = 0;
+    ArgView args;
+    size_t global0 = 0, gstride = 1;  // local model j = model global0 + j * gstride of the caller
+    std::vector<int> chunk_begin;     // [n_chunks + 1]
+    std::unique_ptr<std::atomic<int>[]> chunk_left;
+    std::atomic<int> uploaded{0};     // chunks whose upload is complete (their staging slot is free again)
+    SlotLayout L;
+    char* slots[kSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t slot_ev[kSlots] = {nullptr, nullptr, nullptr};
+    int enqueued = 0, polled = 0;
+    int* marks = nullptr;             // pinned: cumulative model counts per chunk (+ a -1 at the end): sources of the watermark copies
+    void* marks_block = nullptr;
+    int next_group = 0;               // streamed sweep: groups whose rows have been sent to the host
+    int rc = FB200_OK;
+    std::string err;
+    double t_launch_ms = 0., t_uploaded_ms = 0., device_ms = 0.;
+};
+
+struct Shared {
+    Plan P;
+    fb200_config_t cfg{};
+    std::vector<PassbandTable> passbands;
+    std::vector<double> star_table;             // all star geometries back to back
+    std::vector<long long> star_off;            // per caller model
+    std::vector<int> star_ntri;
+    int star_ntri_max = 0;
+    bool keep_initial = false;
+    SweepIO* io = nullptr;
+    size_t n_total = 0;
+    int n_dev = 0;
+    std::atomic<bool> abort{false};
+    std::mutex err_mutex;
+    int err_code = FB200_OK;
+    size_t err_model = ~size_t(0);
+    std::string err_msg;
+    std::chrono::steady_clock::time_point t0;
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    void fail(int code, const std::string& msg, size_t model) {
+        std::lock_guard<std::mutex> g(err_mutex);
+        if (err_code == FB200_OK || model < err_model) {
+            err_code = code;
+            err_msg = msg;
+            err_model = model;
+        }
+        abort.store(true);
+    }
+};
+
+struct DevCaps {
+    bool known = false;
+    int sm_count = 0, smem_optin = 0, resident = 0, resident_big = 0;
+};
+std::mutex g_caps_mutex;
+DevCaps g_caps[64];
+
+int device_caps(int device, bool big, DevCaps& out) {  // the calling thread has `device` selected
+    std::lock_guard<std::mutex> g(g_caps_mutex);
+    DevCaps& c = g_caps[device & 63];
+    if (!c.known) {
+        FB_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
+        FB_CUDA(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        c.resident = -2;
+        c.resident_big = -2;
+        c.known = true;
+    }
+    if (!big && c.resident == -2) c.resident = (size_t(c.smem_optin) >= evolve_smem_bytes()) ? evolve_resident_ctas_per_sm() : 0;
+    if (big && c.resident_big == -2) c.resident_big = (size_t(c.smem_optin) >= fb200_big_evolve_smem_bytes()) ? fb200_big_evolve_resident_ctas_per_sm() : 0;
+    out = c;
+    return FB200_OK;
+}
+
+// Carves the arena (base == nullptr: only measures).  Returns the bytes needed.
+size_t carve(fb200_ensemble* e, const Shared& sh, char* base, size_t scratch_per_cta) {
+    const Plan& P = sh.P;
+    EnsembleDev& D = e->dev;
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> void* {
+        off = (off + 255) & ~size_t(255);
+        void* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    };
+    const size_t n = e->n, NN = n * size_t(P.Nx) * sizeof(double);
+    const size_t n_groups = e->group_begin.size() - 1;
+    // the streamed arrays first (uploads of different chunks never share a 128-byte line: chunk sizes are multiples of 16 models)
+    auto* models = static_cast<fb200_model_dev_t*>(take(n * sizeof(fb200_model_dev_t)));
+    auto* state = static_cast<ModelState*>(take(n * sizeof(ModelState)));
+    auto* h = static_cast<double*>(take(NN));
+    auto* F = static_cast<double*>(take(NN));
+    auto* wA = P.has_A ? static_cast<double*>(take(NN)) : nullptr;
+    auto* wB = P.has_B ? static_cast<double*>(take(NN)) : nullptr;
+    auto* wC = P.has_C ? static_cast<double*>(take(NN)) : nullptr;
+    auto* Fm = P.is_ns ? static_cast<double*>(take(NN)) : nullptr;
+    auto* dFm = P.is_ns ? static_cast<double*>(take(NN)) : nullptr;
+    auto* d2Fm = P.is_ns ? static_cast<double*>(take(NN)) : nullptr;
+    auto* K = static_cast<double*>(take(NN));
+    auto* rows = static_cast<double*>(take(n * size_t(P.n_rows) * P.n_cols * sizeof(double)));
+    auto* queue = static_cast<int*>(take(64));
+    auto* progress = static_cast<int*>(take(n * sizeof(int)));
+    auto* failed = static_cast<int*>(take(n * sizeof(int)));
+    auto* wind_rec = P.has_dyn ? static_cast<WindRecord*>(take(n * size_t(P.n_rows) * sizeof(WindRecord))) : nullptr;
+    auto* cta_scratch = static_cast<double*>(take(size_t(D.max_ctas) * scratch_per_cta * sizeof(double)));
+    auto* star_T = sh.star_ntri_max > 0 ? static_cast<double*>(take(size_t(D.max_ctas) * sh.star_ntri_max * sizeof(double))) : nullptr;
+    auto* prof = static_cast<long long*>(take(16 * sizeof(long long)));
+    double *pb_a = nullptr, *pb_w = nullptr;
+    if (sh.cfg.n_passbands > 0) {
+        size_t len = 0;
+        for (const PassbandTable& t : sh.passbands) len += t.a.size();
+        pb_a = static_cast<double*>(take(len * sizeof(double)));
+        pb_w = static_cast<double*>(take(len * sizeof(double)));
+    }
+    auto* star_data = sh.star_table.empty() ? nullptr : static_cast<double*>(take(sh.star_table.size() * sizeof(double)));
+    double* Fsnap = nullptr;
+    int* bounds = nullptr;
+    if (sh.cfg.record_F) {
+        Fsnap = static_cast<double*>(take(n * size_t(P.n_rows) * P.Nx * sizeof(double)));
+        bounds = static_cast<int*>(take(n * size_t(P.n_rows) * 2 * sizeof(int)));
+    }
+    double* F0 = nullptr;
+    ModelState* state0 = nullptr;
+    if (sh.keep_initial) {
+        F0 = static_cast<double*>(take(NN));
+        state0 = static_cast<ModelState*>(take(n * sizeof(ModelState)));
+    }
+    int *ready = nullptr, *group_count = nullptr;
+    if (sh.io) {
+        ready = static_cast<int*>(take(64));
+        group_count = static_cast<int*>(take(n_groups * sizeof(int)));
+    }
+    if (base) {
+        D.models = models; D.state = state; D.h = h; D.F = F; D.K = K;
+        D.wA = wA; D.wB = wB; D.wCs = wC; D.Fmagn = Fm; D.dFmagn_dh = dFm; D.d2Fmagn_dh2 = d2Fm;
+        D.rows = rows; D.queue = queue; D.progress = progress; D.failed = failed; D.wind_rec = wind_rec;
+        D.cta_scratch = cta_scratch; D.star_T = star_T; D.prof = prof;
+        D.cfg.pb_a = pb_a; D.cfg.pb_w = pb_w; D.cfg.star_data = star_data;
+        D.Fsnap = Fsnap; D.bounds = bounds;
+        e->F0_dev = F0; e->state0_dev = state0;
+        e->ready_dev = ready;
+        D.ready = ready;
+        D.group_count = group_count;
+    }
+    return off + 256;
+}
+
+#define FB_TRYB(call)                                             \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) {                                  \
+            B.rc = fb_cuda_fail(_e, #call);                       \
+            B.err = fb_err_msg();                                 \
+            return B.rc;                                          \
+        }                                                         \
+    } while (0)
+
+// streams, arena, tables and the clearing memsets of one device's ensemble
+int device_alloc(DeviceBuild& B, Shared& sh) {
+    const Plan& P = sh.P;
+    auto fail = [&](int code, const std::string& msg) { B.rc = code; B.err = msg; return code; };
+    int ndev = 0;
+    {
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0) {
+            std::string why = (ce != cudaSuccess) ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(ce) : std::string("no CUDA device");
+            cudaGetLastError();
+            return fail(FB200_ERR_NO_DEVICE, "no CUDA device: " + why + " (there is no CPU fallback)");
+        }
+    }
+    if (B.device < 0 || B.device >= ndev) return fail(FB200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    fb200_ensemble* e = B.e;
+    FB_TRYB(cudaSetDevice(B.device));
+    DevCaps caps;
+    if (device_caps(B.device, P.big, caps) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
+    e->sm_count = caps.sm_count;
+    if (size_t(caps.smem_optin) < (P.big ? fb200_big_evolve_smem_bytes() : evolve_smem_bytes()))
+        return fail(FB200_ERR_UNSUPPORTED, "device offers too little shared memory per block for the sm_100a kernels");
+    FB_TRYB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    FB_TRYB(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+    FB_TRYB(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+    FB_TRYB(cudaEventCreate(&e->ev0));
+    FB_TRYB(cudaEventCreate(&e->ev1));
+    for (int s = 0; s < kSlots; ++s) FB_TRYB(cudaEventCreateWithFlags(&B.slot_ev[s], cudaEventDisableTiming));
+
+    EnsembleDev& D = e->dev;
+    const fb200_config_t& cfg = sh.cfg;
+    D.n_models = int(e->n);
+    D.Nx = P.Nx;
+    D.cfg.n_lambdas = cfg.n_lambdas;
+    D.cfg.cold_disk = cfg.cold_disk;
+    D.cfg.compute_lx = cfg.compute_lx;
+    D.cfg.record_F = cfg.record_F;
+    D.cfg.lx_prune = cfg.exact_lx_walk ? 0 : 1;
+    D.cfg.n_cols = e->n_cols;
+    D.cfg.n_rows = e->n_rows;
+    for (int k = 0; k < FB200_MAX_LAMBDAS; ++k) D.cfg.lambdas[k] = (k < cfg.n_lambdas) ? cfg.lambdas[k] : 0.;
+    D.cfg.n_passbands = cfg.n_passbands;
+    for (int k = 0; k < FB200_MAX_PASSBANDS + 2; ++k) D.cfg.pb_off[k] = 0;
+    for (int k = 0; k < FB200_MAX_PASSBANDS; ++k) D.cfg.pb_tdnu[k] = 1.;
+    D.cfg.star_flux = (cfg.star_flux == 1) ? 1 : 0;  // 2: geometry for fb200_ensemble_flux_rows(region 2) only, no columns
+    D.star_ntri_max = sh.star_ntri_max;
+    {
+        // the chunked scheduler lets a CTA wait for another one: never launch more CTAs than can be resident
+        int resident = P.big ? caps.resident_big : caps.resident;
+        if (resident < 1) return fail(FB200_ERR_UNSUPPORTED, "the evolve kernel does not fit on this device");
+        const int designed = P.big ? fb200_big_evolve_ctas_per_sm() : evolve_ctas_per_sm();
+        if (resident > designed) resident = designed;
+        if (P.big && size_t(e->sm_count) * resident > e->n)  // 3 MB of scratch per CTA: no more CTAs than models
+            resident = int((e->n + e->sm_count - 1) / e->sm_count);
+        D.max_ctas = e->sm_count * resident;
+    }
+    {
+        long long ms = cfg.wait_timeout_ms > 0 ? cfg.wait_timeout_ms : 10000;
+        if (const char* c = getenv("FB200_WAIT_TIMEOUT_US")) D.wait_timeout_ns = 1000ll * atoll(c);  // test hook: forces the give-up path
+        else D.wait_timeout_ns = ms * 1000000ll;
+    }
+    // scheduling groups: the upload chunks for a streamed sweep, one group otherwise
+    const int n_groups = int(e->group_begin.size()) - 1;
+    D.n_groups = n_groups;
+    D.group0 = e->group_begin[1];
+    D.group = n_groups > 1 ? e->group_begin[2] - e->group_begin[1] : 0;  // the last group takes the remainder
+    D.group_done = nullptr;
+
+    const size_t scratch_per_cta = P.big ? fb200_big_evolve_scratch_doubles_per_cta() : evolve_scratch_doubles_per_cta();
+    const size_t need = carve(e, sh, nullptr, scratch_per_cta);
+    void* base = nullptr;
+    if (arena_acquire(B.device, need, &base, &e->arena_bytes) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
+    e->arena = base;
+    carve(e, sh, static_cast<char*>(base), scratch_per_cta);
+
+    if (cfg.n_passbands > 0) {  // all tables back to back: a_j, then w_j
+        std::vector<double> ha, hw;
+        for (int p = 0; p < cfg.n_passbands; ++p) {
+            D.cfg.pb_off[p] = int(ha.size());
+            ha.insert(ha.end(), sh.passbands[p].a.begin(), sh.passbands[p].a.end());
+            hw.insert(hw.end(), sh.passbands[p].w.begin(), sh.passbands[p].w.end());
+            D.cfg.pb_tdnu[p] = sh.passbands[p].t_dnu;
+        }
+        for (int p = cfg.n_passbands; p < FB200_MAX_PASSBANDS + 2; ++p) D.cfg.pb_off[p] = int(ha.size());
+        FB_TRYB(cudaMemcpy(const_cast<double*>(D.cfg.pb_a), ha.data(), sizeof(double) * ha.size(), cudaMemcpyHostToDevice));
+        FB_TRYB(cudaMemcpy(const_cast<double*>(D.cfg.pb_w), hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice));
+    }
+    if (!sh.star_table.empty())
+        FB_TRYB(cudaMemcpy(const_cast<double*>(D.cfg.star_data), sh.star_table.data(), sizeof(double) * sh.star_table.size(), cudaMemcpyHostToDevice));
+
+    const size_t n = e->n;
+    FB_TRYB(cudaMemsetAsync(D.failed, 0, sizeof(int) * n, e->stream));
+    FB_TRYB(cudaMemsetAsync(D.prof, 0, 16 * sizeof(long long), e->stream));
+    if (D.wind_rec) FB_TRYB(cudaMemsetAsync(D.wind_rec, 0, n * size_t(e->n_rows) * sizeof(WindRecord), e->stream));
+    FB_TRYB(cudaMemsetAsync(D.rows, 0xFF, n * size_t(e->n_rows) * e->n_cols * sizeof(double), e->stream));  // all-ones = NaN: rows never written stay NaN
+    if (D.Fsnap) {
+        FB_TRYB(cudaMemsetAsync(D.Fsnap, 0xFF, n * size_t(e->n_rows) * P.Nx * sizeof(double), e->stream));
+        FB_TRYB(cudaMemsetAsync(D.bounds, 0xFF, n * size_t(e->n_rows) * 2 * sizeof(int), e->stream));
+    }
+    if (sh.io) {
+        // the watermark is cleared on the stream that will raise it; the launch waits for that (the arena is recycled memory)
+        FB_TRYB(cudaMemsetAsync(e->ready_dev, 0, sizeof(int), e->copy_in));
+        FB_TRYB(cudaEventRecord(B.slot_ev[0], e->copy_in));
+        FB_TRYB(cudaStreamWaitEvent(e->stream, B.slot_ev[0], 0));
+        FB_TRYB(cudaMemsetAsync(D.group_count, 0, sizeof(int) * n_groups, e->stream));
+        e->pinned_block = pinned_acquire(sizeof(int) * n_groups);
+        if (!e->pinned_block) return fail(FB200_ERR_CUDA, "pinned host memory for the group flags could not be allocated");
+        e->group_done_host = static_cast<int*>(e->pinned_block);
+        std::memset(e->group_done_host, 0, sizeof(int) * n_groups);
+        void* dptr = nullptr;
+        FB_TRYB(cudaHostGetDevicePointer(&dptr, e->group_done_host, 0));
+        D.group_done = static_cast<int*>(dptr);
+    }
+    return FB200_OK;
+}
+
+// resolved model -> its place in the staging slot of its chunk
+void pack_model(DeviceBuild& B, const Shared& sh, int chunk, size_t k /*index inside the chunk*/, Resolved& r, size_t global) {
+    const Plan& P = sh.P;
+    const SlotLayout& L = B.L;
+    char* slot = B.slots[chunk % kSlots];
+    const size_t Nx = size_t(P.Nx), arr = Nx * sizeof(double);
+    if (!sh.star_off.empty()) {
+        r.dev.star_off = sh.star_off[global];
+        r.dev.star_ntri = sh.star_ntri[global];
+    }
+    reinterpret_cast<fb200_model_dev_t*>(slot + L.o_models)[k] = r.dev;
+    ModelState& s = reinterpret_cast<ModelState*>(slot + L.o_state)[k];
+    std::memset(&s, 0, sizeof(s));
+    s.t = r.dev.t0;
+    s.F_in = r.dev.F_in0;
+    s.Mdot_in_prev = -INFINITY;  // cpp/include/freddi_state.hpp:245
+    s.first = r.dev.first0;
+    s.last = P.Nx - 1;
+    std::memcpy(slot + L.o_h + k * arr, r.h.data(), arr);
+    std::memcpy(slot + L.o_F + k * arr, r.F.data(), arr);
+    auto put = [&](size_t off, const std::vector<double>& v) {
+        if (v.empty()) std::memset(slot + off + k * arr, 0, arr);
+        else std::memcpy(slot + off + k * arr, v.data(), arr);
+    };
+    if (P.has_A) put(L.o_A, r.wA);
+    if (P.has_B) put(L.o_B, r.wB);
+    if (P.has_C) {  // static wind C + d2Fmagn_dh2 (FreddiNeutronStarEvolution::windC, cpp/src/ns/ns_evolution.cpp:487-493)
+        double* c = reinterpret_cast<double*>(slot + L.o_C + k * arr);
+        if (r.wC.empty()) std::memset(c, 0, arr);
+        else std::memcpy(c, r.wC.data(), arr);
+        if (!r.d2Fmagn_dh2.empty())
+            for (size_t i = 0; i < Nx; ++i) c[i] += r.d2Fmagn_dh2[i];
+    }
+    if (P.is_ns) {
+        put(L.o_Fm, r.Fmagn);
+        put(L.o_dFm, r.dFmagn_dh);
+        put(L.o_d2Fm, r.d2Fmagn_dh2);
+    }
+}
+
+int enqueue_upload(DeviceBuild& B, const Shared& sh, int c) {
+    fb200_ensemble* e = B.e;
+    const EnsembleDev& D = e->dev;
+    const Plan& P = sh.P;
+    const SlotLayout& L = B.L;
+    const char* slot = B.slots[c % kSlots];
+    const size_t m0 = size_t(B.chunk_begin[c]), cnt = size_t(B.chunk_begin[c + 1]) - m0;
+    const size_t Nx = size_t(P.Nx), arr = cnt * Nx * sizeof(double), o = m0 * Nx;
+    cudaStream_t s = e->copy_in;
+    FB_TRYB(cudaMemcpyAsync(const_cast<fb200_model_dev_t*>(D.models) + m0, slot + L.o_models, cnt * sizeof(fb200_model_dev_t), cudaMemcpyHostToDevice, s));
+    FB_TRYB(cudaMemcpyAsync(D.state + m0, slot + L.o_state, cnt * sizeof(ModelState), cudaMemcpyHostToDevice, s));
+    FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.h) + o, slot + L.o_h, arr, cudaMemcpyHostToDevice, s));
+    FB_TRYB(cudaMemcpyAsync(D.F + o, slot + L.o_F, arr, cudaMemcpyHostToDevice, s));
+    if (P.has_A) FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.wA) + o, slot + L.o_A, arr, cudaMemcpyHostToDevice, s));
+    if (P.has_B) FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.wB) + o, slot + L.o_B, arr, cudaMemcpyHostToDevice, s));
+    if (P.has_C) FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.wCs) + o, slot + L.o_C, arr, cudaMemcpyHostToDevice, s));
+    if (P.is_ns) {
+        FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.Fmagn) + o, slot + L.o_Fm, arr, cudaMemcpyHostToDevice, s));
+        FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.dFmagn_dh) + o, slot + L.o_dFm, arr, cudaMemcpyHostToDevice, s));
+        FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.d2Fmagn_dh2) + o, slot + L.o_d2Fm, arr, cudaMemcpyHostToDevice, s));
+    }
+    if (e->F0_dev) {
+        FB_TRYB(cudaMemcpyAsync(e->F0_dev + o, D.F + o, arr, cudaMemcpyDeviceToDevice, s));
+        FB_TRYB(cudaMemcpyAsync(e->state0_dev + m0, D.state + m0, cnt * sizeof(ModelState), cudaMemcpyDeviceToDevice, s));
+    }
+    if (sh.io)  // the watermark, behind the arrays it announces
+        FB_TRYB(cudaMemcpyAsync(e->ready_dev, B.marks + c, sizeof(int), cudaMemcpyHostToDevice, s));
+    FB_TRYB(cudaEventRecord(B.slot_ev[c % kSlots], s));
+    ++B.enqueued;
+    return FB200_OK;
+}
+
+void poll_uploads(DeviceBuild& B) {
+    while (B.polled < B.enqueued && cudaEventQuery(B.slot_ev[B.polled % kSlots]) == cudaSuccess) {
+        ++B.polled;
+        B.uploaded.store(B.polled, std::memory_order_release);
+    }
+}
+
+// rows of the groups [B.next_group, upto) -> the caller's buffer (models of this device are every gstride-th of the caller's)
+int send_groups(DeviceBuild& B, const Shared& sh, int upto) {
+    fb200_ensemble* e = B.e;
+    const size_t row_bytes = size_t(e->n_rows) * e->n_cols * sizeof(double);
+    for (; B.next_group < upto; ++B.next_group) {
+        const size_t m0 = size_t(e->group_begin[B.next_group]), cnt = size_t(e->group_begin[B.next_group + 1]) - m0;
+        char* dst = reinterpret_cast<char*>(sh.io->rows) + (B.global0 + m0 * B.gstride) * row_bytes;
+        const char* src = reinterpret_cast<const char*>(e->dev.rows) + m0 * row_bytes;
+        if (B.gstride == 1) FB_TRYB(cudaMemcpyAsync(dst, src, cnt * row_bytes, cudaMemcpyDeviceToHost, e->copy_out));
+        else FB_TRYB(cudaMemcpy2DAsync(dst, B.gstride * row_bytes, src, row_bytes, row_bytes, cnt, cudaMemcpyDeviceToHost, e->copy_out));
+    }
+    return FB200_OK;
+}
+
+int poll_groups(DeviceBuild& B, const Shared& sh) {
+    const volatile int* done = B.e->group_done_host;
+    int upto = B.next_group;
+    const int n_groups = int(B.e->group_begin.size()) - 1;
+    while (upto < n_groups && done[upto]) ++upto;
+    if (upto > B.next_group) {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return send_groups(B, sh, upto);
+    }
+    return FB200_OK;
+}
+
+void nap() { std::this_thread::sleep_for(std::chrono::microseconds(20)); }
+
+// the driver thread of one device
+int drive_device(DeviceBuild& B, Shared& sh) {
+    if (device_alloc(B, sh) != FB200_OK) {
+        sh.fail(B.rc, B.err, ~size_t(0));
+        return B.rc;
+    }
+    fb200_ensemble* e = B.e;
+    const int n_chunks = int(B.chunk_begin.size()) - 1;
+    auto cuda_rc = [&](int rc) {
+        if (rc != FB200_OK) sh.fail(B.rc, B.err, ~size_t(0));
+        return rc;
+    };
+    if (sh.io) {
+        if (ensemble_launch(e, -1) != FB200_OK) {
+            B.rc = FB200_ERR_CUDA;
+            B.err = fb_err_msg();
+            sh.fail(B.rc, B.err, ~size_t(0));
+            return B.rc;
+        }
+        B.t_launch_ms = sh.ms();
+    }
+    bool aborted = false;
+    for (int c = 0; c < n_chunks && !aborted; ++c) {
+        while (B.chunk_left[c].load(std::memory_order_acquire) != 0) {
+            if (sh.abort.load()) { aborted = true; break; }
+            poll_uploads(B);
+            if (sh.io && cuda_rc(poll_groups(B, sh)) != FB200_OK) { aborted = true; break; }
+            nap();
+        }
+        if (aborted) break;
+        if (cuda_rc(enqueue_upload(B, sh, c)) != FB200_OK) { aborted = true; break; }
+        poll_uploads(B);
+    }
+    if (aborted || sh.abort.load()) {
+        if (sh.io) {  // withdraw the launch: the kernel's work items stop waiting for uploads
+            cudaMemcpyAsync(e->ready_dev, B.marks + n_chunks, sizeof(int), cudaMemcpyHostToDevice, e->copy_in);
+        }
+        cudaStreamSynchronize(e->copy_in);
+        cudaStreamSynchronize(e->stream);
+        B.uploaded.store(n_chunks);
+        return FB200_ERR_RUNTIME;
+    }
+    FB_TRYB(cudaStreamSynchronize(e->copy_in));
+    B.polled = B.enqueued;
+    B.uploaded.store(n_chunks, std::memory_order_release);
+    B.t_uploaded_ms = sh.ms();
+    if (!sh.io) {
+        FB_TRYB(cudaStreamSynchronize(e->stream));  // the clearing memsets
+        return FB200_OK;
+    }
+    // streamed sweep: read finished groups back while the rest still runs
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(e->ev1);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) {
+            B.rc = fb_cuda_fail(q, "fb200_evolve_kernel");
+            B.err = fb_err_msg();
+            sh.fail(B.rc, B.err, ~size_t(0));
+            return B.rc;
+        }
+        if (cuda_rc(poll_groups(B, sh)) != FB200_OK) return B.rc;
+        nap();
+    }
+    if (cuda_rc(send_groups(B, sh, int(e->group_begin.size()) - 1)) != FB200_OK) return B.rc;
+    {
+        float ms = 0.f;
+        FB_TRYB(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        B.device_ms = ms;
+    }
+    std::vector<ModelState> hs(e->n);
+    std::vector<int> failed(e->n);
+    FB_TRYB(cudaMemcpyAsync(hs.data(), e->dev.state, sizeof(ModelState) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    FB_TRYB(cudaMemcpyAsync(failed.data(), e->dev.failed, sizeof(int) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    FB_TRYB(cudaStreamSynchronize(e->stream));
+    long long steps = 0;
+    for (size_t j = 0; j < e->n; ++j) {
+        const size_t g = B.global0 + j * B.gstride;
+        int st = hs[j].status;
+        if (failed[j] && st == FB200_MODEL_OK) st = FB200_MODEL_FAILED;
+        if (sh.io->status) sh.io->status[g] = st;
+        if (sh.io->rows_valid) sh.io->rows_valid[g] = hs[j].rows_valid;
+        if (sh.io->picard_iters) sh.io->picard_iters[g] = hs[j].picard_iters;
+        steps += hs[j].rows_valid > 0 ? hs[j].rows_valid - 1 : 0;
+    }
+    {
+        std::lock_guard<std::mutex> g(sh.err_mutex);
+        sh.io->model_steps += steps;
+    }
+    FB_TRYB(cudaStreamSynchronize(e->copy_out));
+    return FB200_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ entry points
+int plan_ensemble(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg_in, int* n_rows, int* n_cols, int* Nx, int* is_ns,
+                  size_t* bad_model) {
+    if (bad_model) *bad_model = 0;
+    if (!args || n_models == 0) return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "null argument or empty ensemble");
+    fb200_config_t cfg;
+    if (cfg_in) cfg = *cfg_in; else fb200_config_default(&cfg);
+    Plan P;
+    const int rc = make_plan(args, n_models, cfg, P, bad_model);
+    if (rc != FB200_OK) return rc;
+    if (n_rows) *n_rows = P.n_rows;
+    if (n_cols) *n_cols = P.n_cols;
+    if (Nx) *Nx = P.Nx;
+    if (is_ns) *is_ns = P.is_ns ? 1 : 0;
+    return FB200_OK;
+}
+
+int ensemble_launch(fb200_ensemble* e, long long n_steps) {
+    FB_CUDA(cudaMemsetAsync(e->dev.queue, 0, sizeof(int), e->stream));
+    FB_CUDA(cudaMemsetAsync(e->dev.progress, 0, sizeof(int) * e->n, e->stream));
+    e->dev.n_steps = (n_steps < 0 || n_steps > 0x7fffffff) ? -1 : int(n_steps);
+    {
+        const long long most = (e->dev.n_steps < 0 || e->dev.n_steps > e->max_Nt) ? e->max_Nt : e->dev.n_steps;
+        e->dev.chunk_steps = e->chunk_steps;
+        e->dev.n_rounds = int(std::max<long long>(1, (most + e->chunk_steps - 1) / e->chunk_steps));
+    }
+    FB_CUDA(cudaEventRecord(e->ev0, e->stream));
+    const int n_ctas = int(std::min<size_t>(e->n, size_t(e->dev.max_ctas)));
+    cudaError_t ce = e->big ? fb200_big_launch_evolve(&e->dev, n_ctas, e->stream) : launch_evolve(e->dev, n_ctas, e->stream);
+    if (ce != cudaSuccess) return fb_cuda_fail(ce, "fb200_evolve_kernel launch");
+    FB_CUDA(cudaEventRecord(e->ev1, e->stream));
+    e->last_launches = 1;
+    e->timed = true;
+    return FB200_OK;
+}
+
+void ensemble_free(fb200_ensemble* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->copy_in) cudaStreamSynchronize(e->copy_in);
+    if (e->copy_out) cudaStreamSynchronize(e->copy_out);
+    arena_release(e->device, e->arena);
+    if (e->scratch) cudaFree(e->scratch);
+    pinned_release(e->pinned_block);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
+    delete e;
+}
+
+int build_ensembles(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg_in, const int* devices, int n_devices,
+                    bool keep_initial, SweepIO* io, fb200_ensemble** out, size_t* bad_model) {
+    if (bad_model) *bad_model = 0;
+    if (!args || n_models == 0 || n_devices < 1 || !devices) return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "null argument or empty ensemble");
+    if (n_models > size_t(0x7fffffff) / 64) return fb_set_err(FB200_ERR_UNSUPPORTED, "too many models for one call");
+    const bool dbg = getenv("FB200_DEBUG") != nullptr;  // FB200_DEBUG: where the time of a construction goes, on stderr
+    struct DeviceGuard {  // the caller's current device is left as it was
+        int dev = -1;
+        DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+        ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+    } device_guard;
+    Shared sh;
+    sh.t0 = std::chrono::steady_clock::now();
+    if (cfg_in) sh.cfg = *cfg_in; else fb200_config_default(&sh.cfg);
+    fb200_config_t& cfg = sh.cfg;
+    if (io) cfg.record_F = 0;  // a one-shot sweep returns rows only
+    if (cfg.n_lambdas < 0 || cfg.n_lambdas > FB200_MAX_LAMBDAS) return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "n_lambdas out of range");
+    if (cfg.n_passbands < 0 || cfg.n_passbands > FB200_MAX_PASSBANDS) return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "n_passbands out of range");
+    sh.passbands.resize(cfg.n_passbands);
+    for (int p = 0; p < cfg.n_passbands; ++p) {
+        std::string msg;
+        const int rc = prepare_passband(cfg.passband_lambdas[p], cfg.passband_transmissions[p], cfg.passband_len[p], sh.passbands[p], msg);
+        if (rc != FB200_OK) return fb_set_err(rc, "passband " + std::to_string(p) + ": " + msg);
+    }
+    {
+        const int rc = make_plan(args, n_models, cfg, sh.P, bad_model);
+        if (rc != FB200_OK) return rc;
+    }
+    sh.keep_initial = keep_initial;
+    sh.io = io;
+    sh.n_total = n_models;
+    if (size_t(n_devices) > n_models) n_devices = int(n_models);
+    sh.n_dev = n_devices;
+
+    // ---- companion star (--starflux): one triangle table per distinct (semi-axis, mass ratio, fill factor, starlod) ----
+    if (cfg.star_flux) {
+        struct Key { double semiaxis, q, fill; int lod; long long off; int ntri; };
+        std::vector<Key> keys;
+        sh.star_off.resize(n_models);
+        sh.star_ntri.resize(n_models);
+        for (size_t i = 0; i < n_models; ++i) {
+            const double q = args[i].Mopt / args[i].Mx, sa = star_semiaxis_of(args[i]);
+            const Key* hit = nullptr;
+            for (const Key& k : keys)
+                if (k.semiaxis == sa && k.q == q && k.fill == args[i].rochelobefill && k.lod == args[i].starlod) { hit = &k; break; }
+            if (!hit) {
+                StarGeometry g;
+                std::string msg;
+                const int rc = build_star_geometry(sa, q, args[i].rochelobefill, args[i].starlod, g, msg);
+                if (rc != FB200_OK) {
+                    if (bad_model) *bad_model = i;
+                    return fb_set_err(rc, msg);
+                }
+                keys.push_back(Key{sa, q, args[i].rochelobefill, args[i].starlod, (long long)sh.star_table.size(), g.n_tri});
+                const std::vector<double> packed = g.packed();
+                sh.star_table.insert(sh.star_table.end(), packed.begin(), packed.end());
+                hit = &keys.back();
+            }
+            sh.star_off[i] = hit->off;
+            sh.star_ntri[i] = hit->ntri;
+            sh.star_ntri_max = std::max(sh.star_ntri_max, hit->ntri);
+        }
+    }
+
+    // ---- per-device shares, chunks, staging ----
+    int group0 = 288, group = 576;  // 16-model multiples around one and two work items per resident CTA (2 x 148)
+    if (const char* c = getenv("FB200_GROUP0")) group0 = std::max(16, atoi(c) / 16 * 16);
+    if (const char* c = getenv("FB200_GROUP")) group = std::max(16, atoi(c) / 16 * 16);
+    std::vector<std::unique_ptr<DeviceBuild>> builds;
+    size_t max_chunk = 0;
+    for (int d = 0; d < n_devices; ++d) {
+        builds.emplace_back(new DeviceBuild());
+        DeviceBuild& B = *builds.back();
+        B.device = devices[d];
+        B.global0 = size_t(d);
+        B.gstride = size_t(n_devices);
+        B.args.base = args + d;
+        B.args.stride = size_t(n_devices);
+        B.args.n = (n_models - size_t(d) + size_t(n_devices) - 1) / size_t(n_devices);
+        B.chunk_begin = partition_groups(B.args.n, group0, group);
+        const int n_chunks = int(B.chunk_begin.size()) - 1;
+        B.chunk_left.reset(new std::atomic<int>[n_chunks]);
+        for (int c = 0; c < n_chunks; ++c) {
+            B.chunk_left[c].store(B.chunk_begin[c + 1] - B.chunk_begin[c]);
+            max_chunk = std::max(max_chunk, size_t(B.chunk_begin[c + 1] - B.chunk_begin[c]));
+        }
+        auto* e = new fb200_ensemble();
+        B.e = e;
+        e->device = B.device;
+        e->cfg = cfg;
+        for (int p = 0; p < FB200_MAX_PASSBANDS; ++p) { e->cfg.passband_lambdas[p] = nullptr; e->cfg.passband_transmissions[p] = nullptr; }  // caller-owned
+        e->cfg.device = B.device;
+        e->n = B.args.n;
+        e->Nx = sh.P.Nx;
+        e->is_ns = sh.P.is_ns;
+        e->big = sh.P.big;
+        e->n_rows = sh.P.n_rows;
+        e->max_Nt = sh.P.max_Nt;
+        e->n_cols = sh.P.n_cols;
+        if (const char* c = getenv("FB200_CHUNK_STEPS")) e->chunk_steps = atoi(c) > 0 ? atoi(c) : 0x3fffffff;
+        e->info.resize(e->n);
+        if (io) e->group_begin = B.chunk_begin;
+        else e->group_begin = std::vector<int>{0, int(e->n)};
+    }
+    auto cleanup = [&] {
+        for (auto& b : builds) {
+            for (int s = 0; s < kSlots; ++s) {
+                pinned_release(b->slots[s]);
+                if (b->slot_ev[s]) { cudaSetDevice(b->device); cudaEventDestroy(b->slot_ev[s]); }
+            }
+            pinned_release(b->marks_block);
+        }
+    };
+    auto destroy_all = [&] {
+        for (auto& b : builds) { ensemble_free(b->e); b->e = nullptr; }
+    };
+    {
+        // pinned staging needs a CUDA context: fail here, loudly, when there is no device
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0) {
+            const std::string why = (ce != cudaSuccess) ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(ce) : std::string("no CUDA device");
+            cudaGetLastError();
+            for (auto& b : builds) delete b->e;
+            return fb_set_err(FB200_ERR_NO_DEVICE, "no CUDA device: " + why + " (there is no CPU fallback)");
+        }
+        for (int d = 0; d < n_devices; ++d)
+            if (devices[d] < 0 || devices[d] >= ndev) {
+                for (auto& b : builds) delete b->e;
+                return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+            }
+        cudaSetDevice(devices[0]);
+    }
+    const SlotLayout L = slot_layout(sh.P, max_chunk);
+    for (auto& b : builds) {
+        b->L = L;
+        const int n_chunks = int(b->chunk_begin.size()) - 1;
+        const int n_slots = std::min(kSlots, n_chunks);
+        bool ok = true;
+        for (int s = 0; s < n_slots; ++s) {
+            b->slots[s] = static_cast<char*>(pinned_acquire(L.bytes));
+            ok &= b->slots[s] != nullptr;
+        }
+        b->marks_block = pinned_acquire(sizeof(int) * (n_chunks + 1));
+        ok &= b->marks_block != nullptr;
+        if (!ok) {
+            cleanup();
+            for (auto& bb : builds) delete bb->e;
+            return fb_set_err(FB200_ERR_CUDA, "pinned staging memory could not be allocated");
+        }
+        b->marks = static_cast<int*>(b->marks_block);
+        for (int c = 0; c < n_chunks; ++c) b->marks[c] = b->chunk_begin[c + 1];
+        b->marks[n_chunks] = -1;
+    }
+    if (dbg) fprintf(stderr, "[fb200] build: plan + staging            %8.2f ms\n", sh.ms());
+
+    // ---- upload order: chunk c of every device before chunk c + 1 of any ----
+    struct Segment { int d, c; size_t flat_begin, flat_end; };
+    std::vector<Segment> segs;
+    {
+        size_t flat = 0;
+        int max_chunks = 0;
+        for (auto& b : builds) max_chunks = std::max(max_chunks, int(b->chunk_begin.size()) - 1);
+        for (int c = 0; c < max_chunks; ++c)
+            for (int d = 0; d < n_devices; ++d) {
+                DeviceBuild& B = *builds[d];
+                if (c >= int(B.chunk_begin.size()) - 1) continue;
+                const size_t cnt = size_t(B.chunk_begin[c + 1] - B.chunk_begin[c]);
+                segs.push_back(Segment{d, c, flat, flat + cnt});
+                flat += cnt;
+            }
+    }
+
+    // ---- device driver threads + host workers ----
+    std::vector<std::thread> drivers;
+    std::vector<int> driver_rc(n_devices, FB200_OK);
+    for (int d = 0; d < n_devices; ++d)
+        drivers.emplace_back([&, d] {
+            driver_rc[d] = drive_device(*builds[d], sh);
+            if (driver_rc[d] != FB200_OK) sh.fail(driver_rc[d], builds[d]->err, ~size_t(0));  // (keeps an earlier, more specific error)
+        });
+
+    std::atomic<size_t> next{0};
+    std::atomic<double> resolve_done_ms{0.};
+    unsigned nt = cfg.host_threads > 0 ? unsigned(cfg.host_threads) : HostPool::default_threads();
+    if (nt > n_models) nt = unsigned(n_models);
+    if (nt < 1) nt = 1;
+    HostPool::instance().run(nt, [&](unsigned) {
+        Resolved R;
+        std::string err;
+        size_t seg = 0;
+        for (;;) {
+            const size_t idx = next.fetch_add(1);
+            if (idx >= n_models || sh.abort.load()) break;
+            while (idx >= segs[seg].flat_end) ++seg;
+            const Segment& S = segs[seg];
+            DeviceBuild& B = *builds[S.d];
+            const size_t k = idx - S.flat_begin, j = size_t(B.chunk_begin[S.c]) + k, global = B.global0 + j * B.gstride;
+            while (!sh.abort.load() && S.c >= B.uploaded.load(std::memory_order_acquire) + kSlots) nap();
+            if (sh.abort.load()) break;
+            const int rc = resolve(B.args[j], R, err);
+            if (rc != FB200_OK) {
+                sh.fail(rc, err, global);
+                break;
+            }
+            if (R.dev.Nx != sh.P.Nx || (R.dev.is_ns != 0) != sh.P.is_ns || R.dev.Nt > sh.P.max_Nt || (!R.wA.empty() && !sh.P.has_A) ||
+                (!R.wB.empty() && !sh.P.has_B) || (!R.wC.empty() && !sh.P.has_C) || (R.dev.wind_dynamic && !sh.P.has_dyn)) {
+                sh.fail(FB200_ERR_LOGIC, "internal: the resolved model does not match the allocation plan", global);
+                break;
+            }
+            B.e->info[j] = R.info;
+            pack_model(B, sh, S.c, k, R, global);
+            if (idx + 1 == n_models) resolve_done_ms.store(sh.ms());
+            B.chunk_left[S.c].fetch_sub(1, std::memory_order_acq_rel);
+        }
+    });
+    if (dbg) fprintf(stderr, "[fb200] build: models resolved           %8.2f ms\n", sh.ms());
+    for (auto& t : drivers) t.join();
+    if (dbg) fprintf(stderr, "[fb200] build: devices done              %8.2f ms\n", sh.ms());
+    cleanup();
+
+    int rc = FB200_OK;
+    std::string msg;
+    if (sh.err_code != FB200_OK) {
+        rc = sh.err_code;
+        msg = sh.err_msg;
+        if (bad_model && sh.err_model != ~size_t(0)) *bad_model = sh.err_model;
+    } else {
+        for (int d = 0; d < n_devices; ++d)
+            if (driver_rc[d] != FB200_OK) { rc = builds[d]->rc != FB200_OK ? builds[d]->rc : driver_rc[d]; msg = builds[d]->err; break; }
+    }
+    if (rc != FB200_OK) {
+        destroy_all();
+        return fb_set_err(rc, msg);
+    }
+    if (io) {
+        io->launches = n_devices;
+        io->resolve_ms = resolve_done_ms.load();
+        for (auto& b : builds) {
+            io->device_ms_max = std::max(io->device_ms_max, b->device_ms);
+            io->first_launch_ms = std::max(io->first_launch_ms, b->t_launch_ms);
+            io->uploads_ms = std::max(io->uploads_ms, b->t_uploaded_ms);
+        }
+        destroy_all();
+        io->total_ms = sh.ms();
+    } else {
+        for (int d = 0; d < n_devices; ++d) out[d] = builds[d]->e;
+    }
+    return FB200_OK;
+}
+
+}  // namespace fb200

@@ -28,41 +28,81 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
     // Item (r, m) needs item (r-1, m) finished: it was handed out earlier (the queue is ordered), to a CTA that is
     // resident (grid <= resident capacity) and never waits on a later item, so the wait below cannot deadlock.
     const int n_items = E.n_rounds * E.n_models;
-    __shared__ int s_abort;
+    __shared__ int s_abort, s_round, s_group;
     for (;;) {
         __syncthreads();  // previous item fully done with shared memory and s_model
-        if (tid == 0) s_model = atomicAdd(E.queue, 1);
-        __syncthreads();
-        const int item = s_model;
-        if (item >= n_items) break;
-        const int round = item / E.n_models;
-        const int model = item - round * E.n_models;
         if (tid == 0) {
-            s_abort = 0;
-#pragma unroll
-            for (int c = 0; c < FB_CNT_N; ++c) GpuEx::counters()[c] = 0;  // bookkeeping of this work item (GpuEx::count)
-            if (round > 0) {
-                // Wait for the producer of the previous round, by elapsed time (%globaltimer, ns).  A producer that never
-                // publishes (it can only be a CTA that died) must not hang the launch: after wait_timeout_ns the model is
-                // flagged in E.failed — a flag of its own, set with atomicExch: the state record belongs to the producer, which
-                // may still be writing it — and every later item of that model gives up at once.
-                const volatile int* p = E.progress + model;
-                const volatile int* f = E.failed + model;
-                const unsigned long long t0 = fb_globaltimer();
-                while (*p < round) {
-                    if (*f) { s_abort = 1; break; }
-                    __nanosleep(100);
-                    if (fb_globaltimer() - t0 > (unsigned long long)E.wait_timeout_ns) {
-                        atomicExch(E.failed + model, 1);
-                        s_abort = 1;
-                        break;
+            const int item = atomicAdd(E.queue, 1);
+            int model = -1, round = 0, g = 0;
+            if (item < n_items) {
+                // item -> (group, round, model): groups in order, round-major inside a group
+                const int R = E.n_rounds;
+                int start = 0, size = E.n_models, rem = item;
+                if (E.n_groups > 1) {
+                    const int i0 = E.group0 * R;
+                    if (item < i0) {
+                        size = E.group0;
+                    } else {
+                        const int it = item - i0;
+                        g = 1 + it / (E.group * R);
+                        if (g > E.n_groups - 1) g = E.n_groups - 1;
+                        start = E.group0 + (g - 1) * E.group;
+                        size = (g == E.n_groups - 1) ? E.n_models - start : E.group;
+                        rem = it - (g - 1) * E.group * R;
                     }
                 }
-                __threadfence();
+                round = rem / size;
+                model = start + (rem - round * size);
+                s_abort = 0;
+#pragma unroll
+                for (int c = 0; c < FB_CNT_N; ++c) GpuEx::counters()[c] = 0;  // bookkeeping of this work item (GpuEx::count)
+                const unsigned long long t0 = fb_globaltimer();
+                if (round == 0 && E.ready) {
+                    // streamed construction: wait until the model's group has been uploaded (the host bumps `ready` on the copy
+                    // stream behind the group's arrays); -1 = the host gave up (an argument error in a later model)
+                    const volatile int* rd = E.ready;
+                    for (;;) {
+                        const int have = *rd;
+                        if (have < 0) { s_abort = 2; break; }
+                        if (have >= start + size) break;
+                        __nanosleep(200);
+                        if (fb_globaltimer() - t0 > (unsigned long long)E.wait_timeout_ns) {
+                            atomicExch(E.failed + model, 1);
+                            s_abort = 1;
+                            break;
+                        }
+                    }
+                    __threadfence();
+                }
+                if (round > 0) {
+                    // Wait for the producer of the previous round, by elapsed time (%globaltimer, ns).  A producer that never
+                    // publishes (it can only be a CTA that died) must not hang the launch: after wait_timeout_ns the model is
+                    // flagged in E.failed — a flag of its own, set with atomicExch: the state record belongs to the producer, which
+                    // may still be writing it — and every later item of that model gives up at once.
+                    const volatile int* p = E.progress + model;
+                    const volatile int* f = E.failed + model;
+                    while (*p < round) {
+                        if (*f) { s_abort = 1; break; }
+                        __nanosleep(100);
+                        if (fb_globaltimer() - t0 > (unsigned long long)E.wait_timeout_ns) {
+                            atomicExch(E.failed + model, 1);
+                            s_abort = 1;
+                            break;
+                        }
+                    }
+                    __threadfence();
+                }
             }
+            s_model = model;
+            s_round = round;
+            s_group = g;
         }
         __syncthreads();
-        if (s_abort) continue;  // nothing of this model is touched: no state, no progress
+        const int model = s_model;
+        if (model < 0) break;
+        const int round = s_round;
+        if (s_abort == 2) break;  // the host withdrew the launch
+        if (s_abort) continue;    // nothing of this model is touched: no state, no progress
 
         ModelState st;
         {
@@ -152,7 +192,20 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         }
         __threadfence();   // F, rows and state are visible device-wide before the round is published
         __syncthreads();
-        if (tid == 0) atomicExch(E.progress + model, round + 1);
+        if (tid == 0) {
+            atomicExch(E.progress + model, round + 1);
+            if (E.group_count && round == E.n_rounds - 1) {
+                // last work item of the model: when it is the last one of its group, tell the host (the fence above ordered this
+                // CTA's rows before the count; the counts of the other CTAs were ordered the same way)
+                const int g = s_group;
+                const int start = g ? E.group0 + (g - 1) * E.group : 0;
+                const int size = (g == E.n_groups - 1) ? E.n_models - start : (g ? E.group : E.group0);
+                if (atomicAdd(E.group_count + g, 1) == size - 1) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int*>(E.group_done + g) = 1;
+                }
+            }
+        }
         ex.tick(7);
     }
 #ifdef FB_PROFILE

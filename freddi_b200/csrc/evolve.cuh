@@ -37,7 +37,18 @@ struct EnsembleDev {
     long long* prof;                  // [16] per-phase cycle sums (FB_PROFILE builds only), else null
     double* star_T;                   // [max_ctas][star_ntri_max] companion-star triangle temperatures (--starflux), else null
     int star_ntri_max;
-    int _pad_star;
+    // Scheduling groups.  Work items are numbered group by group, round-major inside a group: the first group holds `group0`
+    // models, the following ones `group` each, the last one the remainder.  One group of n_models models = plain round-major.
+    int n_groups, group0, group;
+    // Streamed construction (fb200_sweep_run; null otherwise): the kernel is launched before the models are in HBM.
+    // ready: number of leading models uploaded so far, written by the copy stream behind each group's arrays (-1: give up);
+    //        the first work item of a model waits until its whole group is there.  Groups are multiples of 16 models, so that no
+    //        128-byte line is shared by two uploads (a line fetched into L1 with a neighbour's tail would otherwise be stale).
+    // group_count[g]: models of group g whose last work item is finished; group_done[g] (host-mapped, pinned): set to 1 by the
+    //        CTA that finishes the last one — the host then reads the group's rows back while later groups still run.
+    const int* ready;
+    int* group_count;
+    int* group_done;
 };
 
 size_t evolve_smem_bytes();

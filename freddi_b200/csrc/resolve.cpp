@@ -692,6 +692,9 @@ int resolve_impl(const fb200_args_t& a, Resolved& out) {
 }  // namespace
 
 int resolve(const fb200_args_t& a, Resolved& out, std::string& err) {
+    // `out` may be a reused object (the fill workers keep one per thread): the optional arrays mean "absent" when empty
+    out.wA.clear(); out.wB.clear(); out.wC.clear();
+    out.Fmagn.clear(); out.dFmagn_dh.clear(); out.d2Fmagn_dh2.clear();
     try {
         return resolve_impl(a, out);
     } catch (const Fail& f) {
@@ -702,6 +705,24 @@ int resolve(const fb200_args_t& a, Resolved& out, std::string& err) {
         return FB200_ERR_RUNTIME;
     }
 }
+
+ModelPlan plan_of(const fb200_args_t& a) {
+    ModelPlan p{};
+    p.Nx = int(a.Nx);
+    p.is_ns = a.is_ns != 0;
+    const double tau = std::isnan(a.tau) ? a.time / 200 : a.tau;                 // as resolve_impl (CalculationArguments)
+    const double nt = std::round(a.time / tau);
+    p.Nt = (nt >= 0. && nt < 2e9) ? int(static_cast<size_t>(nt)) : 0;            // a bad time/tau is reported by resolve()
+    p.has_A = a.windtype == FB200_WIND_TESTA;
+    p.has_B = a.windtype == FB200_WIND_TESTB;
+    p.has_C = a.windtype == FB200_WIND_SS73C || a.windtype == FB200_WIND_CAMBIER2013 || a.windtype == FB200_WIND_TESTC ||
+              (p.is_ns && a.inversebeta != 0.);
+    p.dynamic = a.windtype == FB200_WIND_SHIELDSOSCIL1986 || a.windtype == FB200_WIND_JANIUK2015 || a.windtype == FB200_WIND_SHIELDS1986 ||
+                a.windtype == FB200_WIND_WOODS1996AGN || a.windtype == FB200_WIND_WOODS1996 || a.windtype == FB200_WIND_TOY;
+    return p;
+}
+
+double star_semiaxis_of(const fb200_args_t& a) { return semiaxis(a.Mx + a.Mopt, a.period); }
 
 int prepare_passband(const double* lam, const double* tr, int n, PassbandTable& out, std::string& err) {
     if (!lam || !tr || n < 2 || n > FB200_MAX_PASSBAND_SAMPLES) {

@@ -36,4 +36,14 @@ int prepare_passband(const double* lambdas, const double* transmissions, int n, 
 // Returns FB200_OK or the error class the reference's constructor would have thrown, message in err.
 int resolve(const fb200_args_t& a, Resolved& out, std::string& err);
 
+// What an ensemble has to know about a model before it is resolved (allocation plan of the construction pipeline): read off the
+// argument struct alone, and checked against the resolved model when that arrives.
+struct ModelPlan {
+    int Nx, Nt;
+    bool is_ns, has_A, has_B, has_C, dynamic;  // static wind arrays A / B / C (+ d2Fmagn/dh2 for NS), dynamic wind
+};
+ModelPlan plan_of(const fb200_args_t& a);
+// the semi-axis resolve() stores in fb200_model_dev_t::star_semiaxis (key of the companion-star geometry tables)
+double star_semiaxis_of(const fb200_args_t& a);
+
 }  // namespace fb200

@@ -77,6 +77,114 @@ def resolve(args):
     return info, h, F
 
 
+def make_config(lambdas=(), cold_disk=False, record_F=False, compute_lx=True, host_threads=0, exact_lx_walk=False, passbands=(),
+                star_flux=False):
+    """fb200_config_t of these options -> (cfg, lambdas, passbands); the passband arrays stay referenced by the result."""
+    cfg = FB200Config()
+    _lib.lib.fb200_config_default(C.byref(cfg))
+    lambdas = [float(x) for x in lambdas]
+    if len(lambdas) > FB200_MAX_LAMBDAS:
+        raise ValueError('at most {} lambdas per ensemble'.format(FB200_MAX_LAMBDAS))
+    cfg.n_lambdas = len(lambdas)
+    for k, x in enumerate(lambdas):
+        cfg.lambdas[k] = x
+    cfg.cold_disk = int(bool(cold_disk))
+    cfg.record_F = int(bool(record_F))
+    cfg.compute_lx = int(bool(compute_lx))
+    cfg.host_threads = int(host_threads)
+    cfg.exact_lx_walk = int(bool(exact_lx_walk))
+    passbands = list(passbands)
+    if len(passbands) > FB200_MAX_PASSBANDS:
+        raise ValueError('at most {} passbands per ensemble'.format(FB200_MAX_PASSBANDS))
+    cfg.star_flux = 2 if star_flux == 'readout' else int(bool(star_flux))
+    cfg.n_passbands = len(passbands)
+    dp = C.POINTER(C.c_double)
+    for k, pb in enumerate(passbands):
+        cfg.passband_len[k] = pb.lambdas.size
+        cfg.passband_lambdas[k] = pb.lambdas.ctypes.data_as(dp)
+        cfg.passband_transmissions[k] = pb.transmissions.ctypes.data_as(dp)
+    return cfg, lambdas, passbands
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        _lib.check(_lib.lib.fb200_host_alloc(int(nbytes), C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+        self.__array_interface__ = {'shape': (self.nbytes,), 'typestr': '|u1', 'data': (self.ptr, False), 'version': 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib.fb200_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in pinned (page-locked) host memory from fb200_host_alloc: device <-> host copies into it run at full
+    PCIe rate and asynchronously.  Freed with the last reference."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    blk = _PinnedBlock(max(n, 1))
+    return np.asarray(blk)[:n].view(dtype).reshape(shape)  # the array's base chain keeps the block alive
+
+
+class SweepResult:
+    """What freddi_b200.sweep returns: rows (n_models, n_rows, n_cols), status / rows_valid / picard_iters (n_models,), the column
+    names and the timing the library measured (stats: dict of fb200_sweep_stats_t)."""
+
+    def __init__(self, rows, status, rows_valid, picard_iters, columns, stats):
+        self.rows, self.status, self.rows_valid, self.picard_iters, self.columns, self.stats = rows, status, rows_valid, picard_iters, columns, stats
+
+
+def sweep_plan(args, lambdas=(), cold_disk=False, passbands=(), star_flux=False):
+    """(n_rows, n_cols) of the rows a sweep over these models returns (host only)."""
+    arr = args if isinstance(args, C.Array) else args_array(list(args))
+    cfg, _, _ = make_config(lambdas, cold_disk, False, True, 0, False, passbands, star_flux)
+    nr, nc = C.c_size_t(), C.c_size_t()
+    _lib.check(_lib.lib.fb200_sweep_plan(arr, len(arr), C.byref(cfg), C.byref(nr), C.byref(nc)))
+    return int(nr.value), int(nc.value)
+
+
+def sweep(args, lambdas=(), cold_disk=False, compute_lx=True, devices=None, host_threads=0, exact_lx_walk=False, passbands=(),
+          star_flux=False, out=None):
+    """Argument structs in, light curves out, in one call over one or several GPUs of this process (fb200_sweep_run): the
+    reference's driver loop (cpp/include/application.hpp:17-43) for every model.  Construction is streamed behind the evolve
+    kernels.  devices: None = all visible, or a sequence of ordinals; out: a (n_models, n_rows, n_cols) float64 array to fill
+    (pinned_empty(...) for full-rate copies), allocated pinned when None."""
+    arr = args if isinstance(args, C.Array) else args_array(list(args))
+    cfg, lambdas, passbands = make_config(lambdas, cold_disk, False, compute_lx, host_threads, exact_lx_walk, passbands, star_flux)
+    nr, nc = C.c_size_t(), C.c_size_t()
+    _lib.check(_lib.lib.fb200_sweep_plan(arr, len(arr), C.byref(cfg), C.byref(nr), C.byref(nc)))
+    n = len(arr)
+    shape = (n, int(nr.value), int(nc.value))
+    if out is None:
+        out = pinned_empty(shape)
+    if out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError('out must be a C-contiguous float64 array of shape {}'.format(shape))
+    status = np.empty(n, dtype=np.int32)
+    valid = np.empty(n, dtype=np.int32)
+    picard = np.empty(n, dtype=np.int64)
+    devs = None if devices is None else np.ascontiguousarray(list(devices), dtype=np.int32)
+    stats = _lib.FB200SweepStats()
+    bad = C.c_size_t()
+    i32p = C.POINTER(C.c_int32)
+    rc = _lib.lib.fb200_sweep_run(arr, n, C.byref(cfg), None if devs is None else devs.ctypes.data_as(i32p), 0 if devs is None else devs.size,
+                                  out.ctypes.data_as(C.POINTER(C.c_double)), out.size, status.ctypes.data_as(i32p), valid.ctypes.data_as(i32p),
+                                  picard.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(stats), C.byref(bad))
+    if rc != _lib.FB200_OK:
+        try:
+            _lib.check(rc)
+        except Exception as e:
+            e.bad_model = int(bad.value)
+            raise
+    columns = column_names(len(lambdas), cold_disk, bool(arr[0].is_ns), [pb.name for pb in passbands], bool(star_flux) and star_flux != 'readout')
+    return SweepResult(out, status, valid, picard, columns, {k: getattr(stats, k) for k, _ in _lib.FB200SweepStats._fields_})
+
+
 class Ensemble:
     """``n`` models, one CTA each, evolved by a persistent sm_100a kernel.
 
@@ -87,61 +195,84 @@ class Ensemble:
     star_flux : add the Fnu_star, _star_min, _star_max columns of the irradiated companion star (--starflux);
                 'readout': only triangulate the star so that flux_rows(region='star') works
     record_F  : keep F(h) of every row in HBM (needed for field()/flux() at past rows)
+    device    : a CUDA ordinal (one GPU), or 'all' / a sequence of ordinals: ONE handle over several GPUs of this process —
+                model k on shard k mod G, all devices evolve at once, rows() gathers into one array (fb200_sharded_*);
+                the per-device read-outs (field_rows, flux_rows, mdot_wind, ...) are reached through shards()
     exact_lx_walk : integrate the Lx band integral of every ring like the reference (default: skip the rings that are
                     provably negligible against the hottest one in the X-ray band; changes Lx by < 1e-16 relative)
     """
 
     def __init__(self, args, lambdas=(), cold_disk=False, record_F=False, compute_lx=True, device=0, host_threads=0,
-                 exact_lx_walk=False, passbands=(), star_flux=False):
+                 exact_lx_walk=False, passbands=(), star_flux=False, _borrowed=None):
         self._h = None
+        self._owner = True
         arr = args if isinstance(args, C.Array) else args_array(list(args))
-        cfg = FB200Config()
-        _lib.lib.fb200_config_default(C.byref(cfg))
-        lambdas = [float(x) for x in lambdas]
-        if len(lambdas) > FB200_MAX_LAMBDAS:
-            raise ValueError('at most {} lambdas per ensemble'.format(FB200_MAX_LAMBDAS))
-        cfg.device = int(device)
-        cfg.n_lambdas = len(lambdas)
-        for k, x in enumerate(lambdas):
-            cfg.lambdas[k] = x
-        cfg.cold_disk = int(bool(cold_disk))
-        cfg.record_F = int(bool(record_F))
-        cfg.compute_lx = int(bool(compute_lx))
-        cfg.host_threads = int(host_threads)
-        cfg.exact_lx_walk = int(bool(exact_lx_walk))
-        passbands = list(passbands)
-        if len(passbands) > FB200_MAX_PASSBANDS:
-            raise ValueError('at most {} passbands per ensemble'.format(FB200_MAX_PASSBANDS))
-        cfg.star_flux = 2 if star_flux == 'readout' else int(bool(star_flux))
-        cfg.n_passbands = len(passbands)
-        dp = C.POINTER(C.c_double)
-        for k, pb in enumerate(passbands):
-            cfg.passband_len[k] = pb.lambdas.size
-            cfg.passband_lambdas[k] = pb.lambdas.ctypes.data_as(dp)
-            cfg.passband_transmissions[k] = pb.transmissions.ctypes.data_as(dp)
+        cfg, lambdas, passbands = make_config(lambdas, cold_disk, record_F, compute_lx, host_threads, exact_lx_walk, passbands, star_flux)
         handle = C.c_void_p()
         bad = C.c_size_t()
-        rc = _lib.lib.fb200_ensemble_create(arr, len(arr), C.byref(cfg), C.byref(handle), C.byref(bad))
-        self.bad_model = int(bad.value)
-        _lib.check(rc)
+        # device: an ordinal -> one GPU; 'all' or a sequence of ordinals -> one handle over several GPUs of this process
+        # (model k on shard k mod G; a device may be listed more than once)
+        self._sharded = not isinstance(device, int)
+        self._p = 'fb200_sharded_' if self._sharded else 'fb200_ensemble_'
+        if _borrowed is not None:  # a shard of a sharded ensemble: the parent owns the handle
+            handle, self._owner = _borrowed, False
+        elif self._sharded:
+            devs = None if (isinstance(device, str) and device == 'all') else np.ascontiguousarray(list(device), dtype=np.int32)
+            rc = _lib.lib.fb200_sharded_create(arr, len(arr), C.byref(cfg), None if devs is None else devs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               0 if devs is None else devs.size, C.byref(handle), C.byref(bad))
+            self.bad_model = int(bad.value)
+            _lib.check(rc)
+        else:
+            cfg.device = int(device)
+            rc = _lib.lib.fb200_ensemble_create(arr, len(arr), C.byref(cfg), C.byref(handle), C.byref(bad))
+            self.bad_model = int(bad.value)
+            _lib.check(rc)
         self._h = handle
+        self._args = arr
         self.lambdas = lambdas
         self.cold_disk = bool(cold_disk)
         self.record_F = bool(record_F)
         self.is_ns = bool(arr[0].is_ns)
-        self.n_models = int(_lib.lib.fb200_ensemble_n_models(handle))
-        self.n_rows = int(_lib.lib.fb200_ensemble_n_rows(handle))
-        self.n_cols = int(_lib.lib.fb200_ensemble_n_cols(handle))
-        self.Nx = int(_lib.lib.fb200_ensemble_nx(handle))
+        self.n_models = int(self._f('n_models')(handle))
+        self.n_rows = int(self._f('n_rows')(handle))
+        self.n_cols = int(self._f('n_cols')(handle))
+        self.Nx = int(self._f('nx')(handle))
         self.passbands = passbands
         self.star_flux = bool(star_flux) and star_flux != 'readout'
         self.columns = column_names(len(lambdas), cold_disk, self.is_ns, [pb.name for pb in passbands], self.star_flux)
         self._info = None
+        self._kw = dict(lambdas=lambdas, cold_disk=cold_disk, record_F=record_F, compute_lx=compute_lx, exact_lx_walk=exact_lx_walk,
+                        passbands=passbands, star_flux=star_flux)
+
+    def _f(self, name):
+        """The C entry point `name` of this handle kind (fb200_ensemble_* / fb200_sharded_*)."""
+        f = getattr(_lib.lib, self._p + name, None)
+        if f is None:
+            raise NotImplementedError('{} is per device: call it on the shards (Ensemble.shards())'.format(name))
+        return f
+
+    @property
+    def n_shards(self):
+        return int(_lib.lib.fb200_sharded_n_shards(self._h)) if self._sharded else 1
+
+    def shards(self):
+        """The single-device ensembles behind a multi-GPU handle (views: the parent keeps ownership).  Shard d holds the
+        models d, d + G, d + 2G, ... of the caller."""
+        if not self._sharded:
+            return [self]
+        G = self.n_shards
+        out = []
+        for d in range(G):
+            h = C.c_void_p(_lib.lib.fb200_sharded_shard(self._h, d))
+            sub = (FB200Args * len(range(d, self.n_models, G)))(*[self._args[k] for k in range(d, self.n_models, G)])
+            out.append(Ensemble(sub, _borrowed=h, **self._kw))
+        return out
 
     # -- life cycle --
     def close(self):
         if self._h is not None:
-            _lib.lib.fb200_ensemble_destroy(self._h)
+            if self._owner:
+                self._f('destroy')(self._h)
             self._h = None
 
     def __del__(self):
@@ -158,47 +289,47 @@ class Ensemble:
 
     # -- evolution --
     def evolve(self, n_steps=-1):
-        _lib.check(_lib.lib.fb200_ensemble_evolve(self._h, int(n_steps)))
+        _lib.check(self._f('evolve')(self._h, int(n_steps)))
         return self
 
     def reset(self):
         """Back to the initial state: the resolved initial conditions are copied again host (pinned) -> device."""
-        _lib.check(_lib.lib.fb200_ensemble_reset(self._h))
+        _lib.check(self._f('reset')(self._h))
         return self
 
     def evolve_async(self, n_steps=-1):
-        _lib.check(_lib.lib.fb200_ensemble_evolve_async(self._h, int(n_steps)))
+        _lib.check(self._f('evolve_async')(self._h, int(n_steps)))
         return self
 
     def sync(self):
-        _lib.check(_lib.lib.fb200_ensemble_sync(self._h))
+        _lib.check(self._f('sync')(self._h))
 
     def last_evolve_ms(self):
         ms = C.c_float()
-        _lib.check(_lib.lib.fb200_ensemble_last_evolve_ms(self._h, C.byref(ms)))
+        _lib.check(self._f('last_evolve_ms')(self._h, C.byref(ms)))
         return float(ms.value)
 
     def last_launches(self):
-        return int(_lib.lib.fb200_ensemble_last_launches(self._h))
+        return int(self._f('last_launches')(self._h))
 
     # -- read-out --
     def rows(self, out=None):
         """(n_models, n_rows, n_cols) float64; rows a model never reached are NaN."""
         if out is None:
             out = np.empty((self.n_models, self.n_rows, self.n_cols))
-        _lib.check(_lib.lib.fb200_ensemble_rows(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        _lib.check(self._f('rows')(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
         return out
 
     def rows_device_ptr(self):
         p = C.c_void_p()
-        _lib.check(_lib.lib.fb200_ensemble_rows_device(self._h, C.byref(p)))
+        _lib.check(self._f('rows_device')(self._h, C.byref(p)))
         return p.value
 
     def status(self):
         st = np.empty(self.n_models, dtype=np.int32)
         rv = np.empty(self.n_models, dtype=np.int32)
         pi = np.empty(self.n_models, dtype=np.int64)
-        _lib.check(_lib.lib.fb200_ensemble_status(self._h, st.ctypes.data_as(C.POINTER(C.c_int32)),
+        _lib.check(self._f('status')(self._h, st.ctypes.data_as(C.POINTER(C.c_int32)),
                                                   rv.ctypes.data_as(C.POINTER(C.c_int32)),
                                                   pi.ctypes.data_as(C.POINTER(C.c_int64))))
         return st, rv, pi
@@ -207,7 +338,7 @@ class Ensemble:
         """(picard_iters, lx_trial_steps) per model, summed over the steps done so far."""
         pi, lx = (np.empty(self.n_models, dtype=np.int64) for _ in range(2))
         ip = C.POINTER(C.c_int64)
-        _lib.check(_lib.lib.fb200_ensemble_counters(self._h, pi.ctypes.data_as(ip), lx.ctypes.data_as(ip)))
+        _lib.check(self._f('counters')(self._h, pi.ctypes.data_as(ip), lx.ctypes.data_as(ip)))
         return pi, lx
 
     WORK_COUNTERS = ('picard_iters', 'lx_trials', 'ring_steps', 'ring_iters', 'pow_evals', 'row_rings')
@@ -217,34 +348,34 @@ class Ensemble:
         try_step calls of the Lx quadrature, sum of (last - first) over the solves, the same weighted by the Picard
         iterations, closure pow() calls."""
         out = np.empty((self.n_models, len(self.WORK_COUNTERS)), dtype=np.int64)
-        _lib.check(_lib.lib.fb200_ensemble_work_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size))
+        _lib.check(self._f('work_counters')(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size))
         return {k: out[:, j].copy() for j, k in enumerate(self.WORK_COUNTERS)}
 
     def state(self):
         t = np.empty(self.n_models)
         i_t, first, last = (np.empty(self.n_models, dtype=np.int64) for _ in range(3))
         ip = C.POINTER(C.c_int64)
-        _lib.check(_lib.lib.fb200_ensemble_state(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), i_t.ctypes.data_as(ip),
+        _lib.check(self._f('state')(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), i_t.ctypes.data_as(ip),
                                                  first.ctypes.data_as(ip), last.ctypes.data_as(ip)))
         return dict(t=t, i_t=i_t, first=first, last=last)
 
     def row_bounds(self, row):
         first, last = (np.empty(self.n_models, dtype=np.int64) for _ in range(2))
         ip = C.POINTER(C.c_int64)
-        _lib.check(_lib.lib.fb200_ensemble_row_bounds(self._h, int(row), first.ctypes.data_as(ip), last.ctypes.data_as(ip)))
+        _lib.check(self._f('row_bounds')(self._h, int(row), first.ctypes.data_as(ip), last.ctypes.data_as(ip)))
         return first, last
 
     def info(self):
         if self._info is None:
             arr = (FB200ModelInfo * self.n_models)()
-            _lib.check(_lib.lib.fb200_ensemble_info(self._h, arr))
+            _lib.check(self._f('info')(self._h, arr))
             self._info = arr
         return self._info
 
     def field(self, name, row=-1):
         """(n_models, Nx): the reference getter's array (zeros below first, cold-zone values beyond last)."""
         out = np.empty((self.n_models, self.Nx))
-        _lib.check(_lib.lib.fb200_ensemble_field(self._h, FIELDS[name], int(row), out.ctypes.data_as(C.POINTER(C.c_double)),
+        _lib.check(self._f('field')(self._h, FIELDS[name], int(row), out.ctypes.data_as(C.POINTER(C.c_double)),
                                                  out.size))
         return out
 
@@ -254,7 +385,7 @@ class Ensemble:
         out = np.empty((self.n_models, lam.size))
         reg = {'hot': 0, 'cold': 1}[region]
         dp = C.POINTER(C.c_double)
-        _lib.check(_lib.lib.fb200_ensemble_flux(self._h, reg, int(row), lam.ctypes.data_as(dp), lam.size,
+        _lib.check(self._f('flux')(self._h, reg, int(row), lam.ctypes.data_as(dp), lam.size,
                                                 out.ctypes.data_as(dp), out.size))
         return out
 
@@ -262,7 +393,7 @@ class Ensemble:
         """(n_models, n_rows, Nx) in one launch; pad_nan: NaN outside [first, last] (the EvolutionResult layout)."""
         n_rows = self.n_rows - row_begin if n_rows is None else int(n_rows)
         out = np.empty((self.n_models, n_rows, self.Nx))
-        _lib.check(_lib.lib.fb200_ensemble_field_rows(self._h, FIELDS[name], int(row_begin), n_rows, int(bool(pad_nan)),
+        _lib.check(self._f('field_rows')(self._h, FIELDS[name], int(row_begin), n_rows, int(bool(pad_nan)),
                                                       out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
         return out
 
@@ -276,14 +407,14 @@ class Ensemble:
         ph = None
         if phases is not None:
             ph = np.ascontiguousarray(np.broadcast_to(np.asarray(phases, dtype=np.float64), (n_rows,)))
-        _lib.check(_lib.lib.fb200_ensemble_flux_rows(self._h, reg, int(row_begin), n_rows, lam.ctypes.data_as(dp), lam.size,
+        _lib.check(self._f('flux_rows')(self._h, reg, int(row_begin), n_rows, lam.ctypes.data_as(dp), lam.size,
                                                      ph.ctypes.data_as(dp) if ph is not None else None,
                                                      out.ctypes.data_as(dp), out.size))
         return out
 
     def mdot_wind(self, row=-1):
         out = np.empty(self.n_models)
-        _lib.check(_lib.lib.fb200_ensemble_mdot_wind(self._h, int(row), out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        _lib.check(self._f('mdot_wind')(self._h, int(row), out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
         return out
 
 

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 3
+#define FB200_ABI_VERSION 4
 
 /* ---- return codes ---- */
 enum {
@@ -246,9 +246,9 @@ size_t fb200_ensemble_n_rows(const fb200_ensemble_t* e);  /* rows per model = ma
 size_t fb200_ensemble_nx(const fb200_ensemble_t* e);
 int fb200_ensemble_info(const fb200_ensemble_t* e, fb200_model_info_t* out /*[n_models]*/);
 
-/* Put every model back to its initial state (t = inittime, F = F(t=0), first/last, no rows) by copying the
- * resolved initial conditions again from pinned host memory to the device: the equivalent of constructing the same
- * FreddiEvolution objects again (cpp/include/freddi_evolution.hpp:50) without repeating the argument resolution. */
+/* Put every model back to its initial state (t = inittime, F = F(t=0), first/last, no rows) from the copy of the resolved
+ * initial conditions the ensemble keeps in HBM: the equivalent of constructing the same FreddiEvolution objects again
+ * (cpp/include/freddi_evolution.hpp:50) without repeating the argument resolution. */
 int fb200_ensemble_reset(fb200_ensemble_t* e);
 
 /* Advance every model by n_steps (clipped per model at its Nt; n_steps<0: to the end).  Row i_t is
@@ -302,6 +302,64 @@ int fb200_ensemble_flux_rows(fb200_ensemble_t* e, int region, int64_t row_begin,
                              const double* phases, double* out, size_t out_len);
 /* Mdot_wind of FreddiState::Mdot_wind (cpp/src/freddi_state.cpp:364-383), per model, on the state of `row`. */
 int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size_t out_len);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * In-process multi-GPU: one handle over several devices.  Stands in for running the reference's driver (cpp/main.cpp:7-12
+ * -> cpp/include/application.hpp:17-43: construct, loop over step(), dump a row per step) once per model of a sweep.
+ * Model k of the caller lives on shard k mod G (G = number of devices given; a device may be listed more than once) at
+ * local index k / G; shards never exchange data.  devices == NULL or n_devices <= 0: all visible devices.  Every output
+ * is in the caller's model order.  No torch, no MPI: plain host threads and CUDA streams.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct fb200_sharded fb200_sharded_t;
+int fb200_sharded_create(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg, const int32_t* devices, int32_t n_devices,
+                         fb200_sharded_t** out, size_t* bad_model); /* cfg->device is ignored */
+void fb200_sharded_destroy(fb200_sharded_t* h);
+int32_t fb200_sharded_n_shards(const fb200_sharded_t* h);
+fb200_ensemble_t* fb200_sharded_shard(fb200_sharded_t* h, int32_t k); /* the single-device handle of shard k (owned by h) */
+size_t fb200_sharded_n_models(const fb200_sharded_t* h);
+size_t fb200_sharded_n_rows(const fb200_sharded_t* h);
+size_t fb200_sharded_n_cols(const fb200_sharded_t* h);
+size_t fb200_sharded_nx(const fb200_sharded_t* h);
+int fb200_sharded_info(fb200_sharded_t* h, fb200_model_info_t* out /*[n_models]*/);
+int fb200_sharded_reset(fb200_sharded_t* h);
+int fb200_sharded_evolve(fb200_sharded_t* h, int64_t n_steps);       /* all devices at once; blocks until all are done */
+int fb200_sharded_evolve_async(fb200_sharded_t* h, int64_t n_steps);
+int fb200_sharded_sync(fb200_sharded_t* h);
+int fb200_sharded_last_evolve_ms(fb200_sharded_t* h, float* ms);     /* the longest launch over the devices */
+/* out[n_models][n_rows][n_cols]: every device copies its models into its strided slice of the one buffer, all at once.
+ * A buffer from fb200_host_alloc (pinned) is copied to at full PCIe rate; pageable memory works, slower. */
+int fb200_sharded_rows(fb200_sharded_t* h, double* out, size_t out_len);
+int fb200_sharded_status(fb200_sharded_t* h, int32_t* status, int32_t* rows_valid, int64_t* picard_iters);
+int fb200_sharded_state(fb200_sharded_t* h, double* t, int64_t* i_t, int64_t* first, int64_t* last);
+int fb200_sharded_work_counters(fb200_sharded_t* h, int64_t* out, size_t out_len);
+int fb200_sharded_field(fb200_sharded_t* h, int field, int64_t row, double* out, size_t out_len);
+int fb200_sharded_flux(fb200_sharded_t* h, int region, int64_t row, const double* lambdas, size_t n_lambdas, double* out, size_t out_len);
+
+/* One-shot sweep — the whole of application.hpp:17-43 for every model in one call: argument structs in, light curves out.
+ * Construction is streamed: the evolve kernel of every device is launched first, host threads resolve the models in upload
+ * order into pinned staging, each uploaded group of models is picked up by the running kernel as its watermark arrives, and
+ * the rows of finished groups are copied to `rows` while later groups still run — argument resolution, allocation, H2D and
+ * most of the D2H hide behind the device time.  rows[n_models][n_rows][n_cols] with n_rows, n_cols from fb200_sweep_plan;
+ * status / rows_valid / picard_iters [n_models] may be NULL.  cfg->record_F is ignored (rows only). */
+typedef struct fb200_sweep_stats {
+    double total_ms;        /* the whole call                                                                   */
+    double device_ms_max;   /* longest evolve launch over the devices (CUDA events; includes its waits for uploads) */
+    double first_launch_ms; /* entry -> every device's kernel launched                                          */
+    double resolve_ms;      /* entry -> last model resolved on the host                                         */
+    double uploads_ms;      /* entry -> last upload complete                                                    */
+    int64_t model_steps;    /* sum over the models of the steps they took (rows_valid - 1)                      */
+    int32_t n_devices, launches, n_rows, n_cols;
+} fb200_sweep_stats_t;
+int fb200_sweep_plan(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg, size_t* n_rows, size_t* n_cols);
+int fb200_sweep_run(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg, const int32_t* devices, int32_t n_devices,
+                    double* rows, size_t rows_len, int32_t* status, int32_t* rows_valid, int64_t* picard_iters,
+                    fb200_sweep_stats_t* stats, size_t* bad_model);
+
+/* Pinned (page-locked, portable) host memory for result buffers; fb200_trim releases the device arenas and staging blocks
+ * the library keeps between ensembles (cudaMalloc / cudaHostAlloc cost milliseconds; FB200_NO_CACHE=1 disables the caches). */
+int fb200_host_alloc(size_t bytes, void** p);
+void fb200_host_free(void* p);
+void fb200_trim(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,155 @@
+"""In-process multi-GPU handle (fb200_sharded_*) and the streamed one-shot sweep (fb200_sweep_run) against the
+single-device ensemble: bit for bit, whatever the sharding, the scheduling groups or the upload order.  A device may be
+listed more than once, so the sharding logic is exercised on a one-GPU box too; with >= 2 devices the real thing runs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import common as cm
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(n_alpha=12, n_cirr=10, **kw):
+    return cm.config2_args(np.linspace(0.1, 1.0, n_alpha), np.geomspace(1e-5, 5e-3, n_cirr), **kw)
+
+
+def _single(args, **kw):
+    from freddi_b200 import Ensemble
+    with Ensemble(args, lambdas=cm.LAM3, **kw) as ens:
+        ens.evolve(-1)
+        return ens.rows(), ens.status(), ens.state(), ens.field('F')
+
+
+def _same(a, b):
+    return a.shape == b.shape and (a.view(np.uint64) == b.view(np.uint64)).all()
+
+
+def _device_lists():
+    from freddi_b200 import _lib
+    n = _lib.lib.fb200_device_count()
+    lists = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        lists += [[0, 1], 'all']
+    return lists
+
+
+def test_sharded_handle_equals_single_device_bit_for_bit():
+    from freddi_b200 import Ensemble
+    args = _args(time=10.0)
+    rows1, (st1, rv1, pi1), state1, F1 = _single(args)
+    for devs in _device_lists():
+        with Ensemble(args, lambdas=cm.LAM3, device=devs) as ens:
+            assert ens.n_models == len(args) and ens.n_shards == (len(devs) if devs != 'all' else ens.n_shards)
+            ens.evolve(7)          # in two calls: the state carried between launches is per shard
+            ens.evolve(-1)
+            rows = ens.rows()
+            st, rv, pi = ens.status()
+            state = ens.state()
+            F = ens.field('F')
+            assert _same(rows, rows1), devs
+            assert (st == st1).all() and (rv == rv1).all() and (pi == pi1).all()
+            assert (state['i_t'] == state1['i_t']).all() and (state['last'] == state1['last']).all() and _same(state['t'], state1['t'])
+            assert _same(F, F1)
+            # shard d holds the models d, d + G, ...
+            G = ens.n_shards
+            for d, sh in enumerate(ens.shards()):
+                assert _same(sh.rows(), rows1[d::G])
+            # reset + evolve again reproduces the run
+            ens.reset()
+            ens.evolve(-1)
+            assert _same(ens.rows(), rows1)
+            wc = ens.work_counters()
+            assert (wc['picard_iters'] == pi1).all()
+
+
+def test_sharded_rows_into_pinned_buffer():
+    from freddi_b200 import Ensemble, pinned_empty
+    args = _args(6, 5, time=5.0)
+    rows1 = _single(args)[0]
+    with Ensemble(args, lambdas=cm.LAM3, device=[0, 0]) as ens:
+        ens.evolve(-1)
+        out = pinned_empty((ens.n_models, ens.n_rows, ens.n_cols))
+        out[:] = 7.
+        ens.rows(out)
+        assert _same(out, rows1)
+
+
+@pytest.mark.parametrize('n_alpha,n_cirr', [(3, 2), (20, 16), (40, 25)])
+def test_streamed_sweep_equals_ensemble(n_alpha, n_cirr):
+    """fb200_sweep_run (kernel launched before the models are uploaded, groups picked up by watermark, rows read back per
+    group) == create + evolve + rows.  40 x 25 is BASELINE configs[1] at full size (two scheduling groups per device)."""
+    from freddi_b200 import sweep, sweep_plan
+    args = _args(n_alpha, n_cirr, time=50.0 if n_alpha == 40 else 12.5)
+    rows1, (st1, rv1, pi1), _, _ = _single(args)
+    assert sweep_plan(args, lambdas=cm.LAM3) == rows1.shape[1:]
+    for devs in ([0], [0, 0]) + (([0, 1], None) if len(_device_lists()) > 2 else ()):
+        res = sweep(args, lambdas=cm.LAM3, devices=devs)
+        assert _same(res.rows, rows1), devs
+        assert (res.status == st1).all() and (res.rows_valid == rv1).all() and (res.picard_iters == pi1).all()
+        assert res.stats['model_steps'] == int((rv1 - 1).sum())
+        assert res.stats['launches'] == (len(devs) if devs else res.stats['n_devices'])
+    # pageable output buffer, a second time (caches warm)
+    out = np.empty(rows1.shape)
+    res = sweep(args, lambdas=cm.LAM3, devices=[0], out=out)
+    assert res.rows is out and _same(out, rows1)
+
+
+def test_streamed_sweep_small_groups_many_chunks():
+    """Scheduling groups of 16 / 32 models: every group boundary, the staging-slot ring and the per-group read-back are used."""
+    code = r'''
+import numpy as np
+from tests import common as cm
+from freddi_b200 import sweep, Ensemble
+args = cm.config2_args(np.linspace(0.1, 1.0, 15), np.geomspace(1e-5, 5e-3, 11), time=7.5)
+with Ensemble(args, lambdas=cm.LAM3) as ens:
+    ens.evolve(-1); rows1 = ens.rows(); st1 = ens.status()
+for devs in ([0], [0, 0, 0]):
+    res = sweep(args, lambdas=cm.LAM3, devices=devs)
+    assert (res.rows.view(np.uint64) == rows1.view(np.uint64)).all(), devs
+    assert (res.rows_valid == st1[1]).all()
+print('ok')
+'''
+    env = dict(os.environ, FB200_GROUP0='16', FB200_GROUP='32', PYTHONPATH=cm.ROOT)
+    r = subprocess.run([sys.executable, '-c', code], env=env, cwd=cm.ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stdout + r.stderr
+
+
+def test_streamed_sweep_ns_and_winds():
+    """Optional arrays travel through the staging slots too: NS (Fmagn, dFmagn_dh, d2Fmagn_dh2 + static C) and a dynamic wind."""
+    from freddi_b200 import sweep
+    ns = cm.config3_args(np.geomspace(10 ** 7.5, 10 ** 8.5, 5), np.linspace(0.1, 1.0, 4), time=5.0)
+    rows1, (st1, rv1, _), _, _ = _single(ns)
+    res = sweep(ns, lambdas=cm.LAM3, devices=[0, 0])
+    assert _same(res.rows, rows1) and (res.rows_valid == rv1).all()
+    woods = cm.config4_args(np.linspace(0.1, 1.0, 5), np.geomspace(1e-5, 5e-3, 4), time=5.0)
+    rows1, (st1, rv1, _), _, _ = _single(woods)
+    res = sweep(woods, lambdas=cm.LAM3, devices=[0])
+    assert _same(res.rows, rows1) and (res.rows_valid == rv1).all()
+
+
+def test_streamed_sweep_reports_a_bad_model_and_stays_usable():
+    """An argument error in a late model surfaces as the reference's exception class with its index; the launch that was
+    already waiting for uploads is withdrawn, and the library keeps working."""
+    from freddi_b200 import sweep
+    args = list(_args(20, 20, time=2.5))
+    bad = 377
+    args[bad].opacity = 99  # std::invalid_argument("Wrong opacity") in the reference's OpacityRelated constructor
+    with pytest.raises(ValueError) as ei:
+        sweep(args, lambdas=cm.LAM3, devices=[0, 0])
+    assert ei.value.bad_model == bad and 'opacity' in str(ei.value)
+    good = _args(4, 3, time=2.5)
+    rows1 = _single(good)[0]
+    assert _same(sweep(good, lambdas=cm.LAM3, devices=[0]).rows, rows1)
+
+
+def test_trim_and_cache_reuse():
+    from freddi_b200 import _lib, sweep
+    args = _args(4, 4, time=2.5)
+    a = sweep(args, lambdas=cm.LAM3, devices=[0]).rows.copy()
+    _lib.lib.fb200_trim()
+    b = sweep(args, lambdas=cm.LAM3, devices=[0]).rows
+    assert _same(a, b)

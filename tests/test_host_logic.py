@@ -21,7 +21,7 @@ def test_c_abi_exports_every_declared_symbol(built):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.fb200_abi_version() == 3
+    assert _lib.lib.fb200_abi_version() == 4
 
 
 def test_args_struct_layout_matches_the_header(built):

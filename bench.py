@@ -245,6 +245,9 @@ class Rig:
         torch.cuda.set_device(self.local)
         if self.dist is not None:
             self.dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+        # a barrier the waiting ranks sit in on the CPU (the NCCL barrier parks a spinning kernel on their GPUs, which a
+        # second process using those GPUs would be time-sliced against)
+        self.cpu_group = self.dist.new_group(backend='gloo') if self.dist is not None else None
         self.n_gpus = self.world if self.world > 1 else 1
         self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')  # > 126 MB L2
 
@@ -253,6 +256,11 @@ class Rig:
         if self.dist is not None:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
 
     def reduce(self, times, work):
         t = self.torch.tensor(list(times), dtype=self.torch.float64, device='cuda')
@@ -280,15 +288,41 @@ class Rig:
             self.dist.destroy_process_group()
 
 
+def host_threads_per_rank():
+    """Host threads this rank may use for argument resolution: the box's cores shared between the ranks of the node."""
+    cores = os.cpu_count() or 1
+    return max(1, cores // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))
+
+
 def end_to_end_once(arr, pinned, device):
-    """The call a user makes, host buffers in and out: argument structs -> Ensemble (host argument resolution on the host
-    threads, allocation, H2D) -> evolve to the end -> rows in pinned host memory.  Returns (model-steps, status arrays)."""
-    from freddi_b200 import Ensemble
-    with Ensemble(arr, lambdas=LAMBDAS, device=device) as e:
-        e.evolve(-1)
-        e.rows(out=pinned)
-        st, valid, picard = e.status()
-    return int((valid - 1).sum()), (st, valid, picard)
+    """The call a user makes, host buffers in and out: argument structs -> freddi_b200.sweep (fb200_sweep_run: the evolve kernel
+    is launched first, the host threads resolve the models into pinned staging, uploaded groups are picked up by the running
+    kernel, rows of finished groups stream back) -> rows in pinned host memory.  Returns (model-steps, status arrays, stats)."""
+    from freddi_b200 import sweep
+    res = sweep(arr, lambdas=LAMBDAS, devices=[device], host_threads=host_threads_per_rank(), out=pinned)
+    return int((res.rows_valid - 1).sum()), (res.status, res.rows_valid, res.picard_iters), res.stats
+
+
+def in_process_sweep(name, n_gpus, n_rows, n_cols, check_index, check_rows):
+    """The same full-size sweep from ONE process over all GPUs of the box (fb200_sweep_run with a device list: one driver thread
+    and one stream set per GPU, rows scattered into one pinned buffer) — no torchrun, no torch on the path.  Run by rank 0 while
+    the other ranks idle; checked bit for bit against the rows the ranks produced."""
+    from freddi_b200 import sweep, pinned_empty
+    n_total = workload_size(name, n_gpus)
+    arr = workload(name, n_gpus, None)
+    out = pinned_empty((n_total, n_rows, n_cols))
+    times, stats = [], None
+    for _ in range(2):  # first call: contexts on the other devices, staging, arenas
+        t0 = time.perf_counter()
+        res = sweep(arr, lambdas=LAMBDAS, devices=list(range(n_gpus)), out=out)
+        times.append(time.perf_counter() - t0)
+        stats = res.stats
+    steps = int((res.rows_valid - 1).sum())
+    same = bool((out[check_index].view(np.uint64) == check_rows.view(np.uint64)).all())
+    return dict(value=steps / times[-1], unit=UNIT, seconds=times[-1], first_call_seconds=times[0], model_steps=steps,
+                light_curves_per_s=n_total / times[-1], devices=n_gpus, stats=stats, rows_equal_the_ranks_rows_bit_for_bit=same,
+                note='one Python process, fb200_sweep_run over {} devices: argument structs -> rows of all {} models in one pinned host '
+                     'buffer; wall clock of the call, everything included'.format(n_gpus, n_total))
 
 
 def sample_local(n_local, per_rank):
@@ -305,10 +339,11 @@ def sweep_leg(rig, name, opts):
     mine = shard(n_total, rig.rank, rig.n_gpus)
     arr = workload(name, rig.n_gpus, mine)
     n_local = len(mine)
-    # warm-up: context, module load, first touch of the allocator
-    with Ensemble(workload(name, rig.n_gpus, mine[:min(n_local, 296)]), lambdas=LAMBDAS, device=rig.local) as e:
-        e.evolve(-1)
-        n_rows, n_cols, columns = e.n_rows, e.n_cols, e.columns
+    # warm-up: context, module load, staging slots of the size class the full sweep uses
+    from freddi_b200 import sweep
+    warm = sweep(workload(name, rig.n_gpus, mine[:min(n_local, 1500)]), lambdas=LAMBDAS, devices=[rig.local], host_threads=host_threads_per_rank())
+    (n_rows, n_cols), columns = warm.rows.shape[1:], warm.columns
+    del warm
     pinned = rig.pinned((n_local, n_rows, n_cols))
     # device-timed: inputs resident in HBM, CUDA events around the launch
     with Ensemble(arr, lambdas=LAMBDAS, device=rig.local) as e:
@@ -324,7 +359,7 @@ def sweep_leg(rig, name, opts):
     # end to end, construction included: wall clock between barriers
     rig.barrier()
     t0 = time.perf_counter()
-    steps_e2e, (st2, valid2, picard2) = end_to_end_once(arr, pinned, rig.local)
+    steps_e2e, (st2, valid2, picard2), e2e_stats = end_to_end_once(arr, pinned, rig.local)
     e2e_s = time.perf_counter() - t0
     rig.barrier()
     assert steps_e2e == steps
@@ -337,6 +372,15 @@ def sweep_leg(rig, name, opts):
     g_index = rig.gather(mine[loc].astype(np.int64))
     (t_dev, t_e2e), (steps_all, collapsed_all, models_all, launches_all) = rig.reduce(
         [dev_s, e2e_s], [steps, collapsed, n_local, launches])
+    inproc = None
+    if rig.n_gpus > 1 and not opts.no_in_process:
+        rig.cpu_barrier()  # the other ranks wait on the CPU with idle GPUs
+        if rig.rank == 0:
+            try:
+                inproc = in_process_sweep(name, rig.n_gpus, n_rows, n_cols, g_index.ravel(), g_rows.reshape((-1,) + g_rows.shape[2:]))
+            except Exception as exc:
+                inproc = dict(value=None, error=repr(exc))
+        rig.cpu_barrier()
     if rig.rank != 0:
         return None
     obj = dict(workload=WORKLOAD_TEXT[name], n_gpus=rig.n_gpus, models=int(models_all), models_per_gpu=n_local,
@@ -345,8 +389,11 @@ def sweep_leg(rig, name, opts):
                light_curves_per_s=models_all / t_dev, gpu_launches=int(launches_all),
                e2e=dict(value=steps_all / t_e2e, unit=UNIT, seconds=t_e2e, light_curves_per_s=models_all / t_e2e,
                         h2d_bytes_per_gpu=n_local * C.sizeof(FB200Args), d2h_bytes_per_gpu=int(pinned.nbytes),
-                        note='argument structs -> Ensemble(args) [host argument resolution + allocation + H2D] + evolve + rows() into '
-                             'pinned host memory; wall clock between barriers, max over ranks'))
+                        stats_rank0=e2e_stats,
+                        note='argument structs -> freddi_b200.sweep (fb200_sweep_run: streamed construction behind the running kernel, '
+                             'rows of finished groups copied back meanwhile) -> rows in pinned host memory; one process per GPU; '
+                             'wall clock between barriers, max over ranks'),
+               in_process=inproc)
     if not opts.no_cpu_baseline:
         order = np.argsort(g_index.ravel())
         idx = g_index.ravel()[order]
@@ -411,16 +458,16 @@ def run_gpu(opts):
         e.close()
 
     # ---- end to end through the public API with host buffers, model construction INCLUDED ----
-    # One step = argument structs (host) -> Ensemble(args) [argument resolution on the host cores, allocation, H2D] -> evolve() ->
-    # rows() [device -> pinned host].  The variant with the ensemble already constructed (reset() re-uploads the initial state)
-    # is reported beside it as e2e.resident.
+    # One step = argument structs (host) -> freddi_b200.sweep() [fb200_sweep_run: argument resolution on the host cores, allocation,
+    # H2D, evolve, rows device -> pinned host, all pipelined behind the evolve kernel].  The variant with the ensemble already
+    # constructed (reset() restores the initial state from its copy in HBM) is reported beside it as e2e.resident.
     pinned = rig.pinned((n_local, n_rows, n_cols))
     e2e_times = []
     status_last = None
     for k in range(opts.warmup + opts.steps):
         rig.barrier()
         t0 = time.perf_counter()
-        _steps, status_last = end_to_end_once(arr, pinned, local)
+        _steps, status_last, e2e_stats = end_to_end_once(arr, pinned, local)
         if k >= opts.warmup:
             e2e_times.append(time.perf_counter() - t0)
     h2d = n_local * C.sizeof(FB200Args)
@@ -517,13 +564,17 @@ def run_gpu(opts):
                     roofline=roofline, cpu_baseline=cpu, parity=parity, clocks=clocks,
                     e2e=dict(value=model_steps_all / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=rows_bytes,
                              iter_ms=[round(1e3 * x, 2) for x in e2e_times],
-                             note='per step: argument structs (host) -> Ensemble(args) [argument resolution on the host cores + allocation + '
-                                  'H2D] + evolve() + rows() [device -> pinned host] + destroy; wall clock; model construction INCLUDED, as in '
-                                  'the reference arm',
+                             note='per step: argument structs (host) -> freddi_b200.sweep() = fb200_sweep_run [kernel launched first; host '
+                                  'threads resolve the models into pinned staging; H2D per group, picked up by the running kernel; rows of '
+                                  'finished groups device -> pinned host meanwhile]; wall clock; model construction INCLUDED, as in the '
+                                  'reference arm.  h2d_bytes_per_step counts the argument structs the call takes (the resolved h, F, '
+                                  'constants it uploads: h2d_resolved_bytes_per_step)',
+                             h2d_resolved_bytes_per_step=n_local * (2 * 1000 * 8 + 900),
+                             stats_last=e2e_stats, host_threads=host_threads_per_rank(),
                              resident=dict(value=model_steps_all / t_res, unit=UNIT, iter_ms=[round(1e3 * x, 2) for x in resident_times],
-                                           h2d_bytes_per_step=n_local * (1000 * 8 + 64),
-                                           note='ensemble constructed once; per step reset() [initial F + state, pinned host -> device] + '
-                                                'evolve() + rows()')),
+                                           h2d_bytes_per_step=0,
+                                           note='ensemble constructed once; per step reset() [initial F + state from their copy in HBM] + '
+                                                'evolve() + rows() [device -> pinned host]')),
                     gpu_launches=int(launches_all), light_curves_per_s=models_all / t_dev,
                     model_steps_per_iteration=model_steps_all / opts.steps)
 
@@ -551,6 +602,7 @@ def main():
     ap.add_argument('--sweep', default=None, choices=['sweep_1e5', 'sweep_1e4_wind', 'none'],
                     help='full-size configuration to add to the line (default: sweep_1e5 at 8 GPUs, sweep_1e4_wind at 2/4, none at 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-in-process', action='store_true', help='skip the one-process multi-GPU run of the full-size sweep (N > 1)')
     opts = ap.parse_args()
     if opts.impl == 'reference':
         run_reference(opts)

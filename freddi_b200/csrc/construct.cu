@@ -211,19 +211,30 @@ int arena_acquire(int device, size_t bytes, void** p, size_t* got) {
 void arena_release(int device, void* p) {
     if (!p) return;
     std::lock_guard<std::mutex> g(g_cache_mutex);
-    int kept = 0;
-    for (const Block& b : g_arenas)
-        if (!b.in_use && b.device == device) ++kept;
     for (size_t i = 0; i < g_arenas.size(); ++i)
         if (g_arenas[i].p == p) {
-            if (cache_disabled() || kept >= 2) {  // at most two idle arenas per device
+            if (cache_disabled()) {
                 cudaFree(p);
                 g_arenas.erase(g_arenas.begin() + i);
-            } else {
-                g_arenas[i].in_use = false;
+                return;
             }
-            return;
+            g_arenas[i].in_use = false;
+            break;
         }
+    // at most two idle arenas per device: the smallest go first (cudaFree of a large block costs tens of milliseconds, and a
+    // large block also serves every smaller request up to a quarter of its size)
+    for (;;) {
+        int idle = 0;
+        size_t smallest = ~size_t(0), at = 0;
+        for (size_t i = 0; i < g_arenas.size(); ++i)
+            if (!g_arenas[i].in_use && g_arenas[i].device == device) {
+                ++idle;
+                if (g_arenas[i].bytes < smallest) { smallest = g_arenas[i].bytes; at = i; }
+            }
+        if (idle <= 2) break;
+        cudaFree(g_arenas[at].p);
+        g_arenas.erase(g_arenas.begin() + at);
+    }
 }
 
 void caches_trim() {
@@ -756,6 +767,7 @@ int drive_device(DeviceBuild& B, Shared& sh) {
         return FB200_OK;
     }
     // streamed sweep: read finished groups back while the rest still runs
+    const bool dbg = getenv("FB200_DEBUG") != nullptr;
     for (;;) {
         const cudaError_t q = cudaEventQuery(e->ev1);
         if (q == cudaSuccess) break;
@@ -768,6 +780,8 @@ int drive_device(DeviceBuild& B, Shared& sh) {
         if (cuda_rc(poll_groups(B, sh)) != FB200_OK) return B.rc;
         nap();
     }
+    if (dbg) fprintf(stderr, "[fb200] device %d: kernel done at %8.2f ms, %d of %d groups already sent\n", B.device, sh.ms(), B.next_group,
+                     int(e->group_begin.size()) - 1);
     if (cuda_rc(send_groups(B, sh, int(e->group_begin.size()) - 1)) != FB200_OK) return B.rc;
     {
         float ms = 0.f;
@@ -793,7 +807,9 @@ int drive_device(DeviceBuild& B, Shared& sh) {
         std::lock_guard<std::mutex> g(sh.err_mutex);
         sh.io->model_steps += steps;
     }
+    if (dbg) fprintf(stderr, "[fb200] device %d: status scattered at %8.2f ms\n", B.device, sh.ms());
     FB_TRYB(cudaStreamSynchronize(e->copy_out));
+    if (dbg) fprintf(stderr, "[fb200] device %d: rows on the host at %8.2f ms\n", B.device, sh.ms());
     return FB200_OK;
 }
 
@@ -1097,6 +1113,7 @@ int build_ensembles(const fb200_args_t* args, size_t n_models, const fb200_confi
         }
         destroy_all();
         io->total_ms = sh.ms();
+        if (dbg) fprintf(stderr, "[fb200] build: ensembles destroyed      %8.2f ms\n", sh.ms());
     } else {
         for (int d = 0; d < n_devices; ++d) out[d] = builds[d]->e;
     }

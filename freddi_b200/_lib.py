@@ -25,6 +25,8 @@ SYMBOLS = (
     'fb200_ensemble_rows', 'fb200_ensemble_rows_device', 'fb200_ensemble_status', 'fb200_ensemble_state',
     'fb200_ensemble_row_bounds', 'fb200_ensemble_field', 'fb200_ensemble_flux', 'fb200_ensemble_mdot_wind',
     'fb200_ensemble_field_rows', 'fb200_ensemble_flux_rows', 'fb200_ensemble_work_counters', 'fb200_selftest_trapz',
+    'fb200_ensemble_device_ptr', 'fb200_ensemble_checkpoint_bytes', 'fb200_ensemble_checkpoint_save', 'fb200_ensemble_checkpoint_load',
+    'fb200_ensemble_get_state', 'fb200_ensemble_set_state',
     'fb200_sharded_create', 'fb200_sharded_destroy', 'fb200_sharded_n_shards', 'fb200_sharded_shard', 'fb200_sharded_n_models',
     'fb200_sharded_n_rows', 'fb200_sharded_n_cols', 'fb200_sharded_nx', 'fb200_sharded_info', 'fb200_sharded_reset',
     'fb200_sharded_evolve', 'fb200_sharded_evolve_async', 'fb200_sharded_sync', 'fb200_sharded_last_evolve_ms',
@@ -97,6 +99,13 @@ def _load():
     lib.fb200_ensemble_mdot_wind.argtypes = [vp, C.c_int64, dp, C.c_size_t]
     lib.fb200_ensemble_field_rows.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_int, dp, C.c_size_t]
     lib.fb200_ensemble_flux_rows.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, dp, C.c_size_t, dp, dp, C.c_size_t]
+    lib.fb200_ensemble_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), i32p]
+    lib.fb200_ensemble_checkpoint_bytes.argtypes = [vp, C.c_int]
+    lib.fb200_ensemble_checkpoint_bytes.restype = C.c_size_t
+    lib.fb200_ensemble_checkpoint_save.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    lib.fb200_ensemble_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
+    lib.fb200_ensemble_get_state.argtypes = [vp, dp, dp, ip, ip, ip, dp, dp]
+    lib.fb200_ensemble_set_state.argtypes = [vp, dp, dp, ip, ip, ip, dp, dp]
     # in-process multi-GPU + one-shot sweep
     szp = C.POINTER(C.c_size_t)
     lib.fb200_sharded_create.argtypes = [C.POINTER(FB200Args), C.c_size_t, C.POINTER(FB200Config), i32p, C.c_int32, C.POINTER(vp), szp]

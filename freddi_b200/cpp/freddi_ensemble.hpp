@@ -98,4 +98,71 @@ private:
     fb200_ensemble_t* h_ = nullptr;
 };
 
+// The same over several GPUs of this process (fb200_sharded_*): model k lives on device k mod G, all devices evolve at once,
+// rows() gathers into one array.  devices empty = all visible.
+class ShardedEnsemble {
+public:
+    ShardedEnsemble(const std::vector<Arguments>& args, const Config& cfg = Config(), const std::vector<int32_t>& devices = {}) {
+        std::vector<fb200_args_t> raw(args.begin(), args.end());
+        size_t bad = 0;
+        check(fb200_sharded_create(raw.data(), raw.size(), &cfg, devices.empty() ? nullptr : devices.data(), int32_t(devices.size()), &h_, &bad));
+    }
+    ~ShardedEnsemble() { fb200_sharded_destroy(h_); }
+    ShardedEnsemble(const ShardedEnsemble&) = delete;
+    ShardedEnsemble& operator=(const ShardedEnsemble&) = delete;
+
+    size_t size() const { return fb200_sharded_n_models(h_); }
+    size_t Nx() const { return fb200_sharded_nx(h_); }
+    size_t n_rows() const { return fb200_sharded_n_rows(h_); }
+    size_t n_cols() const { return fb200_sharded_n_cols(h_); }
+    int n_shards() const { return fb200_sharded_n_shards(h_); }
+    void step() { check(fb200_sharded_evolve(h_, 1)); }
+    void evolve(int64_t n_steps = -1) { check(fb200_sharded_evolve(h_, n_steps)); }
+    void reset() { check(fb200_sharded_reset(h_)); }
+    float last_evolve_ms() { float ms = 0; check(fb200_sharded_last_evolve_ms(h_, &ms)); return ms; }
+    std::vector<double> rows() {
+        std::vector<double> out(size() * n_rows() * n_cols());
+        check(fb200_sharded_rows(h_, out.data(), out.size()));
+        return out;
+    }
+    FreddiEnsemble::Status status() {
+        FreddiEnsemble::Status s{std::vector<int32_t>(size()), std::vector<int32_t>(size()), std::vector<int64_t>(size())};
+        check(fb200_sharded_status(h_, s.status.data(), s.rows_valid.data(), s.picard.data()));
+        return s;
+    }
+    std::vector<double> field(int which, int64_t row = -1) {
+        std::vector<double> out(size() * Nx());
+        check(fb200_sharded_field(h_, which, row, out.data(), out.size()));
+        return out;
+    }
+    fb200_sharded_t* handle() { return h_; }
+    fb200_ensemble_t* shard(int k) { return fb200_sharded_shard(h_, k); }
+
+private:
+    fb200_sharded_t* h_ = nullptr;
+};
+
+// The whole driver of the reference (cpp/include/application.hpp:17-43) for every model in one call: argument structs in,
+// light curves out, construction streamed behind the evolve kernels of all `devices` (fb200_sweep_run).
+struct SweepResult {
+    std::vector<double> rows;  // [model][row][col]
+    std::vector<int32_t> status, rows_valid;
+    std::vector<int64_t> picard;
+    fb200_sweep_stats_t stats{};
+    size_t n_rows = 0, n_cols = 0;
+};
+inline SweepResult sweep(const std::vector<Arguments>& args, const Config& cfg = Config(), const std::vector<int32_t>& devices = {}) {
+    std::vector<fb200_args_t> raw(args.begin(), args.end());
+    SweepResult r;
+    check(fb200_sweep_plan(raw.data(), raw.size(), &cfg, &r.n_rows, &r.n_cols));
+    r.rows.resize(raw.size() * r.n_rows * r.n_cols);
+    r.status.resize(raw.size());
+    r.rows_valid.resize(raw.size());
+    r.picard.resize(raw.size());
+    size_t bad = 0;
+    check(fb200_sweep_run(raw.data(), raw.size(), &cfg, devices.empty() ? nullptr : devices.data(), int32_t(devices.size()), r.rows.data(),
+                          r.rows.size(), r.status.data(), r.rows_valid.data(), r.picard.data(), &r.stats, &bad));
+    return r;
+}
+
 }  // namespace fb200

@@ -121,13 +121,50 @@ int main(int ac, char** av) {
         std::vector<Arguments> args(n_models, Arguments(ns));
         for (size_t k = 0; k < n_models; ++k) static_cast<fb200_args_t&>(args[k]) = setups[k].args;
 
-        FreddiEnsemble ens(args, cfg);
+        // --devices all | 0,1,...: the models are spread over several GPUs of the box from this one process (model k -> device
+        // k mod G).  Light curves only: the streamed one-call sweep; with --fulldata the sharded handle (per-row structure read-out).
+        std::vector<int32_t> devices;
+        const bool multi = vm.count("devices") != 0;
+        if (multi && vm.at("devices").s != "all") {
+            std::string tok;
+            for (char c : vm.at("devices").s + ",") {
+                if (c == ',') {
+                    if (!tok.empty()) devices.push_back(int32_t(Parser::to_uint(tok, "devices")));
+                    tok.clear();
+                } else {
+                    tok += c;
+                }
+            }
+            if (devices.empty()) throw OptionError("--devices expects 'all' or a comma-separated list of CUDA ordinals");
+        }
+        std::unique_ptr<FreddiEnsemble> ens;
+        std::unique_ptr<ShardedEnsemble> sharded;
         std::vector<fb200_model_info_t> info(n_models);
-        check(fb200_ensemble_info(ens.handle(), info.data()));
-        ens.evolve(-1);
-        const std::vector<double> rows = ens.rows();
-        const FreddiEnsemble::Status st = ens.status();
-        const size_t ncol = ens.n_cols(), nrows = ens.n_rows(), Nx = ens.Nx();
+        std::vector<double> rows;
+        FreddiEnsemble::Status st;
+        size_t ncol = 0, nrows = 0, Nx = size_t(setups[0].args.Nx);
+        if (multi && !s0.fulldata) {
+            SweepResult r = sweep(args, cfg, devices);
+            rows.swap(r.rows);
+            st = FreddiEnsemble::Status{std::move(r.status), std::move(r.rows_valid), std::move(r.picard)};
+            ncol = r.n_cols;
+            nrows = r.n_rows;
+            for (size_t k = 0; k < n_models; ++k) check(fb200_args_resolve(&setups[k].args, &info[k], nullptr, nullptr));
+        } else if (multi) {
+            sharded.reset(new ShardedEnsemble(args, cfg, devices));
+            check(fb200_sharded_info(sharded->handle(), info.data()));
+            sharded->evolve(-1);
+            rows = sharded->rows();
+            st = sharded->status();
+            ncol = sharded->n_cols(); nrows = sharded->n_rows(); Nx = sharded->Nx();
+        } else {
+            ens.reset(new FreddiEnsemble(args, cfg));
+            check(fb200_ensemble_info(ens->handle(), info.data()));
+            ens->evolve(-1);
+            rows = ens->rows();
+            st = ens->status();
+            ncol = ens->n_cols(); nrows = ens->n_rows(); Nx = ens->Nx();
+        }
 
         const std::vector<FieldMeta> fields = short_fields(ns, s0.cold_disk, s0.lambdas, passband_names, s0.star_flux);
         if (fields.size() != ncol) throw std::logic_error("column count of the engine and of the writer differ");
@@ -172,8 +209,19 @@ int main(int ac, char** av) {
                 bool any = false;
                 for (size_t k = 0; k < n_models; ++k) any |= (r < n_dump[k] && r < st.rows_valid[k] && r % long(setups[k].tempsparsity) == 0);
                 if (!any) continue;
-                for (size_t j = 0; j < long_fields.size(); ++j) cols[j] = ens.field(long_fields[j].field, r);
-                check(fb200_ensemble_row_bounds(ens.handle(), r, first.data(), last.data()));
+                if (sharded) {
+                    for (size_t j = 0; j < long_fields.size(); ++j) cols[j] = sharded->field(long_fields[j].field, r);
+                    const size_t G = size_t(sharded->n_shards());
+                    for (size_t d = 0; d < G; ++d) {  // row bounds are per device: shard d holds the models d, d + G, ...
+                        const size_t nd = (n_models - d + G - 1) / G;
+                        std::vector<int64_t> f(nd), l(nd);
+                        check(fb200_ensemble_row_bounds(sharded->shard(int(d)), r, f.data(), l.data()));
+                        for (size_t j = 0; j < nd; ++j) { first[d + j * G] = f[j]; last[d + j * G] = l[j]; }
+                    }
+                } else {
+                    for (size_t j = 0; j < long_fields.size(); ++j) cols[j] = ens->field(long_fields[j].field, r);
+                    check(fb200_ensemble_row_bounds(ens->handle(), r, first.data(), last.data()));
+                }
                 for (size_t k = 0; k < n_models; ++k) {
                     const RunSetup& s = setups[k];
                     if (!(r < n_dump[k] && r < st.rows_valid[k] && r % long(s.tempsparsity) == 0)) continue;

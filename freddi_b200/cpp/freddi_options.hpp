@@ -15,7 +15,8 @@
 // tokens ignored, INI files with `#` comments and [sections].
 //
 // One extension, because the engine evolves ensembles: `--sweep name=lo:hi:n[:log]` (repeatable) replaces the
-// scalar option `name` by n values; the cartesian product of all sweeps is evolved in one launch.
+// scalar option `name` by n values; the cartesian product of all sweeps is evolved in one launch.  `--devices all` or
+// `--devices 0,1,...` spreads the models over several GPUs of the box from this one process (model k -> device k mod G).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -129,7 +130,7 @@ inline std::vector<Option> option_table(bool ns) {
         opt_dbl_def("inittime", 0.), opt_dbl_req("time", 'T'), opt_dbl("tau"), opt_uint("Nx", 1000), opt_str("gridscale", "log"),
         opt_uint("starlod", 3),
         // extension of this front-end (not echoed into the output files)
-        opt_svec("sweep"),
+        opt_svec("sweep"), opt_str("devices"),
     };
     t.insert(t.end(), rest.begin(), rest.end());
     if (ns) t.push_back(opt_str("angulardistns", "isotropic"));

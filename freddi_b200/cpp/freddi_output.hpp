@@ -132,7 +132,7 @@ inline void echo_parameters(std::ostream& os, const VariablesMap& vm, unsigned p
     for (const auto& kv : vm) {
         const std::string& name = kv.first;
         const Value& v = kv.second;
-        if (name == "sweep") continue;  // this front-end's extension; each file echoes the swept option's own value
+        if (name == "sweep" || name == "devices") continue;  // this front-end's extension; each file echoes the swept option's own value
         switch (v.kind) {
             case Kind::Flag:
             case Kind::String: os << "# " << name << "=" << v.s << "\n"; break;

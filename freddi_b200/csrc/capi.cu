@@ -223,6 +223,153 @@ int fb200_ensemble_rows_device(fb200_ensemble_t* e, const double** dptr) {
     return FB200_OK;
 }
 
+int fb200_ensemble_device_ptr(fb200_ensemble_t* e, int which, const void** dptr, int32_t* device) {
+    if (!e || !dptr) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    const void* p = nullptr;
+    switch (which) {
+        case FB200_DEVPTR_ROWS: p = e->dev.rows; break;
+        case FB200_DEVPTR_F: p = e->dev.F; break;
+        case FB200_DEVPTR_H: p = e->dev.h; break;
+        case FB200_DEVPTR_FSNAP: p = e->dev.Fsnap; break;
+        case FB200_DEVPTR_BOUNDS: p = e->dev.bounds; break;
+        default: return set_err(FB200_ERR_INVALID_ARGUMENT, "unknown device array");
+    }
+    if (!p) return set_err(FB200_ERR_LOGIC, "this array needs an ensemble created with record_F");
+    *dptr = p;
+    if (device) *device = e->device;
+    return FB200_OK;
+}
+
+// ---- checkpoint / resume: the copyable state of the reference (FreddiState's copy constructor, cpp/src/freddi_state.cpp:84-91) ----
+namespace {
+struct CheckpointHeader {
+    unsigned long long magic;
+    unsigned long long n, Nx, n_rows, n_cols, with_rows, state_bytes;
+};
+constexpr unsigned long long kCheckpointMagic = 0x4642323030434b31ull;  // "FB200CK1"
+}  // namespace
+
+size_t fb200_ensemble_checkpoint_bytes(const fb200_ensemble_t* e, int with_rows) {
+    if (!e) return 0;
+    const size_t NN = e->n * size_t(e->Nx);
+    size_t b = sizeof(CheckpointHeader) + e->n * sizeof(ModelState) + e->n * sizeof(int) + 2 * NN * sizeof(double);
+    if (with_rows) b += e->n * size_t(e->n_rows) * e->n_cols * sizeof(double);
+    if (with_rows && e->dev.wind_rec) b += e->n * size_t(e->n_rows) * sizeof(WindRecord);  // what the wind getters of every row reflect
+    return b;
+}
+
+int fb200_ensemble_checkpoint_save(fb200_ensemble_t* e, void* buf, size_t len, int with_rows) {
+    if (!e || !buf) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (len < fb200_ensemble_checkpoint_bytes(e, with_rows)) return set_err(FB200_ERR_INVALID_ARGUMENT, "checkpoint buffer too small");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    const size_t NN = e->n * size_t(e->Nx);
+    char* p = static_cast<char*>(buf);
+    CheckpointHeader h{kCheckpointMagic, e->n, (unsigned long long)e->Nx, (unsigned long long)e->n_rows, (unsigned long long)e->n_cols,
+                       with_rows ? 1ull : 0ull, sizeof(ModelState)};
+    std::memcpy(p, &h, sizeof(h));
+    p += sizeof(h);
+    FB_CUDA(cudaMemcpyAsync(p, e->dev.state, e->n * sizeof(ModelState), cudaMemcpyDeviceToHost, e->stream));
+    p += e->n * sizeof(ModelState);
+    FB_CUDA(cudaMemcpyAsync(p, e->dev.failed, e->n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    p += e->n * sizeof(int);
+    FB_CUDA(cudaMemcpyAsync(p, e->dev.F, NN * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    p += NN * sizeof(double);
+    FB_CUDA(cudaMemcpyAsync(p, e->dev.K, NN * sizeof(double), cudaMemcpyDeviceToHost, e->stream));  // the closure carried with F (k_valid)
+    p += NN * sizeof(double);
+    if (with_rows) {
+        const size_t rb = e->n * size_t(e->n_rows) * e->n_cols * sizeof(double);
+        FB_CUDA(cudaMemcpyAsync(p, e->dev.rows, rb, cudaMemcpyDeviceToHost, e->stream));
+        p += rb;
+        if (e->dev.wind_rec) FB_CUDA(cudaMemcpyAsync(p, e->dev.wind_rec, e->n * size_t(e->n_rows) * sizeof(WindRecord), cudaMemcpyDeviceToHost, e->stream));
+    }
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
+int fb200_ensemble_checkpoint_load(fb200_ensemble_t* e, const void* buf, size_t len) {
+    if (!e || !buf) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    if (len < sizeof(CheckpointHeader)) return set_err(FB200_ERR_INVALID_ARGUMENT, "not a checkpoint");
+    CheckpointHeader h;
+    std::memcpy(&h, buf, sizeof(h));
+    if (h.magic != kCheckpointMagic || h.state_bytes != sizeof(ModelState)) return set_err(FB200_ERR_INVALID_ARGUMENT, "not a checkpoint of this library version");
+    if (h.n != e->n || h.Nx != (unsigned long long)e->Nx || h.n_rows != (unsigned long long)e->n_rows || h.n_cols != (unsigned long long)e->n_cols)
+        return set_err(FB200_ERR_INVALID_ARGUMENT, "the checkpoint belongs to an ensemble of another shape");
+    if (len < fb200_ensemble_checkpoint_bytes(e, int(h.with_rows))) return set_err(FB200_ERR_INVALID_ARGUMENT, "truncated checkpoint");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    const size_t NN = e->n * size_t(e->Nx);
+    const char* p = static_cast<const char*>(buf) + sizeof(h);
+    FB_CUDA(cudaMemcpyAsync(e->dev.state, p, e->n * sizeof(ModelState), cudaMemcpyHostToDevice, e->stream));
+    p += e->n * sizeof(ModelState);
+    FB_CUDA(cudaMemcpyAsync(e->dev.failed, p, e->n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    p += e->n * sizeof(int);
+    FB_CUDA(cudaMemcpyAsync(e->dev.F, p, NN * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    p += NN * sizeof(double);
+    FB_CUDA(cudaMemcpyAsync(e->dev.K, p, NN * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    p += NN * sizeof(double);
+    if (h.with_rows) {
+        const size_t rb = e->n * size_t(e->n_rows) * e->n_cols * sizeof(double);
+        FB_CUDA(cudaMemcpyAsync(e->dev.rows, p, rb, cudaMemcpyHostToDevice, e->stream));
+        p += rb;
+        if (e->dev.wind_rec) FB_CUDA(cudaMemcpyAsync(e->dev.wind_rec, p, e->n * size_t(e->n_rows) * sizeof(WindRecord), cudaMemcpyHostToDevice, e->stream));
+    }
+    FB_CUDA(cudaStreamSynchronize(e->stream));  // the caller's buffer may go away
+    return FB200_OK;
+}
+
+int fb200_ensemble_get_state(fb200_ensemble_t* e, double* F, double* t, int64_t* i_t, int64_t* first, int64_t* last, double* F_in,
+                             double* Mdot_in_prev) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    std::vector<ModelState> hs(e->n);
+    FB_CUDA(cudaMemcpyAsync(hs.data(), e->dev.state, sizeof(ModelState) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    if (F) FB_CUDA(cudaMemcpyAsync(F, e->dev.F, e->n * size_t(e->Nx) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->n; ++i) {
+        if (t) t[i] = hs[i].t;
+        if (i_t) i_t[i] = hs[i].i_t;
+        if (first) first[i] = hs[i].first;
+        if (last) last[i] = hs[i].last;
+        if (F_in) F_in[i] = hs[i].F_in;
+        if (Mdot_in_prev) Mdot_in_prev[i] = hs[i].Mdot_in_prev;
+    }
+    return FB200_OK;
+}
+
+int fb200_ensemble_set_state(fb200_ensemble_t* e, const double* F, const double* t, const int64_t* i_t, const int64_t* first,
+                             const int64_t* last, const double* F_in, const double* Mdot_in_prev) {
+    if (!e) return set_err(FB200_ERR_BAD_HANDLE, "null handle");
+    int rc = select_device(e);
+    if (rc != FB200_OK) return rc;
+    std::vector<ModelState> hs(e->n);
+    FB_CUDA(cudaMemcpyAsync(hs.data(), e->dev.state, sizeof(ModelState) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->n; ++i) {
+        ModelState& s = hs[i];
+        if (t) s.t = t[i];
+        if (F_in) s.F_in = F_in[i];
+        if (Mdot_in_prev) s.Mdot_in_prev = Mdot_in_prev[i];
+        if (first) s.first = int(first[i]);
+        if (last) s.last = int(last[i]);
+        if (i_t) s.i_t = int(i_t[i]);
+        if (s.first < 0 || s.last >= e->Nx || s.first + 2 > s.last || s.i_t < 0 || s.i_t >= e->n_rows)
+            return set_err(FB200_ERR_INVALID_ARGUMENT, "state of model " + std::to_string(i) + ": need 0 <= first, first + 2 <= last < Nx, 0 <= i_t <= Nt");
+        // the caller's state replaces the evolved one: the model is alive again, its next row is i_t + 1 (row 0 is written from
+        // this state when i_t == 0), and the closure K of the old F is void
+        s.status = FB200_MODEL_OK;
+        s.rows_valid = s.i_t + (s.i_t > 0 ? 1 : 0);
+        s.row0_done = s.i_t > 0 ? 1 : 0;
+        s.k_valid = 0;
+    }
+    FB_CUDA(cudaMemcpyAsync(e->dev.state, hs.data(), sizeof(ModelState) * e->n, cudaMemcpyHostToDevice, e->stream));
+    if (F) FB_CUDA(cudaMemcpyAsync(e->dev.F, F, e->n * size_t(e->Nx) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(cudaMemsetAsync(e->dev.failed, 0, e->n * sizeof(int), e->stream));
+    FB_CUDA(cudaStreamSynchronize(e->stream));
+    return FB200_OK;
+}
+
 static int fetch_state(fb200_ensemble_t* e, std::vector<ModelState>& hs) {
     int rc = select_device(e);
     if (rc != FB200_OK) return rc;

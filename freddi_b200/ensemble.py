@@ -325,6 +325,81 @@ class Ensemble:
         _lib.check(self._f('rows_device')(self._h, C.byref(p)))
         return p.value
 
+    # -- device-resident results (zero copy) --
+    _DEVPTR = {'rows': 0, 'F': 1, 'h': 2, 'Fsnap': 3, 'bounds': 4}
+
+    def device_array(self, which):
+        """A view of the ensemble's HBM as an object with ``__cuda_array_interface__`` (version 3): ``torch.as_tensor(x,
+        device='cuda')``, ``cupy.asarray(x)`` and numba take it without a copy.  which: 'rows' (n_models, n_rows, n_cols),
+        'F' / 'h' (n_models, Nx), with record_F 'Fsnap' (n_models, n_rows, Nx; NaN where never written) and 'bounds'
+        (n_models, n_rows, 2) int32.  The view keeps the ensemble alive; call sync() after evolve_async() before reading."""
+        if self._sharded:
+            raise NotImplementedError('device arrays are per device: use Ensemble.shards()')
+        p, dev = C.c_void_p(), C.c_int32()
+        _lib.check(_lib.lib.fb200_ensemble_device_ptr(self._h, self._DEVPTR[which], C.byref(p), C.byref(dev)))
+        shape = {'rows': (self.n_models, self.n_rows, self.n_cols), 'F': (self.n_models, self.Nx), 'h': (self.n_models, self.Nx),
+                 'Fsnap': (self.n_models, self.n_rows, self.Nx), 'bounds': (self.n_models, self.n_rows, 2)}[which]
+        return DeviceArray(self, p.value, shape, '<i4' if which == 'bounds' else '<f8', int(dev.value))
+
+    def rows_device(self):
+        """(n_models, n_rows, n_cols) float64 in HBM, zero copy (see device_array)."""
+        return self.device_array('rows')
+
+    # -- state in / out --
+    def checkpoint(self, with_rows=True):
+        """Opaque blob (numpy uint8) of every model's current state — CurrentState, F and the carried closure, optionally the
+        rows so far; restore() into an ensemble created from the same arguments continues bit-identically."""
+        if self._sharded:
+            return [sh.checkpoint(with_rows) for sh in self.shards()]
+        n = int(_lib.lib.fb200_ensemble_checkpoint_bytes(self._h, int(bool(with_rows))))
+        buf = np.empty(n, dtype=np.uint8)
+        _lib.check(_lib.lib.fb200_ensemble_checkpoint_save(self._h, buf.ctypes.data_as(C.c_void_p), n, int(bool(with_rows))))
+        return buf
+
+    def restore(self, blob):
+        if self._sharded:
+            for sh, b in zip(self.shards(), blob):
+                sh.restore(b)
+            return self
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _lib.check(_lib.lib.fb200_ensemble_checkpoint_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.size))
+        return self
+
+    def get_state(self, with_F=True):
+        """dict(F (n_models, Nx) | None, t, i_t, first, last, F_in, Mdot_in_prev): FreddiState::CurrentState per model."""
+        n = self.n_models
+        F = np.empty((n, self.Nx)) if with_F else None
+        t, F_in, Mp = (np.empty(n) for _ in range(3))
+        i_t, first, last = (np.empty(n, dtype=np.int64) for _ in range(3))
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+        _lib.check(self._f('get_state')(self._h, F.ctypes.data_as(dp) if with_F else None, t.ctypes.data_as(dp), i_t.ctypes.data_as(ip),
+                                        first.ctypes.data_as(ip), last.ctypes.data_as(ip), F_in.ctypes.data_as(dp), Mp.ctypes.data_as(dp)))
+        return dict(F=F, t=t, i_t=i_t, first=first, last=last, F_in=F_in, Mdot_in_prev=Mp)
+
+    def set_state(self, F=None, t=None, i_t=None, first=None, last=None, F_in=None, Mdot_in_prev=None):
+        """Replace (parts of) the models' current state: F (n_models, Nx) and per-model scalars; None keeps a component."""
+        n = self.n_models
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+
+        def dbl(x, shape):
+            if x is None:
+                return None, None
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), shape))
+            return a, a.ctypes.data_as(dp)
+
+        def i64(x):
+            if x is None:
+                return None, None
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.int64), (n,)))
+            return a, a.ctypes.data_as(ip)
+        keep = [dbl(F, (n, self.Nx)), dbl(t, (n,)), i64(i_t), i64(first), i64(last), dbl(F_in, (n,)), dbl(Mdot_in_prev, (n,))]
+        _lib.check(self._f('set_state')(self._h, *[k[1] for k in keep]))
+        return self
+
+    def result(self):
+        """EnsembleResult over all recorded rows (needs record_F for the radial arrays)."""
+        return EnsembleResult(self)
+
     def status(self):
         st = np.empty(self.n_models, dtype=np.int32)
         rv = np.empty(self.n_models, dtype=np.int32)
@@ -416,6 +491,61 @@ class Ensemble:
         out = np.empty(self.n_models)
         _lib.check(self._f('mdot_wind')(self._h, int(row), out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
         return out
+
+
+class DeviceArray:
+    """A typed view of device memory owned by an Ensemble (``__cuda_array_interface__`` version 3)."""
+
+    def __init__(self, owner, ptr, shape, typestr, device):
+        self._owner = owner  # keeps the HBM alive
+        self.shape, self.device = tuple(int(x) for x in shape), device
+        # (torch only imports writable views; the memory belongs to the engine: treat it as read-only)
+        self.__cuda_array_interface__ = {'shape': self.shape, 'typestr': typestr, 'data': (int(ptr), False), 'version': 3, 'strides': None}
+
+    def to_torch(self):
+        import torch
+        return torch.as_tensor(self, device=torch.device('cuda', self.device))
+
+
+class EnsembleResult:
+    """The reference's EvolutionResult (python/freddi/evolution_result.py:24-71) for a whole ensemble: attribute access gives
+    the light-curve columns as (n_models, n_rows) and the radial distributions as (n_models, n_rows, Nx), NaN outside
+    [first, last] and for rows a model never reached — one launch per attribute (fb200_ensemble_field_rows)."""
+
+    def __init__(self, ens):
+        self._ens = ens
+        self._rows = None
+
+    def _col(self, name):
+        if self._rows is None:
+            self._rows = self._ens.rows()
+        return self._rows[:, :, self._ens.columns.index(name)]
+
+    def flux(self, lmbd, region='hot', phase=None):
+        """(n_models, n_rows) + lmbd.shape, like EvolutionResult.flux."""
+        lam = np.asarray(lmbd, dtype=float)
+        e = self._ens
+        parts = {'hot': ['hot'], 'cold': ['cold'], 'disk': ['hot', 'cold'], 'star': ['star'], 'all': ['hot', 'cold', 'star']}[region]
+        total = 0.
+        for part in parts:
+            ph = None
+            if part == 'star':
+                if phase is None:
+                    raise ValueError('Phase must be specified if star flux is required')
+                ph = phase
+            total = total + e.flux_rows(lam.ravel(), part, 0, e.n_rows, ph)
+        return total.reshape((e.n_models, e.n_rows) + lam.shape)
+
+    def __getattr__(self, attr):
+        e = self.__dict__['_ens']
+        if attr in e.columns:
+            return self._col(attr)
+        alias = {'Mdot_in': 'Mdot', 'Fx': 'Fx', 'Lx': 'Lx'}
+        if attr in alias and alias[attr] in e.columns:
+            return self._col(alias[attr])
+        if attr in FIELDS:
+            return e.field_rows(attr, 0, e.n_rows, pad_nan=True)
+        raise AttributeError(attr)
 
 
 def measure_fp64_peak(device=0):

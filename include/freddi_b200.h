@@ -303,6 +303,33 @@ int fb200_ensemble_flux_rows(fb200_ensemble_t* e, int region, int64_t row_begin,
 /* Mdot_wind of FreddiState::Mdot_wind (cpp/src/freddi_state.cpp:364-383), per model, on the state of `row`. */
 int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size_t out_len);
 
+/* --- device-resident results (zero copy) --- */
+/* Pointers into the ensemble's HBM for consumers that stay on the GPU (the reference's Python layer hands out host copies,
+ * cpp/pywrap/converters.cpp:39-48; python/freddi/evolution_result.py:55-71 stacks them): ROWS [n_models][n_rows][n_cols],
+ * F [n_models][Nx] (current state), H [n_models][Nx], and with record_F FSNAP [n_models][n_rows][Nx] (NaN where never written)
+ * and BOUNDS int32 [n_models][n_rows][2] (first, last per row).  Valid until the ensemble is destroyed; synchronise with
+ * fb200_ensemble_sync before reading after an asynchronous evolve.  *device = the CUDA ordinal the memory lives on. */
+enum { FB200_DEVPTR_ROWS = 0, FB200_DEVPTR_F = 1, FB200_DEVPTR_H = 2, FB200_DEVPTR_FSNAP = 3, FB200_DEVPTR_BOUNDS = 4 };
+int fb200_ensemble_device_ptr(fb200_ensemble_t* e, int which, const void** dptr, int32_t* device);
+
+/* --- state in / out: checkpoint and resume --- */
+/* The copyable state of the reference (FreddiState's copy constructor, cpp/src/freddi_state.cpp:84-91: the structure is shared,
+ * CurrentState is copied).  A checkpoint is an opaque blob holding every model's CurrentState (t, i_t, first, last, F_in,
+ * Mdot_in_prev, status, work counters, the last wind update), F, and the closure K carried with it, optionally the rows written
+ * so far; loaded into an ensemble created from the same arguments it makes the continuation bit-identical to an uninterrupted
+ * run. */
+size_t fb200_ensemble_checkpoint_bytes(const fb200_ensemble_t* e, int with_rows);
+int fb200_ensemble_checkpoint_save(fb200_ensemble_t* e, void* buf, size_t len, int with_rows);
+int fb200_ensemble_checkpoint_load(fb200_ensemble_t* e, const void* buf, size_t len);
+/* Explicit state: F[n_models][Nx] and the scalars of CurrentState per model (cpp/include/freddi_state.hpp:242-258); any pointer
+ * may be NULL (get: not wanted; set: keep).  set_state makes every model alive again at row i_t (row 0 is written from the
+ * given state when i_t == 0) and voids the carried closure, so a run continued from an explicit state agrees with an
+ * uninterrupted one to rounding (~1e-16 per step), not bit for bit: use a checkpoint for that. */
+int fb200_ensemble_get_state(fb200_ensemble_t* e, double* F, double* t, int64_t* i_t, int64_t* first, int64_t* last, double* F_in,
+                             double* Mdot_in_prev);
+int fb200_ensemble_set_state(fb200_ensemble_t* e, const double* F, const double* t, const int64_t* i_t, const int64_t* first,
+                             const int64_t* last, const double* F_in, const double* Mdot_in_prev);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * In-process multi-GPU: one handle over several devices.  Stands in for running the reference's driver (cpp/main.cpp:7-12
  * -> cpp/include/application.hpp:17-43: construct, loop over step(), dump a row per step) once per model of a sweep.

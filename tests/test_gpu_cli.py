@@ -98,6 +98,28 @@ def test_ns_executable_fulldata_and_sweep(built, ref, tmp_path):
     assert k == 6 and not (tmp_path / 'sw-6.dat').exists()
 
 
+def test_sweep_over_devices_writes_the_same_files(built, tmp_path):
+    """--devices: the sweep from ONE process over several GPUs (here the same GPU listed twice, plus 'all') writes, byte for
+    byte, the files of the single-device run — light curves through fb200_sweep_run, --fulldata through the sharded handle."""
+    sweep = ['--alpha=0.25', '--Mx=5', '--Mopt=0.5', '--period=0.25', '--distance=10', '--time=5', '--tau=0.25', '--F0=2e38',
+             '--initialcond=quasistat', '--Thot=1e4', '--boundcond=Tirr', '--angulardistdisk=isotropic', '--Cirr=1e-4', '--precision=12',
+             '--lambda=5000', '--sweep', 'alpha=0.2:0.8:5', 'Cirr=1e-4:1e-3:3:log']
+    for extra in ([], ['--fulldata', '--tempsparsity=10']):
+        dirs = {}
+        for name, dev in (('one', []), ('two', ['--devices=0,0']), ('all', ['--devices=all'])):
+            d = tmp_path / (name + str(len(extra)))
+            d.mkdir()
+            p = run_cli(BIN, sweep + extra + dev, d)
+            assert p.returncode == 0, p.stderr
+            dirs[name] = d
+        files = sorted(f.name for f in dirs['one'].iterdir())
+        assert len(files) == (15 if not extra else 15 * 4)  # freddi-k.dat (+ _0, _10, _20 with --fulldata)
+        for name in ('two', 'all'):
+            assert sorted(f.name for f in dirs[name].iterdir()) == files
+            for f in files:
+                assert (dirs[name] / f).read_bytes() == (dirs['one'] / f).read_bytes(), (name, f)
+
+
 def test_executable_reports_collapse_and_errors(built, tmp_path):
     base = ['--alpha=0.7', '--Mx=5', '--Mopt=0.5', '--period=0.25', '--distance=10', '--time=50', '--tau=0.25', '--F0=2e38',
             '--initialcond=quasistat', '--Thot=1e4', '--boundcond=Tirr', '--Cirr=1e-4', '--angulardistdisk=isotropic']

@@ -1,15 +1,40 @@
-"""In-tree build of libfreddi_b200.so (nvcc, sm_100a only)."""
+"""In-tree build of libfreddi_b200.so (nvcc, sm_100a only).
+
+Every translation unit is compiled to an object of its own (in parallel: the evolve kernel is compiled four times — the main,
+small-grid and large-grid builds — at about a minute each) and the objects are linked into the one shared library.
+"""
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['capi.cu', 'construct.cu', 'sharded.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'resolve.cpp', 'star.cpp']
+OBJ = os.path.join(HERE, 'csrc', '_obj')
+SOURCES = ['capi.cu', 'construct.cu', 'sharded.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'evolve_s128.cu',
+           'fields_s128.cu', 'evolve_s256.cu', 'fields_s256.cu', 'resolve.cpp', 'star.cpp']
 HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp', 'star.hpp', 'ensemble_impl.hpp',
            os.path.join('..', '..', 'include', 'freddi_b200.h')]
 OUT = os.path.join(HERE, 'libfreddi_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC,-ffp-contract=off', '-shared']
+              '-Xcompiler', '-fPIC,-ffp-contract=off']
+# what a translation unit includes besides itself (a kernel build includes evolve.cu / fields.cu textually)
+KERNEL_HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', os.path.join('..', '..', 'include', 'freddi_b200.h')]
+
+
+def _deps(src):
+    deps = [src] + HEADERS
+    if src.startswith('evolve_'):
+        deps.append('evolve.cu')
+    if src.startswith('fields_'):
+        deps.append('fields.cu')
+    return [os.path.join(CSRC, d) for d in deps]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def up_to_date():
@@ -23,6 +48,16 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + SOURCES
-    subprocess.run(cmd, cwd=CSRC, check=True)
+    os.makedirs(OBJ, exist_ok=True)
+    flags = NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + '.o')
+        if force or verbose or _stale(obj, _deps(src)):
+            subprocess.run([nvcc] + flags + ['-c', src, '-o', obj], cwd=CSRC, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', OUT] + objs, cwd=CSRC, check=True)
     return OUT

@@ -13,14 +13,6 @@
 
 using namespace fb200;
 
-// the large-grid build of the kernels (evolve_big.cu, fields_big.cu)
-extern "C" {
-cudaError_t fb200_big_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
-cudaError_t fb200_big_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
-                                  const double* phases_dev, double* out, cudaStream_t stream);
-cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
-}
-
 namespace {
 int set_err(int code, const std::string& msg) { return fb_set_err(code, msg); }
 int cuda_fail(cudaError_t e, const char* what) { return fb_cuda_fail(e, what); }
@@ -498,8 +490,7 @@ static int field_rows(fb200_ensemble_t* e, int field, int64_t row0, int n_sel, i
     double* d_o = nullptr;
     rc = readout_scratch(e, need, &d_o);
     if (rc != FB200_OK) return rc;
-    cudaError_t ce = e->big ? fb200_big_launch_field(&e->dev, field, row0, n_sel, pad_nan, d_o, e->stream)
-                            : launch_field(e->dev, field, row0, n_sel, pad_nan, d_o, e->stream);
+    cudaError_t ce = e->kb->launch_field(&e->dev, field, row0, n_sel, pad_nan, d_o, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_field_kernel");
@@ -542,8 +533,7 @@ static int flux_rows(fb200_ensemble_t* e, int region, int64_t row0, int n_sel, c
     cudaError_t ce = cudaMemcpyAsync(d_l, lambdas, n_lambdas * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess && phases) ce = cudaMemcpyAsync(d_p, phases, size_t(n_sel) * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess)
-        ce = e->big ? fb200_big_launch_flux(&e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream)
-                    : launch_flux(e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream);
+        ce = e->kb->launch_flux(&e->dev, region, row0, n_sel, d_l, int(n_lambdas), d_p, d_o, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_o, need * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_flux_kernel");
@@ -573,8 +563,7 @@ int fb200_ensemble_mdot_wind(fb200_ensemble_t* e, int64_t row, double* out, size
     double* d_o = nullptr;
     rc = readout_scratch(e, e->n, &d_o);
     if (rc != FB200_OK) return rc;
-    cudaError_t ce = e->big ? fb200_big_launch_mdot_wind(&e->dev, row, d_o, e->stream)
-                            : launch_mdot_wind(e->dev, row, d_o, e->stream);
+    cudaError_t ce = e->kb->launch_mdot_wind(&e->dev, row, d_o, e->stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "fb200_mdot_wind_kernel launch");
     FB_CUDA(cudaMemcpyAsync(out, d_o, e->n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FB_CUDA(cudaStreamSynchronize(e->stream));

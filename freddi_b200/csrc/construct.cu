@@ -16,15 +16,69 @@
 #include "ensemble_impl.hpp"
 #include "star.hpp"
 
-extern "C" {
+extern "C" {  // the kernel builds (evolve.cu / fields.cu compiled once each per build)
+size_t fb200_s128_evolve_smem_bytes();
+size_t fb200_s128_evolve_scratch_doubles_per_cta();
+int fb200_s128_evolve_ctas_per_sm();
+int fb200_s128_evolve_resident_ctas_per_sm();
+int fb200_s128_evolve_threads();
+cudaError_t fb200_s128_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+cudaError_t fb200_s128_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t fb200_s128_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                    const double* phases_dev, double* out, cudaStream_t stream);
+cudaError_t fb200_s128_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
+size_t fb200_s256_evolve_smem_bytes();
+size_t fb200_s256_evolve_scratch_doubles_per_cta();
+int fb200_s256_evolve_ctas_per_sm();
+int fb200_s256_evolve_resident_ctas_per_sm();
+int fb200_s256_evolve_threads();
+cudaError_t fb200_s256_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+cudaError_t fb200_s256_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t fb200_s256_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                    const double* phases_dev, double* out, cudaStream_t stream);
+cudaError_t fb200_s256_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
+size_t fb200_main_evolve_smem_bytes();
+size_t fb200_main_evolve_scratch_doubles_per_cta();
+int fb200_main_evolve_ctas_per_sm();
+int fb200_main_evolve_resident_ctas_per_sm();
+int fb200_main_evolve_threads();
+cudaError_t fb200_main_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+cudaError_t fb200_main_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t fb200_main_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                    const double* phases_dev, double* out, cudaStream_t stream);
+cudaError_t fb200_main_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
 size_t fb200_big_evolve_smem_bytes();
 size_t fb200_big_evolve_scratch_doubles_per_cta();
 int fb200_big_evolve_ctas_per_sm();
 int fb200_big_evolve_resident_ctas_per_sm();
+int fb200_big_evolve_threads();
 cudaError_t fb200_big_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+cudaError_t fb200_big_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t fb200_big_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                    const double* phases_dev, double* out, cudaStream_t stream);
+cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
 }
 
 namespace fb200 {
+
+// ------------------------------------------------------------------------------------------------ kernel builds
+#define FB_BUILD_ROW(v, nx)                                                                                                          \
+    KernelBuild {                                                                                                                    \
+        #v, nx, fb200_##v##_evolve_smem_bytes, fb200_##v##_evolve_scratch_doubles_per_cta, fb200_##v##_evolve_ctas_per_sm,           \
+            fb200_##v##_evolve_resident_ctas_per_sm, fb200_##v##_evolve_threads, fb200_##v##_launch_evolve, fb200_##v##_launch_field, \
+            fb200_##v##_launch_flux, fb200_##v##_launch_mdot_wind                                                                    \
+    }
+const KernelBuild& kernel_build(int index) {
+    static const KernelBuild builds[kKernelBuilds] = {FB_BUILD_ROW(s128, 128), FB_BUILD_ROW(s256, 256), FB_BUILD_ROW(main, 1024),
+                                                      FB_BUILD_ROW(big, FB200_NX_LIMIT)};
+    return builds[index];
+}
+int kernel_build_index_for(int Nx) {
+    static const bool main_only = [] { const char* c = getenv("FB200_BUILD"); return c && std::string(c) == "main"; }();
+    for (int k = main_only ? 2 : 0; k < kKernelBuilds; ++k)
+        if (Nx <= kernel_build(k).nx_max) return k;
+    return kKernelBuilds - 1;
+}
 
 // ------------------------------------------------------------------------------------------------ errors
 namespace {
@@ -264,6 +318,7 @@ namespace {
 
 struct Plan {
     int Nx = 0, n_rows = 0, n_cols = 0, max_Nt = 0;
+    int build = 2;  // kernel_build index
     bool is_ns = false, big = false, has_A = false, has_B = false, has_C = false, has_dyn = false;
 };
 
@@ -291,6 +346,7 @@ int make_plan(const fb200_args_t* args, size_t n, const fb200_config_t& cfg, Pla
     P.n_rows = P.max_Nt + 1;
     P.n_cols = n_cols_of(cfg, P.is_ns);
     P.big = P.Nx > 1024;
+    P.build = kernel_build_index_for(P.Nx);
     return FB200_OK;
 }
 
@@ -390,23 +446,22 @@ struct Shared {
 
 struct DevCaps {
     bool known = false;
-    int sm_count = 0, smem_optin = 0, resident = 0, resident_big = 0;
+    int sm_count = 0, smem_optin = 0;
+    int resident[kKernelBuilds] = {-2, -2, -2, -2};  // CTAs per SM the occupancy calculator grants each kernel build (-2: not asked yet)
 };
 std::mutex g_caps_mutex;
 DevCaps g_caps[64];
 
-int device_caps(int device, bool big, DevCaps& out) {  // the calling thread has `device` selected
+int device_caps(int device, int build, DevCaps& out) {  // the calling thread has `device` selected
     std::lock_guard<std::mutex> g(g_caps_mutex);
     DevCaps& c = g_caps[device & 63];
     if (!c.known) {
         FB_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
         FB_CUDA(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        c.resident = -2;
-        c.resident_big = -2;
         c.known = true;
     }
-    if (!big && c.resident == -2) c.resident = (size_t(c.smem_optin) >= evolve_smem_bytes()) ? evolve_resident_ctas_per_sm() : 0;
-    if (big && c.resident_big == -2) c.resident_big = (size_t(c.smem_optin) >= fb200_big_evolve_smem_bytes()) ? fb200_big_evolve_resident_ctas_per_sm() : 0;
+    const KernelBuild& kb = kernel_build(build);
+    if (c.resident[build] == -2) c.resident[build] = (size_t(c.smem_optin) >= kb.smem_bytes()) ? kb.resident_ctas_per_sm() : 0;
     out = c;
     return FB200_OK;
 }
@@ -511,9 +566,11 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
     fb200_ensemble* e = B.e;
     FB_TRYB(cudaSetDevice(B.device));
     DevCaps caps;
-    if (device_caps(B.device, P.big, caps) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
+    const KernelBuild& kb = kernel_build(P.build);
+    e->kb = &kb;
+    if (device_caps(B.device, P.build, caps) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
     e->sm_count = caps.sm_count;
-    if (size_t(caps.smem_optin) < (P.big ? fb200_big_evolve_smem_bytes() : evolve_smem_bytes()))
+    if (size_t(caps.smem_optin) < kb.smem_bytes())
         return fail(FB200_ERR_UNSUPPORTED, "device offers too little shared memory per block for the sm_100a kernels");
     FB_TRYB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     FB_TRYB(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
@@ -541,9 +598,9 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
     D.star_ntri_max = sh.star_ntri_max;
     {
         // the chunked scheduler lets a CTA wait for another one: never launch more CTAs than can be resident
-        int resident = P.big ? caps.resident_big : caps.resident;
+        int resident = caps.resident[P.build];
         if (resident < 1) return fail(FB200_ERR_UNSUPPORTED, "the evolve kernel does not fit on this device");
-        const int designed = P.big ? fb200_big_evolve_ctas_per_sm() : evolve_ctas_per_sm();
+        const int designed = kb.ctas_per_sm();
         if (resident > designed) resident = designed;
         if (P.big && size_t(e->sm_count) * resident > e->n)  // 3 MB of scratch per CTA: no more CTAs than models
             resident = int((e->n + e->sm_count - 1) / e->sm_count);
@@ -561,7 +618,7 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
     D.group = n_groups > 1 ? e->group_begin[2] - e->group_begin[1] : 0;  // the last group takes the remainder
     D.group_done = nullptr;
 
-    const size_t scratch_per_cta = P.big ? fb200_big_evolve_scratch_doubles_per_cta() : evolve_scratch_doubles_per_cta();
+    const size_t scratch_per_cta = kb.scratch_doubles_per_cta();
     const size_t need = carve(e, sh, nullptr, scratch_per_cta);
     void* base = nullptr;
     if (arena_acquire(B.device, need, &base, &e->arena_bytes) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
@@ -843,7 +900,7 @@ int ensemble_launch(fb200_ensemble* e, long long n_steps) {
     }
     FB_CUDA(cudaEventRecord(e->ev0, e->stream));
     const int n_ctas = int(std::min<size_t>(e->n, size_t(e->dev.max_ctas)));
-    cudaError_t ce = e->big ? fb200_big_launch_evolve(&e->dev, n_ctas, e->stream) : launch_evolve(e->dev, n_ctas, e->stream);
+    cudaError_t ce = e->kb->launch_evolve(&e->dev, n_ctas, e->stream);
     if (ce != cudaSuccess) return fb_cuda_fail(ce, "fb200_evolve_kernel launch");
     FB_CUDA(cudaEventRecord(e->ev1, e->stream));
     e->last_launches = 1;
@@ -963,7 +1020,6 @@ int build_ensembles(const fb200_args_t* args, size_t n_models, const fb200_confi
         e->n = B.args.n;
         e->Nx = sh.P.Nx;
         e->is_ns = sh.P.is_ns;
-        e->big = sh.P.big;
         e->n_rows = sh.P.n_rows;
         e->max_Nt = sh.P.max_Nt;
         e->n_cols = sh.P.n_cols;

@@ -1151,8 +1151,12 @@ struct DiscEngine {
         // One thread per column, columns dealt round-robin over 8 warps (column c -> lane c / 8 of warp c % 8): every case of the
         // switch below is its own divergent path, and 18 of them in one warp cost more than the rest of the row phase.
         ex.points([&](int ii, int k) {
+#if FB200_NX_MAX >= 256
             if (ii >= 256) return;
             const int i = (ii & 31) * 8 + (ii >> 5);
+#else
+            const int i = ii;  // small-grid builds (one warp per model): a point index per column
+#endif
             if (i >= ncol) return;
             double v;
             switch (i) {

@@ -22,8 +22,31 @@
 #include "evolve.cuh"
 #include "resolve.hpp"
 
+namespace fb200 {
+// One compilation of the kernels (evolve.cu / fields.cu): the main build (Nx <= 1024, 256 threads per model), the small-grid
+// builds (s128: one warp per model, s256: two warps) and the large-grid build (big: arrays in an L2-resident scratch slot).
+struct KernelBuild {
+    const char* name;
+    int nx_max;
+    size_t (*smem_bytes)();
+    size_t (*scratch_doubles_per_cta)();
+    int (*ctas_per_sm)();
+    int (*resident_ctas_per_sm)();
+    int (*threads)();
+    cudaError_t (*launch_evolve)(const void* E, int n_ctas, cudaStream_t stream);
+    cudaError_t (*launch_field)(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+    cudaError_t (*launch_flux)(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                               const double* phases_dev, double* out, cudaStream_t stream);
+    cudaError_t (*launch_mdot_wind)(const void* E, long long row, double* out, cudaStream_t stream);
+};
+constexpr int kKernelBuilds = 4;
+const KernelBuild& kernel_build(int index);        // 0 s128, 1 s256, 2 main, 3 big
+int kernel_build_index_for(int Nx);                // the smallest build that holds Nx (FB200_BUILD=main: no small-grid builds)
+}  // namespace fb200
+
 struct fb200_ensemble {
     int device = 0;
+    const fb200::KernelBuild* kb = nullptr;
     cudaStream_t stream = nullptr;      // evolve / read-out
     cudaStream_t copy_in = nullptr;     // H2D of the construction pipeline
     cudaStream_t copy_out = nullptr;    // D2H of finished groups (streamed sweep)
@@ -31,7 +54,6 @@ struct fb200_ensemble {
     size_t n = 0;
     int Nx = 0, n_rows = 0, n_cols = 0, sm_count = 0, max_Nt = 0, chunk_steps = 25;
     bool is_ns = false;
-    bool big = false;  // Nx > 1024: the large-grid build of the kernels
     fb200_config_t cfg{};
     std::vector<fb200_model_info_t> info;
     fb200::EnsembleDev dev{};

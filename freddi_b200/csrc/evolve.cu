@@ -240,16 +240,23 @@ cudaError_t launch_evolve(const EnsembleDev& E, int n_ctas, cudaStream_t stream)
 
 }  // namespace fb200
 
-#ifdef FB_BIG
-// The large-grid build is a second compilation of this file (evolve_big.cu) in its own namespace; capi.cu reaches it
-// through these plain-C names.  EnsembleDev has the same layout in both builds (nothing in it depends on FB200_NX_MAX).
+// Exports with plain-C names, so that construct.cu / capi.cu can hold one table of kernel builds (ensemble_impl.hpp,
+// KernelBuild): this file is compiled once per build — the main one (Nx <= 1024, 256 threads per model), the large-grid one
+// (evolve_big.cu) and the small-grid ones (evolve_s128.cu: one warp per model, evolve_s256.cu: two warps per model) — each in
+// its own namespace.  EnsembleDev has the same layout in all builds (nothing in it depends on FB200_NX_MAX).
+#ifndef FB_VARIANT
+#define FB_VARIANT main
+#endif
+#define FB_CAT3_(a, b, c) a##b##c
+#define FB_CAT3(a, b, c) FB_CAT3_(a, b, c)
+#define FB_VNAME(name) FB_CAT3(fb200_, FB_VARIANT, name)
 extern "C" {
-size_t fb200_big_evolve_smem_bytes() { return fb200::evolve_smem_bytes(); }
-size_t fb200_big_evolve_scratch_doubles_per_cta() { return fb200::evolve_scratch_doubles_per_cta(); }
-int fb200_big_evolve_ctas_per_sm() { return fb200::evolve_ctas_per_sm(); }
-int fb200_big_evolve_resident_ctas_per_sm() { return fb200::evolve_resident_ctas_per_sm(); }
-cudaError_t fb200_big_launch_evolve(const void* E, int n_ctas, cudaStream_t stream) {
+size_t FB_VNAME(_evolve_smem_bytes)() { return fb200::evolve_smem_bytes(); }
+size_t FB_VNAME(_evolve_scratch_doubles_per_cta)() { return fb200::evolve_scratch_doubles_per_cta(); }
+int FB_VNAME(_evolve_ctas_per_sm)() { return fb200::evolve_ctas_per_sm(); }
+int FB_VNAME(_evolve_resident_ctas_per_sm)() { return fb200::evolve_resident_ctas_per_sm(); }
+int FB_VNAME(_evolve_threads)() { return fb200::kNT; }
+cudaError_t FB_VNAME(_launch_evolve)(const void* E, int n_ctas, cudaStream_t stream) {
     return fb200::launch_evolve(*static_cast<const fb200::EnsembleDev*>(E), n_ctas, stream);
 }
 }
-#endif

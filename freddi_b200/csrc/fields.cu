@@ -348,7 +348,7 @@ cudaError_t measure_fp64_peak(double* tflops) {
     return cudaGetLastError();
 }
 
-#ifndef FB_BIG
+#ifndef FB_VARIANT
 cudaError_t selftest_trapz(const double* x_dev, const double* y_dev, int n, int first, int last, double* out_dev, double* scratch_dev,
                            cudaStream_t stream) {
     cudaError_t e = prep(reinterpret_cast<const void*>(fb200_trapz_kernel));
@@ -387,17 +387,21 @@ cudaError_t launch_mdot_wind(const EnsembleDev& E, long long row, double* out, c
 
 }  // namespace fb200
 
-#ifdef FB_BIG
+#ifndef FB_VARIANT
+#define FB_VARIANT main
+#endif
+#define FB_CAT3_(a, b, c) a##b##c
+#define FB_CAT3(a, b, c) FB_CAT3_(a, b, c)
+#define FB_VNAME(name) FB_CAT3(fb200_, FB_VARIANT, name)
 extern "C" {  // see evolve.cu
-cudaError_t fb200_big_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream) {
+cudaError_t FB_VNAME(_launch_field)(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream) {
     return fb200::launch_field(*static_cast<const fb200::EnsembleDev*>(E), field, row0, n_sel, pad_nan, out, stream);
 }
-cudaError_t fb200_big_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
-                                  const double* phases_dev, double* out, cudaStream_t stream) {
+cudaError_t FB_VNAME(_launch_flux)(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                   const double* phases_dev, double* out, cudaStream_t stream) {
     return fb200::launch_flux(*static_cast<const fb200::EnsembleDev*>(E), region, row0, n_sel, lambdas_dev, n_lambdas, phases_dev, out, stream);
 }
-cudaError_t fb200_big_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream) {
+cudaError_t FB_VNAME(_launch_mdot_wind)(const void* E, long long row, double* out, cudaStream_t stream) {
     return fb200::launch_mdot_wind(*static_cast<const fb200::EnsembleDev*>(E), row, out, stream);
 }
 }
-#endif

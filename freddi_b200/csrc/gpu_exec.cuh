@@ -361,7 +361,7 @@ struct GpuEx {
 // parameter dynamically would make the compiler spill the whole parameter block to local memory.
 __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E) {
     OutCfg* c = smem_cfg();
-    if (threadIdx.x < 64) fb_smem[SmemLayout::o_exptab + threadIdx.x] = c_exp2_table[threadIdx.x];
+    for (int j = threadIdx.x; j < 64; j += kNT) fb_smem[SmemLayout::o_exptab + j] = c_exp2_table[j];
     if (threadIdx.x == 0) {
         c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
         c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows; c->lx_prune = E.cfg.lx_prune;

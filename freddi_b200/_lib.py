@@ -133,7 +133,7 @@ def _load():
     lib.fb200_sharded_flux.argtypes = [vp, C.c_int, C.c_int64, dp, C.c_size_t, dp, C.c_size_t]
     lib.fb200_sweep_plan.argtypes = [C.POINTER(FB200Args), C.c_size_t, C.POINTER(FB200Config), szp, szp]
     lib.fb200_sweep_run.argtypes = [C.POINTER(FB200Args), C.c_size_t, C.POINTER(FB200Config), i32p, C.c_int32, dp, C.c_size_t,
-                                    i32p, i32p, ip, C.POINTER(FB200SweepStats), szp]
+                                    i32p, i32p, ip, dp, C.POINTER(FB200SweepStats), szp]
     lib.fb200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.fb200_host_free.argtypes = [vp]
     lib.fb200_host_free.restype = None

@@ -148,6 +148,7 @@ struct SweepResult {
     std::vector<double> rows;  // [model][row][col]
     std::vector<int32_t> status, rows_valid;
     std::vector<int64_t> picard;
+    std::vector<double> t_end;  // FreddiState::t() where each model stopped [s]
     fb200_sweep_stats_t stats{};
     size_t n_rows = 0, n_cols = 0;
 };
@@ -159,9 +160,10 @@ inline SweepResult sweep(const std::vector<Arguments>& args, const Config& cfg =
     r.status.resize(raw.size());
     r.rows_valid.resize(raw.size());
     r.picard.resize(raw.size());
+    r.t_end.resize(raw.size());
     size_t bad = 0;
     check(fb200_sweep_run(raw.data(), raw.size(), &cfg, devices.empty() ? nullptr : devices.data(), int32_t(devices.size()), r.rows.data(),
-                          r.rows.size(), r.status.data(), r.rows_valid.data(), r.picard.data(), &r.stats, &bad));
+                          r.rows.size(), r.status.data(), r.rows_valid.data(), r.picard.data(), r.t_end.data(), &r.stats, &bad));
     return r;
 }
 

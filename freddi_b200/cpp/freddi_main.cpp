@@ -118,8 +118,20 @@ int main(int ac, char** av) {
             cfg.passband_transmissions[p] = passbands[p].transmissions.data();
             passband_names.push_back(passbands[p].name);
         }
+        // The reference's driver loops i_t = 0 .. int(time / tau) INCLUSIVE and steps after every dump (application.hpp:25-43): one
+        // step more than it dumps, whose only visible effect is the "terminated prematurely" line when that step collapses.
+        // The models are therefore evolved for time + tau (tau made explicit: its default is time / 200); rows are dumped for the
+        // requested time only.
         std::vector<Arguments> args(n_models, Arguments(ns));
-        for (size_t k = 0; k < n_models; ++k) static_cast<fb200_args_t&>(args[k]) = setups[k].args;
+        std::vector<long> n_dump(n_models);
+        for (size_t k = 0; k < n_models; ++k) {
+            fb200_model_info_t pre;
+            check(fb200_args_resolve(&setups[k].args, &pre, nullptr, nullptr));
+            n_dump[k] = long(static_cast<int>(setups[k].args.time / pre.tau)) + 1;  // i_t = 0 .. int(time / tau)
+            static_cast<fb200_args_t&>(args[k]) = setups[k].args;
+            args[k].tau = pre.tau;
+            args[k].time = setups[k].args.time + pre.tau;
+        }
 
         // --devices all | 0,1,...: the models are spread over several GPUs of the box from this one process (model k -> device
         // k mod G).  Light curves only: the streamed one-call sweep; with --fulldata the sharded handle (per-row structure read-out).
@@ -142,20 +154,23 @@ int main(int ac, char** av) {
         std::vector<fb200_model_info_t> info(n_models);
         std::vector<double> rows;
         FreddiEnsemble::Status st;
+        std::vector<double> t_end(n_models);  // FreddiState::t() where each model stopped [s]
         size_t ncol = 0, nrows = 0, Nx = size_t(setups[0].args.Nx);
         if (multi && !s0.fulldata) {
             SweepResult r = sweep(args, cfg, devices);
             rows.swap(r.rows);
+            t_end.swap(r.t_end);
             st = FreddiEnsemble::Status{std::move(r.status), std::move(r.rows_valid), std::move(r.picard)};
             ncol = r.n_cols;
             nrows = r.n_rows;
-            for (size_t k = 0; k < n_models; ++k) check(fb200_args_resolve(&setups[k].args, &info[k], nullptr, nullptr));
+            for (size_t k = 0; k < n_models; ++k) check(fb200_args_resolve(&args[k], &info[k], nullptr, nullptr));
         } else if (multi) {
             sharded.reset(new ShardedEnsemble(args, cfg, devices));
             check(fb200_sharded_info(sharded->handle(), info.data()));
             sharded->evolve(-1);
             rows = sharded->rows();
             st = sharded->status();
+            check(fb200_sharded_state(sharded->handle(), t_end.data(), nullptr, nullptr, nullptr));
             ncol = sharded->n_cols(); nrows = sharded->n_rows(); Nx = sharded->Nx();
         } else {
             ens.reset(new FreddiEnsemble(args, cfg));
@@ -163,6 +178,7 @@ int main(int ac, char** av) {
             ens->evolve(-1);
             rows = ens->rows();
             st = ens->status();
+            check(fb200_ensemble_state(ens->handle(), t_end.data(), nullptr, nullptr, nullptr));
             ncol = ens->n_cols(); nrows = ens->n_rows(); Nx = ens->Nx();
         }
 
@@ -170,11 +186,8 @@ int main(int ac, char** av) {
         if (fields.size() != ncol) throw std::logic_error("column count of the engine and of the writer differ");
         const std::vector<LongField> long_fields = disk_structure_fields(ns);
 
-        // rows dumped per model: i_t = 0 .. int(time / tau), cpp/include/application.hpp:25
-        std::vector<long> n_dump(n_models);
         long max_dump = 0;
         for (size_t k = 0; k < n_models; ++k) {
-            n_dump[k] = long(static_cast<int>(setups[k].args.time / info[k].tau)) + 1;
             if (n_dump[k] > long(nrows)) n_dump[k] = long(nrows);
             max_dump = std::max(max_dump, n_dump[k]);
         }
@@ -189,17 +202,18 @@ int main(int ac, char** av) {
             }
             const double alphacold = std::isnan(s.args.alphacold) ? s.args.alpha / 10.0 : s.args.alphacold;  // arguments.hpp:84
             write_dat_header(*os, fields, vms[k], s.precision, alphacold, info[k].rout, info[k].risco, info[k].tau);
-            for (long r = 0; r < n_dump[k]; ++r) {
-                if (r >= st.rows_valid[k]) {
-                    std::cerr << "Freddi terminated prematurely, i_t = " << r - 1 << ", t = "
-                              << format_double(rows[(k * nrows + size_t(r - 1)) * ncol], s.precision) << " (days), reason: Rout <= Rin";
-                    if (n_models > 1) std::cerr << " [model " << k << "]";
-                    std::cerr << std::endl;
-                    break;
-                }
+            for (long r = 0; r < n_dump[k] && r < st.rows_valid[k]; ++r)
                 if (r % long(s.tempsparsity) == 0) write_row(*os, &rows[(k * nrows + size_t(r)) * ncol], ncol, s.precision);
-            }
             os->flush();
+            if (st.status[k] == FB200_MODEL_COLLAPSED && st.rows_valid[k] <= n_dump[k]) {
+                // The step from state i_t = rows_valid - 1 threw RadiusCollapseException.  freddi->t() already holds the tau
+                // FreddiState::step added when the outer radius collapsed in truncateOuterRadius (freddi_state.cpp:147-153), not
+                // when the NS inner radius did (truncateInnerRadius runs first); std::cerr prints it at its default precision.
+                std::cerr << "Freddi terminated prematurely, i_t = " << st.rows_valid[k] - 1 << ", t = " << t_end[k] / 86400.
+                          << " (days), reason: Rout <= Rin";
+                if (n_models > 1) std::cerr << " [model " << k << "]";
+                std::cerr << std::endl;
+            }
         }
 
         if (s0.fulldata) {  // PREFIX_<i_t>.dat, cpp/src/output.cpp:142-162

@@ -858,6 +858,7 @@ int drive_device(DeviceBuild& B, Shared& sh) {
         if (sh.io->status) sh.io->status[g] = st;
         if (sh.io->rows_valid) sh.io->rows_valid[g] = hs[j].rows_valid;
         if (sh.io->picard_iters) sh.io->picard_iters[g] = hs[j].picard_iters;
+        if (sh.io->t_end) sh.io->t_end[g] = hs[j].t;
         steps += hs[j].rows_valid > 0 ? hs[j].rows_valid - 1 : 0;
     }
     {

@@ -120,6 +120,7 @@ struct SweepIO {
     int32_t* status = nullptr;        // [n_models] or null
     int32_t* rows_valid = nullptr;    // [n_models] or null
     int64_t* picard_iters = nullptr;  // [n_models] or null
+    double* t_end = nullptr;          // [n_models] or null: t of the state each model stopped at [s]
     // filled in by the call
     double device_ms_max = 0.;        // longest evolve launch over the devices (includes its waits for uploads)
     double first_launch_ms = 0.;      // entry -> the last device's kernel launched

@@ -249,8 +249,8 @@ int fb200_sweep_plan(const fb200_args_t* args, size_t n_models, const fb200_conf
 }
 
 int fb200_sweep_run(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg, const int32_t* devices, int32_t n_devices,
-                    double* rows, size_t rows_len, int32_t* status, int32_t* rows_valid, int64_t* picard_iters, fb200_sweep_stats_t* stats,
-                    size_t* bad_model) {
+                    double* rows, size_t rows_len, int32_t* status, int32_t* rows_valid, int64_t* picard_iters, double* t_end,
+                    fb200_sweep_stats_t* stats, size_t* bad_model) {
     if (bad_model) *bad_model = 0;
     if (!args || !rows || n_models == 0) return fb_set_err(FB200_ERR_INVALID_ARGUMENT, "null argument or empty ensemble");
     int n_rows = 0, n_cols = 0;
@@ -265,6 +265,7 @@ int fb200_sweep_run(const fb200_args_t* args, size_t n_models, const fb200_confi
     io.status = status;
     io.rows_valid = rows_valid;
     io.picard_iters = picard_iters;
+    io.t_end = t_end;
     rc = build_ensembles(args, n_models, cfg, devs.data(), int(devs.size()), /*keep_initial=*/false, &io, nullptr, bad_model);
     if (rc != FB200_OK) return rc;
     if (stats) {

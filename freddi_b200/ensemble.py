@@ -136,8 +136,9 @@ class SweepResult:
     """What freddi_b200.sweep returns: rows (n_models, n_rows, n_cols), status / rows_valid / picard_iters (n_models,), the column
     names and the timing the library measured (stats: dict of fb200_sweep_stats_t)."""
 
-    def __init__(self, rows, status, rows_valid, picard_iters, columns, stats):
+    def __init__(self, rows, status, rows_valid, picard_iters, columns, stats, t_end=None):
         self.rows, self.status, self.rows_valid, self.picard_iters, self.columns, self.stats = rows, status, rows_valid, picard_iters, columns, stats
+        self.t_end = t_end  # FreddiState::t() where each model stopped [s]
 
 
 def sweep_plan(args, lambdas=(), cold_disk=False, passbands=(), star_flux=False):
@@ -168,13 +169,15 @@ def sweep(args, lambdas=(), cold_disk=False, compute_lx=True, devices=None, host
     status = np.empty(n, dtype=np.int32)
     valid = np.empty(n, dtype=np.int32)
     picard = np.empty(n, dtype=np.int64)
+    t_end = np.empty(n)
     devs = None if devices is None else np.ascontiguousarray(list(devices), dtype=np.int32)
     stats = _lib.FB200SweepStats()
     bad = C.c_size_t()
     i32p = C.POINTER(C.c_int32)
     rc = _lib.lib.fb200_sweep_run(arr, n, C.byref(cfg), None if devs is None else devs.ctypes.data_as(i32p), 0 if devs is None else devs.size,
                                   out.ctypes.data_as(C.POINTER(C.c_double)), out.size, status.ctypes.data_as(i32p), valid.ctypes.data_as(i32p),
-                                  picard.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(stats), C.byref(bad))
+                                  picard.ctypes.data_as(C.POINTER(C.c_int64)), t_end.ctypes.data_as(C.POINTER(C.c_double)), C.byref(stats),
+                                  C.byref(bad))
     if rc != _lib.FB200_OK:
         try:
             _lib.check(rc)
@@ -182,7 +185,7 @@ def sweep(args, lambdas=(), cold_disk=False, compute_lx=True, devices=None, host
             e.bad_model = int(bad.value)
             raise
     columns = column_names(len(lambdas), cold_disk, bool(arr[0].is_ns), [pb.name for pb in passbands], bool(star_flux) and star_flux != 'readout')
-    return SweepResult(out, status, valid, picard, columns, {k: getattr(stats, k) for k, _ in _lib.FB200SweepStats._fields_})
+    return SweepResult(out, status, valid, picard, columns, {k: getattr(stats, k) for k, _ in _lib.FB200SweepStats._fields_}, t_end)
 
 
 class Ensemble:

@@ -367,7 +367,8 @@ int fb200_sharded_flux(fb200_sharded_t* h, int region, int64_t row, const double
  * order into pinned staging, each uploaded group of models is picked up by the running kernel as its watermark arrives, and
  * the rows of finished groups are copied to `rows` while later groups still run — argument resolution, allocation, H2D and
  * most of the D2H hide behind the device time.  rows[n_models][n_rows][n_cols] with n_rows, n_cols from fb200_sweep_plan;
- * status / rows_valid / picard_iters [n_models] may be NULL.  cfg->record_F is ignored (rows only). */
+ * status / rows_valid / picard_iters / t_end (FreddiState::t() where the model stopped [s]) [n_models] may be NULL.
+ * cfg->record_F is ignored (rows only). */
 typedef struct fb200_sweep_stats {
     double total_ms;        /* the whole call                                                                   */
     double device_ms_max;   /* longest evolve launch over the devices (CUDA events; includes its waits for uploads) */
@@ -379,7 +380,7 @@ typedef struct fb200_sweep_stats {
 } fb200_sweep_stats_t;
 int fb200_sweep_plan(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg, size_t* n_rows, size_t* n_cols);
 int fb200_sweep_run(const fb200_args_t* args, size_t n_models, const fb200_config_t* cfg, const int32_t* devices, int32_t n_devices,
-                    double* rows, size_t rows_len, int32_t* status, int32_t* rows_valid, int64_t* picard_iters,
+                    double* rows, size_t rows_len, int32_t* status, int32_t* rows_valid, int64_t* picard_iters, double* t_end,
                     fb200_sweep_stats_t* stats, size_t* bad_model);
 
 /* Pinned (page-locked, portable) host memory for result buffers; fb200_trim releases the device arenas and staging blocks

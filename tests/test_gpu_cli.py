@@ -127,5 +127,10 @@ def test_executable_reports_collapse_and_errors(built, tmp_path):
     assert p.returncode == 0 and 'Freddi terminated prematurely' in p.stderr and 'Rout <= Rin' in p.stderr
     n_rows = sum(1 for line in (tmp_path / 'freddi.dat').read_text().splitlines() if not line.startswith('#'))
     assert 1 < n_rows < 201
+    # the reference's line (cpp/include/application.hpp:31-40): i_t of the step that threw, and freddi->t() — which FreddiState::step
+    # had already advanced by tau when truncateOuterRadius threw — at std::cerr's default precision
+    import re
+    m = re.search(r'i_t = (\d+), t = (\S+) \(days\), reason: Rout <= Rin', p.stderr)
+    assert m and int(m.group(1)) == n_rows - 1 and m.group(2) == '{:g}'.format(n_rows * 0.25)
     p = run_cli(BIN, base[1:], tmp_path)
     assert p.returncode == 1 and "the option '--alpha' is required but missing" in p.stderr

@@ -44,20 +44,39 @@ def up_to_date():
     return all(os.path.getmtime(os.path.join(CSRC, f)) <= t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, kernel_flags=(), name=None):
+    """The product library, or — with `out` — a kernel-variant library for A/B measurements and profiling
+    (FB200_LIB=<out> python bench.py ...): `kernel_flags` (e.g. -DFB_PROFILE, -DFB_NT=512) go to the kernel translation units
+    (evolve*.cu, fields*.cu); objects live in csrc/_obj/<name>."""
+    variant = out is not None
+    if not variant and not force and up_to_date():
         return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
-    os.makedirs(OBJ, exist_ok=True)
+    obj_dir = os.path.join(OBJ, name or os.path.splitext(os.path.basename(out))[0]) if variant else OBJ
+    os.makedirs(obj_dir, exist_ok=True)
     flags = NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else [])
 
     def compile_one(src):
-        obj = os.path.join(OBJ, os.path.splitext(src)[0] + '.o')
-        if force or verbose or _stale(obj, _deps(src)):
-            subprocess.run([nvcc] + flags + ['-c', src, '-o', obj], cwd=CSRC, check=True)
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + '.o')
+        kernel = src.startswith(('evolve', 'fields'))
+        if force or verbose or (variant and kernel) or _stale(obj, _deps(src)):
+            subprocess.run([nvcc] + flags + (list(kernel_flags) if kernel else []) + ['-c', src, '-o', obj], cwd=CSRC, check=True)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', OUT] + objs, cwd=CSRC, check=True)
-    return OUT
+    target = os.path.abspath(out) if variant else OUT
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', target] + objs, cwd=CSRC, check=True)
+    return target
+
+
+if __name__ == '__main__':
+    import argparse
+    ap = argparse.ArgumentParser(description=build.__doc__)
+    ap.add_argument('--out', default=None, help='variant library to write (default: the product library)')
+    ap.add_argument('--force', action='store_true')
+    ap.add_argument('--verbose', action='store_true', help='-Xptxas -v')
+    ap.add_argument('kernel_flags', nargs='*', help='extra nvcc flags for the kernel translation units, after --')
+    o = ap.parse_args()
+    print(build(force=o.force, verbose=o.verbose, out=o.out, kernel_flags=o.kernel_flags))

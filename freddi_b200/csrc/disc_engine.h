@@ -156,40 +156,55 @@ FB_HD double passband_ring_sum(double T, const double* __restrict__ a, const dou
     return s0 + s1;
 }
 
-// nu^3 / (exp(a) - 1), a = (h/k_B) nu / T: B_nu without its constant factor 2h/c^2, which planck_nu1_nu2 applies once to the
-// finished integral.  kClamp = false: the caller guarantees a < 700 over the whole band (no range checks: 2 DSETP and 7
-// integer-pipe instructions fewer per evaluation).
-template <bool kClamp>
-FB_HD double planck_nu_core(double hk_over_T, double nu) {
-    const double a = hk_over_T * nu;
-    if (kClamp) {
-        const double b = p3(nu) * fb_rcp(fb_exp_tab((a < 700.) ? a : 700.) - 1.);
-        return (a < 700.) ? b : 0.;
-    }
-    return p3(nu) * fb_rcp(fb_exp_tab(a) - 1.);
-}
-
-// The adaptive walk of planck_nu1_nu2 over the scaled integrand planck_nu_core.
-template <bool kClamp>
+// The adaptive walk of planck_nu1_nu2 over the scaled integrand nu^3 / (exp(a nu) - 1), a = (h/k_B) / T (B_nu without its constant
+// factor 2h/c^2, which planck_nu1_nu2 applies once to the finished integral), written as nu^3 w / (1 - w) with w = exp(-a nu):
+//   * the walk is FP64-pipe-bound (profiles/r02_lx_pass_experiment.md: 143 FP64 instructions per trial step, 96 of them in the
+//     four exponentials of the stages), and the four stage abscissae of a Cash-Karp step sit at t + {12, 24, 40, 35}/40 dt: ONE
+//     exponential v = exp(-a dt / 40) and a product chain give all four factors (v^12, v^24, v^35, v^40), and w at the new t
+//     is w_t v^40 — 24 FP64 instructions instead of 56.  A product of <= 40 factors carries <= 50 ulp = 5.5e-15 relative, w_t
+//     collects that once per accepted step (a walk has ~10): 1e-13 at most, three orders below the 1e-10 parity tolerance and
+//     far below what could flip a controller decision (|err - threshold| would have to be < 1e-13 of the threshold);
+//   * where w < 2^-54 (a nu > 37.4: most of the band for most rings) 1 - w is exactly 1 and the reciprocal drops out — decided
+//     per warp, and the bits do not depend on the decision (fb_rcp(1) is exactly 1);
+//   * exp(-a nu) underflows smoothly, so the walk needs no overflow guards (the argument of the one direct exponential is held at
+//     -700, fb_exp_tab's range: e^-700 against the hottest ring's e^-1 is zero at any precision).
 FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* trials) {
     const double b1 = FB_KC(CK_B1), b3 = FB_KC(CK_B3), b4 = FB_KC(CK_B4), b6 = FB_KC(CK_B6);
     const double db1 = FB_KC(CK_DB1), db3 = FB_KC(CK_DB3), db4 = FB_KC(CK_DB4), db5 = FB_KC(CK_DB5), db6 = FB_KC(CK_DB6);
-    const double c3 = FB_KC(CK_C3), c4 = FB_KC(CK_C4), c5 = 1., c6 = 7. / 8.;
+    const double c3 = FB_KC(CK_C3), c4 = FB_KC(CK_C4), c6 = 7. / 8.;
     const double eps_mach = 2.220446049250313e-16;
+    const double tiny_w = 5.551115123125783e-17;  // 2^-54: 1 - w == 1 below
     double x = 0., t = nu1, dt = 1e-2 * (nu2 - nu1);
     int fails = 0, n = 0;
-    double k1 = planck_nu_core<kClamp>(hkT, t);
+    double wt;  // exp(-a t)
+    {
+        const double a = hkT * t;
+        wt = fb_exp_tab(-((a < 700.) ? a : 700.));
+    }
+    double k1 = (p3(t) * wt) * fb_rcp(1. - wt);
     while (nu2 - t > eps_mach) {
         if ((t + dt) - nu2 > eps_mach) dt = nu2 - t;  // less_with_sign(end, t + dt, dt)
         // stage 2 has zero weight in both the solution and the error estimate (b2 = db2 = 0) and the integrand does not depend
         // on the state: it is not evaluated
-        const double k3 = planck_nu_core<kClamp>(hkT, t + c3 * dt);
-        const double k4 = planck_nu_core<kClamp>(hkT, t + c4 * dt);
-        const double k5 = planck_nu_core<kClamp>(hkT, t + c5 * dt);
-        const double k6 = planck_nu_core<kClamp>(hkT, t + c6 * dt);
+        double w3, w4, w5, w6;
+        {
+            const double u = (hkT * dt) * 0.025;
+            const double v = fb_exp_tab(-((u < 700.) ? u : 700.));
+            const double v2 = v * v, v3 = v2 * v, v5 = v3 * v2, v6 = v3 * v3, v11 = v6 * v5, v12 = v6 * v6, v24 = v12 * v12;
+            const double v35 = v24 * v11;
+            w3 = wt * v12; w4 = wt * v24; w6 = wt * v35; w5 = wt * (v35 * v5);
+        }
+        bool no_rcp = wt < tiny_w;  // every stage's w is below w_t
+#ifdef __CUDA_ARCH__
+        no_rcp = __all_sync(__activemask(), no_rcp);
+#endif
+        double k3 = p3(t + c3 * dt) * w3, k4 = p3(t + c4 * dt) * w4, k5 = p3(t + dt) * w5, k6 = p3(t + c6 * dt) * w6;
+        if (!no_rcp) {
+            k3 *= fb_rcp(1. - w3); k4 *= fb_rcp(1. - w4); k5 *= fb_rcp(1. - w5); k6 *= fb_rcp(1. - w6);
+        }
         ++n;
         // odeint forms x + (b1 dt) k1 + (b3 dt) k3 + ...; with dt factored out the two sums are 11 instead of 19 FP64
-        // instructions (the kernel is FP64-throughput-bound here) and differ from that order by rounding only.
+        // instructions and differ from that order by rounding only.
         const double xnew = fma(dt, fma(b6, k6, fma(b4, k4, fma(b3, k3, b1 * k1))), x);
         const double xerr = dt * fma(db6, k6, fma(db5, k5, fma(db4, k4, fma(db3, k3, db1 * k1))));
         const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
@@ -211,10 +226,11 @@ FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* tr
             continue;
         }
         fails = 0;
-        t += dt;  // == the abscissa of stage 5 (c5 = 1): the derivative at the new t is k5, bit for bit
+        t += dt;  // == the abscissa of stage 5 (c5 = 1): the derivative at the new t is k5, and w there is w5
         if (err < 0.5) dt *= fac;
         x = xnew;
         k1 = k5;
+        wt = w5;
     }
     if (trials) *trials = n;
     return x;
@@ -235,14 +251,7 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
     if (!(T > 0.)) return 0.;
     const double hkT = FB_H_OVER_KB * fb_rcp(T);
     if (hkT * nu1 > 710.) return 0.;
-    // Both walks return the same bits where the unchecked one is valid, so the choice is free: on the device it is made per
-    // warp (a warp whose lanes disagreed would run the two walks one after the other).
-    bool unchecked = hkT * nu2 < 699.;
-#ifdef __CUDA_ARCH__
-    unchecked = __all_sync(__activemask(), unchecked);
-#endif
-    const double x = unchecked ? planck_walk<false>(hkT, nu1, nu2, tol, trials) : planck_walk<true>(hkT, nu1, nu2, tol, trials);
-    return FB_DOUBLE_H_OVER_C2 * x;
+    return FB_DOUBLE_H_OVER_C2 * planck_walk(hkT, nu1, nu2, tol, trials);
 }
 
 // ------------------------------------------------------------------------------------------------

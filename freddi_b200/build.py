@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 SOURCES = ['capi.cu', 'construct.cu', 'sharded.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'evolve_s128.cu',
-           'fields_s128.cu', 'evolve_s256.cu', 'fields_s256.cu', 'resolve.cpp', 'star.cpp']
+           'fields_s128.cu', 'evolve_s256.cu', 'fields_s256.cu', 'evolve_s512.cu', 'fields_s512.cu', 'resolve.cpp', 'star.cpp']
 HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp', 'star.hpp', 'ensemble_impl.hpp',
            os.path.join('..', '..', 'include', 'freddi_b200.h')]
 OUT = os.path.join(HERE, 'libfreddi_b200.so')

@@ -37,6 +37,16 @@ cudaError_t fb200_s256_launch_field(const void* E, int field, long long row0, in
 cudaError_t fb200_s256_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
                                     const double* phases_dev, double* out, cudaStream_t stream);
 cudaError_t fb200_s256_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
+size_t fb200_s512_evolve_smem_bytes();
+size_t fb200_s512_evolve_scratch_doubles_per_cta();
+int fb200_s512_evolve_ctas_per_sm();
+int fb200_s512_evolve_resident_ctas_per_sm();
+int fb200_s512_evolve_threads();
+cudaError_t fb200_s512_launch_evolve(const void* E, int n_ctas, cudaStream_t stream);
+cudaError_t fb200_s512_launch_field(const void* E, int field, long long row0, int n_sel, int pad_nan, double* out, cudaStream_t stream);
+cudaError_t fb200_s512_launch_flux(const void* E, int region, long long row0, int n_sel, const double* lambdas_dev, int n_lambdas,
+                                    const double* phases_dev, double* out, cudaStream_t stream);
+cudaError_t fb200_s512_launch_mdot_wind(const void* E, long long row, double* out, cudaStream_t stream);
 size_t fb200_main_evolve_smem_bytes();
 size_t fb200_main_evolve_scratch_doubles_per_cta();
 int fb200_main_evolve_ctas_per_sm();
@@ -69,13 +79,13 @@ namespace fb200 {
             fb200_##v##_launch_flux, fb200_##v##_launch_mdot_wind                                                                    \
     }
 const KernelBuild& kernel_build(int index) {
-    static const KernelBuild builds[kKernelBuilds] = {FB_BUILD_ROW(s128, 128), FB_BUILD_ROW(s256, 256), FB_BUILD_ROW(main, 1024),
-                                                      FB_BUILD_ROW(big, FB200_NX_LIMIT)};
+    static const KernelBuild builds[kKernelBuilds] = {FB_BUILD_ROW(s128, 128), FB_BUILD_ROW(s256, 256), FB_BUILD_ROW(s512, 512),
+                                                      FB_BUILD_ROW(main, 1024), FB_BUILD_ROW(big, FB200_NX_LIMIT)};
     return builds[index];
 }
 int kernel_build_index_for(int Nx) {
     static const bool main_only = [] { const char* c = getenv("FB200_BUILD"); return c && std::string(c) == "main"; }();
-    for (int k = main_only ? 2 : 0; k < kKernelBuilds; ++k)
+    for (int k = main_only ? 3 : 0; k < kKernelBuilds; ++k)
         if (Nx <= kernel_build(k).nx_max) return k;
     return kKernelBuilds - 1;
 }
@@ -318,7 +328,7 @@ namespace {
 
 struct Plan {
     int Nx = 0, n_rows = 0, n_cols = 0, max_Nt = 0;
-    int build = 2;  // kernel_build index
+    int build = 3;  // kernel_build index
     bool is_ns = false, big = false, has_A = false, has_B = false, has_C = false, has_dyn = false;
 };
 
@@ -447,7 +457,7 @@ struct Shared {
 struct DevCaps {
     bool known = false;
     int sm_count = 0, smem_optin = 0;
-    int resident[kKernelBuilds] = {-2, -2, -2, -2};  // CTAs per SM the occupancy calculator grants each kernel build (-2: not asked yet)
+    int resident[kKernelBuilds] = {-2, -2, -2, -2, -2};  // CTAs per SM the occupancy calculator grants each kernel build (-2: not asked yet)
 };
 std::mutex g_caps_mutex;
 DevCaps g_caps[64];

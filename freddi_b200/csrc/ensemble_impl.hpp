@@ -24,7 +24,7 @@
 
 namespace fb200 {
 // One compilation of the kernels (evolve.cu / fields.cu): the main build (Nx <= 1024, 256 threads per model), the small-grid
-// builds (s128: one warp per model, s256: two warps) and the large-grid build (big: arrays in an L2-resident scratch slot).
+// builds (s128: one warp per model, s256: two warps, s512: four) and the large-grid build (big: arrays in an L2-resident scratch slot).
 struct KernelBuild {
     const char* name;
     int nx_max;
@@ -39,8 +39,8 @@ struct KernelBuild {
                                const double* phases_dev, double* out, cudaStream_t stream);
     cudaError_t (*launch_mdot_wind)(const void* E, long long row, double* out, cudaStream_t stream);
 };
-constexpr int kKernelBuilds = 4;
-const KernelBuild& kernel_build(int index);        // 0 s128, 1 s256, 2 main, 3 big
+constexpr int kKernelBuilds = 5;
+const KernelBuild& kernel_build(int index);        // 0 s128, 1 s256, 2 s512, 3 main, 4 big
 int kernel_build_index_for(int Nx);                // the smallest build that holds Nx (FB200_BUILD=main: no small-grid builds)
 }  // namespace fb200
 

@@ -329,7 +329,7 @@ def test_reset_replays_the_ensemble_bit_for_bit():
         np.testing.assert_array_equal(a, b)
 
 
-@pytest.mark.parametrize('Nx', [8, 33, 255, 1024])
+@pytest.mark.parametrize('Nx', [8, 33, 128, 129, 255, 257, 512, 513, 1024])  # every kernel build and its edges (s128, s256, s512, main)
 def test_grid_sizes_from_tiny_to_maximum(ref, Nx):
     """Nx = 1024 is the largest grid the kernels take (one CTA holds the model); tiny grids exercise partial
     blocks of the partitioned solve (block of 1, 2, ... rows) and partial warps."""

@@ -10,6 +10,7 @@ On top of that line, at N>1 the run also does the BASELINE configuration that is
 and reports it as an object of the same JSON line:
     N = 8      sweep_1e5       configs[4]: 10^5 models, Mx(10) x alpha(20) x Mdisk0(25) x Cirr(20)  (the north-star target)
     N = 2, 4   sweep_1e4_wind  configs[3]: 10^4 models, Woods1996 wind + irradiation, alpha(100) x Cirr(100), 3 bands per row
+    N = 1      sweep_1e4_ns    configs[2]: 10^4 neutron-star models, Bx(100) x alpha(100)
 each with device-timed and construction-inclusive end-to-end throughput, the reference's CPU code on a stride sample of
 the same sweep on all host cores (rank 0), the speed-up, and PARITY of the sampled models' rows against that reference.
 
@@ -60,6 +61,7 @@ def config2_grid(n_gpus):
 
 SWEEP5_GRID = (np.linspace(3, 15, 10), np.linspace(0.1, 1.0, 20), np.geomspace(1e25, 1e27, 25), np.geomspace(1e-5, 5e-3, 20))
 SWEEP4_GRID = (np.linspace(0.1, 1.0, 100), np.geomspace(1e-5, 5e-3, 100))
+SWEEP3_GRID = (np.geomspace(10 ** 7.5, 10 ** 8.5, 100), np.linspace(0.1, 1.0, 100))
 
 
 def workload(name, n_gpus, indices=None):
@@ -70,11 +72,13 @@ def workload(name, n_gpus, indices=None):
         return w.config5_sweep(*SWEEP5_GRID, indices=indices)
     if name == 'sweep_1e4_wind':
         return w.config4_sweep(*SWEEP4_GRID, indices=indices)
+    if name == 'sweep_1e4_ns':
+        return w.config3_sweep(*SWEEP3_GRID, indices=indices)
     raise KeyError(name)
 
 
 def workload_size(name, n_gpus):
-    return {'config2': N_ALPHA * n_gpus * N_CIRR, 'sweep_1e5': 100000, 'sweep_1e4_wind': 10000}[name]
+    return {'config2': N_ALPHA * n_gpus * N_CIRR, 'sweep_1e5': 100000, 'sweep_1e4_wind': 10000, 'sweep_1e4_ns': 10000}[name]
 
 
 WORKLOAD_TEXT = {
@@ -82,6 +86,8 @@ WORKLOAD_TEXT = {
     'sweep_1e5': 'BASELINE configs[4]: Mx(10) x alpha(20) x Mdisk0(25) x Cirr(20) = 100000 models, Nx=1000, 200 steps, 3 band fluxes per row',
     'sweep_1e4_wind': 'BASELINE configs[3]: Woods1996 wind + irradiation (Readme.md:997-1003), alpha(100) x Cirr(100) = 10000 models, Nx=1000, '
                       '200 steps, 3 band fluxes every row',
+    'sweep_1e4_ns': 'BASELINE configs[2]: neutron star, freddi-ns CI command (.github/workflows/main.yml:27), Bx(100) x alpha(100) = 10000 '
+                    'models, Nx=1000, 200 steps, 3 band fluxes per row, 25 + 3 columns',
 }
 
 
@@ -579,7 +585,7 @@ def run_gpu(opts):
                     model_steps_per_iteration=model_steps_all / opts.steps)
 
     # ---- the BASELINE configuration quoted on this many GPUs, at full size ----
-    sweep_name = {8: 'sweep_1e5', 2: 'sweep_1e4_wind', 4: 'sweep_1e4_wind'}.get(n_gpus)
+    sweep_name = {1: 'sweep_1e4_ns', 8: 'sweep_1e5', 2: 'sweep_1e4_wind', 4: 'sweep_1e4_wind'}.get(n_gpus)
     if opts.sweep:
         sweep_name = opts.sweep
     if sweep_name and sweep_name != 'none':
@@ -599,8 +605,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--ref-models', type=int, default=None, help='models in the CPU sample (default 8 x cores, max 1000)')
     ap.add_argument('--sweep-ref-models', type=int, default=None, help='models in the CPU sample of the full-size sweep (default 256)')
-    ap.add_argument('--sweep', default=None, choices=['sweep_1e5', 'sweep_1e4_wind', 'none'],
-                    help='full-size configuration to add to the line (default: sweep_1e5 at 8 GPUs, sweep_1e4_wind at 2/4, none at 1)')
+    ap.add_argument('--sweep', default=None, choices=['sweep_1e5', 'sweep_1e4_wind', 'sweep_1e4_ns', 'none'],
+                    help='full-size configuration to add to the line (default: sweep_1e5 at 8 GPUs, sweep_1e4_wind at 2/4, sweep_1e4_ns at 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-in-process', action='store_true', help='skip the one-process multi-GPU run of the full-size sweep (N > 1)')
     opts = ap.parse_args()

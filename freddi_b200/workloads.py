@@ -100,6 +100,14 @@ def config2_sweep(alphas, cirrs, indices=None):
     return sweep_array(base, k.size, alpha=alphas[k // cirrs.size], Cirr=cirrs[k % cirrs.size])
 
 
+def config3_sweep(bxs, alphas, indices=None):
+    """config3_args(bxs, alphas) as a packed array (Bx-major)."""
+    bxs, alphas = np.asarray(bxs, dtype=float), np.asarray(alphas, dtype=float)
+    k = np.arange(bxs.size * alphas.size) if indices is None else np.asarray(indices)
+    base = config3_args(bxs[:1], alphas[:1])[0]
+    return sweep_array(base, k.size, Bx=bxs[k // alphas.size], alpha=alphas[k % alphas.size])
+
+
 def config4_sweep(alphas, cirrs, indices=None):
     alphas, cirrs = np.asarray(alphas, dtype=float), np.asarray(cirrs, dtype=float)
     k = np.arange(alphas.size * cirrs.size) if indices is None else np.asarray(indices)

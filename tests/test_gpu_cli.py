@@ -120,6 +120,16 @@ def test_sweep_over_devices_writes_the_same_files(built, tmp_path):
                 assert (dirs[name] / f).read_bytes() == (dirs['one'] / f).read_bytes(), (name, f)
 
 
+def test_cpp_host_example_runs_and_sweep_matches(built, tmp_path):
+    """examples/ensemble_sweep.cpp (the C++ host over the C ABI, built by __graft_entry__.build()): the ensemble handle on one GPU
+    and fb200::sweep over all GPUs give identical rows."""
+    exe = os.path.join(cm.ROOT, 'build', 'ensemble_sweep')
+    p = subprocess.run([exe, '5', '4'], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert '# 20 models, 201 rows x 16 columns each' in p.stdout and 'rows identical' in p.stdout
+    assert sum(1 for line in p.stdout.splitlines() if line.startswith('model ')) == 20
+
+
 def test_executable_reports_collapse_and_errors(built, tmp_path):
     base = ['--alpha=0.7', '--Mx=5', '--Mopt=0.5', '--period=0.25', '--distance=10', '--time=50', '--tau=0.25', '--F0=2e38',
             '--initialcond=quasistat', '--Thot=1e4', '--boundcond=Tirr', '--Cirr=1e-4', '--angulardistdisk=isotropic']

@@ -153,3 +153,53 @@ def test_trim_and_cache_reuse():
     _lib.lib.fb200_trim()
     b = sweep(args, lambdas=cm.LAM3, devices=[0]).rows
     assert _same(a, b)
+
+
+def test_many_sweeps_of_changing_shape_and_two_threads():
+    """The caches (device arenas, pinned staging, host workers) across calls of changing size, model class and device list,
+    and two host threads sweeping at once: every result equals the plain ensemble's bit for bit."""
+    import threading
+    from freddi_b200 import sweep
+    rng = np.random.default_rng(0)
+    bh = _args(30, 30, time=3.0)     # 900 models to draw from
+    ns = cm.config3_args(np.geomspace(10 ** 7.5, 10 ** 8.5, 10), np.linspace(0.1, 1.0, 10), time=3.0)
+    want = {}
+
+    def reference(kind, idx):
+        key = (kind, tuple(idx))
+        if key not in want:
+            pool = bh if kind == 'bh' else ns
+            want[key] = _single([pool[i] for i in idx])[0]
+        return want[key]
+
+    cases = []
+    for n in (1, 7, 16, 17, 300, 640, 900, 33, 2, 450):
+        kind = 'ns' if n in (7, 33) else 'bh'
+        pool = bh if kind == 'bh' else ns
+        idx = sorted(rng.choice(len(pool), size=min(n, len(pool)), replace=False).tolist())
+        cases.append((kind, idx, [0] if n % 2 else [0, 0]))
+    for kind, idx, devs in cases:
+        pool = bh if kind == 'bh' else ns
+        res = sweep([pool[i] for i in idx], lambdas=cm.LAM3, devices=devs)
+        assert _same(res.rows, reference(kind, idx)), (kind, len(idx), devs)
+
+    errors = []
+
+    def worker(which):
+        try:
+            for kind, idx, devs in cases[which::2]:
+                pool = bh if kind == 'bh' else ns
+                res = sweep([pool[i] for i in idx], lambdas=cm.LAM3, devices=devs)
+                if not _same(res.rows, reference(kind, idx)):
+                    errors.append((which, kind, len(idx)))
+        except Exception as exc:  # noqa: BLE001
+            errors.append((which, repr(exc)))
+
+    for kind, idx, _ in cases:
+        reference(kind, idx)  # (filled before the threads start)
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

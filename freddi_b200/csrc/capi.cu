@@ -455,11 +455,14 @@ int fb200_ensemble_row_bounds(fb200_ensemble_t* e, int64_t row, int64_t* first, 
 static int readout_scratch(fb200_ensemble_t* e, size_t need, double** p) {
     if (need > e->scratch_len) {
         FB_CUDA(cudaStreamSynchronize(e->stream));
-        if (e->scratch) FB_CUDA(cudaFree(e->scratch));
+        arena_release(e->scratch, e->stream);
         e->scratch = nullptr;
         e->scratch_len = 0;
         const size_t len = need + need / 4;
-        FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->scratch), len * sizeof(double)));
+        void* q = nullptr;
+        const int rc = arena_acquire(e->device, len * sizeof(double), e->stream, &q);
+        if (rc != FB200_OK) return rc;
+        e->scratch = static_cast<double*>(q);
         e->scratch_len = len;
     }
     *p = e->scratch;

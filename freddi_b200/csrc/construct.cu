@@ -184,10 +184,10 @@ struct Block {
     void* p;
     size_t bytes;
     bool in_use;
-    int device;  // arenas only
+    int device;
 };
 std::mutex g_cache_mutex;
-std::vector<Block> g_pinned, g_arenas;
+std::vector<Block> g_pinned;
 bool cache_disabled() {
     static const bool off = getenv("FB200_NO_CACHE") != nullptr;
     return off;
@@ -230,90 +230,59 @@ void pinned_release(void* block) {
         }
 }
 
-// the calling thread has `device` selected
-int arena_acquire(int device, size_t bytes, void** p, size_t* got) {
-    {
-        std::lock_guard<std::mutex> g(g_cache_mutex);
-        Block* best = nullptr;
-        for (Block& b : g_arenas)
-            if (!b.in_use && b.device == device && b.bytes >= bytes && b.bytes <= 4 * bytes + (size_t(64) << 20) && (!best || b.bytes < best->bytes))
-                best = &b;
-        if (best) {
-            best->in_use = true;
-            *p = best->p;
-            *got = best->bytes;
-            return FB200_OK;
-        }
+// Device arenas come from a stream-ordered memory pool of the library's own per device (cudaMallocFromPoolAsync / cudaFreeAsync):
+// neither call synchronises the device — cudaFree does, and with a second ensemble's kernel waiting for ITS uploads at that
+// moment (two sweeps at once in one process) the uploads queue up behind the blocked free until the kernel's waits time out.
+// The pool keeps what is freed (release threshold: unlimited) until fb200_trim(); FB200_NO_CACHE=1: nothing is kept.
+namespace {
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+int device_pool(int device, cudaMemPool_t* out) {
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    cudaMemPool_t& pool = g_pools[device & 63];
+    if (!pool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        FB_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = cache_disabled() ? 0ull : ~0ull;
+        FB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    const size_t want = bytes + bytes / 8 + (size_t(1) << 20);
-    void* q = nullptr;
-    cudaError_t ce = cudaMalloc(&q, want);
-    if (ce != cudaSuccess) {  // give the cached blocks of this device back and try once more, without the head-room
+    *out = pool;
+    return FB200_OK;
+}
+}  // namespace
+
+// the calling thread has `device` selected; `stream` is an idle stream of that device
+int arena_acquire(int device, size_t bytes, cudaStream_t stream, void** p) {
+    cudaMemPool_t pool;
+    int rc = device_pool(device, &pool);
+    if (rc != FB200_OK) return rc;
+    cudaError_t ce = cudaMallocFromPoolAsync(p, bytes, pool, stream);
+    if (ce == cudaErrorMemoryAllocation) {  // give back what the pool holds idle and try once more
         cudaGetLastError();
-        {
-            std::lock_guard<std::mutex> g(g_cache_mutex);
-            for (size_t i = 0; i < g_arenas.size();)
-                if (!g_arenas[i].in_use && g_arenas[i].device == device) {
-                    cudaFree(g_arenas[i].p);
-                    g_arenas.erase(g_arenas.begin() + i);
-                } else {
-                    ++i;
-                }
-        }
-        ce = cudaMalloc(&q, bytes);
-        if (ce != cudaSuccess) return fb_cuda_fail(ce, "cudaMalloc (ensemble arena)");
-        *got = bytes;
-    } else {
-        *got = want;
+        cudaMemPoolTrimTo(pool, 0);
+        ce = cudaMallocFromPoolAsync(p, bytes, pool, stream);
     }
-    *p = q;
-    std::lock_guard<std::mutex> g(g_cache_mutex);
-    g_arenas.push_back(Block{q, *got, true, device});
+    if (ce != cudaSuccess) return fb_cuda_fail(ce, "cudaMallocFromPoolAsync (ensemble arena)");
+    // the block is used from three streams: let the allocation complete (the stream is idle) instead of ordering each of them behind it
+    FB_CUDA(cudaStreamSynchronize(stream));
     return FB200_OK;
 }
 
-void arena_release(int device, void* p) {
-    if (!p) return;
-    std::lock_guard<std::mutex> g(g_cache_mutex);
-    for (size_t i = 0; i < g_arenas.size(); ++i)
-        if (g_arenas[i].p == p) {
-            if (cache_disabled()) {
-                cudaFree(p);
-                g_arenas.erase(g_arenas.begin() + i);
-                return;
-            }
-            g_arenas[i].in_use = false;
-            break;
-        }
-    // at most two idle arenas per device: the smallest go first (cudaFree of a large block costs tens of milliseconds, and a
-    // large block also serves every smaller request up to a quarter of its size)
-    for (;;) {
-        int idle = 0;
-        size_t smallest = ~size_t(0), at = 0;
-        for (size_t i = 0; i < g_arenas.size(); ++i)
-            if (!g_arenas[i].in_use && g_arenas[i].device == device) {
-                ++idle;
-                if (g_arenas[i].bytes < smallest) { smallest = g_arenas[i].bytes; at = i; }
-            }
-        if (idle <= 2) break;
-        cudaFree(g_arenas[at].p);
-        g_arenas.erase(g_arenas.begin() + at);
-    }
+void arena_release(void* p, cudaStream_t stream) {
+    if (p) cudaFreeAsync(p, stream);
 }
 
 void caches_trim() {
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        for (cudaMemPool_t pool : g_pools)
+            if (pool) cudaMemPoolTrimTo(pool, 0);
+    }
     std::lock_guard<std::mutex> g(g_cache_mutex);
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (size_t i = 0; i < g_arenas.size();)
-        if (!g_arenas[i].in_use) {
-            cudaSetDevice(g_arenas[i].device);
-            cudaFree(g_arenas[i].p);
-            g_arenas.erase(g_arenas.begin() + i);
-        } else {
-            ++i;
-        }
-    cudaSetDevice(cur);
     for (size_t i = 0; i < g_pinned.size();)
         if (!g_pinned[i].in_use) {
             cudaFreeHost(g_pinned[i].p);
@@ -631,8 +600,9 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
     const size_t scratch_per_cta = kb.scratch_doubles_per_cta();
     const size_t need = carve(e, sh, nullptr, scratch_per_cta);
     void* base = nullptr;
-    if (arena_acquire(B.device, need, &base, &e->arena_bytes) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
+    if (arena_acquire(B.device, need, e->stream, &base) != FB200_OK) return fail(FB200_ERR_CUDA, fb_err_msg());
     e->arena = base;
+    e->arena_bytes = need;
     carve(e, sh, static_cast<char*>(base), scratch_per_cta);
 
     if (cfg.n_passbands > 0) {  // all tables back to back: a_j, then w_j
@@ -925,8 +895,10 @@ void ensemble_free(fb200_ensemble* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->copy_in) cudaStreamSynchronize(e->copy_in);
     if (e->copy_out) cudaStreamSynchronize(e->copy_out);
-    arena_release(e->device, e->arena);
-    if (e->scratch) cudaFree(e->scratch);
+    if (e->stream) {
+        arena_release(e->arena, e->stream);
+        arena_release(e->scratch, e->stream);
+    }
     pinned_release(e->pinned_block);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);

@@ -109,10 +109,11 @@ private:
 // Pinned (portable, mapped) host blocks, cached for the life of the process: cudaHostAlloc costs ~0.2 ms per MB.
 void* pinned_acquire(size_t bytes);   // nullptr when pinned memory cannot be had
 void pinned_release(void* block);
-// Device arenas, cached per device (cudaMalloc / cudaFree cost milliseconds and synchronise the device).
-int arena_acquire(int device, size_t bytes, void** p, size_t* got);
-void arena_release(int device, void* p);
-void caches_trim();                   // frees every cached block that is not in use
+// Device memory from the library's stream-ordered pool of the device (kept across ensembles; no device synchronisation on
+// either call).  `stream`: an idle stream of the device (acquire) / the stream the last use was ordered on (release).
+int arena_acquire(int device, size_t bytes, cudaStream_t stream, void** p);
+void arena_release(void* p, cudaStream_t stream);
+void caches_trim();                   // gives back what the pools and the pinned cache hold idle
 
 // Where a streamed sweep delivers its results (all host pointers; rows may be pageable, pinned is faster).
 struct SweepIO {

@@ -231,6 +231,7 @@ class Ensemble:
             self.bad_model = int(bad.value)
             _lib.check(rc)
         self._h = handle
+        self._shard_views = None
         self._args = arr
         self.lambdas = lambdas
         self.cold_disk = bool(cold_disk)
@@ -253,6 +254,27 @@ class Ensemble:
         if f is None:
             raise NotImplementedError('{} is per device: call it on the shards (Ensemble.shards())'.format(name))
         return f
+
+    def _gather(self, method, *a, **kw):
+        """A per-device read-out on a multi-GPU handle: call it on every shard and interleave the results into the caller's
+        model order (model k = shard k mod G, local index k // G).  Arrays, tuples and dicts of arrays are handled."""
+        if self._shard_views is None:
+            self._shard_views = self.shards()
+        parts = [getattr(sh, method)(*a, **kw) for sh in self._shard_views]
+        G = len(parts)
+
+        def weave(xs):
+            if isinstance(xs[0], tuple):
+                return tuple(weave([x[j] for x in xs]) for j in range(len(xs[0])))
+            if isinstance(xs[0], dict):
+                return {k: weave([x[k] for x in xs]) for k in xs[0]}
+            if xs[0] is None:
+                return None
+            out = np.empty((self.n_models,) + xs[0].shape[1:], dtype=xs[0].dtype)
+            for d, x in enumerate(xs):
+                out[d::G] = x
+            return out
+        return weave(parts)
 
     @property
     def n_shards(self):
@@ -313,6 +335,8 @@ class Ensemble:
         return float(ms.value)
 
     def last_launches(self):
+        if self._sharded:
+            return sum(sh.last_launches() for sh in self.shards())
         return int(self._f('last_launches')(self._h))
 
     # -- read-out --
@@ -370,6 +394,8 @@ class Ensemble:
 
     def get_state(self, with_F=True):
         """dict(F (n_models, Nx) | None, t, i_t, first, last, F_in, Mdot_in_prev): FreddiState::CurrentState per model."""
+        if self._sharded:
+            return self._gather('get_state', with_F)
         n = self.n_models
         F = np.empty((n, self.Nx)) if with_F else None
         t, F_in, Mp = (np.empty(n) for _ in range(3))
@@ -382,6 +408,18 @@ class Ensemble:
     def set_state(self, F=None, t=None, i_t=None, first=None, last=None, F_in=None, Mdot_in_prev=None):
         """Replace (parts of) the models' current state: F (n_models, Nx) and per-model scalars; None keeps a component."""
         n = self.n_models
+        if self._sharded:
+            G = self.n_shards
+            full = dict(F=F, t=t, i_t=i_t, first=first, last=last, F_in=F_in, Mdot_in_prev=Mdot_in_prev)
+            for d, sh in enumerate(self.shards()):
+                part = {}
+                for k, v in full.items():
+                    if v is None:
+                        continue
+                    v = np.asarray(v)
+                    part[k] = v if v.ndim == 0 or v.shape[0] != n else v[d::G]
+                sh.set_state(**part)
+            return self
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
 
         def dbl(x, shape):
@@ -414,6 +452,8 @@ class Ensemble:
 
     def counters(self):
         """(picard_iters, lx_trial_steps) per model, summed over the steps done so far."""
+        if self._sharded:
+            return self._gather('counters')
         pi, lx = (np.empty(self.n_models, dtype=np.int64) for _ in range(2))
         ip = C.POINTER(C.c_int64)
         _lib.check(self._f('counters')(self._h, pi.ctypes.data_as(ip), lx.ctypes.data_as(ip)))
@@ -438,6 +478,8 @@ class Ensemble:
         return dict(t=t, i_t=i_t, first=first, last=last)
 
     def row_bounds(self, row):
+        if self._sharded:
+            return self._gather('row_bounds', row)
         first, last = (np.empty(self.n_models, dtype=np.int64) for _ in range(2))
         ip = C.POINTER(C.c_int64)
         _lib.check(self._f('row_bounds')(self._h, int(row), first.ctypes.data_as(ip), last.ctypes.data_as(ip)))
@@ -469,6 +511,8 @@ class Ensemble:
 
     def field_rows(self, name, row_begin=0, n_rows=None, pad_nan=True):
         """(n_models, n_rows, Nx) in one launch; pad_nan: NaN outside [first, last] (the EvolutionResult layout)."""
+        if self._sharded:
+            return self._gather('field_rows', name, row_begin, n_rows, pad_nan)
         n_rows = self.n_rows - row_begin if n_rows is None else int(n_rows)
         out = np.empty((self.n_models, n_rows, self.Nx))
         _lib.check(self._f('field_rows')(self._h, FIELDS[name], int(row_begin), n_rows, int(bool(pad_nan)),
@@ -477,6 +521,8 @@ class Ensemble:
 
     def flux_rows(self, lambdas, region='hot', row_begin=0, n_rows=None, phases=None):
         """(n_models, n_rows, len(lambdas)) in one launch; region 'star' needs one orbital phase [rad] per row."""
+        if self._sharded:
+            return self._gather('flux_rows', lambdas, region, row_begin, n_rows, phases)
         n_rows = self.n_rows - row_begin if n_rows is None else int(n_rows)
         lam = np.ascontiguousarray(np.atleast_1d(lambdas), dtype=np.float64).ravel()
         out = np.empty((self.n_models, n_rows, lam.size))
@@ -491,6 +537,8 @@ class Ensemble:
         return out
 
     def mdot_wind(self, row=-1):
+        if self._sharded:
+            return self._gather('mdot_wind', row)
         out = np.empty(self.n_models)
         _lib.check(self._f('mdot_wind')(self._h, int(row), out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
         return out

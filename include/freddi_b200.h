@@ -383,8 +383,9 @@ int fb200_sweep_run(const fb200_args_t* args, size_t n_models, const fb200_confi
                     double* rows, size_t rows_len, int32_t* status, int32_t* rows_valid, int64_t* picard_iters, double* t_end,
                     fb200_sweep_stats_t* stats, size_t* bad_model);
 
-/* Pinned (page-locked, portable) host memory for result buffers; fb200_trim releases the device arenas and staging blocks
- * the library keeps between ensembles (cudaMalloc / cudaHostAlloc cost milliseconds; FB200_NO_CACHE=1 disables the caches). */
+/* Pinned (page-locked, portable) host memory for result buffers; fb200_trim gives back the device memory (a stream-ordered pool
+ * per device) and the pinned staging blocks the library keeps between ensembles (allocation costs milliseconds, and cudaFree
+ * would synchronise the device under a running sweep; FB200_NO_CACHE=1: nothing is kept). */
 int fb200_host_alloc(size_t bytes, void** p);
 void fb200_host_free(void* p);
 void fb200_trim(void);

@@ -203,3 +203,32 @@ def test_many_sweeps_of_changing_shape_and_two_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_per_device_readouts_through_the_multi_gpu_handle():
+    """field_rows / flux_rows / mdot_wind / row_bounds / counters / get_state / set_state / result() on a multi-GPU handle gather
+    from the shards into the caller's model order: equal to the single-device ensemble."""
+    from freddi_b200 import Ensemble
+    args = cm.config4_args(np.linspace(0.1, 1.0, 5), np.geomspace(1e-5, 5e-3, 3), time=4.0)  # Woods1996: a dynamic wind
+    with Ensemble(args, lambdas=cm.LAM3, record_F=True) as one, Ensemble(args, lambdas=cm.LAM3, record_F=True, device=[0, 0, 0]) as many:
+        for e in (one, many):
+            e.evolve(-1)
+        assert _same(many.field_rows('Sigma'), one.field_rows('Sigma'))
+        assert _same(many.flux_rows([4e-5, 6e-5], 'hot'), one.flux_rows([4e-5, 6e-5], 'hot'))
+        assert _same(many.mdot_wind(row=7), one.mdot_wind(row=7))
+        for a, b in zip(many.row_bounds(5), one.row_bounds(5)):
+            assert (a == b).all()
+        for a, b in zip(many.counters(), one.counters()):
+            assert (a == b).all()
+        sa, sb = many.get_state(), one.get_state()
+        assert all(_same(np.asarray(sa[k], dtype=np.float64), np.asarray(sb[k], dtype=np.float64)) for k in sa)
+        assert _same(many.result().Tph, one.result().Tph) and _same(many.result().Mdot, one.result().Mdot)
+        # put both back to the state after 3 steps and continue
+        with Ensemble(args, lambdas=cm.LAM3) as src:
+            src.evolve(3)
+            st = src.get_state()
+        for e in (one, many):
+            e.reset()
+            e.set_state(**st)
+            e.evolve(-1)
+        assert _same(many.rows(), one.rows()) and np.isnan(one.rows()[:, :4]).all() and np.isfinite(one.rows()[:, 4:, 0]).all()

@@ -218,7 +218,8 @@ FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* tr
         if (!reject && !(floor_ < err)) {
             fac = 4.5;  // 0.9 * (5^-5)^(-1/5): the growth limit — the common case on the exponential tail of the band
         } else {
-            fac = FB_KL(CK_NINE_TENTHS) * fb_pow_coarse((err < FB_KL(CK_HUGE)) ? err : FB_KL(CK_HUGE), reject ? FB_KL(CK_M_THIRD) : FB_KL(CK_M_FIFTH));
+            // (a rejected step with err >= 91.125 = (0.9 / 0.2)^3 gets the floor 0.2 below whatever the power: err is held at 100)
+            fac = FB_KL(CK_NINE_TENTHS) * fb_pow_step_factor((err < 100.) ? err : 100., reject);
         }
         if (reject) {
             dt *= (fac < FB_KL(CK_FIFTH)) ? FB_KL(CK_FIFTH) : fac;

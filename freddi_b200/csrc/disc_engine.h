@@ -207,7 +207,7 @@ FB_HD double planck_walk(double hkT, double nu1, double nu2, double tol, int* tr
         // instructions and differ from that order by rounding only.
         const double xnew = fma(dt, fma(b6, k6, fma(b4, k4, fma(b3, k3, b1 * k1))), x);
         const double xerr = dt * fma(db6, k6, fma(db5, k5, fma(db4, k4, fma(db3, k3, db1 * k1))));
-        const double err = fabs(xerr) * fb_rcp(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
+        const double err = fabs(xerr) * fb_rcp14(tol * (fabs(x) + fabs(dt) * fabs(k1)));  // feeds comparisons and the step factor only
         // Step-size controller.  Both adjustments are powers of the error, so one power evaluation serves the
         // rejecting and the accepting lanes of a warp alike:
         //   reject (err > 1):      dt *= max(0.9 err^(-1/3), 0.2)
@@ -876,7 +876,7 @@ struct DiscEngine {
                     const double y = (j == 0) ? z0 : ((j == nb - 1) ? z1 : yg);
                     const double y_old = S.F[i];
                     const double K0 = S.s_K[i];
-                    const double inv = fb_rcp(y);
+                    const double inv = fb_rcp14(y);  // x is a small correction: 1e-14 of it is 1e-16 of K
                     const double x = (y_old - y) * inv;
                     double sr = b7;
                     sr = fma(sr, x, b6); sr = fma(sr, x, b5); sr = fma(sr, x, b4); sr = fma(sr, x, b3);

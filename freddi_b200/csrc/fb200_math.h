@@ -283,6 +283,19 @@ FB_HD double fb_rcp(double y) {
 #endif
 }
 
+// 1/y to ~1e-14 (hardware seed 2^-23 + ONE Newton step): for quotients that only feed a comparison or a correction term that is
+// itself small (the controller's error ratio; x = (y_old - y) / y of the incremental K update, |x| < 2^-6)
+FB_HD double fb_rcp14(double y) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    const double e = fma(-y, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / y;
+#endif
+}
+
 // x^a for normal positive x and |a log2 x| < 1000, ~1 ulp — the opacity closure W ~ |F|^(1-m) and the disc height
 // ~ F^(3/20), evaluated once per ring per Picard iteration.  Same structure as a libm pow without its special-case
 // branches: log2 x in double-double (x = 2^e m, m in [sqrt(1/2), sqrt 2), log m = 2 atanh((m-1)/(m+1)) with the leading

@@ -104,6 +104,7 @@ struct PtrArrays {
     double *hn;                        // h^n / (1-m) / D of the opacity closure (shared)
     double *ca, *cb, *cc, *frac;       // interior finite-difference coefficients, nonlinear_diffusion.cpp:46-51 (scratch)
     double *c1, *hm175, *hotR, *Gb;    // per-point constants of the row, see init_points (scratch)
+    double *sgA, *qB, *tv4;            // grid-only factors of the row's structure pass: Sigma / W, (Qx / sigma_SB) / (Kirr L), (Tvis / F^(1/4))^4
     // this step's tridiagonal system  l_i y_{i-1} + d_i y_i + u_i y_{i+1} = rhs_i  (l = -a_i, u = -b_i, d = c0_i + K_i);
     // s_l, s_u, s_d, s_rhs and the block-elimination results p_a, p_c, p_g use the swizzled index pidx() (shared)
     double *s_l, *s_u, *s_d, *s_rhs, *s_cc, *s_frac;
@@ -485,18 +486,20 @@ FB_HD PointStructure hot_structure(const fb200_model_dev_t& M, const StateScalar
 struct RowStructure {
     double Sigma, Tph, Tirr, H2R;
 };
-FB_HD RowStructure hot_structure_lean(const fb200_model_dev_t& M, const StateScalars& sc, double h, double R, double hn, double hm175,
+// sgA = GM^2 / (4 pi h^3), qB = 1 / (4 pi R^2 sigma_SB), tv4 = (GM h^-1.75)^4: the grid-only factors, set up once per model
+// (init_points) instead of two reciprocals and a fourth power per ring and row.
+FB_HD RowStructure hot_structure_lean(const fb200_model_dev_t& M, const StateScalars& sc, double R, double hn, double sgA, double qB, double tv4,
                                       double hotR, double F, double W_known, bool need_height) {
     RowStructure q;
     const double W = (W_known >= 0.) ? W_known : wunc_point(M, F, hn);
-    q.Sigma = W * (p2(M.GM) * fb_rcp(4. * FB_PI * p3(h)));
+    q.Sigma = W * sgA;
     const double mu = need_height ? hotR * fb_pow_pos(F, M.Height_exp_F) * fb_rcp(R) : 0.;
     q.H2R = mu;
     const double Kirr = M.Cirr * ((M.irrindex == 0.) ? 1.0 : pow(mu / 0.05, M.irrindex));
     double L = sc.Lbol_disk * angular_dist(M.angdist_disk, mu);
     if (M.is_ns) L += sc.Lbol_ns * angular_dist(M.angdist_ns, mu);
-    const double Qs = Kirr * L * (fb_rcp(4. * FB_PI * p2(R)) * (1. / FB_SIGMA_SB));  // Qx / sigma_SB
-    const double Tvis4 = p4(hm175) * ((3. / (8. * FB_PI) / FB_SIGMA_SB) * F);
+    const double Qs = Kirr * L * qB;  // Qx / sigma_SB
+    const double Tvis4 = tv4 * ((3. / (8. * FB_PI) / FB_SIGMA_SB) * F);
     q.Tph = pow025(Tvis4 + Qs);
     q.Tirr = (Qs == 0.) ? 0. : pow025(Qs);
     return q;
@@ -610,6 +613,9 @@ struct DiscEngine {
             S.hn[i] = pow(h, M.n_op) / M.one_minus_m / M.D;
             S.c1[i] = 3. / (8. * FB_PI) * p4(M.GM) / p7(h);                                      // freddi_state.cpp:300
             S.hm175[i] = M.GM * pow(h, -1.75);                                                    // freddi_state.cpp:284
+            S.sgA[i] = p2(M.GM) * fb_rcp(4. * FB_PI * p3(h));                                     // Sigma = W GM^2 / (4 pi h^3), :198
+            S.qB[i] = fb_rcp(4. * FB_PI * p2(R)) * (1. / FB_SIGMA_SB);                            // Qx / (Kirr L sigma_SB), :240
+            S.tv4[i] = p4(S.hm175[i]);
             S.hotR[i] = R * M.Height_coef * pow(R / 1e10, M.Height_exp_R - M.Height_exp_F / 2.);  // opacity_related.cpp:86
             int inside;
             const double g = tgr_geom(M, R, &inside);
@@ -972,7 +978,7 @@ struct DiscEngine {
                     if (kExtras && cfg.star_flux) S.aux[i] = q.Height / S.R[i];
                 } else {
                     const double Wk = (do_truncate && i > first) ? S.s_K[i] * S.F[i] * fb_rcp(S.s_frac[i]) : -1.;
-                    const RowStructure q = hot_structure_lean(M, sc, S.h[i], S.R[i], S.hn[i], S.hm175[i], S.hotR[i], S.F[i], Wk, height_everywhere);
+                    const RowStructure q = hot_structure_lean(M, sc, S.R[i], S.hn[i], S.sgA[i], S.qB[i], S.tv4[i], S.hotR[i], S.F[i], Wk, height_everywhere);
                     Tph = q.Tph; Tirr = q.Tirr; Sigma = q.Sigma;
                     if (kExtras && cfg.star_flux) S.aux[i] = q.H2R;  // for Height2R of the star's irradiation sources
                 }

@@ -45,7 +45,7 @@ __constant__ double c_exp2_table[64] = {FB_EXP2_TABLE, FB_EXP2_TABLE_LO};
 
 // Shared memory per CTA: reduced-system PCR ping-pong, F, hn, s_cc, s_frac (plain index), s_l, s_u, s_d, s_rhs,
 // p_a, p_c, p_g (padded index), then the reduction scratch, the model constants and the output configuration.
-// Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb (9 point arrays, read once per step).
+// Global scratch slot per CTA: R, ca, cb, cc, frac, c1, hm175, hotR, Gb, sgA, qB, tv4 (12 point arrays, read once per step).
 struct SmemLayout {
     static constexpr int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
     static constexpr int o_exptab = 0;  // fixed: fb200_math.h reads the table at fb_smem[0..63]
@@ -82,11 +82,11 @@ struct SmemLayout {
     static_assert(FB_CTAS_PER_SM != 2 || sizeof(double) * size_t(kTotalDoubles) <= 115712, "shared memory per CTA too large for 2 CTAs/SM");
 #endif
 #ifdef FB_BIG
-    // R ca cb cc frac c1 hm175 hotR Gb | F hn s_cc s_frac s_K | s_l s_u s_d s_rhs p_a p_c p_g | lu0 lu1 (2 NR each) rr0 rr1
-    static constexpr int kScratchArrays = 21;
+    // R ca cb cc frac c1 hm175 hotR Gb sgA qB tv4 | F hn s_cc s_frac s_K | s_l s_u s_d s_rhs p_a p_c p_g | lu0 lu1 (2 NR each) rr0 rr1
+    static constexpr int kScratchArrays = 24;
     static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX + 6 * size_t(NR);
 #else
-    static constexpr int kScratchArrays = 9;
+    static constexpr int kScratchArrays = 12;
     static constexpr size_t kScratchDoublesPerCta = size_t(kScratchArrays) * FB200_NX_MAX;
 #endif
     static constexpr size_t scratch_doubles_per_cta() { return kScratchDoublesPerCta; }
@@ -115,6 +115,7 @@ __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double
     S.h = h_global;
     S.R = take(N); S.ca = take(N); S.cb = take(N); S.cc = take(N); S.frac = take(N);
     S.c1 = take(N); S.hm175 = take(N); S.hotR = take(N); S.Gb = take(N);
+    S.sgA = take(N); S.qB = take(N); S.tv4 = take(N);
     S.F = take(N); S.hn = take(N); S.s_cc = take(N); S.s_frac = take(N); S.s_K = take(N);
     S.s_l = take(N); S.s_u = take(N); S.s_d = take(N); S.s_rhs = take(N); S.p_a = take(N); S.p_c = take(N); S.p_g = take(N);
     S.lu[0] = reinterpret_cast<double2*>(take(2 * NR)); S.lu[1] = reinterpret_cast<double2*>(take(2 * NR));
@@ -127,7 +128,7 @@ __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double
 struct GpuArrays {
     typedef SmemLayout L;
     const double* h;                                   // the ensemble's grid array of this model (global)
-    double *R, *ca, *cb, *cc, *frac, *c1, *hm175, *hotR, *Gb;  // the CTA's global scratch slot
+    double *R, *ca, *cb, *cc, *frac, *c1, *hm175, *hotR, *Gb, *sgA, *qB, *tv4;  // the CTA's global scratch slot
     ShD<L::o_F> F; ShD<L::o_hn> hn; ShD<L::o_cc> s_cc; ShD<L::o_frac> s_frac; ShD<L::o_K> s_K;
     ShD<L::o_l> s_l; ShD<L::o_u> s_u; ShD<L::o_d> s_d; ShD<L::o_rhs> s_rhs;
     ShD<L::o_pa> p_a; ShD<L::o_pc> p_c; ShD<L::o_pg> p_g;
@@ -145,6 +146,7 @@ __device__ __forceinline__ GpuArrays carve_arrays(double* gscratch, const double
     S.h = h_global;
     S.R = gscratch + 0 * N; S.ca = gscratch + 1 * N; S.cb = gscratch + 2 * N; S.cc = gscratch + 3 * N; S.frac = gscratch + 4 * N;
     S.c1 = gscratch + 5 * N; S.hm175 = gscratch + 6 * N; S.hotR = gscratch + 7 * N; S.Gb = gscratch + 8 * N;
+    S.sgA = gscratch + 9 * N; S.qB = gscratch + 10 * N; S.tv4 = gscratch + 11 * N;
     return S;
 }
 

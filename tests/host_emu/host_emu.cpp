@@ -145,7 +145,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     for (int k = 0; k < n_lambdas; ++k) cfg.lambdas[k] = lambdas[k];
 
     const int N = FB200_NX_MAX, NP = FB200_NPAD, NR = FB200_NRED_MAX;
-    std::vector<double> pool(15 * size_t(N) + 7 * size_t(NP) + 6 * size_t(NR), 0.);
+    std::vector<double> pool(18 * size_t(N) + 7 * size_t(NP) + 6 * size_t(NR), 0.);
     double* p = pool.data();
     auto take = [&](size_t n) { double* q = p; p += n; return q; };
     double* hbuf = take(N);
@@ -153,6 +153,7 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     S.h = hbuf; S.R = take(N); S.F = take(N); S.hn = take(N);
     S.ca = take(N); S.cb = take(N); S.cc = take(N); S.frac = take(N);
     S.c1 = take(N); S.hm175 = take(N); S.hotR = take(N); S.Gb = take(N);
+    S.sgA = take(N); S.qB = take(N); S.tv4 = take(N);
     S.s_cc = take(N); S.s_frac = take(N); S.s_K = take(N);
     S.s_l = take(NP); S.s_u = take(NP); S.s_d = take(NP); S.s_rhs = take(NP); S.p_a = take(NP); S.p_c = take(NP); S.p_g = take(NP);
     S.lu[0] = reinterpret_cast<double2*>(take(2 * NR)); S.lu[1] = reinterpret_cast<double2*>(take(2 * NR));

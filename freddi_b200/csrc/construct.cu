@@ -387,7 +387,7 @@ struct DeviceBuild {
     int enqueued = 0, polled = 0;
     int* marks = nullptr;             // pinned: cumulative model counts per chunk (+ a -1 at the end): sources of the watermark copies
     void* marks_block = nullptr;
-    int next_group = 0;               // streamed sweep: groups whose rows have been sent to the host
+    int next_block = 0;               // streamed sweep: read-back blocks whose rows have been sent to the host
     int rc = FB200_OK;
     std::string err;
     double t_launch_ms = 0., t_uploaded_ms = 0., device_ms = 0.;
@@ -498,10 +498,11 @@ size_t carve(fb200_ensemble* e, const Shared& sh, char* base, size_t scratch_per
         F0 = static_cast<double*>(take(NN));
         state0 = static_cast<ModelState*>(take(n * sizeof(ModelState)));
     }
-    int *ready = nullptr, *group_count = nullptr;
+    int *ready = nullptr, *block_count = nullptr;
+    const size_t n_blocks = (n + kDoneBlock - 1) / kDoneBlock;
     if (sh.io) {
         ready = static_cast<int*>(take(64));
-        group_count = static_cast<int*>(take(n_groups * sizeof(int)));
+        block_count = static_cast<int*>(take(n_blocks * sizeof(int)));
     }
     if (base) {
         D.models = models; D.state = state; D.h = h; D.F = F; D.K = K;
@@ -513,7 +514,7 @@ size_t carve(fb200_ensemble* e, const Shared& sh, char* base, size_t scratch_per
         e->F0_dev = F0; e->state0_dev = state0;
         e->ready_dev = ready;
         D.ready = ready;
-        D.group_count = group_count;
+        D.block_count = block_count;
     }
     return off + 256;
 }
@@ -595,7 +596,7 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
     D.n_groups = n_groups;
     D.group0 = e->group_begin[1];
     D.group = n_groups > 1 ? e->group_begin[2] - e->group_begin[1] : 0;  // the last group takes the remainder
-    D.group_done = nullptr;
+    D.block_done = nullptr;
 
     const size_t scratch_per_cta = kb.scratch_doubles_per_cta();
     const size_t need = carve(e, sh, nullptr, scratch_per_cta);
@@ -634,14 +635,15 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
         FB_TRYB(cudaMemsetAsync(e->ready_dev, 0, sizeof(int), e->copy_in));
         FB_TRYB(cudaEventRecord(B.slot_ev[0], e->copy_in));
         FB_TRYB(cudaStreamWaitEvent(e->stream, B.slot_ev[0], 0));
-        FB_TRYB(cudaMemsetAsync(D.group_count, 0, sizeof(int) * n_groups, e->stream));
-        e->pinned_block = pinned_acquire(sizeof(int) * n_groups);
+        const size_t n_blocks = (n + kDoneBlock - 1) / kDoneBlock;
+        FB_TRYB(cudaMemsetAsync(D.block_count, 0, sizeof(int) * n_blocks, e->stream));
+        e->pinned_block = pinned_acquire(sizeof(int) * n_blocks);
         if (!e->pinned_block) return fail(FB200_ERR_CUDA, "pinned host memory for the group flags could not be allocated");
-        e->group_done_host = static_cast<int*>(e->pinned_block);
-        std::memset(e->group_done_host, 0, sizeof(int) * n_groups);
+        e->block_done_host = static_cast<int*>(e->pinned_block);
+        std::memset(e->block_done_host, 0, sizeof(int) * n_blocks);
         void* dptr = nullptr;
-        FB_TRYB(cudaHostGetDevicePointer(&dptr, e->group_done_host, 0));
-        D.group_done = static_cast<int*>(dptr);
+        FB_TRYB(cudaHostGetDevicePointer(&dptr, e->block_done_host, 0));
+        D.block_done = static_cast<int*>(dptr);
     }
     return FB200_OK;
 }
@@ -725,28 +727,29 @@ void poll_uploads(DeviceBuild& B) {
     }
 }
 
-// rows of the groups [B.next_group, upto) -> the caller's buffer (models of this device are every gstride-th of the caller's)
-int send_groups(DeviceBuild& B, const Shared& sh, int upto) {
+// rows of the read-back blocks [B.next_block, upto) -> the caller's buffer, one copy for the whole run of blocks (models of this
+// device are every gstride-th of the caller's)
+int send_blocks(DeviceBuild& B, const Shared& sh, int upto) {
     fb200_ensemble* e = B.e;
+    if (upto <= B.next_block) return FB200_OK;
     const size_t row_bytes = size_t(e->n_rows) * e->n_cols * sizeof(double);
-    for (; B.next_group < upto; ++B.next_group) {
-        const size_t m0 = size_t(e->group_begin[B.next_group]), cnt = size_t(e->group_begin[B.next_group + 1]) - m0;
-        char* dst = reinterpret_cast<char*>(sh.io->rows) + (B.global0 + m0 * B.gstride) * row_bytes;
-        const char* src = reinterpret_cast<const char*>(e->dev.rows) + m0 * row_bytes;
-        if (B.gstride == 1) FB_TRYB(cudaMemcpyAsync(dst, src, cnt * row_bytes, cudaMemcpyDeviceToHost, e->copy_out));
-        else FB_TRYB(cudaMemcpy2DAsync(dst, B.gstride * row_bytes, src, row_bytes, row_bytes, cnt, cudaMemcpyDeviceToHost, e->copy_out));
-    }
+    const size_t m0 = size_t(B.next_block) * kDoneBlock, m1 = std::min(size_t(upto) * kDoneBlock, e->n), cnt = m1 - m0;
+    char* dst = reinterpret_cast<char*>(sh.io->rows) + (B.global0 + m0 * B.gstride) * row_bytes;
+    const char* src = reinterpret_cast<const char*>(e->dev.rows) + m0 * row_bytes;
+    if (B.gstride == 1) FB_TRYB(cudaMemcpyAsync(dst, src, cnt * row_bytes, cudaMemcpyDeviceToHost, e->copy_out));
+    else FB_TRYB(cudaMemcpy2DAsync(dst, B.gstride * row_bytes, src, row_bytes, row_bytes, cnt, cudaMemcpyDeviceToHost, e->copy_out));
+    B.next_block = upto;
     return FB200_OK;
 }
 
-int poll_groups(DeviceBuild& B, const Shared& sh) {
-    const volatile int* done = B.e->group_done_host;
-    int upto = B.next_group;
-    const int n_groups = int(B.e->group_begin.size()) - 1;
-    while (upto < n_groups && done[upto]) ++upto;
-    if (upto > B.next_group) {
+int poll_blocks(DeviceBuild& B, const Shared& sh) {
+    const volatile int* done = B.e->block_done_host;
+    int upto = B.next_block;
+    const int n_blocks = int((B.e->n + kDoneBlock - 1) / kDoneBlock);
+    while (upto < n_blocks && done[upto]) ++upto;
+    if (upto > B.next_block) {
         std::atomic_thread_fence(std::memory_order_acquire);
-        return send_groups(B, sh, upto);
+        return send_blocks(B, sh, upto);
     }
     return FB200_OK;
 }
@@ -779,7 +782,7 @@ int drive_device(DeviceBuild& B, Shared& sh) {
         while (B.chunk_left[c].load(std::memory_order_acquire) != 0) {
             if (sh.abort.load()) { aborted = true; break; }
             poll_uploads(B);
-            if (sh.io && cuda_rc(poll_groups(B, sh)) != FB200_OK) { aborted = true; break; }
+            if (sh.io && cuda_rc(poll_blocks(B, sh)) != FB200_OK) { aborted = true; break; }
             nap();
         }
         if (aborted) break;
@@ -814,12 +817,12 @@ int drive_device(DeviceBuild& B, Shared& sh) {
             sh.fail(B.rc, B.err, ~size_t(0));
             return B.rc;
         }
-        if (cuda_rc(poll_groups(B, sh)) != FB200_OK) return B.rc;
+        if (cuda_rc(poll_blocks(B, sh)) != FB200_OK) return B.rc;
         nap();
     }
-    if (dbg) fprintf(stderr, "[fb200] device %d: kernel done at %8.2f ms, %d of %d groups already sent\n", B.device, sh.ms(), B.next_group,
-                     int(e->group_begin.size()) - 1);
-    if (cuda_rc(send_groups(B, sh, int(e->group_begin.size()) - 1)) != FB200_OK) return B.rc;
+    if (dbg) fprintf(stderr, "[fb200] device %d: kernel done at %8.2f ms, %d of %d read-back blocks already sent\n", B.device, sh.ms(), B.next_block,
+                     int((e->n + kDoneBlock - 1) / kDoneBlock));
+    if (cuda_rc(send_blocks(B, sh, int((e->n + kDoneBlock - 1) / kDoneBlock))) != FB200_OK) return B.rc;
     {
         float ms = 0.f;
         FB_TRYB(cudaEventElapsedTime(&ms, e->ev0, e->ev1));

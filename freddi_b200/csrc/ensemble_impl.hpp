@@ -69,8 +69,8 @@ struct fb200_ensemble {
     // scheduling groups of a streamed sweep (one group otherwise)
     std::vector<int> group_begin;      // [n_groups + 1]
     int* ready_dev = nullptr;          // upload watermark (device)
-    int* group_done_host = nullptr;    // [n_groups] mapped pinned flags
-    void* pinned_block = nullptr;      // what group_done_host was cut from
+    int* block_done_host = nullptr;    // [ceil(n / kDoneBlock)] mapped pinned flags of the read-back blocks
+    void* pinned_block = nullptr;      // what block_done_host was cut from
 };
 
 namespace fb200 {

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
     // Item (r, m) needs item (r-1, m) finished: it was handed out earlier (the queue is ordered), to a CTA that is
     // resident (grid <= resident capacity) and never waits on a later item, so the wait below cannot deadlock.
     const int n_items = E.n_rounds * E.n_models;
-    __shared__ int s_abort, s_round, s_group;
+    __shared__ int s_abort, s_round;
     for (;;) {
         __syncthreads();  // previous item fully done with shared memory and s_model
         if (tid == 0) {
@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
             }
             s_model = model;
             s_round = round;
-            s_group = g;
         }
         __syncthreads();
         const int model = s_model;
@@ -194,15 +193,14 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         __syncthreads();
         if (tid == 0) {
             atomicExch(E.progress + model, round + 1);
-            if (E.group_count && round == E.n_rounds - 1) {
-                // last work item of the model: when it is the last one of its group, tell the host (the fence above ordered this
-                // CTA's rows before the count; the counts of the other CTAs were ordered the same way)
-                const int g = s_group;
-                const int start = g ? E.group0 + (g - 1) * E.group : 0;
-                const int size = (g == E.n_groups - 1) ? E.n_models - start : (g ? E.group : E.group0);
-                if (atomicAdd(E.group_count + g, 1) == size - 1) {
+            if (E.block_count && round == E.n_rounds - 1) {
+                // last work item of the model: when it is the last one of its read-back block, tell the host (the fence above
+                // ordered this CTA's rows before the count; the counts of the other CTAs were ordered the same way)
+                const int blk = model / kDoneBlock;
+                const int size = (E.n_models - blk * kDoneBlock < kDoneBlock) ? E.n_models - blk * kDoneBlock : kDoneBlock;
+                if (atomicAdd(E.block_count + blk, 1) == size - 1) {
                     __threadfence_system();
-                    *reinterpret_cast<volatile int*>(E.group_done + g) = 1;
+                    *reinterpret_cast<volatile int*>(E.block_done + blk) = 1;
                 }
             }
         }

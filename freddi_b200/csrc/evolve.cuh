@@ -6,6 +6,8 @@
 
 namespace fb200 {
 
+constexpr int kDoneBlock = 64;  // models per read-back block of a streamed sweep
+
 struct EnsembleDev {
     int n_models;
     int Nx;            // every model of an ensemble has the same Nx
@@ -44,11 +46,13 @@ struct EnsembleDev {
     // ready: number of leading models uploaded so far, written by the copy stream behind each group's arrays (-1: give up);
     //        the first work item of a model waits until its whole group is there.  Groups are multiples of 16 models, so that no
     //        128-byte line is shared by two uploads (a line fetched into L1 with a neighbour's tail would otherwise be stale).
-    // group_count[g]: models of group g whose last work item is finished; group_done[g] (host-mapped, pinned): set to 1 by the
-    //        CTA that finishes the last one — the host then reads the group's rows back while later groups still run.
+    // block_count[b]: models of read-back block b (kDoneBlock consecutive models) whose last work item is finished;
+    //        block_done[b] (host-mapped, pinned): set to 1 by the CTA that finishes the last one — the host then reads the block's
+    //        rows back while the kernel still runs (blocks finish roughly in order: in the last round of a group the work items
+    //        are handed out in model order), so that only the last block's copy is left when the kernel ends.
     const int* ready;
-    int* group_count;
-    int* group_done;
+    int* block_count;
+    int* block_done;
 };
 
 size_t evolve_smem_bytes();

@@ -121,12 +121,15 @@ void fb200_trim(void) { caches_trim(); }
 
 int fb200_host_alloc(size_t bytes, void** p) {
     if (!p) return set_err(FB200_ERR_INVALID_ARGUMENT, "null argument");
+    std::unique_lock<std::shared_mutex> no_open_window(g_upload_window);
     FB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
     return FB200_OK;
 }
 
 void fb200_host_free(void* p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    std::unique_lock<std::shared_mutex> no_open_window(g_upload_window);
+    cudaFreeHost(p);
 }
 
 size_t fb200_ensemble_n_models(const fb200_ensemble_t* e) { return e ? e->n : 0; }

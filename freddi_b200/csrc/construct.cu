@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <shared_mutex>
 #include <thread>
 
 #include "ensemble_impl.hpp"
@@ -179,6 +180,14 @@ void HostPool::run(unsigned n_workers, const std::function<void(unsigned)>& body
 }
 
 // ------------------------------------------------------------------------------------------------ caches
+// A streamed sweep launches its kernel before the models are uploaded: from the launch until its last upload is complete the
+// kernel depends on this process's host threads.  Driver calls that may wait for the device to go idle — page-locked host
+// allocation, growth of a memory pool, the frees of fb200_trim — issued by ANOTHER host thread in that window would keep the
+// uploads' driver calls waiting behind them while the kernel waits for the uploads (seen as 10 s work-item time-outs with two
+// sweeps at once).  So every streamed sweep holds this lock shared during its upload window (milliseconds), and the allocation
+// paths take it exclusively: an allocation waits for the open windows to close, never for a kernel that waits for it.
+std::shared_mutex g_upload_window;
+
 namespace {
 struct Block {
     void* p;
@@ -206,9 +215,12 @@ void* pinned_acquire(size_t bytes) {
             }
     }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
+    {
+        std::unique_lock<std::shared_mutex> no_open_window(g_upload_window);
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
     }
     std::lock_guard<std::mutex> g(g_cache_mutex);
     g_pinned.push_back(Block{p, want, true, -1});
@@ -260,6 +272,7 @@ int arena_acquire(int device, size_t bytes, cudaStream_t stream, void** p) {
     cudaMemPool_t pool;
     int rc = device_pool(device, &pool);
     if (rc != FB200_OK) return rc;
+    std::unique_lock<std::shared_mutex> no_open_window(g_upload_window);  // (the pool may have to grow)
     cudaError_t ce = cudaMallocFromPoolAsync(p, bytes, pool, stream);
     if (ce == cudaErrorMemoryAllocation) {  // give back what the pool holds idle and try once more
         cudaGetLastError();
@@ -277,6 +290,7 @@ void arena_release(void* p, cudaStream_t stream) {
 }
 
 void caches_trim() {
+    std::unique_lock<std::shared_mutex> no_open_window(g_upload_window);
     {
         std::lock_guard<std::mutex> g(g_pool_mutex);
         for (cudaMemPool_t pool : g_pools)
@@ -406,6 +420,7 @@ struct Shared {
     size_t n_total = 0;
     int n_dev = 0;
     std::atomic<bool> abort{false};
+    std::atomic<int> allocated{0};  // devices whose arena is in place (no upload window opens before all of them are: g_upload_window)
     std::mutex err_mutex;
     int err_code = FB200_OK;
     size_t err_model = ~size_t(0);
@@ -457,7 +472,6 @@ size_t carve(fb200_ensemble* e, const Shared& sh, char* base, size_t scratch_per
         return p;
     };
     const size_t n = e->n, NN = n * size_t(P.Nx) * sizeof(double);
-    const size_t n_groups = e->group_begin.size() - 1;
     // the streamed arrays first (uploads of different chunks never share a 128-byte line: chunk sizes are multiples of 16 models)
     auto* models = static_cast<fb200_model_dev_t*>(take(n * sizeof(fb200_model_dev_t)));
     auto* state = static_cast<ModelState*>(take(n * sizeof(ModelState)));
@@ -591,11 +605,6 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
         if (const char* c = getenv("FB200_WAIT_TIMEOUT_US")) D.wait_timeout_ns = 1000ll * atoll(c);  // test hook: forces the give-up path
         else D.wait_timeout_ns = ms * 1000000ll;
     }
-    // scheduling groups: the upload chunks for a streamed sweep, one group otherwise
-    const int n_groups = int(e->group_begin.size()) - 1;
-    D.n_groups = n_groups;
-    D.group0 = e->group_begin[1];
-    D.group = n_groups > 1 ? e->group_begin[2] - e->group_begin[1] : 0;  // the last group takes the remainder
     D.block_done = nullptr;
 
     const size_t scratch_per_cta = kb.scratch_doubles_per_cta();
@@ -758,17 +767,23 @@ void nap() { std::this_thread::sleep_for(std::chrono::microseconds(20)); }
 
 // the driver thread of one device
 int drive_device(DeviceBuild& B, Shared& sh) {
-    if (device_alloc(B, sh) != FB200_OK) {
+    const int alloc_rc = device_alloc(B, sh);
+    sh.allocated.fetch_add(1);
+    if (alloc_rc != FB200_OK) {
         sh.fail(B.rc, B.err, ~size_t(0));
         return B.rc;
     }
+    // every device of this call allocates before any of them opens its upload window (an allocation waits for open windows)
+    while (sh.allocated.load() < sh.n_dev && !sh.abort.load()) nap();
     fb200_ensemble* e = B.e;
     const int n_chunks = int(B.chunk_begin.size()) - 1;
     auto cuda_rc = [&](int rc) {
         if (rc != FB200_OK) sh.fail(B.rc, B.err, ~size_t(0));
         return rc;
     };
+    std::shared_lock<std::shared_mutex> upload_window(g_upload_window, std::defer_lock);
     if (sh.io) {
+        upload_window.lock();  // from the launch until the last upload is complete (see g_upload_window)
         if (ensemble_launch(e, -1) != FB200_OK) {
             B.rc = FB200_ERR_CUDA;
             B.err = fb_err_msg();
@@ -799,6 +814,7 @@ int drive_device(DeviceBuild& B, Shared& sh) {
         return FB200_ERR_RUNTIME;
     }
     FB_TRYB(cudaStreamSynchronize(e->copy_in));
+    if (upload_window.owns_lock()) upload_window.unlock();  // the kernel no longer depends on this process's host threads
     B.polled = B.enqueued;
     B.uploaded.store(n_chunks, std::memory_order_release);
     B.t_uploaded_ms = sh.ms();
@@ -976,7 +992,8 @@ int build_ensembles(const fb200_args_t* args, size_t n_models, const fb200_confi
     }
 
     // ---- per-device shares, chunks, staging ----
-    int group0 = 288, group = 576;  // 16-model multiples around one and two work items per resident CTA (2 x 148)
+    // upload chunks: 16-model multiples (EnsembleDev::ready); a small first one so that a streamed kernel gets to work early
+    int group0 = 288, group = 576;
     if (const char* c = getenv("FB200_GROUP0")) group0 = std::max(16, atoi(c) / 16 * 16);
     if (const char* c = getenv("FB200_GROUP")) group = std::max(16, atoi(c) / 16 * 16);
     std::vector<std::unique_ptr<DeviceBuild>> builds;
@@ -1011,8 +1028,6 @@ int build_ensembles(const fb200_args_t* args, size_t n_models, const fb200_confi
         e->n_cols = sh.P.n_cols;
         if (const char* c = getenv("FB200_CHUNK_STEPS")) e->chunk_steps = atoi(c) > 0 ? atoi(c) : 0x3fffffff;
         e->info.resize(e->n);
-        if (io) e->group_begin = B.chunk_begin;
-        else e->group_begin = std::vector<int>{0, int(e->n)};
     }
     auto cleanup = [&] {
         for (auto& b : builds) {

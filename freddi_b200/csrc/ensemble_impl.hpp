@@ -16,6 +16,8 @@
 #include <atomic>
 #include <functional>
 #include <memory>
+#include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -66,8 +68,6 @@ struct fb200_ensemble {
     // device copies of the initial conditions (fb200_ensemble_reset is a device-to-device copy); null for a one-shot sweep
     double* F0_dev = nullptr;
     fb200::ModelState* state0_dev = nullptr;
-    // scheduling groups of a streamed sweep (one group otherwise)
-    std::vector<int> group_begin;      // [n_groups + 1]
     int* ready_dev = nullptr;          // upload watermark (device)
     int* block_done_host = nullptr;    // [ceil(n / kDoneBlock)] mapped pinned flags of the read-back blocks
     void* pinned_block = nullptr;      // what block_done_host was cut from
@@ -114,6 +114,9 @@ void pinned_release(void* block);
 int arena_acquire(int device, size_t bytes, cudaStream_t stream, void** p);
 void arena_release(void* p, cudaStream_t stream);
 void caches_trim();                   // gives back what the pools and the pinned cache hold idle
+}  // namespace fb200
+namespace fb200 {
+extern std::shared_mutex g_upload_window;  // construct.cu: shared by streamed sweeps during their upload window, exclusive for allocations
 
 // Where a streamed sweep delivers its results (all host pointers; rows may be pageable, pinned is faster).
 struct SweepIO {

@@ -25,6 +25,10 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 
     // Work items are (round, model) pairs in round-major order: a model runs chunk_steps steps per item and goes
     // back to the queue, so that the tail of the launch is a fraction of a model's run instead of a whole one.
+    // (A streamed sweep keeps this order: the first round simply follows the uploads, which stay ahead of it — a round of
+    // 10^3 models is 6 ms of work for the GPU, their resolution and upload 1 ms for the host.  Numbering the items upload
+    // group by upload group instead made a group of fewer models than CTAs run its rounds in lock step: measured 1 ms lost
+    // per 10^3-model sweep.)
     // Item (r, m) needs item (r-1, m) finished: it was handed out earlier (the queue is ordered), to a CTA that is
     // resident (grid <= resident capacity) and never waits on a later item, so the wait below cannot deadlock.
     const int n_items = E.n_rounds * E.n_models;
@@ -33,38 +37,23 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
         __syncthreads();  // previous item fully done with shared memory and s_model
         if (tid == 0) {
             const int item = atomicAdd(E.queue, 1);
-            int model = -1, round = 0, g = 0;
+            int model = -1, round = 0;
             if (item < n_items) {
-                // item -> (group, round, model): groups in order, round-major inside a group
-                const int R = E.n_rounds;
-                int start = 0, size = E.n_models, rem = item;
-                if (E.n_groups > 1) {
-                    const int i0 = E.group0 * R;
-                    if (item < i0) {
-                        size = E.group0;
-                    } else {
-                        const int it = item - i0;
-                        g = 1 + it / (E.group * R);
-                        if (g > E.n_groups - 1) g = E.n_groups - 1;
-                        start = E.group0 + (g - 1) * E.group;
-                        size = (g == E.n_groups - 1) ? E.n_models - start : E.group;
-                        rem = it - (g - 1) * E.group * R;
-                    }
-                }
-                round = rem / size;
-                model = start + (rem - round * size);
+                round = item / E.n_models;
+                model = item - round * E.n_models;
                 s_abort = 0;
 #pragma unroll
                 for (int c = 0; c < FB_CNT_N; ++c) GpuEx::counters()[c] = 0;  // bookkeeping of this work item (GpuEx::count)
                 const unsigned long long t0 = fb_globaltimer();
                 if (round == 0 && E.ready) {
-                    // streamed construction: wait until the model's group has been uploaded (the host bumps `ready` on the copy
-                    // stream behind the group's arrays); -1 = the host gave up (an argument error in a later model)
+                    // streamed construction: wait until the model has been uploaded (the host bumps `ready`, the number of leading
+                    // models in HBM, on the copy stream behind each chunk's arrays); -1 = the host gave up (an argument error in a
+                    // later model)
                     const volatile int* rd = E.ready;
                     for (;;) {
                         const int have = *rd;
                         if (have < 0) { s_abort = 2; break; }
-                        if (have >= start + size) break;
+                        if (have > model) break;
                         __nanosleep(200);
                         if (fb_globaltimer() - t0 > (unsigned long long)E.wait_timeout_ns) {
                             atomicExch(E.failed + model, 1);

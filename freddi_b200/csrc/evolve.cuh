@@ -39,13 +39,11 @@ struct EnsembleDev {
     long long* prof;                  // [16] per-phase cycle sums (FB_PROFILE builds only), else null
     double* star_T;                   // [max_ctas][star_ntri_max] companion-star triangle temperatures (--starflux), else null
     int star_ntri_max;
-    // Scheduling groups.  Work items are numbered group by group, round-major inside a group: the first group holds `group0`
-    // models, the following ones `group` each, the last one the remainder.  One group of n_models models = plain round-major.
-    int n_groups, group0, group;
+    int _pad_star;
     // Streamed construction (fb200_sweep_run; null otherwise): the kernel is launched before the models are in HBM.
-    // ready: number of leading models uploaded so far, written by the copy stream behind each group's arrays (-1: give up);
-    //        the first work item of a model waits until its whole group is there.  Groups are multiples of 16 models, so that no
-    //        128-byte line is shared by two uploads (a line fetched into L1 with a neighbour's tail would otherwise be stale).
+    // ready: number of leading models uploaded so far, written by the copy stream behind each upload chunk's arrays (-1: give
+    //        up); the first work item of a model waits until it covers the model.  Chunks are multiples of 16 models, so that
+    //        no 128-byte line is shared by two uploads (a line fetched into L1 with a neighbour's tail would otherwise be stale).
     // block_count[b]: models of read-back block b (kDoneBlock consecutive models) whose last work item is finished;
     //        block_done[b] (host-mapped, pinned): set to 1 by the CTA that finishes the last one — the host then reads the block's
     //        rows back while the kernel still runs (blocks finish roughly in order: in the last round of a group the work items

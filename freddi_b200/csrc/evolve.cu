@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
                 }
             }
             int todo = eng.st.target_i_t - eng.st.i_t;
-            if (todo > E.chunk_steps) todo = E.chunk_steps;
+            const int chunk = (round < E.n_head) ? E.chunk_steps : E.tail_steps;
+            if (todo > chunk) todo = chunk;
             for (int s = 0; s < todo; ++s) {
                 const int r = eng.st.i_t + 1;
                 const bool ok = eng.step_and_row(rows + size_t(r) * ncol, Fsnap ? Fsnap + size_t(r) * Nx : nullptr,

@@ -33,6 +33,8 @@ struct EnsembleDev {
     long long wait_timeout_ns;        // how long a work item waits for the previous round of its model before giving up
     WindRecord* wind_rec;             // [n_models][n_rows] or null: arguments of the wind update() behind every row (dynamic winds)
     int chunk_steps;                  // steps per work item; a model is handed back to the queue after that many
+    int n_head, tail_steps;           // rounds >= n_head are short (tail_steps per work item): the last wave of the launch, in which
+                                      // most CTAs idle, then lasts half as long
     int n_rounds;                     // work items per model in this launch
     double* cta_scratch;              // [max_ctas][scratch_doubles_per_cta()] once-per-step arrays of the model a CTA holds
     int max_ctas;                     // CTAs the scratch was sized for (2 per SM)

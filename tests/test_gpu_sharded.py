@@ -232,3 +232,23 @@ def test_per_device_readouts_through_the_multi_gpu_handle():
             e.set_state(**st)
             e.evolve(-1)
         assert _same(many.rows(), one.rows()) and np.isnan(one.rows()[:, :4]).all() and np.isfinite(one.rows()[:, 4:, 0]).all()
+
+
+def test_streamed_sweep_with_passbands_star_and_cold_disk():
+    """The second instantiation of the kernel (passband / companion-star columns) and the star-geometry tables through the
+    streamed construction, over two shards: rows equal the plain ensemble's bit for bit."""
+    from freddi_b200 import Ensemble, sweep
+    from freddi_b200.ensemble import Passband
+    pb = Passband('box', np.linspace(4e-5, 6e-5, 40), np.linspace(4e-5, 6e-5, 40) * 1.0)
+    args = cm.config2_args(np.linspace(0.2, 0.9, 6), np.geomspace(1e-4, 1e-3, 4), time=3.0, Topt=4000, inclination=40, h2rcold=0.03)
+    for k, a in enumerate(args):  # two star geometries in one sweep
+        if k % 2:
+            a.Mopt = 0.8 * a.Mopt
+    kw = dict(lambdas=cm.LAM3[:2], cold_disk=True, passbands=[pb], star_flux=True)
+    with Ensemble(args, **kw) as ens:
+        ens.evolve(-1)
+        rows1, cols = ens.rows(), ens.columns
+    assert 'Fnubox_star_max' in cols and 'Fnu1_cold' in cols
+    for devs in ([0], [0, 0]):
+        res = sweep(args, devices=devs, **kw)
+        assert res.columns == cols and _same(res.rows, rows1), devs

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
 #pragma unroll
                 for (int c = 0; c < FB_CNT_N; ++c) GpuEx::counters()[c] = 0;  // bookkeeping of this work item (GpuEx::count)
                 const unsigned long long t0 = fb_globaltimer();
-                if (round == 0 && E.ready) {
+                if (E.ready && *reinterpret_cast<const volatile int*>(E.ready) < 0) s_abort = 2;  // the host withdrew the launch
+                if (round == 0 && E.ready && !s_abort) {
                     // streamed construction: wait until the model has been uploaded (the host bumps `ready`, the number of leading
                     // models in HBM, on the copy stream behind each chunk's arrays); -1 = the host gave up (an argument error in a
                     // later model)
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
                     }
                     __threadfence();
                 }
-                if (round > 0) {
+                if (round > 0 && !s_abort) {
                     // Wait for the producer of the previous round, by elapsed time (%globaltimer, ns).  A producer that never
                     // publishes (it can only be a CTA that died) must not hang the launch: after wait_timeout_ns the model is
                     // flagged in E.failed — a flag of its own, set with atomicExch: the state record belongs to the producer, which
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(kNT, kCtasPerSm) fb200_evolve_kernel(const Ens
                     const volatile int* f = E.failed + model;
                     while (*p < round) {
                         if (*f) { s_abort = 1; break; }
+                        if (E.ready && *reinterpret_cast<const volatile int*>(E.ready) < 0) { s_abort = 2; break; }  // withdrawn: its producer may have left
                         __nanosleep(100);
                         if (fb_globaltimer() - t0 > (unsigned long long)E.wait_timeout_ns) {
                             atomicExch(E.failed + model, 1);

@@ -135,12 +135,20 @@ def test_streamed_sweep_reports_a_bad_model_and_stays_usable():
     """An argument error in a late model surfaces as the reference's exception class with its index; the launch that was
     already waiting for uploads is withdrawn, and the library keeps working."""
     from freddi_b200 import sweep
-    args = list(_args(20, 20, time=2.5))
+    import time
+    args = list(_args(20, 20, time=50.0))  # 200 steps: work items of several rounds are in flight when the launch is withdrawn
     bad = 377
     args[bad].opacity = 99  # std::invalid_argument("Wrong opacity") in the reference's OpacityRelated constructor
+    t0 = time.perf_counter()
     with pytest.raises(ValueError) as ei:
         sweep(args, lambdas=cm.LAM3, devices=[0, 0])
     assert ei.value.bad_model == bad and 'opacity' in str(ei.value)
+    assert time.perf_counter() - t0 < 5., 'a withdrawn launch must not sit out the work-item time-outs'
+    args[bad].opacity = 0
+    args[3].opacity = 99  # ... and in the very first chunk, of one device only
+    with pytest.raises(ValueError) as ei:
+        sweep(args, lambdas=cm.LAM3, devices=[0])
+    assert ei.value.bad_model == 3
     good = _args(4, 3, time=2.5)
     rows1 = _single(good)[0]
     assert _same(sweep(good, lambdas=cm.LAM3, devices=[0]).rows, rows1)

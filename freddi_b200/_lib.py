@@ -18,7 +18,7 @@ MODEL_OK, MODEL_COLLAPSED, MODEL_FAILED = 0, 1, 2
 
 # every symbol include/freddi_b200.h declares
 SYMBOLS = (
-    'fb200_abi_version', 'fb200_last_error', 'fb200_device_count', 'fb200_measure_fp64_peak', 'fb200_ensemble_counters', 'fb200_args_default', 'fb200_config_default',
+    'fb200_abi_version', 'fb200_last_error', 'fb200_device_count', 'fb200_measure_fp64_peak', 'fb200_lx_table_selftest', 'fb200_ensemble_counters', 'fb200_args_default', 'fb200_config_default',
     'fb200_args_resolve', 'fb200_ensemble_create', 'fb200_ensemble_destroy', 'fb200_ensemble_n_models',
     'fb200_ensemble_n_cols', 'fb200_ensemble_n_rows', 'fb200_ensemble_nx', 'fb200_ensemble_info', 'fb200_ensemble_evolve',
     'fb200_ensemble_evolve_async', 'fb200_ensemble_reset', 'fb200_ensemble_sync', 'fb200_ensemble_last_evolve_ms', 'fb200_ensemble_last_launches',
@@ -65,6 +65,7 @@ def _load():
     lib.fb200_abi_version.restype = C.c_int
     lib.fb200_last_error.restype = C.c_char_p
     lib.fb200_device_count.restype = C.c_int
+    lib.fb200_lx_table_selftest.argtypes = [C.c_double] * 4 + [C.c_long, C.c_ulonglong, dp, C.POINTER(C.c_long), dp, C.POINTER(C.c_int)]
     lib.fb200_args_default.argtypes = [C.POINTER(FB200Args), C.c_int]
     lib.fb200_args_default.restype = None
     lib.fb200_config_default.argtypes = [C.POINTER(FB200Config)]

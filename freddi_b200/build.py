@@ -11,14 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 SOURCES = ['capi.cu', 'construct.cu', 'sharded.cu', 'evolve.cu', 'fields.cu', 'evolve_big.cu', 'fields_big.cu', 'evolve_s128.cu',
-           'fields_s128.cu', 'evolve_s256.cu', 'fields_s256.cu', 'evolve_s512.cu', 'fields_s512.cu', 'resolve.cpp', 'star.cpp']
-HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp', 'star.hpp', 'ensemble_impl.hpp',
+           'fields_s128.cu', 'evolve_s256.cu', 'fields_s256.cu', 'evolve_s512.cu', 'fields_s512.cu', 'resolve.cpp', 'star.cpp', 'lx_table.cpp']
+HEADERS = ['disc_engine.h', 'lx_table.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', 'resolve.hpp', 'star.hpp', 'ensemble_impl.hpp',
            os.path.join('..', '..', 'include', 'freddi_b200.h')]
 OUT = os.path.join(HERE, 'libfreddi_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC,-ffp-contract=off']
 # what a translation unit includes besides itself (a kernel build includes evolve.cu / fields.cu textually)
-KERNEL_HEADERS = ['disc_engine.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', os.path.join('..', '..', 'include', 'freddi_b200.h')]
+KERNEL_HEADERS = ['disc_engine.h', 'lx_table.h', 'fb200_math.h', 'fb200_model.h', 'evolve.cuh', 'gpu_exec.cuh', os.path.join('..', '..', 'include', 'freddi_b200.h')]
 
 
 def _deps(src):

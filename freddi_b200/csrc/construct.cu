@@ -415,6 +415,9 @@ struct Shared {
     std::vector<long long> star_off;            // per caller model
     std::vector<int> star_ntri;
     int star_ntri_max = 0;
+    const double* lx_table = nullptr;           // host blob of the band-integral table (lx_table.h), or nullptr: every ring walks
+    size_t lx_doubles = 0;
+    double lx_r = 0.;                           // its band ratio emax / emin
     bool keep_initial = false;
     SweepIO* io = nullptr;
     size_t n_total = 0;
@@ -500,6 +503,7 @@ size_t carve(fb200_ensemble* e, const Shared& sh, char* base, size_t scratch_per
         pb_w = static_cast<double*>(take(len * sizeof(double)));
     }
     auto* star_data = sh.star_table.empty() ? nullptr : static_cast<double*>(take(sh.star_table.size() * sizeof(double)));
+    auto* lx_table = sh.lx_table ? static_cast<double*>(take(sh.lx_doubles * sizeof(double))) : nullptr;
     double* Fsnap = nullptr;
     int* bounds = nullptr;
     if (sh.cfg.record_F) {
@@ -523,7 +527,7 @@ size_t carve(fb200_ensemble* e, const Shared& sh, char* base, size_t scratch_per
         D.wA = wA; D.wB = wB; D.wCs = wC; D.Fmagn = Fm; D.dFmagn_dh = dFm; D.d2Fmagn_dh2 = d2Fm;
         D.rows = rows; D.queue = queue; D.progress = progress; D.failed = failed; D.wind_rec = wind_rec;
         D.cta_scratch = cta_scratch; D.star_T = star_T; D.prof = prof;
-        D.cfg.pb_a = pb_a; D.cfg.pb_w = pb_w; D.cfg.star_data = star_data;
+        D.cfg.pb_a = pb_a; D.cfg.pb_w = pb_w; D.cfg.star_data = star_data; D.cfg.lx_table = lx_table;
         D.Fsnap = Fsnap; D.bounds = bounds;
         e->F0_dev = F0; e->state0_dev = state0;
         e->ready_dev = ready;
@@ -629,6 +633,8 @@ int device_alloc(DeviceBuild& B, Shared& sh) {
     }
     if (!sh.star_table.empty())
         FB_TRYB(cudaMemcpy(const_cast<double*>(D.cfg.star_data), sh.star_table.data(), sizeof(double) * sh.star_table.size(), cudaMemcpyHostToDevice));
+    if (sh.lx_table)  // 40-70 KB; the host blob lives as long as the process
+        FB_TRYB(cudaMemcpyAsync(const_cast<double*>(D.cfg.lx_table), sh.lx_table, sizeof(double) * sh.lx_doubles, cudaMemcpyHostToDevice, e->stream));
 
     const size_t n = e->n;
     FB_TRYB(cudaMemsetAsync(D.failed, 0, sizeof(int) * n, e->stream));
@@ -667,6 +673,7 @@ void pack_model(DeviceBuild& B, const Shared& sh, int chunk, size_t k /*index in
         r.dev.star_off = sh.star_off[global];
         r.dev.star_ntri = sh.star_ntri[global];
     }
+    r.dev.lx_tab = (sh.lx_table && fabs(r.dev.emax / r.dev.emin - sh.lx_r) <= 4e-16 * sh.lx_r) ? 1 : 0;
     reinterpret_cast<fb200_model_dev_t*>(slot + L.o_models)[k] = r.dev;
     ModelState& s = reinterpret_cast<ModelState*>(slot + L.o_state)[k];
     std::memset(&s, 0, sizeof(s));
@@ -968,6 +975,11 @@ int build_ensembles(const fb200_args_t* args, size_t n_models, const fb200_confi
     {
         const int rc = make_plan(args, n_models, cfg, sh.P, bad_model);
         if (rc != FB200_OK) return rc;
+    }
+    // the band-integral table of the first model's band (a sweep shares one band; models with another ratio walk)
+    if (cfg.compute_lx && !cfg.exact_lx_walk && args[0].emin > 0. && args[0].emax > args[0].emin) {
+        sh.lx_r = args[0].emax / args[0].emin;
+        sh.lx_table = lx_table_get(sh.lx_r, &sh.lx_doubles);
     }
     sh.keep_initial = keep_initial;
     sh.io = io;

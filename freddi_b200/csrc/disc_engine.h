@@ -25,6 +25,7 @@
 #define FB200_DISC_ENGINE_H
 
 #include "fb200_math.h"
+#include "lx_table.h"
 
 #ifndef __CUDACC__
 // host-only builds (tests/host_emu): the two CUDA vector helpers the engine uses
@@ -57,6 +58,9 @@ struct OutCfg {
     const double* star_data;
     int star_flux;
     int _pad;
+    // the band integral of the Planck function as a table in x1 = h nu1 / kT (lx_table.h), or nullptr: walk every ring.
+    // Valid for the models whose fb200_model_dev_t::lx_tab is set (their emax / emin is the table's band ratio).
+    const double* lx_table;
 };
 
 // Mutable per-model state carried between evolve calls (FreddiState::CurrentState, cpp/include/freddi_state.hpp:242-258)
@@ -253,6 +257,23 @@ FB_HD double planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* t
     if (!(T > 0.)) return 0.;
     const double hkT = FB_H_OVER_KB * fb_rcp(T);
     if (hkT * nu1 > 710.) return 0.;
+    return FB_DOUBLE_H_OVER_C2 * planck_walk(hkT, nu1, nu2, tol, trials);
+}
+
+// The same integral through the table of the walk's result (lx_table.h): nu1^4 q(x1) e^{-x1}, x1 = h nu1 / kT — one look-up,
+// one exponential and a degree-11 polynomial, <= 1e-12 from the walk, with the walk's own try_step count.  `tab` = nullptr, or
+// x1 outside the table: the walk.
+FB_HD double planck_nu1_nu2_tab(const double* __restrict__ tab, double T, double nu1, double nu2, double tol, int* trials) {
+    *trials = 0;
+    if (!(T > 0.)) return 0.;
+    const double hkT = FB_H_OVER_KB * fb_rcp(T);
+    const double x1 = hkT * nu1;
+    if (x1 > 710.) return 0.;
+    if (tab != nullptr && x1 >= FB_LX_X_LO && x1 < FB_LX_X_HI) {
+        const double q = lx_table_q(tab, x1, trials);
+        if (*trials >= 0) return (FB_DOUBLE_H_OVER_C2 * p4(nu1)) * (q * fb_exp_tab(-x1));
+        // a sliver around a breakpoint of the walk (a few 1e-9 wide; a ring lands in one about once in 1e8): walk
+    }
     return FB_DOUBLE_H_OVER_C2 * planck_walk(hkT, nu1, nu2, tol, trials);
 }
 
@@ -1107,6 +1128,7 @@ struct DiscEngine {
         double cold_K = 0.;
         const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
+        const double* lx_tab = M.lx_tab ? cfg.lx_table : nullptr;
         ex.reduce_sums(nq + 1, [&](int i, int k, int q) -> double {
             if (i >= Nx) return 0.;
             if (q == 1) S.aux[i] = 0.;
@@ -1125,7 +1147,7 @@ struct DiscEngine {
                     if (!cfg.compute_lx) return 0.;
                     int trials = 0;
                     const double T = S.TphX[i];
-                    y = (T < T_prune) ? 0. : planck_nu1_nu2(T, M.emin, M.emax, FB_KL(CK_TOL), &trials);
+                    y = (T < T_prune) ? 0. : planck_nu1_nu2_tab(lx_tab, T, M.emin, M.emax, FB_KL(CK_TOL), &trials);
                     S.aux[i] = double(trials);
                 } else {
                     y = planck_lambda_pref(S.Tph[i], cfg.lambdas[q - 2], ex.lambda_pref(q - 2));
@@ -1322,8 +1344,10 @@ struct DiscEngine {
             case FB200_NSCOL_LXNS:
             case FB200_NSCOL_FXNS: {  // ns_evolution.cpp:398-422
                 const double T = pow025(sc.Lbol_ns_rest / (area * FB_SIGMA_SB));
-                const double intensity =
-                    cfg.compute_lx ? planck_nu1_nu2(T, M.emin / M.redshift, M.emax / M.redshift, FB_KL(CK_TOL), nullptr) : NAN;
+                int trials;
+                const double intensity = cfg.compute_lx ? planck_nu1_nu2_tab(M.lx_tab ? cfg.lx_table : nullptr, T, M.emin / M.redshift,
+                                                                             M.emax / M.redshift, FB_KL(CK_TOL), &trials)
+                                                        : NAN;
                 const double Lx_ns = M.redshift * (area * FB_PI * intensity);
                 if (k == FB200_NSCOL_LXNS) return Lx_ns;
                 return Lx_ns * angular_dist(M.angdist_ns, M.cosi) / (4.0 * FB_PI * p2(M.distance));

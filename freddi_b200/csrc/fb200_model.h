@@ -43,7 +43,7 @@ typedef struct fb200_model_dev {
     int32_t wind_static;  /* 1: A/B/C arrays uploaded (static winds), 0: none */
     int32_t wind_dynamic; /* 1: C (or B) recomputed from Mdot_in every step */
     int32_t has_AB;       /* wind A or B can be non-zero (coefficients a,b,c0 then depend on the wind) */
-    int32_t _pad;
+    int32_t lx_tab;       /* 1: emax / emin is the band ratio of the ensemble's Lx table (OutCfg::lx_table, lx_table.h) */
     double tau, eps, t0;
     /* --- central object / geometry --- */
     double GM, Mx, kerr, eta, R_g, cosi, distance, cosiOverD2;

@@ -215,6 +215,16 @@ int fb200_device_count(void);       /* number of CUDA devices visible, <0 on dri
  * the FP64 pipe, not by HBM). */
 int fb200_measure_fp64_peak(int device, double* tflops);
 
+/* Self-test of the band-integral table (freddi_b200/csrc/lx_table.h): Lx sums, per ring, the integral of B_nu over [emin, emax]
+ * that the reference takes with an adaptive Cash-Karp walk (Spectrum::Planck_nu1_nu2, cpp/src/spectrum.cpp:26-37).  For a fixed
+ * band ratio that walk's result is a piecewise-analytic function of x1 = h nu1 / kT; the library tabulates it on first use and the
+ * kernels look it up.  This entry builds (or fetches) the table of the band [nu1, nu2] (Hz) and compares it on the host with the
+ * direct walk at `n` temperatures, log-uniform in x1 over [x_lo, x_hi]: the largest relative deviation, the number of points
+ * whose try_step count differs, the x1 of the largest deviation, the table's number of sub-pieces.  FB200_ERR_UNSUPPORTED when no
+ * table can be built for this ratio (the kernels then walk).  Needs no device. */
+int fb200_lx_table_selftest(double nu1, double nu2, double x_lo, double x_hi, long n, unsigned long long seed, double* max_rel_err,
+                            long* trials_mismatches, double* worst_x1, int* n_sub);
+
 /* Self-test: trapz(x, y, first, last) of the reference (cpp/src/util.cpp:9-19) evaluated by the CTA-wide weighted sum the
  * kernels use for every radial integral (Mdisk, Lx, Fnu, Mdot_wind), on caller data: 2 <= n <= 1024 host doubles.  The
  * reference's known answer (cpp/test/util.cpp:31-41) is asserted through this entry. */

@@ -79,6 +79,7 @@ struct HostEx {
 
 static long long g_last_lx_trials = 0;
 static std::vector<PassbandTable> g_passbands;  // set by emu_set_passbands for the runs that follow
+static int g_lx_table = 1;                       // emu_set_lx_table(0): every ring walks (as exact_lx_walk)
 static int g_star_flux = 0;                      // set by emu_set_star_flux for the runs that follow
 
 extern "C" {
@@ -116,6 +117,11 @@ int64_t emu_run(const fb200_args_t* a, const double* lambdas, int n_lambdas, int
     cfg.cold_disk = cold_disk;
     cfg.compute_lx = 1;
     cfg.lx_prune = 1;
+    if (g_lx_table) {  // as build_ensembles (construct.cu): the table of this model's band
+        size_t len = 0;
+        cfg.lx_table = lx_table_get(a->emax / a->emin, &len);
+        res.dev.lx_tab = cfg.lx_table ? 1 : 0;
+    }
     const int npb = int(g_passbands.size());
     std::vector<double> pb_a, pb_w;
     cfg.n_passbands = npb;
@@ -217,6 +223,7 @@ long emu_star_triangles(const fb200_args_t* a, double* out, long cap) {
 
 int emu_n_passbands() { return int(g_passbands.size()); }
 void emu_set_star_flux(int on) { g_star_flux = on; }
+void emu_set_lx_table(int on) { g_lx_table = on; }
 int emu_star_flux() { return g_star_flux; }
 
 long long emu_last_lx_trials() { return g_last_lx_trials; }

@@ -368,7 +368,7 @@ __device__ __forceinline__ const OutCfg& stage_cfg(const EnsembleDev& E) {
         c->n_lambdas = E.cfg.n_lambdas; c->cold_disk = E.cfg.cold_disk; c->compute_lx = E.cfg.compute_lx;
         c->record_F = E.cfg.record_F; c->n_cols = E.cfg.n_cols; c->n_rows = E.cfg.n_rows; c->lx_prune = E.cfg.lx_prune;
         c->n_passbands = E.cfg.n_passbands; c->pb_a = E.cfg.pb_a; c->pb_w = E.cfg.pb_w;
-        c->star_flux = E.cfg.star_flux; c->star_data = E.cfg.star_data;
+        c->star_flux = E.cfg.star_flux; c->star_data = E.cfg.star_data; c->lx_table = E.cfg.lx_table;
 #pragma unroll
         for (int k = 0; k < FB200_MAX_PASSBANDS + 2; ++k) c->pb_off[k] = E.cfg.pb_off[k];
 #pragma unroll

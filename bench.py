@@ -538,8 +538,9 @@ def run_gpu(opts):
                                    'row, S={:.2f} quadrature trial steps per ring and row — the trial steps the kernel executes: rings it prunes are '
                                    'not counted) x flop per call measured with ncu (profiles/sass_flop_weights.txt: pow {:.0f}, exp {:.0f}, log {:.0f}, '
                                    'div {:.0f}, sqrt {:.0f}).  The kernel reaches the same results with fewer operations (incremental K update: '
-                                   '{:.3f} pow per ring and iteration instead of 2), so this fraction is NOT pipe utilisation: see `executed` and '
-                                   '`fp64_pipe_active`.'.format(n_solve, P, counters_all['row_rings'] / rows_all, S, W_POW, W_EXP, W_LOG, W_DIV, W_SQRT,
+                                   '{:.3f} pow per ring and iteration instead of 2; the band integral of Lx read from a table of the adaptive walk\'s own '
+                                   'result, csrc/lx_table.h, instead of S trial steps per ring), so this fraction is NOT pipe utilisation: see '
+                                   '`executed` and `fp64_pipe_active`.'.format(n_solve, P, counters_all['row_rings'] / rows_all, S, W_POW, W_EXP, W_LOG, W_DIV, W_SQRT,
                                                                 counters_all['pow_evals'] / max(1., counters_all['ring_iters'])),
                         flops_per_model_step=fl, executed=executed, fp64_pipe_active=ncu.get('fp64_pipe_active_pct'),
                         issue_active=ncu.get('issue_active_pct'),

@@ -145,8 +145,10 @@ typedef struct fb200_config {
     int32_t host_threads;   /* threads for host-side argument resolution, 0 = all cores                   */
     int32_t threads_per_model; /* reserved (the CTA size is a build-time constant)                       */
     int32_t exact_lx_walk;  /* 0 (default): rings whose X-ray band emission is provably negligible against the
-                             * hottest ring's are not integrated (changes Lx by < 1e-16 relative, bound per row);
-                             * 1: integrate every ring like the reference does                              */
+                             * hottest ring's are not integrated (changes Lx by < 1e-16 relative, bound per row),
+                             * and a ring's band integral is read from the table of the adaptive walk's own result
+                             * (csrc/lx_table.h: the walk is a function of h emin / kT alone; <= 2e-12 per ring);
+                             * 1: walk every ring like the reference does (Spectrum::Planck_nu1_nu2)            */
     /* Tabulated passbands, FluxArguments::passbands (cpp/include/arguments.hpp:287): one Fnu<name> column each
      * (+ Fnu<name>_cold with cold_disk) after the Fnu{k} columns, cpp/src/output.cpp:258-271.  The arrays are what
      * EnergyPassband holds (cpp/include/passband.hpp:33-36): wavelengths [cm] and transmission factors, for the

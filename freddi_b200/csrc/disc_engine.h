@@ -754,7 +754,7 @@ struct DiscEngine {
 
         ex.tick(0);
         int iters = 0;
-        double maxrel;
+        bool exceeds;  // max_dif_rel(K1, K0) > eps: the loop needs the comparison only, so the CTA reduces the predicate, not the maximum
         do {
             // -- block elimination: every block thread reduces its <= 8 rows to two rows in (x_0, x_last) --
             ex.blocks(nblk, [&](int b) {
@@ -938,10 +938,10 @@ struct DiscEngine {
                     });
                     ex.note_pow_fallbacks(nbad);
                 }
-                maxrel = ex.reduce_max_of(vmax);
+                exceeds = ex.any_of(vmax > M.eps);  // vmax is never NaN (fmax skipped them, as `x > max` does in max_dif_rel)
             } else {
                 ex.count(FB_CNT_POW_EVALS, m - 1);
-                maxrel = ex.reduce_max([&](int i, int k) -> double {
+                const double maxrel = ex.reduce_max([&](int i, int k) -> double {
                     if (i == first) S.F[i] = F_in;
                     if (!(i > first && i <= last)) return 0.;
                     const int un = i - first - 1, b = un / FB200_BLK, j = un - b * FB200_BLK;
@@ -960,11 +960,12 @@ struct DiscEngine {
                     S.s_d[pi] = S.s_cc[i] + K1;
                     return fabs((K1 - K0) * fb_rcp(fabs(K1)));  // only compared with eps; a NaN is skipped by the reduction
                 });
+                exceeds = maxrel > M.eps;
             }
             ex.tick(2);
             ++iters;
             if (iters >= 100000) return -1;
-        } while (maxrel > M.eps);
+        } while (exceeds);
         ex.sync();
         k_valid = true;
         ex.count(FB_CNT_RING_STEPS, m);
@@ -1120,7 +1121,7 @@ struct DiscEngine {
 
         // ---- radial trapezoids (util.cpp:9-41): Mdisk, Lx, Fnu[k] (hot), Fnu[k] (cold) ----
         // slots: 0 Mdisk, 1 Lx, [2, 2+nl) Fnu hot, [2+nl, 2+2nl) Fnu cold, [q_pb, q_pb+npb) passbands hot,
-        //        [q_pb+npb, q_pb+2npb) passbands cold, nq: Lx trial count
+        //        [q_pb+npb, q_pb+2npb) passbands cold
         const int nl = cfg.n_lambdas, npb = kExtras ? cfg.n_passbands : 0;
         const int per = cfg.cold_disk ? 2 : 1;
         const int q_pb = 2 + nl * per;
@@ -1129,10 +1130,9 @@ struct DiscEngine {
         const double cold_mu = M.h2rcold;  // Height/R of the cold zone, freddi_state.cpp:271-273
         if (cfg.cold_disk) cold_K = M.Cirr_cold * ((M.irrindex_cold == 0.) ? 1.0 : pow((M.h2rcold * 1.0) / (1.0 * 0.05), M.irrindex_cold));
         const double* lx_tab = M.lx_tab ? cfg.lx_table : nullptr;
-        ex.reduce_sums(nq + 1, [&](int i, int k, int q) -> double {
+        int my_trials = 0;  // try_step calls of this thread's rings (roofline bookkeeping): summed by ex.note_lx_trials, not by a reduction pass
+        ex.reduce_sums(nq, [&](int i, int k, int q) -> double {
             if (i >= Nx) return 0.;
-            if (q == 1) S.aux[i] = 0.;
-            if (q == nq) return S.aux[i];  // this point's Lx trial-step count, parked by q == 1
             const bool hot_pb = (q >= q_pb && q < q_pb + npb);
             if (q < 2 + nl || hot_pb) {  // hot zone [first, last]: weights prepared above (0 outside)
                 const double wq = S.wq[i];
@@ -1148,7 +1148,7 @@ struct DiscEngine {
                     int trials = 0;
                     const double T = S.TphX[i];
                     y = (T < T_prune) ? 0. : planck_nu1_nu2_tab(lx_tab, T, M.emin, M.emax, FB_KL(CK_TOL), &trials);
-                    S.aux[i] = double(trials);
+                    my_trials += trials;
                 } else {
                     y = planck_lambda_pref(S.Tph[i], cfg.lambdas[q - 2], ex.lambda_pref(q - 2));
                 }
@@ -1178,7 +1178,7 @@ struct DiscEngine {
         });
         ex.tick(4);
         // ---- the row (output.cpp:197-233, ns_output.cpp:6-19) ----
-        ex.count(FB_CNT_LX_TRIALS, (long long)(ex.sum(nq) + 0.5));
+        ex.note_lx_trials(my_trials);
         ex.count(FB_CNT_ROW_RINGS, last - first + 1);
         const double Mdisk = 0.5 * ex.sum(0);
         const double Lx = cfg.compute_lx ? (2. * FB_PI * (0.5 * ex.sum(1))) / p4(M.colourfactor) : NAN;

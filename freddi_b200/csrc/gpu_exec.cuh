@@ -246,6 +246,15 @@ struct GpuEx {
         if (((FB_COUNT_MASK) >> FB_CNT_POW_FALLBACKS) & 1)
             if (n) atomicAdd(reinterpret_cast<int*>(counters() + FB_CNT_POW_FALLBACKS), n);
     }
+    // per-thread counts of the Lx quadrature's try_step calls: one REDUX per warp and a 32-bit shared-memory atomic (< 2^31 per work item)
+    __device__ __forceinline__ void note_lx_trials(int n) {
+        if (((FB_COUNT_MASK) >> FB_CNT_LX_TRIALS) & 1) {
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (lane == 0 && n) atomicAdd(reinterpret_cast<int*>(counters() + FB_CNT_LX_TRIALS), n);
+        }
+    }
+    // CTA-wide OR of a predicate; a full barrier like sync()
+    __device__ __forceinline__ bool any_of(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
     __device__ __forceinline__ static WindRecord& wind_update() { return *reinterpret_cast<WindRecord*>(fb_smem + L::o_count + FB_CNT_N); }
     __device__ __forceinline__ void note_wind_update(double Mdot, int first, int last) {
         if (tid == 0) wind_update() = WindRecord{Mdot, first, last};

@@ -43,6 +43,8 @@ struct HostEx {
     long long counters[FB_CNT_N] = {0};
     void count(int c, long long v) { counters[c] += v; }
     void note_pow_fallbacks(int n) { counters[FB_CNT_POW_FALLBACKS] += n; }
+    void note_lx_trials(int n) { counters[FB_CNT_LX_TRIALS] += n; }
+    bool any_of(bool p) const { return p; }  // the sequential policy accumulated the predicate's operand over all points already
     WindRecord wind{0., 1, 0};
     void note_wind_update(double Mdot, int first, int last) { wind = WindRecord{Mdot, first, last}; }
     double sum(int q) const { return sums[q]; }

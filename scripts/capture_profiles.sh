@@ -4,7 +4,7 @@
 tag=${1:-vX}
 out=gpurun_out
 mkdir -p $out
-timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_tests.log 2>&1; tail -2 $out/${tag}_tests.log
+if [ -z "$SKIP_TESTS" ]; then timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_tests.log 2>&1; tail -2 $out/${tag}_tests.log; fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log
 timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 400 $out/${tag}_bench.json
 timeout 900 python bench.py --impl reference > $out/${tag}_bench_reference.json 2>> $out/${tag}_bench.err; tail -c 300 $out/${tag}_bench_reference.json
@@ -15,3 +15,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fb20
 ls -la $out/${tag}_full.ncu-rep
 FB200_LIB=$PWD/build/prof_default.so timeout 300 python scripts/phase_profile.py > $out/${tag}_phase_cycles.txt 2>&1; cat $out/${tag}_phase_cycles.txt
 timeout 600 python scripts/bench_configs.py > $out/${tag}_other_configs.jsonl 2>&1; tail -5 $out/${tag}_other_configs.jsonl
+if [ -n "$SMALL_NX" ]; then timeout 600 python scripts/small_nx_bench.py > $out/${tag}_small_nx.jsonl 2>&1; tail -12 $out/${tag}_small_nx.jsonl; fi

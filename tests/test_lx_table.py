@@ -113,3 +113,23 @@ def test_neutron_star_hot_spot_through_the_table():
         for c in ('Lx', 'Fx', 'Lxns', 'Fxns'):
             i = cols.index(c)
             assert cm.rel_err(tab[k, :v, i], walk[k, :v, i]).max() <= 5e-12, (k, c)
+
+
+@pytest.mark.gpu
+def test_a_model_with_another_band_walks():
+    """One table per ensemble (the first model's band ratio): a model with another emax / emin in the same ensemble is walked ring by
+    ring (pruned rings aside), so its Lx equals the exact walk's far below the fit tolerance; the first model goes through the table."""
+    from freddi_b200 import Ensemble
+    args = cm.config2_args([0.4], [1e-3]) + cm.config2_args([0.4], [1e-3], emax=10)
+    with Ensemble(args, lambdas=cm.LAM3) as ens:
+        ens.evolve(-1)
+        mixed, valid, cols = ens.rows(), ens.status()[1], ens.columns
+    with Ensemble(args, lambdas=cm.LAM3, exact_lx_walk=True) as ens:
+        ens.evolve(-1)
+        walk = ens.rows()
+    i = cols.index('Lx')
+    e_tab = cm.rel_err(mixed[0, :valid[0], i], walk[0, :valid[0], i]).max()
+    e_walk = cm.rel_err(mixed[1, :valid[1], i], walk[1, :valid[1], i]).max()
+    assert 1e-14 < e_tab <= 5e-12, e_tab   # table
+    assert e_walk <= 1e-14, e_walk         # walked: only the pruning differs
+    assert not np.array_equal(mixed[0, :, i], mixed[1, :, i])

@@ -11,13 +11,15 @@
 //
 // J is piecewise analytic in x1: it jumps (by ~1e-6 relative) where a controller decision flips, i.e. where one step's error
 // ratio crosses 1 (accept / reject) or 0.5 (grow or not), has a kink where it crosses 5^-5 or 91.125 (the clamps of the step
-// factor), and where the last step's clipping changes.  lx_table.cpp locates these breakpoints down to adjacent doubles,
-// and fits q(x1) = J(x1) e^{x1} on every piece (split further where needed) by a degree-11 polynomial to <= 2e-12 relative
-// — six orders below the walk's own quadrature error, two below the 1e-10 parity tolerance.  A ring then costs one table
-// look-up, one exponential and 11 FMAs instead of ~5.5 trial steps of ~100 FP64 instructions; rings outside the table's range
-// (x1 < 2^-5 or >= 2^8), models whose band ratio is not the table's, and ensembles created with exact_lx_walk walk as before.
-// The look-up reproduces the walk of THIS library (planck_walk, disc_engine.h), whose decisions agree with odeint's except
-// within ~1e-14 relative of a breakpoint — the same set the direct walk cannot decide either.
+// factor), and where the last step's clipping changes.  lx_table.cpp locates these breakpoints down to slivers of 2e-9 relative
+// (an error ratio carries ~1e-10 of rounding noise: closer to a threshold the decisions alternate from one double to the next, in
+// the reference as in any restatement) and fits q(x1) = J(x1) e^{x1} on every piece in between (split further where needed) by a
+// degree-11 polynomial to <= 2e-12 relative — six orders below the walk's own quadrature error, two below the 1e-10 parity
+// tolerance.  A ring then costs one table look-up, one exponential and 11 FMAs instead of ~5.5 trial steps of ~100 FP64
+// instructions.  Rings in a sliver (about one in 1e8) or in a sub-piece that could not be fitted (flagged trials = -1), rings
+// outside the table's range (x1 < 2^-5 or >= 2^8), models whose band ratio is not the table's, and ensembles created with
+// exact_lx_walk walk as before.  The look-up reproduces the walk of THIS library (planck_walk, disc_engine.h), whose decisions
+// agree with odeint's except within rounding of a threshold — the set no restatement can decide.
 #ifndef FB200_LX_TABLE_H
 #define FB200_LX_TABLE_H
 
@@ -29,12 +31,13 @@
 namespace fb200 {
 
 // Blob layout, in doubles (the blob is 128-byte aligned):
-//   [0] r = nu2 / nu1   [1] number of sub-pieces   [2] eps_rel   [3] fit tolerance reached   [4..7] reserved
+//   [0] r = nu2 / nu1   [1] number of sub-pieces   [2] eps_rel   [3] largest fit error   [4] breakpoints   [5] walked sub-pieces
+//   [6] their ln-width   [7] reserved
 //   [FB_LX_O_CELL ...)  one int2 per cell: (first, last) sub-piece overlapping the cell.  A cell is 1/64 of an octave of x1:
 //                       its index is the top 18 bits of the double (sign, exponent, 6 mantissa bits) minus that of 2^-5.
 //   [FB_LX_O_EDGE ...)  edges[k] = the first double of sub-piece k (edges[n_sub] = 2^8)
 //   [FB_LX_O_REC ...)   16 doubles per sub-piece: mid, 1 / half-width, a_0 .. a_11 (q = sum a_j u^j, u = (x1 - mid) / half-width),
-//                       the walk's try_step count on this piece, unused
+//                       the walk's try_step count on this piece (-1: not fitted, the kernels walk), unused
 #define FB_LX_DEG 11
 #define FB_LX_CELLS (13 * 64)
 #define FB_LX_MAX_SUB 2047

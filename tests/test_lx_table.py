@@ -133,3 +133,20 @@ def test_a_model_with_another_band_walks():
     assert 1e-14 < e_tab <= 5e-12, e_tab   # table
     assert e_walk <= 1e-14, e_walk         # walked: only the pruning differs
     assert not np.array_equal(mixed[0, :, i], mixed[1, :, i])
+
+
+def test_random_band_ratios_never_return_a_wrong_piece():
+    """Whatever the band ratio, a table that builds agrees with the walk to the fit tolerance at every sampled temperature (a look-up
+    on a wrong piece would be off by the quadrature error, ~1e-6); a ratio without a tidy piece structure gets no table at all.
+    (The try_step counts may differ by the walk's closing step: t + (nu2 - t) can miss nu2 by an ulp, a step that adds nothing.)"""
+    rng = np.random.default_rng(7)
+    built = 0
+    for r in np.exp(rng.uniform(np.log(1.05), np.log(300.), 12)):
+        err, mism, wx, nsub = C.c_double(), C.c_long(), C.c_double(), C.c_int()
+        nu1 = 2.4e17
+        rc = _lib.lib.fb200_lx_table_selftest(nu1, nu1 * r, 2.0 ** -5, 256.0, 20000, 3, C.byref(err), C.byref(mism), C.byref(wx), C.byref(nsub))
+        assert rc in (0, _lib.ERR_UNSUPPORTED), (r, rc)
+        if rc == 0:
+            built += 1
+            assert err.value <= 2e-11, (r, err.value, wx.value)
+    assert built >= 8

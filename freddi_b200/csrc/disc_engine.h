@@ -613,6 +613,18 @@ struct DiscEngine {
 
     // storage position of reduced unknown q (see solve_step)
     FB_HD static int rpos(int q) { return Ex::kWarpPcr ? ((q & 7) * 32 + (q >> 3)) : q; }
+#ifndef FB_PCR_FULL
+    // Odd-only reduced solve (solve_step): where block b's two reduced rows are stored in buffer 0.  Plain policies: q = 2b (the
+    // row of the block's first unknown, "even") and 2b + 1 ("odd").  Hybrid (warp) solver: the odd rows in the lower half of the
+    // buffer in the warp-major order of its four warps (unknown p = warp + 4 lane at position 32 warp + lane), the even rows
+    // likewise in the upper half.
+    FB_HD static int ppos(int b) { return (b & 3) * 32 + (b >> 2); }
+    FB_HD static int epos(int b) { return Ex::kWarpPcr ? FB200_NRED_MAX / 2 + ppos(b) : 2 * b; }
+    FB_HD static int opos(int b) { return Ex::kWarpPcr ? ppos(b) : 2 * b + 1; }
+#else
+    FB_HD static int epos(int b) { return rpos(2 * b); }
+    FB_HD static int opos(int b) { return rpos(2 * b + 1); }
+#endif
 
     // nonlinear_diffusion.cpp:46-51 for an interior point i (1 <= i <= Nx-2), wind terms A, B
     FB_HD void interior_coeffs(int i, double A, double B) const {
@@ -803,15 +815,140 @@ struct DiscEngine {
                 }
                 const double inv0 = fb_rcp(D0), inv1 = fb_rcp(D1);
                 // reduced row q is stored at rpos(q): the identity, or the warp-major order of the hybrid solver below
-                S.lu[0][rpos(2 * b)] = make_double2(L0 * inv0, U0 * inv0);
-                S.rr[0][rpos(2 * b)] = R0 * inv0;
-                S.lu[0][rpos(2 * b + 1)] = make_double2(L1 * inv1, U1 * inv1);
-                S.rr[0][rpos(2 * b + 1)] = R1 * inv1;
+                S.lu[0][epos(b)] = make_double2(L0 * inv0, U0 * inv0);
+                S.rr[0][epos(b)] = R0 * inv0;
+                S.lu[0][opos(b)] = make_double2(L1 * inv1, U1 * inv1);
+                S.rr[0][opos(b)] = R1 * inv1;
             });
             ex.sync();
             ex.tick(8);
             // -- reduced system (nred unknowns): parallel cyclic reduction, diagonal normalised to 1 --
             int cur = 0;
+#ifndef FB_PCR_FULL
+            // After the first level of a cyclic reduction the even and the odd unknowns form two independent systems, and a full
+            // PCR solves both.  Only the odd one (the last unknown of every block, o_b) is solved here — level for level the
+            // arithmetic a full PCR applies to its odd rows — and the even unknowns (the first of every block, e_b) follow from
+            // their own level-0 rows:  e_b = r_b - l_b o_{b-1} - u_b o_b.  Half the rows at every level: half the warps.
+            if constexpr (Ex::kWarpPcr) {
+                // Hybrid over four warps: thread t < 128 owns o_p, p = warp + 4 lane.  The first level takes its three level-0
+                // rows from buffer 0 (opos / epos); the strides 1, 2 (in p) couple different warps and go through shared memory;
+                // after them the couplings are at distance 4 = the neighbouring LANE, and strides 4 .. 64 are warp shuffles.
+                // Five barriers per Picard iteration, all of them reached by every thread.
+                constexpr int H = FB200_NRED_MAX / 2;
+                const int t = ex.thread(), lane = t & 31;
+                const int p = (t >> 5) + 4 * lane;
+                const bool mine = t < H && p < nblk;
+                double lo = 0., up = 0., r = 0.;
+                if (t < H) {
+                    if (mine) {
+                        const double2 me = S.lu[0][t], a = S.lu[0][H + t];
+                        const double rme = S.rr[0][t], ra = S.rr[0][H + t];
+                        double2 b = make_double2(0., 0.);
+                        double rb = 0.;
+                        if (p + 1 < nblk) { b = S.lu[0][epos(p + 1)]; rb = S.rr[0][epos(p + 1)]; }
+                        const double inv = fb_rcp(1.0 - me.x * a.y - me.y * b.x);
+                        lo = -me.x * a.x * inv; up = -me.y * b.y * inv; r = (rme - me.x * ra - me.y * rb) * inv;
+                    }
+                    S.lu[1][t] = make_double2(lo, up);
+                    S.rr[1][t] = r;
+                }
+                ex.sync();
+                if (t < H) {
+                    if (mine) {  // stride 1
+                        double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
+                        double ra = 0., rb = 0.;
+                        if (p - 1 >= 0) { a = S.lu[1][ppos(p - 1)]; ra = S.rr[1][ppos(p - 1)]; }
+                        if (p + 1 < nblk) { b = S.lu[1][ppos(p + 1)]; rb = S.rr[1][ppos(p + 1)]; }
+                        const double inv = fb_rcp(1.0 - lo * a.y - up * b.x);
+                        const double nlo = -lo * a.x * inv, nup = -up * b.y * inv;
+                        r = (r - lo * ra - up * rb) * inv;
+                        lo = nlo; up = nup;
+                    }
+                    // the odd level-0 rows in the lower half of buffer 0 are dead (read before the barrier above)
+                    S.lu[0][t] = make_double2(lo, up);
+                    S.rr[0][t] = r;
+                }
+                ex.sync();
+                ex.tick(9);
+                if (t < H) {
+                    if (mine) {  // stride 2; the result stays in registers
+                        double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
+                        double ra = 0., rb = 0.;
+                        if (p - 2 >= 0) { a = S.lu[0][ppos(p - 2)]; ra = S.rr[0][ppos(p - 2)]; }
+                        if (p + 2 < nblk) { b = S.lu[0][ppos(p + 2)]; rb = S.rr[0][ppos(p + 2)]; }
+                        const double inv = fb_rcp(1.0 - lo * a.y - up * b.x);
+                        const double nlo = -lo * a.x * inv, nup = -up * b.y * inv;
+                        r = (r - lo * ra - up * rb) * inv;
+                        lo = nlo; up = nup;
+                    }
+                    // No selects on the neighbours' values in the shuffle levels: a row without a lower (upper) neighbour at the
+                    // current stride has lo (up) == +-0 exactly — the guards of the levels above made it a product with 0, and
+                    // every later level multiplies it on — so whatever finite value the shuffle delivers (the lane's own one at the
+                    // warp's edge, the zeros of a padding row) drops out as 0 * finite.  Padding rows (p >= nblk) hold 0 / 0 / 0.
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double a_x = ex.shfl_up(lo, d), a_y = ex.shfl_up(up, d), ra = ex.shfl_up(r, d);
+                        const double b_x = ex.shfl_down(lo, d), b_y = ex.shfl_down(up, d), rb = ex.shfl_down(r, d);
+                        const double inv = fb_rcp(1.0 - lo * a_y - up * b_x);
+                        const double nlo = -lo * a_x * inv, nup = -up * b_y * inv;
+                        r = (r - lo * ra - up * rb) * inv;
+                        lo = nlo; up = nup;
+                    }
+                    // o_p into the final layout z[2 p + 1] (buffer 1: last read before the previous barrier)
+                    if (mine) S.rr[1][2 * p + 1] = r;
+                }
+                ex.sync();
+                if (mine) {  // e_p from its level-0 row (upper half of buffer 0, untouched since the block elimination)
+                    const double2 e = S.lu[0][H + t];
+                    const double om = (p > 0) ? S.rr[1][2 * p - 1] : 0.;
+                    S.rr[1][2 * p] = S.rr[0][H + t] - e.x * om - e.y * r;
+                }
+                ex.sync();
+                cur = 1;
+            } else {
+                constexpr int H = FB200_NRED_MAX / 2;
+                // first level, odd rows only: row 2 p + 1 with its neighbours 2 p and 2 p + 2, into the lower half of buffer 1
+                ex.reduced(nblk, [&](int p) {
+                    const int q = 2 * p + 1;
+                    const double2 me = S.lu[0][q], a = S.lu[0][q - 1];
+                    const double rme = S.rr[0][q], ra = S.rr[0][q - 1];
+                    double2 b = make_double2(0., 0.);
+                    double rb = 0.;
+                    if (q + 1 < nred) { b = S.lu[0][q + 1]; rb = S.rr[0][q + 1]; }
+                    const double inv = fb_rcp(1.0 - me.x * a.y - me.y * b.x);
+                    S.lu[1][p] = make_double2(-me.x * a.x * inv, -me.y * b.y * inv);
+                    S.rr[1][p] = (rme - me.x * ra - me.y * rb) * inv;
+                });
+                ex.sync();
+                // PCR of the nblk odd unknowns, ping-pong between the two halves of buffer 1 (buffer 0 keeps the even rows)
+                int off = 0;
+                for (int s = 1; s < nblk; s <<= 1) {
+                    ex.reduced(nblk, [&](int p) {
+                        const double2 me = S.lu[1][off + p];
+                        const double rme = S.rr[1][off + p];
+                        const int pm = p - s, pp = p + s;
+                        double2 a = make_double2(0., 0.), b = make_double2(0., 0.);
+                        double ra = 0., rb = 0.;
+                        if (pm >= 0) { a = S.lu[1][off + pm]; ra = S.rr[1][off + pm]; }
+                        if (pp < nblk) { b = S.lu[1][off + pp]; rb = S.rr[1][off + pp]; }
+                        const double inv = fb_rcp(1.0 - me.x * a.y - me.y * b.x);
+                        S.lu[1][(off ^ H) + p] = make_double2(-me.x * a.x * inv, -me.y * b.y * inv);
+                        S.rr[1][(off ^ H) + p] = (rme - me.x * ra - me.y * rb) * inv;
+                    });
+                    ex.sync();
+                    off ^= H;
+                }
+                // z[2 p + 1] = o_p, z[2 p] = e_p, in buffer 0 (a thread overwrites the two level-0 right-hand sides of its own block only)
+                ex.reduced(nblk, [&](int p) {
+                    const double op = S.rr[1][off + p];
+                    const double om = (p > 0) ? S.rr[1][off + p - 1] : 0.;
+                    const double2 e = S.lu[0][2 * p];
+                    S.rr[0][2 * p] = S.rr[0][2 * p] - e.x * om - e.y * op;
+                    S.rr[0][2 * p + 1] = op;
+                });
+                ex.sync();
+                cur = 0;
+            }
+#else
             if constexpr (Ex::kWarpPcr) {
                 // Hybrid: thread t owns unknown q = warp + 8 lane.  The strides 1, 2, 4 couple different warps and go
                 // through shared memory (two barriers; the third level stays in registers); after them the couplings are
@@ -874,6 +1011,7 @@ struct DiscEngine {
                     cur ^= 1;
                 }
             }
+#endif
             const auto z = S.rr[cur];
             const bool incremental = iters > 0 || !has_C;
             ex.tick(1);

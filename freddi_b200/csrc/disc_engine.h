@@ -613,8 +613,9 @@ struct DiscEngine {
 
     // storage position of reduced unknown q (see solve_step)
     FB_HD static int rpos(int q) { return Ex::kWarpPcr ? ((q & 7) * 32 + (q >> 3)) : q; }
-#ifndef FB_PCR_FULL
-    // Odd-only reduced solve (solve_step): where block b's two reduced rows are stored in buffer 0.  Plain policies: q = 2b (the
+#ifdef FB_PCR_ODD
+    // Odd-only reduced solve (solve_step, -DFB_PCR_ODD: measured equal in time to the full PCR): where block b's two
+    // reduced rows are stored in buffer 0.  Plain policies: q = 2b (the
     // row of the block's first unknown, "even") and 2b + 1 ("odd").  Hybrid (warp) solver: the odd rows in the lower half of the
     // buffer in the warp-major order of its four warps (unknown p = warp + 4 lane at position 32 warp + lane), the even rows
     // likewise in the upper half.
@@ -824,7 +825,9 @@ struct DiscEngine {
             ex.tick(8);
             // -- reduced system (nred unknowns): parallel cyclic reduction, diagonal normalised to 1 --
             int cur = 0;
-#ifndef FB_PCR_FULL
+#ifdef FB_PCR_ODD
+            // (Variant, not the default: 8 % fewer executed instructions, the same time — the solve is bound by its chain of
+            // dependent levels and barriers, not by issue slots.  126 GPU tests green with it.)
             // After the first level of a cyclic reduction the even and the odd unknowns form two independent systems, and a full
             // PCR solves both.  Only the odd one (the last unknown of every block, o_b) is solved here — level for level the
             // arithmetic a full PCR applies to its odd rows — and the even unknowns (the first of every block, e_b) follow from

@@ -27,6 +27,7 @@
 #include <freddi_evolution.hpp>
 #include <ns/ns_arguments.hpp>
 #include <ns/ns_evolution.hpp>
+#include <spectrum.hpp>
 #include <unit_transformation.hpp>
 #include <util.hpp>
 
@@ -358,6 +359,12 @@ double ref_flux(void* h, int region, double lambda) {
 double ref_flux_star(void* h, double lambda, double phase) { return static_cast<Model*>(h)->ev()->flux_star(lambda, phase); }
 
 void ref_define_mdot0(double v) { g_define_mdot0 = v; }
+
+// Spectrum::Planck_nu1_nu2 of the reference (cpp/src/spectrum.cpp:26-37) at the tolerance FreddiState::Lx passes (1e-4,
+// cpp/src/freddi_state.cpp:339-345) for n temperatures: the band integral the library's walk restates and its table tabulates
+void ref_planck_nu1_nu2(const double* T, long n, double nu1, double nu2, double tol, double* out) {
+    for (long i = 0; i < n; ++i) out[i] = Spectrum::Planck_nu1_nu2(T[i], nu1, nu2, tol);
+}
 
 // trapz of the reference (cpp/src/util.cpp:9-19) on caller data
 double ref_trapz(const double* x, const double* y, size_t n, size_t first, size_t last) {

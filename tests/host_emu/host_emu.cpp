@@ -255,4 +255,23 @@ double emu_trapz(const double* x, const double* y, int n, int first, int last) {
 
 double emu_planck_nu1_nu2(double T, double nu1, double nu2, double tol, int* trials) { return planck_nu1_nu2(T, nu1, nu2, tol, trials); }
 
+// the same through the table of the band ratio nu2 / nu1 (lx_table.h), as the kernels evaluate it; *walked = rings the table did not answer
+void emu_planck_tab(const double* T, long n, double nu1, double nu2, double tol, double* out, long* walked) {
+    size_t len = 0;
+    const double* tab = lx_table_get(nu2 / nu1, &len);
+    long w = 0;
+    for (long i = 0; i < n; ++i) {
+        int trials = 0;
+        out[i] = planck_nu1_nu2_tab(tab, T[i], nu1, nu2, tol, &trials);
+        if (tab) {
+            const double x1 = FB_H_OVER_KB / T[i] * nu1;
+            int t2 = 0;
+            if (!(x1 >= FB_LX_X_LO && x1 < FB_LX_X_HI) || (lx_table_q(tab, x1, &t2), t2 < 0)) ++w;
+        } else {
+            ++w;
+        }
+    }
+    if (walked) *walked = w;
+}
+
 }  // extern "C"

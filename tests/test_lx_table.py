@@ -150,3 +150,28 @@ def test_random_band_ratios_never_return_a_wrong_piece():
             built += 1
             assert err.value <= 2e-11, (r, err.value, wx.value)
     assert built >= 8
+
+
+def test_table_against_the_reference_s_own_band_integral():
+    """Spectrum::Planck_nu1_nu2 of the reference itself (oracle/_ref: cpp/src/spectrum.cpp compiled in place, odeint restated by the
+    shim) against the table as the kernels evaluate it, at 10^5 temperatures over the table's range and beyond (the ends walk):
+    the 1e-10 parity tolerance with two orders to spare at every one of them."""
+    from oracle.pyoracle import REF_SO
+    ref, emu = C.CDLL(REF_SO), C.CDLL(cm.EMU_SO)
+    dp = C.POINTER(C.c_double)
+    ref.ref_planck_nu1_nu2.argtypes = [dp, C.c_long, C.c_double, C.c_double, C.c_double, dp]
+    emu.emu_planck_tab.argtypes = [dp, C.c_long, C.c_double, C.c_double, C.c_double, dp, C.POINTER(C.c_long)]
+    nu1, nu2 = kev_to_hertz(1.0), kev_to_hertz(12.0)
+    h_over_k = 6.62606896e-27 / 1.3806504e-16
+    n = 100000
+    x1 = np.exp(np.random.default_rng(0).uniform(np.log(0.02), np.log(400.), n))
+    T = h_over_k * nu1 / x1
+    a, b, walked = np.empty(n), np.empty(n), C.c_long()
+    ref.ref_planck_nu1_nu2(T.ctypes.data_as(dp), n, nu1, nu2, 1e-4, a.ctypes.data_as(dp))
+    emu.emu_planck_tab(T.ctypes.data_as(dp), n, nu1, nu2, 1e-4, b.ctypes.data_as(dp), C.byref(walked))
+    inside = (x1 >= 2.0 ** -5) & (x1 < 256.)
+    assert walked.value <= (~inside).sum() + 2   # slivers: a few 1e-9 of the range
+    rel = np.abs(a - b) / np.abs(a)
+    assert np.isfinite(rel).all()
+    assert rel.max() <= 1e-11, (rel.max(), x1[rel.argmax()])
+    assert np.median(rel) <= 1e-13

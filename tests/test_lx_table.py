@@ -175,3 +175,13 @@ def test_table_against_the_reference_s_own_band_integral():
     assert np.isfinite(rel).all()
     assert rel.max() <= 1e-11, (rel.max(), x1[rel.argmax()])
     assert np.median(rel) <= 1e-13
+
+
+def test_switching_the_table_off_and_bad_bands(monkeypatch):
+    """FB200_LX_TABLE=0 disables the table for the process (every ring walks); a band with nu2 <= nu1 has none."""
+    assert _selftest(12.0, 1.0, 10)[0] == _lib.ERR_UNSUPPORTED
+    assert _selftest(1.0, 1.0, 10)[0] == _lib.ERR_UNSUPPORTED
+    monkeypatch.setenv('FB200_LX_TABLE', '0')
+    assert _selftest(1.0, 12.0, 10)[0] == _lib.ERR_UNSUPPORTED
+    monkeypatch.delenv('FB200_LX_TABLE')
+    assert _selftest(1.0, 12.0, 10)[0] == 0
